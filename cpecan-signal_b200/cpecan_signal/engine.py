@@ -1,0 +1,241 @@
+"""ctypes binding of the C-ABI in include/cpecan_cuda.h (libcpecan_cuda.so, built by __graft_entry__.build()).
+
+There is no CPU path here: if the shared library or a CUDA device is missing, construction raises."""
+import ctypes as C
+import os
+
+import numpy as np
+
+PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(PKG_ROOT, "libcpecan_cuda.so")
+
+SM_THREE_STATE = 2
+SM_VANILLA = 4
+MODE_POSTERIOR = 0
+MODE_EXPECTATION = 1
+MODE_UNBANDED = 2
+N_KMERS = 4096
+
+ITEM_PAIR_OVERFLOW = 1
+ITEM_NONFINITE = 2
+ITEM_BAND_STEP = 4
+
+# stateMachine3_setTransitionsToNanoporeDefaults (reference impl/stateMachine.c:1278-1289), StateMachine3 field order
+NANOPORE_TRANSITIONS = (-0.23552123624314988, -0.21880828092192281, -0.013406326748077823, -1.6269694202638481,
+                        -4.3187242127300092, -1.6269694202638481, -4.3187242127239411, -np.inf, -np.inf)
+
+
+class Params(C.Structure):
+    """PairwiseAlignmentParameters (reference inc/pairwiseAligner.h:80-91)."""
+    _fields_ = [("threshold", C.c_double), ("minDiagsBetweenTraceBack", C.c_int64),
+                ("traceBackDiagonals", C.c_int64), ("diagonalExpansion", C.c_int64),
+                ("constraintDiagonalTrim", C.c_int64), ("splitMatrixBiggerThanThis", C.c_int64)]
+
+
+def default_params(**kw):
+    """pairwiseAlignmentBandingParameters_construct (reference impl/pairwiseAligner.c:1428-1441)."""
+    p = Params(0.01, 1000, 40, 20, 14, 3000 * 3000)
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+class Hmm(C.Structure):
+    _fields_ = [("sm_type", C.c_int32), ("reserved", C.c_int32), ("transitions", C.c_double * 9),
+                ("vanilla", C.c_double * 5)]
+
+
+def three_state_hmm(transitions=None):
+    h = Hmm()
+    h.sm_type = SM_THREE_STATE
+    t = NANOPORE_TRANSITIONS if transitions is None else transitions
+    for i in range(9):
+        h.transitions[i] = float(t[i])
+    return h
+
+
+class Batch(C.Structure):
+    _fields_ = [("n_items", C.c_int64), ("ref", C.c_void_p), ("ref_off", C.c_void_p), ("events", C.c_void_p),
+                ("ev_off", C.c_void_p), ("anchors", C.c_void_p), ("anchor_off", C.c_void_p),
+                ("model_id", C.c_void_p), ("scale", C.c_void_p), ("ragged", C.c_void_p)]
+
+
+class Result(C.Structure):
+    _fields_ = [("n_pairs", C.c_int64), ("pair_off", C.c_int64), ("band_cells", C.c_int64),
+                ("total_logprob", C.c_double), ("status", C.c_int32), ("n_tracebacks", C.c_int32)]
+
+
+RESULT_DTYPE = np.dtype([("n_pairs", np.int64), ("pair_off", np.int64), ("band_cells", np.int64),
+                         ("total_logprob", np.float64), ("status", np.int32), ("n_tracebacks", np.int32)])
+
+
+class Timing(C.Structure):
+    _fields_ = [("h2d_ms", C.c_double), ("prep_ms", C.c_double), ("plan_ms", C.c_double), ("align_ms", C.c_double),
+                ("d2h_ms", C.c_double), ("total_ms", C.c_double), ("kernel_launches", C.c_int64),
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("band_cells", C.c_int64),
+                ("warps_per_item", C.c_int32), ("ctas", C.c_int32)]
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def load_library():
+    if not os.path.exists(LIB_PATH):
+        raise EngineError("%s is missing: run __graft_entry__.build() (there is no CPU fallback)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    lib.cpecan_cuda_last_error.restype = C.c_char_p
+    lib.cpecan_cuda_last_error.argtypes = [C.c_void_p]
+    lib.cpecan_cuda_destroy.argtypes = [C.c_void_p]
+    lib.cpecan_cuda_destroy.restype = None
+    return lib
+
+
+class HostBatch:
+    """Flat (structure-of-arrays) host batch in the layout cpecan_batch describes."""
+
+    def __init__(self, refs, events, anchors, model_ids=None, scales=None, ragged=None):
+        n = len(refs)
+        self.n = n
+        ref_len = np.fromiter((len(r) for r in refs), dtype=np.int64, count=n)
+        self.ref_off = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(ref_len, out=self.ref_off[1:])
+        self.ref = np.frombuffer("".join(refs).encode(), dtype=np.uint8).copy() if n else np.zeros(1, np.uint8)
+        evs = [np.ascontiguousarray(e, dtype=np.float64).reshape(-1, 3) for e in events]
+        self.ev_off = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(np.fromiter((len(e) for e in evs), dtype=np.int64, count=n), out=self.ev_off[1:])
+        self.events = np.ascontiguousarray(np.concatenate(evs, axis=0)) if n and self.ev_off[-1] else np.zeros((1, 3))
+        ans = [np.asarray(a, dtype=np.int64).reshape(-1, 2) for a in anchors]
+        self.anchor_off = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(np.fromiter((len(a) for a in ans), dtype=np.int64, count=n), out=self.anchor_off[1:])
+        self.anchors = np.ascontiguousarray(np.concatenate(ans, axis=0)) if n and self.anchor_off[-1] else np.zeros((1, 2), np.int64)
+        self.model_id = np.zeros(n, dtype=np.int32) if model_ids is None else np.ascontiguousarray(model_ids, dtype=np.int32)
+        self.scale = None if scales is None else np.ascontiguousarray(scales, dtype=np.float64).reshape(n, 5)
+        self.ragged = np.zeros(n, dtype=np.uint8) if ragged is None else np.ascontiguousarray(
+            [(int(a) & 1) | ((int(b) & 1) << 1) for a, b in ragged], dtype=np.uint8)
+
+    @property
+    def lX(self):
+        return np.maximum(np.diff(self.ref_off) - 5, 0)
+
+    @property
+    def lY(self):
+        return np.diff(self.ev_off)
+
+    def cstruct(self):
+        b = Batch()
+        b.n_items = self.n
+        b.ref = self.ref.ctypes.data
+        b.ref_off = self.ref_off.ctypes.data
+        b.events = self.events.ctypes.data
+        b.ev_off = self.ev_off.ctypes.data
+        b.anchors = self.anchors.ctypes.data
+        b.anchor_off = self.anchor_off.ctypes.data
+        b.model_id = self.model_id.ctypes.data
+        b.scale = None if self.scale is None else self.scale.ctypes.data
+        b.ragged = self.ragged.ctypes.data
+        return b
+
+
+class Engine:
+    def __init__(self, device=0):
+        self.lib = load_library()
+        self.ctx = C.c_void_p()
+        rc = self.lib.cpecan_cuda_init(int(device), C.byref(self.ctx))
+        if rc != 0:
+            raise EngineError("cpecan_cuda_init failed (rc=%d): no usable CUDA device; there is no CPU fallback" % rc)
+
+    def close(self):
+        if self.ctx:
+            self.lib.cpecan_cuda_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise EngineError("%s failed (rc=%d): %s" % (what, rc, self.lib.cpecan_cuda_last_error(self.ctx).decode()))
+
+    def upload_model(self, match, gapy, gapx):
+        match = np.ascontiguousarray(match, dtype=np.float64)
+        gapy = np.ascontiguousarray(gapy, dtype=np.float64)
+        gapx = np.ascontiguousarray(gapx, dtype=np.float64)
+        assert match.size == 1 + N_KMERS * 5 and gapy.size == 1 + N_KMERS * 5
+        mid = C.c_int32(-1)
+        self._check(self.lib.cpecan_cuda_upload_model(self.ctx, match.ctypes.data_as(C.c_void_p),
+                                                      gapy.ctypes.data_as(C.c_void_p), gapx.ctypes.data_as(C.c_void_p),
+                                                      C.c_int32(gapx.size), C.byref(mid)), "upload_model")
+        return mid.value
+
+    def device_info(self):
+        sm, clk, mem = C.c_int32(), C.c_int32(), C.c_int64()
+        self._check(self.lib.cpecan_cuda_device_info(self.ctx, C.byref(sm), C.byref(clk), C.byref(mem)), "device_info")
+        return dict(sm_count=sm.value, clock_khz=clk.value, hbm_bytes=mem.value)
+
+    def timing(self):
+        t = Timing()
+        self._check(self.lib.cpecan_cuda_get_timing(self.ctx, C.byref(t)), "get_timing")
+        return {k: getattr(t, k) for k, _ in Timing._fields_}
+
+    @staticmethod
+    def default_pair_capacity(batch, per_event=4):
+        return int(per_event * int(batch.ev_off[-1]) + 64 * batch.n + 1024)
+
+    def align_batch(self, batch, hmm=None, params=None, mode=MODE_POSTERIOR, pair_cap=None, want_totals=False):
+        """Returns (results structured array, pairs int32[n,3], totals list or None).  Pairs of item i are
+        pairs[r['pair_off'] : r['pair_off'] + min(r['n_pairs'], cap_i)] in the reference's emission order."""
+        hmm = hmm or three_state_hmm()
+        params = params or default_params()
+        pair_cap = pair_cap or self.default_pair_capacity(batch)
+        pairs = np.zeros((pair_cap, 3), dtype=np.int32)
+        results = np.zeros(batch.n, dtype=RESULT_DTYPE)
+        totals = tot_off = None
+        if want_totals:
+            tot_off = np.zeros(batch.n + 1, dtype=np.int64)
+            np.cumsum(3 * (batch.lX + batch.lY + 1), out=tot_off[1:])
+            totals = np.full(int(tot_off[-1]), np.nan)
+        cb = batch.cstruct()
+        rc = self.lib.cpecan_cuda_align_batch(
+            self.ctx, C.byref(hmm), C.byref(params), C.c_int32(mode), C.byref(cb), pairs.ctypes.data_as(C.c_void_p),
+            C.c_int64(pair_cap), results.ctypes.data_as(C.c_void_p),
+            None if totals is None else totals.ctypes.data_as(C.c_void_p),
+            None if tot_off is None else tot_off.ctypes.data_as(C.c_void_p))
+        self._check(rc, "align_batch")
+        tl = None
+        if want_totals:
+            # per item: rows = (total handed to the diagonal, term 1, term 2); want_totals="terms" keeps all three
+            tl = [totals[tot_off[i]:tot_off[i + 1]].reshape(3, -1) for i in range(batch.n)]
+            if want_totals != "terms":
+                tl = [t[0] for t in tl]
+        return results, pairs, tl
+
+    # device-resident variant (kernel-only timing)
+    def stage(self, batch, hmm=None, params=None, mode=MODE_POSTERIOR, pair_cap=None):
+        hmm = hmm or three_state_hmm()
+        params = params or default_params()
+        pair_cap = pair_cap or self.default_pair_capacity(batch)
+        cb = batch.cstruct()
+        self._staged_n = batch.n
+        self._staged_cap = pair_cap
+        self._check(self.lib.cpecan_cuda_stage(self.ctx, C.byref(hmm), C.byref(params), C.c_int32(mode), C.byref(cb),
+                                               C.c_int64(pair_cap)), "stage")
+
+    def run_staged(self):
+        self._check(self.lib.cpecan_cuda_run_staged(self.ctx), "run_staged")
+
+    def fetch_staged(self):
+        pairs = np.zeros((self._staged_cap, 3), dtype=np.int32)
+        results = np.zeros(self._staged_n, dtype=RESULT_DTYPE)
+        self._check(self.lib.cpecan_cuda_fetch_staged(self.ctx, pairs.ctypes.data_as(C.c_void_p),
+                                                      results.ctypes.data_as(C.c_void_p)), "fetch_staged")
+        return results, pairs
+
+
+def item_pairs(results, pairs, i, cap=None):
+    r = results[i]
+    n = int(r["n_pairs"])
+    return pairs[int(r["pair_off"]): int(r["pair_off"]) + n]

@@ -1,0 +1,506 @@
+// cpecan_cuda.cu -- host side of the C-ABI declared in include/cpecan_cuda.h: context, staging, kernel launches.
+// All device work runs on the engine's own stream; timings come from CUDA events on that stream.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "cpecan_cuda.h"
+#include "cpecan_kernels.cuh"
+
+using namespace cpecan;
+
+namespace {
+
+constexpr int KSLOTS = 4;                         // cells per thread
+constexpr int NBUCKET = 6;                        // G = 1, 2, 4, 8, 16, 32 warps per alignment
+constexpr int bucketG[NBUCKET] = { 1, 2, 4, 8, 16, 32 };
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct Model { double *match = nullptr, *gapy = nullptr, *gapx = nullptr; int n_gapx = 0; };
+
+struct Bucket {
+    std::vector<int> order;      // item indices, largest first
+    int nCta = 0, ringRows = 0;
+    long long stride = 0;        // floats per CTA
+    size_t scratchOff = 0;       // floats into the scratch buffer
+    size_t rowoffOff = 0;        // ints into the rowoff buffer
+    size_t orderOff = 0;         // ints into the order buffer
+};
+
+}  // namespace
+
+struct cpecan_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {};
+    cudaDeviceProp prop{};
+    std::string err;
+    std::mutex mu;
+    std::vector<Model> models;
+    DevBuf dModels;
+    bool modelsDirty = true;
+
+    // staged batch
+    int64_t n = 0;
+    int mode = 0;
+    DevParams P{};
+    bool hasSX = false;
+    std::vector<Item> hItems;
+    std::vector<ItemOut> hOut;
+    DevBuf dItems, dOut, dRef, dRefOff, dEvSrc, dEvSrcOff, dAnchors, dScale, dCentre, dXp, dEv, dPairs, dOrder,
+           dQueue, dScratch, dRowoff, dTotals, dCompact, dCompactOff;
+    int64_t pairCapTotal = 0, totalsLen = 0;
+    Bucket buckets[NBUCKET];
+    bool wantTotals = false;
+    std::vector<int64_t> hTotOff;
+    cpecan_timing timing{};
+    int occ[NBUCKET][2] = {};
+};
+
+namespace {
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                         \
+            return CPECAN_ERR_CUDA;                                                                \
+        }                                                                                          \
+    } while (0)
+
+template <int G, bool SX> void launchAlign(const KernelArgs &a, int nCta, cudaStream_t s) {
+    k_align<G, KSLOTS, SX><<<nCta, 32 * G, 0, s>>>(a);
+}
+template <int G> int occupancyOf(bool sx) {
+    int nb = 0;
+    if (sx) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_align<G, KSLOTS, true>, 32 * G, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_align<G, KSLOTS, false>, 32 * G, 0);
+    return nb;
+}
+int occupancy(int b, bool sx) {
+    switch (b) {
+        case 0: return occupancyOf<1>(sx);
+        case 1: return occupancyOf<2>(sx);
+        case 2: return occupancyOf<4>(sx);
+        case 3: return occupancyOf<8>(sx);
+        case 4: return occupancyOf<16>(sx);
+        default: return occupancyOf<32>(sx);
+    }
+}
+void launchBucket(int b, bool sx, const KernelArgs &a, int nCta, cudaStream_t s) {
+    switch (b) {
+        case 0: sx ? launchAlign<1, true>(a, nCta, s) : launchAlign<1, false>(a, nCta, s); break;
+        case 1: sx ? launchAlign<2, true>(a, nCta, s) : launchAlign<2, false>(a, nCta, s); break;
+        case 2: sx ? launchAlign<4, true>(a, nCta, s) : launchAlign<4, false>(a, nCta, s); break;
+        case 3: sx ? launchAlign<8, true>(a, nCta, s) : launchAlign<8, false>(a, nCta, s); break;
+        case 4: sx ? launchAlign<16, true>(a, nCta, s) : launchAlign<16, false>(a, nCta, s); break;
+        default: sx ? launchAlign<32, true>(a, nCta, s) : launchAlign<32, false>(a, nCta, s); break;
+    }
+}
+
+__global__ void k_compact(const Item *items, const ItemOut *out, const long long *dstOff, int n, const int *src, int *dst) {
+    const int i = blockIdx.x;
+    if (i >= n) return;
+    const Item it = items[i];
+    const int np = min(out[i].n_pairs, it.pair_cap);
+    const int *s = src + 3 * it.pair_off;
+    int *d = dst + 3 * dstOff[i];
+    for (int j = threadIdx.x; j < 3 * np; j += blockDim.x) d[j] = s[j];
+}
+
+int fillDevParams(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *p, int mode) {
+    if (hmm->sm_type != CPECAN_SM_THREE_STATE) { ctx->err = "only the three-state machine is implemented on device"; return CPECAN_ERR_ARG; }
+    if (p->diagonalExpansion < 0 || p->diagonalExpansion % 2 != 0 || p->traceBackDiagonals < 1 ||
+        p->minDiagsBetweenTraceBack < 2 || p->traceBackDiagonals + 1 >= p->minDiagsBetweenTraceBack) {
+        ctx->err = "invalid banding parameters (see impl/pairwiseAligner.c:880-884 of the reference)";
+        return CPECAN_ERR_ARG;
+    }
+    DevParams &P = ctx->P;
+    const double *t = hmm->transitions;
+    P.tMC = (float) t[0]; P.tMX = (float) t[1]; P.tMY = (float) t[2]; P.tOX = (float) t[3]; P.tOY = (float) t[4];
+    P.tEX = (float) t[5]; P.tEY = (float) t[6]; P.tSX = (float) t[7]; P.tSY = (float) t[8];
+    const float NI = -INFINITY;
+    P.startv[0] = 0.f; P.startv[1] = NI; P.startv[2] = NI;                 // impl/stateMachine.c:1168-1172
+    P.rstartv[0] = NI; P.rstartv[1] = 0.f; P.rstartv[2] = 0.f;             // :1174-1177
+    P.endv[0] = (float) t[0]; P.endv[1] = (float) t[1]; P.endv[2] = (float) t[2];           // :1179-1192
+    P.rendv[0] = (float) ((t[3] + t[4]) / 2.0); P.rendv[1] = (float) t[5]; P.rendv[2] = (float) t[6];  // :1194-1207
+    P.threshold = (float) p->threshold;
+    P.minDiags = (int) p->minDiagsBetweenTraceBack;
+    P.tbDiags = (int) p->traceBackDiagonals;
+    P.expansion = (int) p->diagonalExpansion;
+    P.totalEvery = 10;
+    P.rebaseEvery = 8;
+    P.mode = mode;
+    ctx->hasSX = !(std::isinf(t[7]) && t[7] < 0);
+    P.hasSX = ctx->hasSX;
+    P.dbgLogP = getenv("CPECAN_DEBUG_LOGP") ? atoi(getenv("CPECAN_DEBUG_LOGP")) : 0;
+    return CPECAN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cpecan_cuda_init(int device, cpecan_ctx **ctx_out) {
+    if (!ctx_out) return CPECAN_ERR_ARG;
+    *ctx_out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device < 0 || device >= count) return CPECAN_ERR_CUDA;
+    cpecan_ctx *ctx = new cpecan_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&ctx->prop, device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return CPECAN_ERR_CUDA;
+    }
+    for (auto &e : ctx->ev) cudaEventCreate(&e);
+    for (int b = 0; b < NBUCKET; b++) { ctx->occ[b][0] = occupancy(b, false); ctx->occ[b][1] = occupancy(b, true); }
+    *ctx_out = ctx;
+    return CPECAN_OK;
+}
+
+void cpecan_cuda_destroy(cpecan_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &m : ctx->models) { cudaFree(m.match); cudaFree(m.gapy); cudaFree(m.gapx); }
+    DevBuf *bufs[] = { &ctx->dModels, &ctx->dItems, &ctx->dOut, &ctx->dRef, &ctx->dRefOff, &ctx->dEvSrc, &ctx->dEvSrcOff,
+                       &ctx->dAnchors, &ctx->dScale, &ctx->dCentre, &ctx->dXp, &ctx->dEv, &ctx->dPairs, &ctx->dOrder,
+                       &ctx->dQueue, &ctx->dScratch, &ctx->dRowoff, &ctx->dTotals, &ctx->dCompact, &ctx->dCompactOff };
+    for (auto *b : bufs) b->release();
+    for (auto &e : ctx->ev) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *cpecan_cuda_last_error(cpecan_ctx *ctx) { return ctx ? ctx->err.c_str() : "no context (no usable CUDA device?)"; }
+
+int cpecan_cuda_upload_model(cpecan_ctx *ctx, const double *match, const double *gapy, const double *gapx,
+                             int32_t n_gapx, int32_t *model_id_out) {
+    if (!ctx || !match || !gapy || !gapx || n_gapx <= 0 || !model_id_out) return CPECAN_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    const size_t tbl = (1 + 4096 * 5) * sizeof(double);
+    Model m;
+    m.n_gapx = n_gapx;
+    CK(cudaMalloc(&m.match, tbl));
+    CK(cudaMalloc(&m.gapy, tbl));
+    CK(cudaMalloc(&m.gapx, n_gapx * sizeof(double)));
+    CK(cudaMemcpy(m.match, match, tbl, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(m.gapy, gapy, tbl, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(m.gapx, gapx, n_gapx * sizeof(double), cudaMemcpyHostToDevice));
+    ctx->models.push_back(m);
+    ctx->modelsDirty = true;
+    *model_id_out = (int32_t) ctx->models.size() - 1;
+    return CPECAN_OK;
+}
+
+int cpecan_cuda_stage(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *params, int32_t mode,
+                      const cpecan_batch *B, int64_t pair_cap_total) {
+    if (!ctx || !hmm || !params || !B || B->n_items < 0) return CPECAN_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    int rc = fillDevParams(ctx, hmm, params, mode);
+    if (rc != CPECAN_OK) return rc;
+    const int64_t n = B->n_items;
+    ctx->n = n;
+    ctx->mode = mode;
+    ctx->timing = cpecan_timing{};
+    if (n == 0) return CPECAN_OK;
+    cudaStream_t s = ctx->stream;
+
+    if (ctx->modelsDirty) {
+        std::vector<ModelTables> mt(ctx->models.size());
+        for (size_t i = 0; i < mt.size(); i++) { mt[i].match = ctx->models[i].match; mt[i].gapy = ctx->models[i].gapy; mt[i].gapx = ctx->models[i].gapx; mt[i].n_gapx = ctx->models[i].n_gapx; }
+        CK(ctx->dModels.ensure(std::max<size_t>(1, mt.size()) * sizeof(ModelTables)));
+        if (!mt.empty()) CK(cudaMemcpy(ctx->dModels.p, mt.data(), mt.size() * sizeof(ModelTables), cudaMemcpyHostToDevice));
+        ctx->modelsDirty = false;
+    }
+
+    // ---- host-side layout: prefix sums, per-item records -------------------------------------------------
+    ctx->hItems.resize(n);
+    std::vector<double> centre(n);
+    long long xpTot = 0, evTot = 0, totTot = 0;
+    int64_t sumLY = 0;
+    for (int64_t i = 0; i < n; i++) sumLY += (B->ev_off[i + 1] - B->ev_off[i]) + 32;
+    long long pairTot = 0;
+    ctx->hTotOff.assign(n + 1, 0);
+    int maxLX = 0, maxLY = 0;
+    for (int64_t i = 0; i < n; i++) {
+        Item &it = ctx->hItems[i];
+        const int64_t refLen = B->ref_off[i + 1] - B->ref_off[i];
+        const int64_t lX = refLen >= 5 ? refLen - 5 : 0, lY = B->ev_off[i + 1] - B->ev_off[i];
+        if (B->model_id[i] < 0 || B->model_id[i] >= (int) ctx->models.size()) { ctx->err = "bad model id"; return CPECAN_ERR_ARG; }
+        it.xp_off = xpTot; it.ev_off = evTot; it.an_off = B->anchor_off[i];
+        it.lX = (int) lX; it.lY = (int) lY; it.nA = (int) (B->anchor_off[i + 1] - B->anchor_off[i]);
+        it.flags = B->ragged ? B->ragged[i] : 0;
+        it.model_id = B->model_id[i];
+        it.pad0 = it.pad1 = 0;
+        // pair capacity: proportional share of the caller's buffer
+        long long cap = (long long) ((long double) pair_cap_total * (long double) (lY + 32) / (long double) sumLY);
+        it.pair_off = pairTot; it.pair_cap = (int) std::min<long long>(cap, 0x7fffffff);
+        pairTot += it.pair_cap;
+        it.tot_off = ctx->wantTotals ? totTot : -1;
+        ctx->hTotOff[i] = totTot;
+        totTot += 3 * (lX + lY + 1);   // total, term 1, term 2 per diagonal
+        xpTot += lX + 1; evTot += lY + 1;
+        maxLX = std::max(maxLX, (int) lX); maxLY = std::max(maxLY, (int) lY);
+        const double sc = B->scale ? B->scale[5 * i] : 1.0, sh = B->scale ? B->scale[5 * i + 1] : 0.0;
+        centre[i] = 68.0 * sc + sh;
+    }
+    ctx->hTotOff[n] = totTot;
+    ctx->pairCapTotal = pairTot;
+    ctx->totalsLen = totTot;
+    const int64_t refBytes = B->ref_off[n], nEv = B->ev_off[n], nAn = B->anchor_off[n];
+
+    // ---- H2D ---------------------------------------------------------------------------------------------
+    CK(cudaEventRecord(ctx->ev[0], s));
+    CK(ctx->dItems.ensure(n * sizeof(Item)));
+    CK(ctx->dOut.ensure(n * sizeof(ItemOut)));
+    CK(ctx->dRef.ensure(refBytes + 16));
+    CK(ctx->dRefOff.ensure((n + 1) * sizeof(long long)));
+    CK(ctx->dEvSrc.ensure(std::max<int64_t>(1, nEv) * 3 * sizeof(double)));
+    CK(ctx->dEvSrcOff.ensure((n + 1) * sizeof(long long)));
+    CK(ctx->dAnchors.ensure(std::max<int64_t>(1, nAn) * 2 * sizeof(long long)));
+    CK(ctx->dCentre.ensure(n * sizeof(double)));
+    CK(ctx->dXp.ensure(xpTot * 3 * sizeof(float4)));
+    CK(ctx->dEv.ensure(evTot * sizeof(float2)));
+    CK(ctx->dPairs.ensure(std::max<long long>(1, pairTot) * 3 * sizeof(int)));
+    CK(cudaMemcpyAsync(ctx->dItems.p, ctx->hItems.data(), n * sizeof(Item), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->dRef.p, B->ref, refBytes, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->dRefOff.p, B->ref_off, (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, s));
+    if (nEv) CK(cudaMemcpyAsync(ctx->dEvSrc.p, B->events, nEv * 3 * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->dEvSrcOff.p, B->ev_off, (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, s));
+    if (nAn) CK(cudaMemcpyAsync(ctx->dAnchors.p, B->anchors, nAn * 2 * sizeof(long long), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->dCentre.p, centre.data(), n * sizeof(double), cudaMemcpyHostToDevice, s));
+    const double *dScale = nullptr;
+    if (B->scale) {
+        CK(ctx->dScale.ensure(n * 5 * sizeof(double)));
+        CK(cudaMemcpyAsync(ctx->dScale.p, B->scale, n * 5 * sizeof(double), cudaMemcpyHostToDevice, s));
+        dScale = ctx->dScale.as<double>();
+    }
+    ctx->timing.h2d_bytes = n * (int64_t) sizeof(Item) + refBytes + 2 * (n + 1) * 8 + nEv * 24 + nAn * 16 + n * 8 + (B->scale ? n * 40 : 0);
+    CK(cudaEventRecord(ctx->ev[1], s));
+
+    // ---- preparation kernels -----------------------------------------------------------------------------
+    {
+        dim3 ge((unsigned) n, (unsigned) std::min(64, (maxLY + 256) / 256 + 1));
+        k_prep_events<<<ge, 256, 0, s>>>(ctx->dItems.as<Item>(), ctx->dEvSrcOff.as<long long>(), ctx->dEvSrc.as<double>(),
+                                        ctx->dCentre.as<double>(), ctx->dEv.as<float2>());
+        dim3 gx((unsigned) n, (unsigned) std::min(64, (maxLX + 256) / 256 + 1));
+        k_prep_xparams3<<<gx, 256, 0, s>>>(ctx->dItems.as<Item>(), ctx->dRefOff.as<long long>(), ctx->dRef.as<char>(),
+                                          ctx->dModels.as<ModelTables>(), dScale, ctx->dCentre.as<double>(), ctx->dXp.as<float4>());
+        ctx->timing.kernel_launches += 2;
+    }
+    CK(cudaEventRecord(ctx->ev[2], s));
+
+    // ---- plan: band cells, widest diagonal, longest run of live forward rows -------------------------------
+    k_plan<<<(unsigned) ((n + 127) / 128), 128, 0, s>>>(ctx->dItems.as<Item>(), (int) n, ctx->dAnchors.as<long long>(), ctx->P, ctx->dOut.as<ItemOut>());
+    ctx->timing.kernel_launches += 1;
+    ctx->hOut.resize(n);
+    CK(cudaMemcpyAsync(ctx->hOut.data(), ctx->dOut.p, n * sizeof(ItemOut), cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(ctx->ev[3], s));
+    CK(cudaStreamSynchronize(s));
+    {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->timing.h2d_ms = ms;
+        cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); ctx->timing.prep_ms = ms;
+        cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); ctx->timing.plan_ms = ms;
+    }
+
+    // ---- bucket by required warps per alignment, order largest first ----------------------------------------
+    for (auto &b : ctx->buckets) { b.order.clear(); b.nCta = 0; b.ringRows = 0; }
+    int64_t cells = 0;
+    for (int64_t i = 0; i < n; i++) {
+        const ItemOut &o = ctx->hOut[i];
+        cells += o.band_cells;
+        int b = 0;
+        while (b < NBUCKET && 32 * bucketG[b] * KSLOTS - KSLOTS < o.max_width) b++;
+        if (b == NBUCKET) { ctx->err = "band wider than 4092 cells is not supported"; return CPECAN_ERR_BAND_TOO_WIDE; }
+        ctx->buckets[b].order.push_back((int) i);
+        ctx->buckets[b].ringRows = std::max(ctx->buckets[b].ringRows, o.max_rows);
+    }
+    ctx->timing.band_cells = cells;
+    size_t scratchFloats = 0, rowoffInts = 0, orderInts = 0;
+    std::vector<int> orderAll;
+    orderAll.reserve(n);
+    for (int b = 0; b < NBUCKET; b++) {
+        Bucket &bk = ctx->buckets[b];
+        if (bk.order.empty()) continue;
+        std::stable_sort(bk.order.begin(), bk.order.end(), [&](int a, int c) { return ctx->hOut[a].band_cells > ctx->hOut[c].band_cells; });
+        const int occ = std::max(1, ctx->occ[b][ctx->hasSX ? 1 : 0]);
+        bk.nCta = (int) std::min<int64_t>((int64_t) bk.order.size(), (int64_t) ctx->prop.multiProcessorCount * occ);
+        bk.stride = (long long) bk.ringRows * 3 * 32 * bucketG[b] * KSLOTS;
+        bk.scratchOff = scratchFloats; scratchFloats += (size_t) bk.stride * bk.nCta;
+        bk.rowoffOff = rowoffInts; rowoffInts += (size_t) bk.ringRows * bk.nCta * 32 * bucketG[b];
+        bk.orderOff = orderInts; orderInts += bk.order.size();
+        orderAll.insert(orderAll.end(), bk.order.begin(), bk.order.end());
+        ctx->timing.warps_per_item = bucketG[b];
+        ctx->timing.ctas = bk.nCta;
+    }
+    CK(ctx->dScratch.ensure(std::max<size_t>(1, scratchFloats) * sizeof(float)));
+    CK(ctx->dRowoff.ensure(std::max<size_t>(1, rowoffInts) * sizeof(int)));
+    CK(ctx->dOrder.ensure(std::max<size_t>(1, orderInts) * sizeof(int)));
+    CK(ctx->dQueue.ensure(NBUCKET * sizeof(int)));
+    CK(cudaMemcpyAsync(ctx->dOrder.p, orderAll.data(), orderAll.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    if (ctx->wantTotals) CK(ctx->dTotals.ensure(std::max<int64_t>(1, totTot) * sizeof(double)));
+    CK(cudaStreamSynchronize(s));
+    return CPECAN_OK;
+}
+
+int cpecan_cuda_run_staged(cpecan_ctx *ctx) {
+    if (!ctx) return CPECAN_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->n == 0) return CPECAN_OK;
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemsetAsync(ctx->dQueue.p, 0, NBUCKET * sizeof(int), s));
+    if (ctx->wantTotals) {
+        // NaN fill (all-ones bit pattern is a NaN)
+        CK(cudaMemsetAsync(ctx->dTotals.p, 0xff, ctx->totalsLen * sizeof(double), s));
+    }
+    CK(cudaEventRecord(ctx->ev[4], s));
+    int launches = 0;
+    for (int b = 0; b < NBUCKET; b++) {
+        Bucket &bk = ctx->buckets[b];
+        if (bk.order.empty()) continue;
+        KernelArgs a;
+        a.items = ctx->dItems.as<Item>();
+        a.order = ctx->dOrder.as<int>() + bk.orderOff;
+        a.n_items = (int) bk.order.size();
+        a.queue = ctx->dQueue.as<int>() + b;
+        a.anchors = ctx->dAnchors.as<long long>();
+        a.xparams = ctx->dXp.as<float4>();
+        a.events = ctx->dEv.as<float2>();
+        a.scratch = ctx->dScratch.as<float>() + bk.scratchOff;
+        a.scratch_off = ctx->dRowoff.as<int>() + bk.rowoffOff;
+        a.scratch_stride = bk.stride;
+        a.ring_rows = bk.ringRows;
+        a.pairs = ctx->dPairs.as<int>();
+        a.out = ctx->dOut.as<ItemOut>();
+        a.totals = ctx->wantTotals ? ctx->dTotals.as<double>() : nullptr;
+        a.P = ctx->P;
+        launchBucket(b, ctx->hasSX, a, bk.nCta, s);
+        launches++;
+    }
+    CK(cudaEventRecord(ctx->ev[5], s));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]);
+    ctx->timing.align_ms = ms;
+    ctx->timing.kernel_launches += launches;
+    return CPECAN_OK;
+}
+
+int cpecan_cuda_fetch_staged(cpecan_ctx *ctx, int32_t *pairs_out, cpecan_result *results) {
+    if (!ctx || !results) return CPECAN_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    const int64_t n = ctx->n;
+    if (n == 0) return CPECAN_OK;
+    cudaStream_t s = ctx->stream;
+    CK(cudaEventRecord(ctx->ev[6], s));
+    // the plan wrote band_cells / max_width into dOut, the align kernel the rest
+    std::vector<ItemOut> out(n);
+    CK(cudaMemcpyAsync(out.data(), ctx->dOut.p, n * sizeof(ItemOut), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    std::vector<long long> dst(n + 1, 0);
+    for (int64_t i = 0; i < n; i++) {
+        const int np = std::min(out[i].n_pairs, ctx->hItems[i].pair_cap);
+        dst[i + 1] = dst[i] + np;
+        results[i].n_pairs = out[i].n_pairs;
+        results[i].pair_off = dst[i];
+        results[i].band_cells = out[i].band_cells;
+        results[i].total_logprob = out[i].total_logprob;
+        results[i].status = out[i].status;
+        results[i].n_tracebacks = out[i].n_tracebacks;
+    }
+    ctx->timing.d2h_bytes = n * (int64_t) sizeof(ItemOut);
+    if (pairs_out && dst[n] > 0) {
+        CK(ctx->dCompactOff.ensure((n + 1) * sizeof(long long)));
+        CK(ctx->dCompact.ensure(dst[n] * 3 * sizeof(int)));
+        CK(cudaMemcpyAsync(ctx->dCompactOff.p, dst.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, s));
+        k_compact<<<(unsigned) n, 128, 0, s>>>(ctx->dItems.as<Item>(), ctx->dOut.as<ItemOut>(), ctx->dCompactOff.as<long long>(), (int) n,
+                                              ctx->dPairs.as<int>(), ctx->dCompact.as<int>());
+        ctx->timing.kernel_launches += 1;
+        CK(cudaMemcpyAsync(pairs_out, ctx->dCompact.p, dst[n] * 3 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        ctx->timing.d2h_bytes += dst[n] * 12;
+    }
+    CK(cudaEventRecord(ctx->ev[7], s));
+    CK(cudaStreamSynchronize(s));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]);
+    ctx->timing.d2h_ms = ms;
+    ctx->timing.total_ms = ctx->timing.h2d_ms + ctx->timing.prep_ms + ctx->timing.plan_ms + ctx->timing.align_ms + ctx->timing.d2h_ms;
+    return CPECAN_OK;
+}
+
+int cpecan_cuda_align_batch(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *params, int32_t mode,
+                            const cpecan_batch *batch, int32_t *pairs_out, int64_t pair_cap_total,
+                            cpecan_result *results, double *totals_out, const int64_t *tot_off) {
+    if (!ctx) return CPECAN_ERR_CUDA;
+    if (mode != CPECAN_MODE_POSTERIOR && mode != CPECAN_MODE_UNBANDED) { ctx->err = "align_batch: mode must be POSTERIOR or UNBANDED"; return CPECAN_ERR_ARG; }
+    ctx->wantTotals = totals_out != nullptr;
+    int rc = cpecan_cuda_stage(ctx, hmm, params, mode, batch, pair_cap_total);
+    if (rc == CPECAN_OK) rc = cpecan_cuda_run_staged(ctx);
+    if (rc == CPECAN_OK) rc = cpecan_cuda_fetch_staged(ctx, pairs_out, results);
+    if (rc == CPECAN_OK && totals_out && ctx->n > 0) {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        // debug totals: copy each item's slice to the caller's layout
+        std::vector<double> tmp(ctx->totalsLen);
+        CK(cudaMemcpy(tmp.data(), ctx->dTotals.p, ctx->totalsLen * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int64_t i = 0; i < ctx->n; i++) {
+            const int64_t len = ctx->hTotOff[i + 1] - ctx->hTotOff[i];
+            const int64_t dstOff = tot_off ? tot_off[i] : ctx->hTotOff[i];
+            memcpy(totals_out + dstOff, tmp.data() + ctx->hTotOff[i], len * sizeof(double));
+        }
+    }
+    ctx->wantTotals = false;
+    return rc;
+}
+
+int cpecan_cuda_expectations_batch(cpecan_ctx *ctx, const cpecan_hmm *, const cpecan_params *, const cpecan_batch *,
+                                   double *, cpecan_result *) {
+    if (!ctx) return CPECAN_ERR_CUDA;
+    ctx->err = "expectations_batch: not implemented yet";
+    return CPECAN_ERR_ARG;
+}
+
+int cpecan_cuda_get_timing(cpecan_ctx *ctx, cpecan_timing *out) {
+    if (!ctx || !out) return CPECAN_ERR_ARG;
+    *out = ctx->timing;
+    return CPECAN_OK;
+}
+
+int cpecan_cuda_device_info(cpecan_ctx *ctx, int32_t *sm_count, int32_t *clock_khz, int64_t *hbm_bytes) {
+    if (!ctx) return CPECAN_ERR_ARG;
+    if (sm_count) *sm_count = ctx->prop.multiProcessorCount;
+    if (clock_khz) *clock_khz = ctx->prop.clockRate;
+    if (hbm_bytes) *hbm_bytes = (int64_t) ctx->prop.totalGlobalMem;
+    return CPECAN_OK;
+}
+
+}  // extern "C"

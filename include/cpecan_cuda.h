@@ -1,0 +1,160 @@
+/*
+ * cpecan_cuda.h -- C-ABI of the B200 (sm_100a) banded signal pair-HMM engine.
+ *
+ * This is the additive device boundary SURVEY.md 8(b) calls for: plain pointers and sizes, integer status
+ * codes, no torch / C++ types.  One call evaluates a BATCH of independent read-vs-reference alignments; each
+ * batch entry ("work item") is what ONE call of the reference's
+ *     getPosteriorProbsWithBanding           (impl/pairwiseAligner.c:870-1006)
+ * computes, i.e. one banded region after getSplitPoints (impl/pairwiseAligner.c:1313-1340).  The host mirror of
+ * the reference's public entry points (getAlignedPairsUsingAnchors, getExpectationsUsingAnchors,
+ * getAlignedPairsWithoutBanding; include/cpecan_host.h) is a thin layer over these calls.
+ *
+ * There is no CPU fallback: every entry point returns CPECAN_ERR_CUDA when no usable device exists.
+ */
+#ifndef CPECAN_CUDA_H_
+#define CPECAN_CUDA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    CPECAN_OK = 0,
+    CPECAN_ERR_CUDA = 1,        /* CUDA runtime error; see cpecan_cuda_last_error() */
+    CPECAN_ERR_ARG = 2,         /* invalid argument */
+    CPECAN_ERR_BAND_TOO_WIDE = 3,/* a band diagonal exceeds the widest kernel instantiation */
+    CPECAN_ERR_NOMEM = 4
+};
+
+/* State-machine types, numbered as the reference's StateMachineType (inc/stateMachine.h:20-29). */
+enum { CPECAN_SM_THREE_STATE = 2, CPECAN_SM_VANILLA = 4 };
+
+/* Work modes. */
+enum {
+    CPECAN_MODE_POSTERIOR = 0,  /* diagonalCalculationPosteriorMatchProbs   (impl/pairwiseAligner.c:756-795) */
+    CPECAN_MODE_EXPECTATION = 1,/* diagonalCalculation_Expectations         (impl/pairwiseAligner.c:841-863) */
+    CPECAN_MODE_UNBANDED = 2    /* getAlignedPairsWithoutBanding schedule   (impl/pairwiseAligner.c:1512-1569) */
+};
+
+/* per-item status bits returned in cpecan_result.status */
+enum {
+    CPECAN_ITEM_OK = 0,
+    CPECAN_ITEM_PAIR_OVERFLOW = 1, /* more aligned pairs than pair_cap; n_pairs holds the true count */
+    CPECAN_ITEM_NONFINITE = 2,     /* total probability was -inf / NaN (read skipped, reference would emit NaNs) */
+    CPECAN_ITEM_BAND_STEP = 4      /* band edge moved by more than one cell between diagonals (never for valid anchors) */
+};
+
+typedef struct cpecan_ctx cpecan_ctx;
+
+/* PairwiseAlignmentParameters (inc/pairwiseAligner.h:80-91; defaults impl/pairwiseAligner.c:1428-1441). */
+typedef struct {
+    double threshold;
+    int64_t minDiagsBetweenTraceBack;
+    int64_t traceBackDiagonals;
+    int64_t diagonalExpansion;
+    int64_t constraintDiagonalTrim;
+    int64_t splitMatrixBiggerThanThis;
+} cpecan_params;
+
+/* What a StateMachine3 / StateMachine3Vanilla carries besides its tables (inc/stateMachine.h:176-231). */
+typedef struct {
+    int32_t sm_type;        /* CPECAN_SM_* */
+    int32_t reserved;
+    double transitions[9];  /* threeState, StateMachine3 field order: MATCH_CONTINUE, MATCH_FROM_GAP_X,
+                               MATCH_FROM_GAP_Y, GAP_OPEN_X, GAP_OPEN_Y, GAP_EXTEND_X, GAP_EXTEND_Y,
+                               GAP_SWITCH_TO_X, GAP_SWITCH_TO_Y (log space, -inf allowed) */
+    double vanilla[5];      /* vanilla: TRANSITION_M_TO_Y_NOT_X, TRANSITION_E_TO_E, DEFAULT_END_MATCH_PROB,
+                               DEFAULT_END_FROM_X_PROB, DEFAULT_END_FROM_Y_PROB */
+} cpecan_hmm;
+
+/* A batch of work items in flat (structure-of-arrays) host buffers.  All *_off arrays have n_items+1 entries.
+ *   ref        nucleotides of every item back to back; item i owns ref[ref_off[i] .. ref_off[i+1]) and has
+ *              lX = max(len - 5, 0) k-mers (sequence_correctSeqLength, impl/pairwiseAligner.c:339-354)
+ *   events     reference layout: 3 doubles (mean, noise, duration) per event (inc/nanopore.h NB_EVENT_PARAMS);
+ *              item i owns events[3*ev_off[i] .. 3*ev_off[i+1])
+ *   anchors    (x, y) int64 pairs in sequence coordinates, strictly increasing in both (filterToRemoveOverlap);
+ *              item i owns pairs anchor_off[i] .. anchor_off[i+1]
+ *   model_id   per item, from cpecan_cuda_upload_model
+ *   scale      per item 5 doubles (scale, shift, var, scale_sd, var_sd) applied to the MATCH table exactly as
+ *              emissions_signal_scaleModel does (impl/stateMachine.c:631-651), or NULL when the uploaded tables
+ *              are already scaled
+ *   ragged     per item bit0 = alignmentHasRaggedLeftEnd, bit1 = alignmentHasRaggedRightEnd
+ */
+typedef struct {
+    int64_t n_items;
+    const char *ref;        const int64_t *ref_off;
+    const double *events;   const int64_t *ev_off;
+    const int64_t *anchors; const int64_t *anchor_off;
+    const int32_t *model_id;
+    const double *scale;
+    const uint8_t *ragged;
+} cpecan_batch;
+
+/* Per-item results (host buffers owned by the caller). */
+typedef struct {
+    int64_t n_pairs;        /* aligned pairs found (may exceed the capacity given; see status) */
+    int64_t pair_off;       /* offset (in pairs) of this item's pairs inside the pairs buffer */
+    int64_t band_cells;     /* C = sum over diagonals of the band width (SURVEY.md 8(d) work unit) */
+    double total_logprob;   /* totalProbability handed to the LAST diagonal (xay = lX+lY) of the item */
+    int32_t status;         /* CPECAN_ITEM_* bits */
+    int32_t n_tracebacks;
+} cpecan_result;
+
+/* Timing of the last batch call, measured with CUDA events on the engine's own streams. */
+typedef struct {
+    double h2d_ms, prep_ms, plan_ms, align_ms, d2h_ms, total_ms;
+    int64_t kernel_launches;    /* launches of this library's kernels during the call */
+    int64_t h2d_bytes, d2h_bytes;
+    int64_t band_cells;         /* sum over items */
+    int32_t warps_per_item;     /* kernel instantiation used for the widest bucket */
+    int32_t ctas;
+} cpecan_timing;
+
+int cpecan_cuda_init(int device, cpecan_ctx **ctx_out);
+void cpecan_cuda_destroy(cpecan_ctx *ctx);
+const char *cpecan_cuda_last_error(cpecan_ctx *ctx);
+
+/* Upload one pore model: the three lines of a .model file as emissions_signal_loadPoreModel leaves them
+ * (impl/stateMachine.c:242-320).  match/gapy: 1 + 4096*5 doubles; gapx: n_gapx doubles (threeState: 4096 log
+ * probabilities = EMISSION_GAP_X_PROBS; vanilla: 60 skip-bin probabilities). */
+int cpecan_cuda_upload_model(cpecan_ctx *ctx, const double *match, const double *gapy, const double *gapx,
+                             int32_t n_gapx, int32_t *model_id_out);
+
+/* Posterior match probabilities for a batch.
+ *   pairs_out   int32 triples (score, x, y), score = floor(p * 1e7) (PAIR_ALIGNMENT_PROB_1), x / y sequence
+ *               coordinates local to the item; pair_cap_total = capacity of pairs_out in triples.  Item i gets a
+ *               slice proportional to its event count; results[i].pair_off/n_pairs locate it.  Pairs appear in
+ *               the order the reference's traceback emits them (descending diagonals inside a traceback,
+ *               ascending x inside a diagonal); getAlignedPairsUsingAnchors then reverses each region
+ *               (alignedPairCoordinateCorrectionFn pops, impl/pairwiseAligner.c:1447-1454) -- the host mirror does that.
+ *   totals_out  optional debug output, may be NULL: item i owns 3 * (lX + lY + 1) doubles starting at tot_off[i]
+ *               (or packed back to back when tot_off is NULL): [xay] the totalProbability handed to diagonal xay
+ *               (NaN where no posterior was computed), [(lX+lY+1) + xay] and [2*(lX+lY+1) + xay] the two terms of
+ *               diagonalCalculationTotalProbability on the diagonals where it was recomputed.
+ */
+int cpecan_cuda_align_batch(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *params, int32_t mode,
+                            const cpecan_batch *batch, int32_t *pairs_out, int64_t pair_cap_total,
+                            cpecan_result *results, double *totals_out, const int64_t *tot_off);
+
+/* Baum-Welch expectations for a batch (getExpectationsUsingAnchors, impl/pairwiseAligner.c:1571-1591), summed over
+ * the batch on device.  expectations_out: threeState 9 + 4096 + 1 doubles (transitions row-major from*3+to, k-mer
+ * skip counts, likelihood); vanilla 60 + 1.  Values are ADDED to what the buffer already holds (pseudocounts). */
+int cpecan_cuda_expectations_batch(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *params,
+                                   const cpecan_batch *batch, double *expectations_out, cpecan_result *results);
+
+/* Device-resident variant used to measure kernel-only throughput: stage() copies and prepares a batch in HBM once,
+ * run_staged() re-runs plan + align kernels on it (results stay on device), fetch_staged() copies results back. */
+int cpecan_cuda_stage(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *params, int32_t mode,
+                      const cpecan_batch *batch, int64_t pair_cap_total);
+int cpecan_cuda_run_staged(cpecan_ctx *ctx);
+int cpecan_cuda_fetch_staged(cpecan_ctx *ctx, int32_t *pairs_out, cpecan_result *results);
+
+int cpecan_cuda_get_timing(cpecan_ctx *ctx, cpecan_timing *out);
+int cpecan_cuda_device_info(cpecan_ctx *ctx, int32_t *sm_count, int32_t *clock_khz, int64_t *hbm_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -203,6 +203,14 @@ int64_t oracle_split_points(const int64_t *anchors, int64_t nA, int64_t lX, int6
     return n;
 }
 
+/* optional debug capture of the two terms of the total (set by oracle_debug_terms) */
+static int g_dbg_logp = 0;   /* when set, the score slot carries round(log p * 1e9) of the UNCLAMPED posterior */
+void oracle_debug_logp(int on) { g_dbg_logp = on; }
+static int64_t g_dbg_row = -1; static double *g_dbg_F = NULL, *g_dbg_B = NULL;   /* capture one diagonal's cells */
+void oracle_debug_row(int64_t d, double *F, double *B) { g_dbg_row = d; g_dbg_F = F; g_dbg_B = B; }
+static double *g_dbg_t1 = NULL, *g_dbg_t2 = NULL;
+void oracle_debug_terms(double *t1, double *t2) { g_dbg_t1 = t1; g_dbg_t2 = t2; }
+
 /* ------------------------------------------------------------ DP plumbing */
 typedef struct {
     const OracleModel *m;
@@ -343,12 +351,15 @@ static double diag_dot(Dp *dp, double *a, double *b, int64_t xay) {
 /* ref:736-754 */
 static double total_probability(Dp *dp, int64_t xay) {
     double tot = diag_dot(dp, dp->F[xay], dp->B[xay], xay);
+    if (g_dbg_t1) { g_dbg_t1[xay] = tot; g_dbg_t2[xay] = NAN; }
     if (xay + 1 <= dp->lX + dp->lY && dp->B[xay + 1] != NULL && xay - 1 >= 0 && dp->F[xay - 1] != NULL) {
         /* match-only forward step from F[xay-1] into a -inf clone shaped like B[xay+1] */
         double **tmp = calloc(dp->lX + dp->lY + 2, sizeof(double *));
         new_diag(dp, tmp, xay + 1, NEG_INF);
         sweep(dp, MODE_FWD, tmp, xay + 1, NULL, dp->F, 0);
-        tot = LA(tot, diag_dot(dp, tmp[xay + 1], dp->B[xay + 1], xay + 1));
+        double t2 = diag_dot(dp, tmp[xay + 1], dp->B[xay + 1], xay + 1);
+        if (g_dbg_t2) g_dbg_t2[xay] = t2;
+        tot = LA(tot, t2);
         free(tmp[xay + 1]);
         free(tmp);
     }
@@ -359,14 +370,19 @@ typedef struct { int64_t *out; int64_t cap, n; int64_t offX, offY; } PairSink;
 
 /* ref:756-795 */
 static void posterior_diag(Dp *dp, int64_t xay, double total, double threshold, PairSink *sink) {
+    if (xay == g_dbg_row && g_dbg_F) {
+        int64_t w = (dp->xmyR[xay] - dp->xmyL[xay]) / 2 + 1;
+        for (int64_t i = 0; i < 3 * w; i++) { g_dbg_F[i] = dp->F[xay][i]; g_dbg_B[i] = dp->B[xay][i]; }
+    }
     for (int64_t xmy = dp->xmyL[xay]; xmy <= dp->xmyR[xay]; xmy += 2) {
         int64_t x = (xay + xmy) / 2, y = (xay - xmy) / 2;
         if (x > 0 && y > 0) {
-            double p = exp(cell_at(dp, dp->F, xay, xmy)[ST_M] + cell_at(dp, dp->B, xay, xmy)[ST_M] - total);
+            double lp = cell_at(dp, dp->F, xay, xmy)[ST_M] + cell_at(dp, dp->B, xay, xmy)[ST_M] - total;
+            double p = exp(lp);
             if (p >= threshold) {
                 if (p > 1.0) p = 1.0;
                 if (sink->n < sink->cap) {
-                    sink->out[3 * sink->n] = (int64_t) floor(p * 10000000);
+                    sink->out[3 * sink->n] = g_dbg_logp ? (int64_t) llround(lp * 1e9) : (int64_t) floor(p * 10000000);
                     sink->out[3 * sink->n + 1] = x - 1 + sink->offX;
                     sink->out[3 * sink->n + 2] = y - 1 + sink->offY;
                 }

@@ -1,0 +1,122 @@
+#!/usr/bin/env python
+"""TEST INFRASTRUCTURE ONLY.  Regenerates tests/golden/zymo_golden.npz and tests/golden/synthetic_golden.npz by
+running the UNMODIFIED reference (oracle/_ref/libcpecan_ref.so + its vendored lastz, both built by oracle/Makefile
+from /root/reference) on
+
+  * the reference's own fixture read (tests/test_npReads/ZymoC_ch_1_file1.npRead vs ZymoRef.txt; the configuration of
+    tests/signalPairwiseTest.c:1116-1183 and :1250-1310) -- anchors come from the reference's lastz pipeline;
+  * a few small seeded synthetic reads (cpecan_signal.synth), including multi-traceback and split-region cases.
+
+Only runs where /root/reference exists (the build container).  The outputs are committed; tests never need the
+reference at run time.   Usage:  make -C oracle ref lastz && python oracle/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.join(ROOT, "cpecan-signal_b200"))
+
+import refshim as R  # noqa: E402
+from cpecan_signal import synth  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+REFERENCE = os.environ.get("CPECAN_REFERENCE", "/root/reference")
+T_MODEL = os.path.join(REFERENCE, "models", "template_median68pA.model")
+C_MODEL = os.path.join(REFERENCE, "models", "complement_median68pA_pop2.model")
+
+
+def revcomp(s):
+    return s[::-1].translate(str.maketrans("ACGTacgt", "TGCAtgca"))
+
+
+def main():
+    os.chdir(os.path.join(HERE, "_ref"))  # the reference shells out to ./cPecanLastz
+    ref = open(os.path.join(GOLDEN, "ZymoRef.txt")).readline().strip()
+    npfile = os.path.join(GOLDEN, "ZymoC_ch_1_file1.npRead")
+    rd = R.load_npread(npfile)
+    out = {}
+    anch_t, raw = R.fixture_anchors(ref, npfile, 0)
+    anch_c, _ = R.fixture_anchors(ref, npfile, 1)
+    out["anchors_raw_count"] = np.int64(raw)
+    out["anchors_template"] = anch_t
+    out["anchors_complement"] = anch_c
+    tp, cp = rd["template_params"], rd["complement_params"]
+    tev, cev = rd["template_events"], rd["complement_events"]
+
+    def banded(tag, smt, model, refseq, ev, anchors, scale, strand, e, ragged):
+        p = R.default_params(diagonalExpansion=e)
+        pairs, totals = R.align_banded(smt, model, refseq, ev, anchors, params=p, scale5=scale, strand=strand,
+                                       ragged=ragged, want_totals=True)
+        out[tag + "_pairs"] = pairs
+        out[tag + "_totals"] = totals
+        print(tag, len(pairs), int(pairs[:, 0].sum()))
+
+    # signalPairwiseTest.c:1154 (987 pairs) and the vanilla twin :1287 (999 pairs); ragged (0,0), e = 20
+    banded("three_e20_r00", R.THREE_STATE, T_MODEL, ref, tev, anch_t, tp, 0, 20, (0, 0))
+    banded("vanilla_e20_r00", R.VANILLA, T_MODEL, ref, tev, anch_t, tp, 0, 20, (0, 0))
+    # vanillaAlign's configuration (vanillaAlign.c:202,371-373): e = 50, ragged (1,1); template and complement
+    banded("three_e50_r11", R.THREE_STATE, T_MODEL, ref, tev, anch_t, tp, 0, 50, (1, 1))
+    banded("three_e50_r11_complement", R.THREE_STATE, C_MODEL, revcomp(ref), cev, anch_c, cp, 1, 50, (1, 1))
+    banded("vanilla_e50_r11", R.VANILLA, T_MODEL, ref, tev, anch_t, tp, 0, 50, (1, 1))
+    for tag, smt in (("three", R.THREE_STATE), ("vanilla", R.VANILLA)):
+        pairs, total = R.align_unbanded(smt, T_MODEL, ref, tev, scale5=tp)
+        out[tag + "_unbanded_pairs"] = pairs
+        out[tag + "_unbanded_total"] = np.float64(total)
+        print(tag, "unbanded", len(pairs), total)
+        out[tag + "_expectations_e20_r00"] = R.expectations(smt, T_MODEL, ref, tev, anch_t, scale5=tp)
+        out[tag + "_expectations_e50_r11"] = R.expectations(smt, T_MODEL, ref, tev, anch_t, scale5=tp, ragged=(1, 1),
+                                                            params=R.default_params(diagonalExpansion=50))
+    # the tiny full-matrix known-answer case of signalPairwiseTest.c:580-685 (8 pairs at threshold 0.2)
+    tiny_ref = "ACGATACGGACAT"
+    tiny_ev = np.array([58.743435, 0.887833, 0.0571, 53.604965, 0.816836, 0.0571, 58.432015, 0.735143, 0.0571,
+                        63.684352, 0.795437, 0.0571, 58.921430, 0.812959, 0.0571, 59.895882, 0.740952, 0.0571,
+                        61.684303, 0.722332, 0.0571]).reshape(-1, 3)
+    pairs, total = R.align_unbanded(R.THREE_STATE, T_MODEL, tiny_ref, tiny_ev, params=R.default_params(threshold=0.2))
+    out["tiny_three_pairs"] = pairs
+    out["tiny_three_total"] = np.float64(total)
+    pairs, total = R.align_unbanded(R.VANILLA, T_MODEL, tiny_ref, tiny_ev, params=R.default_params(threshold=0.5))
+    out["tiny_vanilla_pairs"] = pairs
+    print("tiny", len(out["tiny_three_pairs"]), len(pairs))
+    np.savez_compressed(os.path.join(GOLDEN, "zymo_golden.npz"), **out)
+
+    # ---- seeded synthetic reads (small, so the committed file stays small) -------------------------------------
+    match = synth.load_model_file(T_MODEL)[0]
+    syn = {}
+    cases = [  # (tag, read index, lX, expansion, ragged, anchor_every, minDiags)
+        ("s0", 0, 300, 20, (1, 1), 50, 1000),
+        ("s1", 1, 900, 40, (1, 1), 50, 1000),       # one intermediate traceback
+        ("s2", 2, 1500, 64, (0, 0), 50, 1000),      # two intermediate tracebacks
+        ("s3", 3, 700, 20, (1, 1), 50, 200),        # frequent tracebacks
+        ("s4", 4, 500, 30, (0, 1), 500, 1000),      # sparse anchors -> wide band
+    ]
+    for tag, idx, lX, e, ragged, every, mind in cases:
+        r = synth.make_read(match, idx, lX=lX, anchor_every=every)
+        p = R.default_params(diagonalExpansion=e, minDiagsBetweenTraceBack=mind)
+        pairs, totals = R.align_banded(R.THREE_STATE, T_MODEL, r.ref, r.events, r.anchors, params=p, scale5=r.scale5,
+                                       ragged=ragged, want_totals=True)
+        syn[tag + "_meta"] = np.array([idx, lX, e, ragged[0], ragged[1], every, mind], dtype=np.int64)
+        syn[tag + "_pairs"] = pairs
+        syn[tag + "_totals"] = totals
+        syn[tag + "_expect"] = R.expectations(R.THREE_STATE, T_MODEL, r.ref, r.events, r.anchors, params=p,
+                                              scale5=r.scale5, ragged=ragged)
+        print(tag, r.lX, r.lY, len(r.anchors), len(pairs))
+    # a split-region case: one anchor gap bigger than splitMatrixBiggerThanThis
+    r = synth.make_read(match, 5, lX=1200, anchor_every=50)
+    keep = (r.anchors[:, 0] < 300) | (r.anchors[:, 0] > 900)
+    p = R.default_params(diagonalExpansion=20, splitMatrixBiggerThanThis=300 * 300)
+    pairs, _ = R.align_banded(R.THREE_STATE, T_MODEL, r.ref, r.events, r.anchors[keep], params=p, scale5=r.scale5,
+                              ragged=(1, 1))
+    syn["split_meta"] = np.array([5, 1200, 20, 1, 1, 50, 1000, 300 * 300], dtype=np.int64)
+    syn["split_keep_lo_hi"] = np.array([300, 900], dtype=np.int64)
+    syn["split_pairs"] = pairs
+    syn["split_points"] = R.split_points(r.anchors[keep], r.lX, r.lY, 300 * 300, 1, 1)
+    print("split", len(pairs), syn["split_points"].tolist())
+    np.savez_compressed(os.path.join(GOLDEN, "synthetic_golden.npz"), **syn)
+
+
+if __name__ == "__main__":
+    main()

@@ -159,6 +159,18 @@ def band_cells(anchors, lX, lY, params=None, ragged=(0, 0)):
                                    C.byref(params), int(ragged[0]), int(ragged[1]))
 
 
+def debug_terms(n):
+    """Arms capture of the two terms of diagonalCalculationTotalProbability; returns the (t1, t2) arrays."""
+    t1 = np.full(n, np.nan)
+    t2 = np.full(n, np.nan)
+    lib().oracle_debug_terms(_iptr(t1), _iptr(t2))
+    return t1, t2
+
+
+def debug_terms_off():
+    lib().oracle_debug_terms(None, None)
+
+
 def align_banded(model, ref_seq, events, anchors, params=None, ragged=(0, 0), want_totals=False):
     events = np.ascontiguousarray(events, dtype=np.float64).reshape(-1, 3)
     anchors = np.ascontiguousarray(np.asarray(anchors, dtype=np.int64).reshape(-1, 2))

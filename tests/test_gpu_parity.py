@@ -1,0 +1,109 @@
+"""GPU parity: the CUDA path (through the C-ABI of include/cpecan_cuda.h) against the golden vectors produced by the
+unmodified reference (tests/golden/*.npz, generator oracle/make_golden.py) and against the oracle restatement on
+seeded synthetic reads."""
+import os
+
+import numpy as np
+import pytest
+
+import parity
+
+pytestmark = pytest.mark.gpu
+
+
+def _three_state_batch(eng, tables, refs, events, anchors, scales, ragged):
+    from cpecan_signal import HostBatch
+    l1, _, l3 = tables
+    mid = eng.upload_model(l1, l3, np.full(4096, -2.3025850929940455))
+    return HostBatch(refs, events, anchors, model_ids=[mid] * len(refs), scales=scales, ragged=ragged)
+
+
+@pytest.mark.parametrize("tag,e,ragged", [("three_e20_r00", 20, (0, 0)), ("three_e50_r11", 50, (1, 1))])
+def test_fixture_banded_three_state(engine, zymo, template_tables, tag, e, ragged):
+    """BASELINE config 1: reference tests/signalPairwiseTest.c:1116-1183 (987 aligned pairs)."""
+    from cpecan_signal import default_params
+    from cpecan_signal.engine import item_pairs
+    rd = zymo["read"]
+    batch = _three_state_batch(engine, template_tables, [zymo["ref"]], [rd["template_events"]],
+                               [zymo["anchors_template"]], [rd["template_params"]], [ragged])
+    res, pairs, totals = engine.align_batch(batch, params=default_params(diagonalExpansion=e), want_totals=True)
+    assert res[0]["status"] == 0
+    got = item_pairs(res, pairs, 0)
+    want = zymo[tag + "_pairs"]
+    stats = parity.compare_pairs(got, want)
+    worst_total = parity.compare_totals(totals[0], zymo[tag + "_totals"])
+    print(tag, stats, "worst |total diff|", worst_total, "cells", res[0]["band_cells"])
+    assert abs(stats["n_got"] - 987) <= 2
+    # emission order: the device list reversed is the reference's list
+    if stats["n_got"] == stats["n_want"]:
+        assert np.array_equal(parity.reverse_regions(got)[:, 1:], want[:, 1:])
+    if e == 20:
+        assert res[0]["band_cells"] == 140469
+
+
+def test_fixture_unbanded_three_state(engine, zymo, template_tables):
+    """getAlignedPairsWithoutBanding on the fixture: 986 pairs (tests/signalPairwiseTest.c:1166-1173)."""
+    from cpecan_signal.engine import MODE_UNBANDED, item_pairs
+    rd = zymo["read"]
+    batch = _three_state_batch(engine, template_tables, [zymo["ref"]], [rd["template_events"]], [np.zeros((0, 2))],
+                               [rd["template_params"]], [(0, 0)])
+    res, pairs, _ = engine.align_batch(batch, mode=MODE_UNBANDED)
+    assert res[0]["status"] == 0
+    got = item_pairs(res, pairs, 0)
+    stats = parity.compare_pairs(got, zymo["three_unbanded_pairs"])
+    print(stats, res[0]["total_logprob"], float(zymo["three_unbanded_total"]))
+    assert abs(res[0]["total_logprob"] - float(zymo["three_unbanded_total"])) <= 1e-4 * abs(float(zymo["three_unbanded_total"]))
+    assert abs(stats["n_got"] - 986) <= 2
+
+
+def test_tiny_known_answer(engine, zymo, template_tables):
+    """tests/signalPairwiseTest.c:580-685: exactly 8 pairs {(0,0),(1,1),(2,2),(3,3),(4,3),(5,4),(6,5),(7,6)} at 0.2."""
+    from cpecan_signal import default_params
+    from cpecan_signal.engine import MODE_UNBANDED, item_pairs
+    ev = np.array([58.743435, 0.887833, 0.0571, 53.604965, 0.816836, 0.0571, 58.432015, 0.735143, 0.0571,
+                   63.684352, 0.795437, 0.0571, 58.921430, 0.812959, 0.0571, 59.895882, 0.740952, 0.0571,
+                   61.684303, 0.722332, 0.0571]).reshape(-1, 3)
+    batch = _three_state_batch(engine, template_tables, ["ACGATACGGACAT"], [ev], [np.zeros((0, 2))], None, [(0, 0)])
+    res, pairs, _ = engine.align_batch(batch, params=default_params(threshold=0.2), mode=MODE_UNBANDED)
+    got = item_pairs(res, pairs, 0)
+    assert {(int(x), int(y)) for _, x, y in got} == {(0, 0), (1, 1), (2, 2), (3, 3), (4, 3), (5, 4), (6, 5), (7, 6)}
+    parity.compare_pairs(got, zymo["tiny_three_pairs"], threshold=0.2)
+
+
+@pytest.mark.parametrize("tag", ["s0", "s1", "s2", "s3", "s4"])
+def test_synthetic_golden(engine, syn_golden, template_tables, tag):
+    from cpecan_signal import default_params, synth
+    from cpecan_signal.engine import item_pairs
+    idx, lX, e, r0, r1, every, mind = (int(v) for v in syn_golden[tag + "_meta"])
+    r = synth.make_read(template_tables[0], idx, lX=lX, anchor_every=every)
+    batch = _three_state_batch(engine, template_tables, [r.ref], [r.events], [r.anchors], [r.scale5], [(r0, r1)])
+    res, pairs, totals = engine.align_batch(batch, params=default_params(diagonalExpansion=e, minDiagsBetweenTraceBack=mind),
+                                            want_totals=True)
+    assert res[0]["status"] == 0
+    got = item_pairs(res, pairs, 0)
+    stats = parity.compare_pairs(got, syn_golden[tag + "_pairs"])
+    worst_total = parity.compare_totals(totals[0], syn_golden[tag + "_totals"])
+    print(tag, stats, worst_total, res[0]["n_tracebacks"])
+
+
+def test_batch_mixed_widths_vs_oracle(engine, template_tables):
+    """A batch mixing band widths (several kernel instantiations in one call), checked against the oracle."""
+    import oracleshim as O
+    from cpecan_signal import default_params, synth
+    from cpecan_signal.engine import item_pairs
+    l1, l2, l3 = template_tables
+    reads = [synth.make_read(l1, 100 + i, lX=lx, anchor_every=ev)
+             for i, (lx, ev) in enumerate([(400, 50), (1300, 50), (350, 400), (800, 50), (250, 50), (600, 300)])]
+    e = 40
+    batch = _three_state_batch(engine, template_tables, [r.ref for r in reads], [r.events for r in reads],
+                               [r.anchors for r in reads], [r.scale5 for r in reads], [(1, 1)] * len(reads))
+    res, pairs, totals = engine.align_batch(batch, params=default_params(diagonalExpansion=e), want_totals=True)
+    op = O.default_params(diagonalExpansion=e)
+    for i, r in enumerate(reads):
+        m = O.Model(O.THREE_STATE, tables=(l1, l2, l3), scale5=r.scale5)
+        want, wtot = O.align_banded(m, r.ref, r.events, r.anchors, params=op, ragged=(1, 1), want_totals=True)
+        assert res[i]["status"] == 0
+        assert res[i]["band_cells"] == O.band_cells(r.anchors, r.lX, r.lY, op, (1, 1))
+        stats = parity.compare_pairs(item_pairs(res, pairs, i), want)
+        parity.compare_totals(totals[i], wtot)
+        print(i, stats)
