@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py -- banded signal pair-HMM forward/backward/posterior throughput (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--reads-per-gpu B] [--impl reference]
+
+Workload (configuration C3): seeded synthetic reads, lX ~ 6700 reference k-mers, lY ~ 8000 events,
+6-mer template model, anchors every 50 k-mers, three-state machine, threshold 0.01, ragged ends (1,1); the batch is
+split evenly over the three band expansions e = 64 / 128 / 256 ("anchored band width 64-256").  One STEP = one pass of
+the hot path over the whole batch of B reads per GPU (three kernel launches, one per expansion).  Reads are sharded
+across ranks with no data-path collective (weak scaling: B reads per GPU).
+
+  value      GCUPS = 2 * band cells / time / 1e9 with the batch resident in HBM (kernels only)
+  e2e        the same metric through the C-ABI call with HOST buffers: H2D of the batch, preparation, plan, kernels
+             and D2H of the aligned pairs all inside the timed region
+  roofline   HBM bytes (25 B per band cell) / kernel time against MEASURED_PEAKS.json, plus the FP32
+             issue-rate roofline SURVEY.md 8(d) defines (165 issue-ops per band cell)
+  cpu_baseline / --impl reference
+             the reference's own C code (oracle/_ref, unmodified sources; else the oracle port) on all host cores,
+             one process per read as the reference's drivers do, on a bounded sample of the same reads.
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "cpecan-signal_b200"))
+
+EXPANSIONS = (64, 128, 256)
+LX = 6700
+HBM_BYTES_PER_CELL = 25.0       # forward cell written + read once (24 B) + inputs/outputs (<1 B)
+ISSUE_OPS_PER_CELL = 165.0
+METRIC = "banded_fwd_bwd_posterior_gcups"
+
+
+# ----------------------------------------------------------------------------------------------- synthetic input
+def _gen_chunk(args):
+    first, count, lX = args
+    from cpecan_signal import synth
+    match = synth.load_model_file(synth.TEMPLATE_MODEL)[0]
+    return [synth.make_read(match, first + i, lX=lX) for i in range(count)]
+
+
+def generate_reads(n, first_index, lX=LX, procs=None):
+    procs = procs or min(32, os.cpu_count() or 1)
+    chunk = max(1, (n + procs * 4 - 1) // (procs * 4))
+    jobs = [(first_index + s, min(chunk, n - s), lX) for s in range(0, n, chunk)]
+    if procs == 1 or n <= 8:
+        parts = [_gen_chunk(j) for j in jobs]
+    else:
+        with mp.get_context("fork").Pool(procs) as pool:
+            parts = pool.map(_gen_chunk, jobs)
+    return [r for p in parts for r in p]
+
+
+# ----------------------------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(smax)) if smax else None,
+                "power_w_max": float(max(power)) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU reference arm
+def _cpu_one(args):
+    """One read through the reference's getAlignedPairsUsingAnchors (process-per-read, as scripts/signalAlign.py)."""
+    kind, read, e = args
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    if kind == "reference":
+        import refshim as R
+        from cpecan_signal import synth
+        sec, n = R.time_align_banded(R.THREE_STATE, synth.TEMPLATE_MODEL, read.ref, read.events, read.anchors,
+                                     params=R.default_params(diagonalExpansion=e), scale5=read.scale5, ragged=(1, 1))
+    else:
+        import oracleshim as O
+        from cpecan_signal import synth
+        m = O.Model(O.THREE_STATE, model_file=synth.TEMPLATE_MODEL, scale5=read.scale5)
+        t0 = time.perf_counter()
+        pairs, _ = O.align_banded(m, read.ref, read.events, read.anchors,
+                                  params=O.default_params(diagonalExpansion=e), ragged=(1, 1))
+        sec, n = time.perf_counter() - t0, len(pairs)
+    return sec, n
+
+
+def cpu_kind():
+    return "reference" if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libcpecan_ref.so")) else "port"
+
+
+def cpu_cells(reads, exps):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracleshim as O
+    return sum(O.band_cells(r.anchors, r.lX, r.lY, O.default_params(diagonalExpansion=e), (1, 1))
+               for r, e in zip(reads, exps))
+
+
+def run_cpu_sample(reads, exps, cores):
+    """All `cores` host cores, one process per read.  Returns (wall seconds, band cells, summed core-seconds)."""
+    kind = cpu_kind()
+    cells = cpu_cells(reads, exps)
+    jobs = [(kind, r, e) for r, e in zip(reads, exps)]
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(cores) as pool:
+        res = pool.map(_cpu_one, jobs, chunksize=1)
+    wall = time.perf_counter() - t0
+    return wall, cells, sum(s for s, _ in res)
+
+
+def reference_arm(args):
+    """--impl reference: the reference's CPU implementation of the path on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_step = max(3, min(3 * cores, 192))
+    per_step -= per_step % 3
+    reads = generate_reads(per_step, 10_000_000, procs=min(cores, 32))
+    exps = [EXPANSIONS[i % 3] for i in range(per_step)]
+    for _ in range(args.warmup if args.warmup < 2 else 1):       # one warm pass is enough for a CPU code path
+        run_cpu_sample(reads[:min(len(reads), cores)], exps[:min(len(reads), cores)], cores)
+    walls, cells = [], 0
+    for _ in range(args.steps):
+        wall, c, _ = run_cpu_sample(reads, exps, cores)
+        walls.append(wall); cells = c
+    t = float(np.mean(walls))
+    gcups = 2.0 * cells / t / 1e9
+    line = {"metric": METRIC, "value": gcups, "unit": "GCUPS", "impl": "reference", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "reads_per_s": len(reads) / t, "band_cells_per_s": cells / t,
+            "config": {"workload": "C3 synthetic reads lX~6700 lY~8000, expansions 64/128/256 evenly, three-state, "
+                                   "bounded sample of %d reads per step" % len(reads), "reads_per_step": len(reads)},
+            "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": cores, "kind": cpu_kind(),
+                             "sample": "%d reads per step, one process per read on %d cores" % (len(reads), cores)},
+            "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--reads-per-gpu", type=int, default=1536)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from cpecan_signal import Engine, HostBatch, default_params
+    from cpecan_signal.engine import RESULT_DTYPE
+
+    B = args.reads_per_gpu - args.reads_per_gpu % 3
+    reads = generate_reads(B, rank * 1_000_000, procs=max(1, min(32, (os.cpu_count() or 1) // max(1, world))))
+    engines, batches, outs = [], [], []
+    l1 = l3 = None
+    from cpecan_signal import synth
+    l1, _, l3 = synth.load_model_file(synth.TEMPLATE_MODEL)
+    for j, e in enumerate(EXPANSIONS):
+        sub = reads[j::3]
+        eng = Engine(local)
+        mid = eng.upload_model(l1, l3, np.full(4096, -2.3025850929940455))
+        hb = HostBatch([r.ref for r in sub], [r.events for r in sub], [r.anchors for r in sub],
+                       model_ids=[mid] * len(sub), scales=[r.scale5 for r in sub], ragged=[(1, 1)] * len(sub))
+        eng.pin_batch(hb)
+        cap = eng.default_pair_capacity(hb, per_event=3)
+        outs.append((eng.pinned_empty(hb.n, RESULT_DTYPE), eng.pinned_empty((cap, 3), np.int32)))
+        engines.append(eng); batches.append(hb)
+    params = [default_params(diagonalExpansion=e) for e in EXPANSIONS]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- resident (kernel-only) measurement -----------------------------------------------------------------
+    for eng, hb, p, o in zip(engines, batches, params, outs):
+        eng.stage(hb, params=p, pair_cap=len(o[1]))
+    cells_rank = sum(eng.timing()["band_cells"] for eng in engines)
+    for _ in range(args.warmup):
+        for eng in engines:
+            eng.run_staged()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    t0 = time.perf_counter()
+    kern_ms = 0.0
+    launches = 0
+    for _ in range(args.steps):
+        for eng in engines:
+            eng.run_staged()
+            tm = eng.timing()
+            kern_ms += tm["align_ms"]
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    launches = len(engines) * args.steps
+    wall = max_over_ranks(wall)
+    kern_ms_max = max_over_ranks(kern_ms)
+    cells_total = sum_over_ranks(float(cells_rank))
+    reads_total = sum_over_ranks(float(B))
+    gcups = 2.0 * cells_total * args.steps / wall / 1e9
+
+    # sanity: results of the last resident pass
+    n_pairs = 0
+    for eng in engines:
+        res, _ = eng.fetch_staged()
+        assert int((res["status"] != 0).sum()) == 0, "non-zero item status"
+        n_pairs += int(res["n_pairs"].sum())
+
+    # ---- end-to-end through the C-ABI with host buffers ---------------------------------------------------
+    for _ in range(2):
+        for eng, hb, p, o in zip(engines, batches, params, outs):
+            eng.align_batch(hb, params=p, out=o)
+    barrier()
+    t0 = time.perf_counter()
+    h2d = d2h = 0
+    e2e_launches = 0
+    for _ in range(args.steps):
+        for eng, hb, p, o in zip(engines, batches, params, outs):
+            eng.align_batch(hb, params=p, out=o)
+            tm = eng.timing()
+            h2d += tm["h2d_bytes"]; d2h += tm["d2h_bytes"]; e2e_launches += tm["kernel_launches"]
+    barrier()
+    e2e_wall = max_over_ranks(time.perf_counter() - t0)
+    e2e_gcups = 2.0 * cells_total * args.steps / e2e_wall / 1e9
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (k_align), from the live event timings of the resident steps ------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured" if "hbm_gbs" in peaks else "fallback"
+    info = engines[0].device_info()
+    kern_s = kern_ms / 1e3                                   # this rank's kernels
+    cells_steps = cells_rank * args.steps
+    achieved_gbs = HBM_BYTES_PER_CELL * cells_steps / kern_s / 1e9
+    sm_clock_hz = (clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)) * 1e6 if clocks else 1965e6
+    issue_peak = info["sm_count"] * 128 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6
+    issue_ach = ISSUE_OPS_PER_CELL * cells_steps / kern_s
+    line = {
+        "metric": METRIC, "value": gcups, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "reads_per_s": reads_total * args.steps / wall, "band_cells_per_s": cells_total * args.steps / wall,
+        "config": {"workload": "C3: batched synthetic reads lX~6700 x lY~8000 events, 6-mer template model, anchors "
+                               "every 50 k-mers, expansions 64/128/256 evenly, three-state, threshold 0.01, ragged (1,1)",
+                   "reads_per_gpu": B, "reads_total": int(reads_total), "band_cells_per_step": int(cells_total),
+                   "aligned_pairs_rank0": n_pairs, "sharding": "reads partitioned over ranks, no collective",
+                   "l2": "inputs + forward spill per step >> 126 MB L2 (no flush needed)"},
+        "e2e": {"value": e2e_gcups, "unit": "GCUPS", "h2d_bytes_per_step": int(h2d / args.steps),
+                "d2h_bytes_per_step": int(d2h / args.steps), "ms_per_step": e2e_wall / args.steps * 1e3,
+                "reads_per_s": reads_total * args.steps / e2e_wall},
+        "gpu_launches": int(launches),
+        "gpu_launches_e2e": int(e2e_launches),
+        "kernel_ms_per_step": kern_ms_max / args.steps,
+        "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_band_cell": HBM_BYTES_PER_CELL},
+        "roofline_issue": {"bound": "fp32_issue", "achieved": issue_ach / 1e12, "peak": issue_peak / 1e12,
+                           "unit": "Tissue-op/s", "frac": issue_ach / issue_peak,
+                           "ops_per_band_cell": ISSUE_OPS_PER_CELL, "sm_count": info["sm_count"],
+                           "clock_mhz_for_peak": float(peaks.get("sm_max_mhz", 1965.0)),
+                           "frac_at_observed_clock": issue_ach / (info["sm_count"] * 128 * sm_clock_hz)},
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        n_s = max(3, min(3 * cores, 192, B))
+        n_s -= n_s % 3
+        sample = reads[:n_s]
+        exps = [EXPANSIONS[i % 3] for i in range(n_s)]    # reads[j::3] went to expansion j
+        wall_c, cells_c, core_s = run_cpu_sample(sample, exps, cores)
+        line["cpu_baseline"] = {"value": 2.0 * cells_c / wall_c / 1e9, "unit": "GCUPS", "cores": cores,
+                                "kind": cpu_kind(),
+                                "sample": "%d reads of the same batch, one process per read on %d cores, %.1f s wall, "
+                                          "%.1f core-s" % (n_s, cores, wall_c, core_s),
+                                "band_cells_per_core_s": cells_c / core_s}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

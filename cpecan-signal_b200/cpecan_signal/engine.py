@@ -147,6 +147,10 @@ class Engine:
 
     def close(self):
         if self.ctx:
+            self.lib.cpecan_cuda_host_free.argtypes = [C.c_void_p, C.c_void_p]
+            for p in getattr(self, "_pinned", []):
+                self.lib.cpecan_cuda_host_free(self.ctx, p)
+            self._pinned = []
             self.lib.cpecan_cuda_destroy(self.ctx)
             self.ctx = C.c_void_p()
 
@@ -185,14 +189,45 @@ class Engine:
     def default_pair_capacity(batch, per_event=4):
         return int(per_event * int(batch.ev_off[-1]) + 64 * batch.n + 1024)
 
-    def align_batch(self, batch, hmm=None, params=None, mode=MODE_POSTERIOR, pair_cap=None, want_totals=False):
+    def pinned_empty(self, shape, dtype):
+        """numpy array over page-locked host memory (cpecan_cuda_host_alloc); freed with the engine."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) if np.ndim(shape) else int(shape)
+        nbytes = max(1, n * dtype.itemsize)
+        self.lib.cpecan_cuda_host_alloc.restype = C.c_void_p
+        p = self.lib.cpecan_cuda_host_alloc(self.ctx, C.c_int64(nbytes))
+        if not p:
+            raise EngineError("cpecan_cuda_host_alloc(%d) failed" % nbytes)
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append(p)
+        buf = (C.c_char * nbytes).from_address(p)
+        return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+
+    def pin_batch(self, batch):
+        """Moves a HostBatch's arrays into page-locked memory (in place)."""
+        for name in ("ref", "ref_off", "events", "ev_off", "anchors", "anchor_off", "model_id", "scale", "ragged"):
+            a = getattr(batch, name)
+            if a is None:
+                continue
+            b = self.pinned_empty(a.shape, a.dtype)
+            b[...] = a
+            setattr(batch, name, b)
+        return batch
+
+    def align_batch(self, batch, hmm=None, params=None, mode=MODE_POSTERIOR, pair_cap=None, want_totals=False,
+                    out=None):
         """Returns (results structured array, pairs int32[n,3], totals list or None).  Pairs of item i are
-        pairs[r['pair_off'] : r['pair_off'] + min(r['n_pairs'], cap_i)] in the reference's emission order."""
+        pairs[r['pair_off'] : r['pair_off'] + min(r['n_pairs'], cap_i)] in the reference's emission order.
+        out = (results, pairs) lets the caller supply (e.g. page-locked) output buffers."""
         hmm = hmm or three_state_hmm()
         params = params or default_params()
-        pair_cap = pair_cap or self.default_pair_capacity(batch)
-        pairs = np.zeros((pair_cap, 3), dtype=np.int32)
-        results = np.zeros(batch.n, dtype=RESULT_DTYPE)
+        if out is not None:
+            results, pairs = out
+            pair_cap = len(pairs)
+        else:
+            pair_cap = pair_cap or self.default_pair_capacity(batch)
+            pairs = np.zeros((pair_cap, 3), dtype=np.int32)
+            results = np.zeros(batch.n, dtype=RESULT_DTYPE)
         totals = tot_off = None
         if want_totals:
             tot_off = np.zeros(batch.n + 1, dtype=np.int64)

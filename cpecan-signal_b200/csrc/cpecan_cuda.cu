@@ -489,6 +489,18 @@ int cpecan_cuda_expectations_batch(cpecan_ctx *ctx, const cpecan_hmm *, const cp
     return CPECAN_ERR_ARG;
 }
 
+void *cpecan_cuda_host_alloc(cpecan_ctx *ctx, int64_t bytes) {
+    if (!ctx || bytes <= 0) return nullptr;
+    void *p = nullptr;
+    cudaSetDevice(ctx->device);
+    if (cudaHostAlloc(&p, (size_t) bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+
+void cpecan_cuda_host_free(cpecan_ctx *ctx, void *p) {
+    if (ctx && p) { cudaSetDevice(ctx->device); cudaFreeHost(p); }
+}
+
 int cpecan_cuda_get_timing(cpecan_ctx *ctx, cpecan_timing *out) {
     if (!ctx || !out) return CPECAN_ERR_ARG;
     *out = ctx->timing;

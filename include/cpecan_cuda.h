@@ -151,6 +151,10 @@ int cpecan_cuda_stage(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_param
 int cpecan_cuda_run_staged(cpecan_ctx *ctx);
 int cpecan_cuda_fetch_staged(cpecan_ctx *ctx, int32_t *pairs_out, cpecan_result *results);
 
+/* Page-locked host buffers for callers that want asynchronous, full-rate host<->device copies. */
+void *cpecan_cuda_host_alloc(cpecan_ctx *ctx, int64_t bytes);
+void cpecan_cuda_host_free(cpecan_ctx *ctx, void *p);
+
 int cpecan_cuda_get_timing(cpecan_ctx *ctx, cpecan_timing *out);
 int cpecan_cuda_device_info(cpecan_ctx *ctx, int32_t *sm_count, int32_t *clock_khz, int64_t *hbm_bytes);
 

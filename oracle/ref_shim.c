@@ -168,6 +168,37 @@ int64_t ref_align_unbanded(int smType, const char *modelFile, const double *scal
     return n;
 }
 
+/* CPU-baseline helper: the same call as ref_align_banded, but only getAlignedPairsUsingAnchors itself is timed
+ * (state-machine construction, i.e. parsing the .model text file, is outside the clock).  Returns the pair count. */
+#include <time.h>
+int64_t ref_time_align_banded(int smType, const char *modelFile, const double *scale5, int strand,
+                              const char *refSeq, const double *events, int64_t lY,
+                              const int64_t *anchors, int64_t nAnchors, const RefParams *rp,
+                              int raggedLeft, int raggedRight, double *secondsOut) {
+    StateMachine *sM = makeStateMachine(smType, modelFile, scale5, strand, NULL, NULL);
+    if (!sM) return -1;
+    PairwiseAlignmentParameters *p = makeParams(rp);
+    int64_t lX = sequence_correctSeqLength(strlen(refSeq), event);
+    Sequence *sX = sequence_construct2(lX, (void *) refSeq, smType == vanilla ? sequence_getKmer2 : sequence_getKmer,
+                                       sequence_sliceNucleotideSequence2);
+    Sequence *sY = sequence_construct2(lY, (void *) events, sequence_getEvent, sequence_sliceEventSequence2);
+    stList *anchorList = makeAnchors(anchors, nAnchors);
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    stList *pairs = getAlignedPairsUsingAnchors(sM, sX, sY, anchorList, p, diagonalCalculationPosteriorMatchProbs,
+                                                raggedLeft, raggedRight);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    if (secondsOut) *secondsOut = (double) (t1.tv_sec - t0.tv_sec) + 1e-9 * (double) (t1.tv_nsec - t0.tv_nsec);
+    int64_t n = stList_length(pairs);
+    stList_destruct(pairs);
+    stList_destruct(anchorList);
+    sequence_sequenceDestroy(sX);
+    sequence_sequenceDestroy(sY);
+    pairwiseAlignmentBandingParameters_destruct(p);
+    freeStateMachine(sM);
+    return n;
+}
+
 /* threeState: expOut = 9 transitions (row major from*3+to) + 4096 kmer-skip counts + 1 likelihood = 4106 doubles.
  * vanilla   : expOut = 60 skip-bin counts + 1 likelihood = 61 doubles. */
 int64_t ref_expectations(int smType, const char *modelFile, const double *scale5, int strand,

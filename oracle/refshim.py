@@ -102,6 +102,20 @@ def align_banded(sm_type, model_file, ref_seq, events, anchors, params=None, sca
     return out[:n].copy(), totals
 
 
+def time_align_banded(sm_type, model_file, ref_seq, events, anchors, params=None, scale5=None, strand=0, ragged=(0, 0)):
+    """Seconds spent inside the reference's getAlignedPairsUsingAnchors for one read (CPU baseline)."""
+    events = np.ascontiguousarray(events, dtype=np.float64).reshape(-1, 3)
+    anchors = np.ascontiguousarray(np.asarray(anchors, dtype=np.int64).reshape(-1, 2))
+    params = params or default_params()
+    sec = C.c_double(0.0)
+    f = lib().ref_time_align_banded
+    f.restype = C.c_int64
+    n = f(int(sm_type), model_file.encode(), _dptr(scale5), int(strand), ref_seq.encode(), _dptr(events),
+          C.c_int64(len(events)), _iptr(anchors), C.c_int64(len(anchors)), C.byref(params), int(ragged[0]),
+          int(ragged[1]), C.byref(sec))
+    return sec.value, n
+
+
 def align_unbanded(sm_type, model_file, ref_seq, events, params=None, scale5=None, strand=0, transitions=None,
                    gap_x=None, ragged=(0, 0)):
     events = np.ascontiguousarray(events, dtype=np.float64).reshape(-1, 3)

@@ -1,0 +1,45 @@
+"""Developer perf probe (not a test): kernel-only timing of one expansion; the command ncu captures.
+   python tests/dev_perf.py --e 64 --n 1776 --reps 3 [--lx 6700]"""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "cpecan-signal_b200"))
+from bench import generate_reads  # noqa: E402
+from cpecan_signal import Engine, HostBatch, default_params, synth  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--e", type=int, default=64)
+    ap.add_argument("--n", type=int, default=1776)
+    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--lx", type=int, default=6700)
+    ap.add_argument("--unique", type=int, default=0, help="generate only this many distinct reads and tile them")
+    a = ap.parse_args()
+    nu = a.unique or a.n
+    reads = generate_reads(nu, 5_000_000, lX=a.lx)
+    reads = [reads[i % nu] for i in range(a.n)]
+    l1, _, l3 = synth.load_model_file(synth.TEMPLATE_MODEL)
+    eng = Engine(0)
+    mid = eng.upload_model(l1, l3, np.full(4096, -2.3025850929940455))
+    hb = HostBatch([r.ref for r in reads], [r.events for r in reads], [r.anchors for r in reads],
+                   model_ids=[mid] * len(reads), scales=[r.scale5 for r in reads], ragged=[(1, 1)] * len(reads))
+    eng.stage(hb, params=default_params(diagonalExpansion=a.e), pair_cap=eng.default_pair_capacity(hb, 3))
+    cells = eng.timing()["band_cells"]
+    for i in range(a.reps):
+        eng.run_staged()
+        t = eng.timing()
+        print("e=%d n=%d cells=%.3e align_ms=%.2f  %.2f Gcells/s  %.2f GCUPS  G=%d ctas=%d" % (
+            a.e, a.n, cells, t["align_ms"], cells / t["align_ms"] / 1e6, 2 * cells / t["align_ms"] / 1e6,
+            t["warps_per_item"], t["ctas"]), flush=True)
+    res, _ = eng.fetch_staged()
+    print("status!=0:", int((res["status"] != 0).sum()), "pairs:", int(res["n_pairs"].sum()))
+
+
+if __name__ == "__main__":
+    main()
