@@ -1,0 +1,403 @@
+// cpecan_align2.cuh -- second-generation sm_100a kernel for the banded signal pair-HMM (three-state machine).
+//
+// Same semantics as k_align (cpecan_kernels.cuh; reference impl/pairwiseAligner.c:870-1006, :714-795 and
+// impl/stateMachine.c:1305-1334) with a mapping chosen from the ncu profiles of the first kernel (profiles/r1_*):
+// lanes outside the ragged band, ALU-pipe selects inside logAdd and per-diagonal CTA barriers were its losses, and a
+// register-resident variant of this kernel (K unrolled register rows per warp) was instruction-cache bound.
+//
+//   * ONE WARP per alignment, no block barriers.  The reference positions x are cut into CHUNKS of 32 consecutive x
+//     (lane = x mod 32).  Per diagonal the warp loops (a run-time loop, one copy of the code) over just the chunks
+//     that intersect the band, so the cost of a diagonal follows the band width, not the widest diagonal of the read.
+//   * All per-cell state lives in a shared-memory ring of N positions (x mod N), two float4 (M, X, Y, offset) per
+//     position: the values of diagonals d-1 and d-2.  A cell reads its own and its neighbour's entries (LDS.128) and
+//     writes the new value over its own d-2 entry; walking the chunks in DESCENDING x on the way forward (ASCENDING
+//     on the way back) makes that in-place update safe, so two buffers suffice.  The k-mer side of the emissions is
+//     streamed from L1 (3 x LDG.128 per cell update, each record re-read ~W times while its column is in the band).
+//   * Every cell carries its own offset (an integer stored as float): values are FP32 relative to it.  logAdd is
+//     translation invariant, so a cell is computed in the units U = max(own, neighbours' offsets) and re-based to
+//     its own maximum afterwards; nothing is lost at log-probabilities of -40 000 and nothing depends on where in
+//     the diagonal the probability mass sits.
+//   * logAdd: the reference's 4-segment cubic and 7.5 cut-off (impl/pairwiseAligner.c:235-255) as max + q(|x-y|),
+//     q = cubic - identity, the segment chosen by predicated immediate-operand FFMAs (FMA pipe) instead of a tree of
+//     selects (ALU pipe, half rate).
+//   * Aligned pairs leave in the reference's order for free: the backward walk visits x ascending inside a diagonal.
+#pragma once
+#include "cpecan_kernels.cuh"
+
+namespace cpecan {
+
+#define CP_BIG 1.0e30f
+
+// max(x, y) + q(|x - y|) for |x - y| < 7.5, else max(x, y).  NaN (both -inf) and +inf differences fall to max.
+__device__ __forceinline__ float logadd2(float x, float y) {
+    float r;
+    asm("{\n\t"
+        ".reg .pred p1, p2, p3, p5;\n\t"
+        ".reg .f32 d, a, a2, u, v;\n\t"
+        "sub.f32 d, %1, %2;\n\t"
+        "abs.f32 a, d;\n\t"
+        "max.f32 %0, %1, %2;\n\t"
+        "setp.le.f32 p3, a, 0f40900000;\n\t"            // 4.5
+        "setp.le.f32 p2, a, 0f40200000;\n\t"            // 2.5
+        "setp.le.f32 p1, a, 0f3F800000;\n\t"            // 1.0
+        "setp.lt.f32 p5, a, 0f40F00000;\n\t"            // 7.5
+        "mul.f32 a2, a, a;\n\t"
+        "fma.rn.f32 u, a, 0fB9F07885, 0f3C1EDBBF;\n\t"  // (4.5, 7.5)
+        "fma.rn.f32 v, a, 0fBD8DDAF8, 0f3E2C11EF;\n\t"
+        "@p3 fma.rn.f32 u, a, 0fBB96E5CE, 0f3D81E63C;\n\t"  // (2.5, 4.5]
+        "@p3 fma.rn.f32 v, a, 0fBE9BAB98, 0f3F03A75F;\n\t"
+        "@p2 fma.rn.f32 u, a, 0fBC6E18FA, 0f3E0F4D0A;\n\t"  // (1, 2.5]
+        "@p2 fma.rn.f32 v, a, 0fBF011E08, 0f3F313020;\n\t"
+        "@p1 fma.rn.f32 u, a, 0fBC19343D, 0f3E05CB9C;\n\t"  // [0, 1]
+        "@p1 fma.rn.f32 v, a, 0fBF004EA8, 0f3F3175C2;\n\t"
+        "fma.rn.f32 u, u, a2, v;\n\t"
+        "@p5 add.f32 %0, %0, u;\n\t"
+        "}"
+        : "=f"(r) : "f"(x), "f"(y));
+    return r;
+}
+
+struct KernelArgs2 {
+    const Item *items;
+    const int *order;
+    int n_items;
+    int *queue;
+    const long long *anchors;
+    const float4 *xparams;        // 3 float4 per matrix column x = 0 .. lX+1 (the last record is the all -inf dummy)
+    const float2 *events;
+    float4 *scratch;              // per warp: ring of forward rows, N float4 (M, X, Y, offset) each
+    long long scratch_stride;     // float4 per warp
+    int ring_rows;
+    int ringN;                    // ring positions (power of two)
+    int *pairs;
+    ItemOut *out;
+    double *totals;
+    DevParams P;
+};
+
+__host__ __device__ inline size_t align2_smem_bytes(int ringN) { return (size_t) ringN * (2 * 16 + 2 * 4); }
+
+// left fold in ascending x over ring-positioned values: element i lives at (start + i) & (N - 1)
+__device__ __forceinline__ float warp_ordered_fold_ring(const float *buf, int start, int w, int NM) {
+    const int lane = threadIdx.x & 31;
+    float acc = CP_NEG_INF, runmax = CP_NEG_INF;
+    for (int base = 0; base < w; base += 32) {
+        const int idx = base + lane;
+        const float v = idx < w ? buf[(start + idx) & NM] : CP_NEG_INF;
+        float m = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { float t = __shfl_up_sync(CP_FULL, m, o); if (lane >= o) m = fmaxf(m, t); }
+        float excl = __shfl_up_sync(CP_FULL, m, 1);
+        excl = lane == 0 ? runmax : fmaxf(excl, runmax);
+        const bool live = v > excl - 7.6f;     // anything further below the running maximum cannot change the fold
+        unsigned mask = __ballot_sync(CP_FULL, live);
+        while (mask) {
+            const int b = __ffs(mask) - 1;
+            mask &= mask - 1;
+            acc = logadd2(acc, __shfl_sync(CP_FULL, v, b));
+        }
+        runmax = fmaxf(runmax, __shfl_sync(CP_FULL, m, 31));
+    }
+    return acc;
+}
+
+// re-base a cell to its own maximum (integer shift, exact); a cell that is all -inf drifts down by 64 per step
+__device__ __forceinline__ void rebase(float &a, float &b, float &c, float &off) {
+    const float m = fmaxf(fmaxf(a, b), fmaxf(c, -64.0f));
+    const float s = (m + 12582912.0f) - 12582912.0f;
+    a -= s; b -= s; c -= s; off += s;
+}
+
+template <bool HAS_SX>
+__global__ void __launch_bounds__(32) k_align2(const KernelArgs2 A) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int N = A.ringN, NM = N - 1;
+    float4 *ring = reinterpret_cast<float4 *>(smraw);             // 2 * N entries
+    float *sm_c1 = reinterpret_cast<float *>(ring + 2 * N);       // N
+    float *sm_us = sm_c1 + N;                                     // N
+
+    const int lane = threadIdx.x;
+    const DevParams &P = A.P;
+    const float NI = CP_NEG_INF;
+    float4 *rows = A.scratch + (long long) blockIdx.x * A.scratch_stride;
+    const int R = A.ring_rows;
+    const float4 NIENT = make_float4(NI, NI, NI, -CP_BIG);
+    const float tMC = P.tMC, tMX = P.tMX, tMY = P.tMY, tOX = P.tOX, tOY = P.tOY, tEX = P.tEX, tEY = P.tEY, tSX = P.tSX;
+
+    for (;;) {
+        int qi = 0;
+        if (lane == 0) qi = atomicAdd(A.queue, 1);
+        qi = __shfl_sync(CP_FULL, qi, 0);
+        if (qi >= A.n_items) break;
+        const int itemIdx = A.order[qi];
+        const Item it = A.items[itemIdx];
+        const int lX = it.lX, lY = it.lY, D = lX + lY;
+        const float4 *xp = A.xparams + 3 * it.xp_off;
+        const float2 *evp = A.events + it.ev_off;
+        int *pairs = A.pairs + 3 * it.pair_off;
+        double *dbgTot = (A.totals != nullptr && it.tot_off >= 0) ? A.totals + it.tot_off : nullptr;
+        int nPairs = 0, status = 0, nTb = 0;
+        double lastTotal = 0.0;
+        const bool unbanded = P.mode == 2;
+
+        if (D == 0) {
+            if (lane == 0) { ItemOut &o = A.out[itemIdx]; o.n_pairs = 0; o.status = 0; o.total_logprob = 0.0; o.n_tracebacks = 0; }
+            continue;
+        }
+        BandWalker bw;
+        bw.init(A.anchors + 2 * it.an_off, it.nA, lX, lY, P.expansion);
+
+        auto resetRing = [&]() {
+            __syncwarp();
+            for (int i = lane; i < 2 * N; i += 32) ring[i] = NIENT;
+            __syncwarp();
+        };
+
+        // ---- diagonal 0: the single cell (0,0) holds the start vector (impl/pairwiseAligner.c:897-898) ----------
+        resetRing();
+        float4 *A1 = ring, *A2 = ring + N;       // A1: newest diagonal, A2: the one before (forward); mirrored backward
+        if (lane == 0) {
+            const float *sv = (it.flags & 1) ? P.rstartv : P.startv;
+            const float4 e = make_float4(sv[0], sv[1], sv[2], 0.f);
+            A1[0] = e; rows[0] = e;
+        }
+        __syncwarp();
+
+        int dcur = 0, tracedBackTo = 0;
+        int lo = 0, hi = 0;
+
+        while (tracedBackTo < D) {
+            // =============================== forward sweep ===============================================
+            int Dt = -1;
+            bool atEnd = false;
+            {
+                int rowF = dcur % R;
+                while (true) {
+                    const int d = dcur + 1;
+                    const int plo = lo, phi = hi;
+                    bw.range(d, lo, hi);
+                    if (lo < plo || lo > plo + 1 || hi < phi || hi > phi + 1) status |= 4;
+                    rowF = rowF + 1 == R ? 0 : rowF + 1;
+                    float4 *frow = rows + (long long) rowF * N;
+                    const int cLo = max(lo - 1, 0) >> 5, cHi = min(hi + 1, lX) >> 5;
+                    for (int c = cHi; c >= cLo; c--) {               // descending x: in-place update of the d-2 entries
+                        const int x = (c << 5) + lane;
+                        const int s = x & NM, sl = (x - 1) & NM;
+                        const float4 own = A1[s], L = A1[sl], Mi = A2[sl];
+                        const int xx = min(x, lX + 1);
+                        const float4 pa = xp[3 * xx], pb = xp[3 * xx + 1], pc = xp[3 * xx + 2];
+                        const float2 ev = evp[min(max(d - x, 0), lY)];
+                        const bool inb = x >= lo && x <= hi;
+                        __syncwarp();
+                        const float U = fmaxf(own.w, fmaxf(L.w, Mi.w));
+                        // impl/stateMachine.c:1314-1333: transitions folded in code order, emission added once
+                        float tX = logadd2(L.x + tOX, L.y + tEX);
+                        if (HAS_SX) tX = logadd2(tX, L.z + tSX);
+                        float tM = logadd2(logadd2(Mi.x + tMC, Mi.y + tMX), Mi.z + tMY);
+                        float tY = logadd2(own.x + tOY, own.z + tEY);
+                        const float dmM = ev.x - pa.x, dnM = ev.y - pa.z, dmY = ev.x - pb.y, dnY = ev.y - pb.w;
+                        const float eM = fmaf(pa.y, dmM * dmM, fmaf(pa.w, dnM * dnM, pb.x));
+                        const float eY = fmaf(pb.z, dmY * dmY, fmaf(pc.x, dnY * dnY, pc.y));
+                        tX += pc.z + (L.w - U);
+                        tM += eM + (Mi.w - U);
+                        tY += eY + (own.w - U);
+                        float cM = inb ? tM : NI, cX = inb ? tX : NI, cY = inb ? tY : NI, co = inb ? U : -CP_BIG;
+                        rebase(cM, cX, cY, co);
+                        const float4 e = make_float4(cM, cX, cY, co);
+                        A2[s] = e;
+                        if (inb) frow[s] = e;
+                        __syncwarp();
+                    }
+                    { float4 *t = A1; A1 = A2; A2 = t; }
+                    dcur = d;
+                    atEnd = d == D;
+                    const bool tbPoint = !unbanded && d >= tracedBackTo + P.minDiags && (hi - lo + 1) <= 2 * P.expansion + 1;
+                    if (atEnd || tbPoint) { Dt = d; break; }
+                }
+            }
+
+            // =============================== traceback ===================================================
+            // impl/pairwiseAligner.c:920-992.  The ring now holds G = B + emission of diagonals d+1 (A1) and d+2 (A2).
+            nTb++;
+            const int tracedBackFrom = Dt - (atEnd ? 0 : P.tbDiags + 1);
+            BandWalker bb = bw;
+            int blo = lo, bhi = hi;
+            resetRing();
+            const float *endv = (atEnd && (it.flags & 2)) ? P.rendv : P.endv;
+            const float endM = endv[0], endX = endv[1], endY = endv[2];
+            float totSt = NI, totBase = 0.f;
+            int count = 0;
+            {
+                int rowB = Dt % R;
+                for (int d = Dt; d > tracedBackTo; d--) {
+                    if (d < Dt) {
+                        const int pl = blo, ph = bhi;
+                        bb.range(d, blo, bhi);
+                        if (blo > pl || blo < pl - 1 || bhi > ph || bhi < ph - 1) status |= 4;
+                        rowB = rowB == 0 ? R - 1 : rowB - 1;
+                    }
+                    const float4 *frow = rows + (long long) rowB * N;
+                    const bool post = d <= tracedBackFrom;
+                    const int cLo = max(blo - 1, 0) >> 5, cHi = min(bhi + 1, lX) >> 5;
+                    bool doTotal = false;
+                    if (post) { doTotal = unbanded ? (d == Dt) : (count % P.totalEvery == 0); count++; }
+
+                    // B of one cell from the ring (pull form of impl/pairwiseAligner.c:378-383: first from diagonal
+                    // d+2 as "middle", then d+1 in ascending x-y as "upper", then "lower"), in units U
+                    auto cellB = [&](int x, int s, float &bM, float &bX, float &bY, float &U) {
+                        if (d == Dt) { bM = endM; bX = endX; bY = endY; U = 0.f; return; }
+                        const int sr = (x + 1) & NM;
+                        const float4 own = A1[s], R1 = A1[sr], R2 = A2[sr];
+                        U = fmaxf(own.w, fmaxf(R1.w, R2.w));
+                        const float gm2 = R2.x + (R2.w - U), gx1 = R1.y + (R1.w - U), gy1 = own.z + (own.w - U);
+                        bM = logadd2(logadd2(gm2 + tMC, gy1 + tOY), gx1 + tOX);
+                        bX = logadd2(gm2 + tMX, gx1 + tEX);
+                        bY = logadd2(gm2 + tMY, gy1 + tEY);
+                        if (HAS_SX) bY = logadd2(bY, gx1 + tSX);
+                    };
+                    // posterior of one cell + G = B + emission, re-based, back into the ring
+                    auto cellPost = [&](int x, int s, bool inb, float bM, float bX, float bY, float U) {
+                        const int y = d - x;
+                        if (post) {
+                            float4 F = NIENT;
+                            if (inb) F = frow[s];
+                            const float lp = (F.x + bM) + (((F.w + U) - totBase) - totSt);
+                            float p = __expf(lp);
+                            const bool ok = inb && x > 0 && y > 0 && p >= P.threshold;
+                            p = fminf(p, 1.0f);
+                            const unsigned mask = __ballot_sync(CP_FULL, ok);
+                            if (ok) {
+                                const int pos = nPairs + __popc(mask & ((1u << lane) - 1u));
+                                if (pos < it.pair_cap) {
+                                    pairs[3 * pos] = P.dbgLogP ? __float_as_int(lp) : (int) floorf(p * 10000000.0f);
+                                    pairs[3 * pos + 1] = x - 1; pairs[3 * pos + 2] = y - 1;
+                                }
+                            }
+                            nPairs += __popc(mask);
+                        }
+                        const int xx = min(x, lX + 1);
+                        const float4 pa = xp[3 * xx], pb = xp[3 * xx + 1], pc = xp[3 * xx + 2];
+                        const float2 ev = evp[min(max(y, 0), lY)];
+                        const float dmM = ev.x - pa.x, dnM = ev.y - pa.z, dmY = ev.x - pb.y, dnY = ev.y - pb.w;
+                        const float eM = fmaf(pa.y, dmM * dmM, fmaf(pa.w, dnM * dnM, pb.x));
+                        const float eY = fmaf(pb.z, dmY * dmY, fmaf(pc.x, dnY * dnY, pc.y));
+                        float gM = inb ? bM + eM : NI, gX = inb ? bX + pc.z : NI, gY = inb ? bY + eY : NI, go = inb ? U : -CP_BIG;
+                        rebase(gM, gX, gY, go);
+                        A2[s] = make_float4(gM, gX, gY, go);
+                    };
+
+                    if (!doTotal) {
+                        for (int c = cLo; c <= cHi; c++) {             // ascending x: in-place update of the d+2 entries
+                            const int x = (c << 5) + lane, s = x & NM;
+                            const bool inb = x >= blo && x <= bhi;
+                            float bM, bX, bY, U;
+                            cellB(x, s, bM, bX, bY, U);
+                            __syncwarp();
+                            cellPost(x, s, inb, bM, bX, bY, U);
+                            __syncwarp();
+                        }
+                    } else {
+                        // ---- totalProbability (impl/pairwiseAligner.c:736-754), recomputed every 10th posterior diagonal
+                        // pass 1: B into the ring (units in .w), dot-product terms and their units aside
+                        int lmax = CP_INT_MIN;
+                        for (int c = cLo; c <= cHi; c++) {
+                            const int x = (c << 5) + lane, s = x & NM;
+                            const bool inb = x >= blo && x <= bhi;
+                            float bM, bX, bY, U;
+                            cellB(x, s, bM, bX, bY, U);
+                            __syncwarp();
+                            A2[s] = make_float4(inb ? bM : NI, inb ? bX : NI, inb ? bY : NI, inb ? U : -CP_BIG);
+                            if (inb) {
+                                const float4 F = frow[s];
+                                const float c1 = logadd2(logadd2(F.x + bM, F.y + bX), F.z + bY);
+                                const float us = F.w + U;
+                                sm_c1[s] = c1; sm_us[s] = us;
+                                if (c1 > -1e30f) lmax = max(lmax, (int) us + (int) floorf(c1));
+                            }
+                            __syncwarp();
+                        }
+                        const int base = __reduce_max_sync(CP_FULL, lmax);
+                        const float fbase = base == CP_INT_MIN ? 0.f : (float) base;
+                        for (int x = blo + lane; x <= bhi; x += 32) { const int s = x & NM; sm_c1[s] = sm_c1[s] + (sm_us[s] - fbase); }
+                        __syncwarp();
+                        const float t1 = warp_ordered_fold_ring(sm_c1, blo & NM, bhi - blo + 1, NM);
+                        float tot = t1, t2v = NI;
+                        if (d < Dt && base != CP_INT_MIN) {
+                            // term 2: matches jumping over diagonal d = a match-only forward step from F[d-1] into the
+                            // cells of diagonal d+1, dotted with B[d+1] (G_M of d+1 is still in A1)
+                            BandWalker b2w = bb;
+                            int l1, h1, lm1, hm1;
+                            b2w.range(d + 1, l1, h1);
+                            b2w.range(d - 1, lm1, hm1);
+                            const int rowM = rowB == 0 ? R - 1 : rowB - 1;
+                            const float4 *fprev = rows + (long long) rowM * N;
+                            __syncwarp();
+                            for (int x = l1 + lane; x <= h1; x += 32) {
+                                float val = NI;
+                                if (x - 1 >= lm1 && x - 1 <= hm1) {
+                                    const float4 F = fprev[(x - 1) & NM];
+                                    const float4 Gn = A1[x & NM];
+                                    const float md = logadd2(logadd2(F.x + tMC, F.y + tMX), F.z + tMY);
+                                    val = (md + Gn.x) + ((F.w + Gn.w) - fbase);
+                                }
+                                sm_c1[x & NM] = val;
+                            }
+                            __syncwarp();
+                            t2v = warp_ordered_fold_ring(sm_c1, l1 & NM, h1 - l1 + 1, NM);
+                            tot = logadd2(t1, t2v);
+                        }
+                        totSt = tot;
+                        totBase = fbase;
+                        if (!(tot > -1e30f)) status |= 2;
+                        if (dbgTot != nullptr && lane == 0) {
+                            dbgTot[(D + 1) + d] = (double) t1 + (double) totBase;
+                            dbgTot[2 * (D + 1) + d] = d < Dt ? (double) t2v + (double) totBase : (double) NAN;
+                        }
+                        __syncwarp();
+                        // pass 2: posteriors and G from the parked B
+                        for (int c = cLo; c <= cHi; c++) {
+                            const int x = (c << 5) + lane, s = x & NM;
+                            const bool inb = x >= blo && x <= bhi;
+                            const float4 b = A2[s];
+                            __syncwarp();
+                            cellPost(x, s, inb, b.x, b.y, b.z, b.w);
+                            __syncwarp();
+                        }
+                    }
+                    if (post) {
+                        const double totAbs = (double) totSt + (double) totBase;
+                        if (d == D) lastTotal = totAbs;
+                        if (dbgTot != nullptr && lane == 0) dbgTot[d] = totAbs;
+                    }
+                    { float4 *t = A1; A1 = A2; A2 = t; }
+                }
+            }
+            tracedBackTo = tracedBackFrom;
+
+            // =============================== restore the forward state at Dt ==============================
+            if (tracedBackTo < D) {
+                resetRing();
+                A1 = ring; A2 = ring + N;
+                int l1, h1;
+                BandWalker br = bw;
+                br.range(Dt - 1, l1, h1);
+                br.range(Dt, lo, hi);
+                const float4 *f0 = rows + (long long) (Dt % R) * N;
+                const float4 *f1 = rows + (long long) ((Dt - 1) % R) * N;
+                for (int x = lo + lane; x <= hi; x += 32) A1[x & NM] = f0[x & NM];
+                for (int x = l1 + lane; x <= h1; x += 32) A2[x & NM] = f1[x & NM];
+                __syncwarp();
+            }
+        }
+
+        if (lane == 0) {
+            ItemOut &o = A.out[itemIdx];
+            o.n_pairs = nPairs;
+            o.status = status | (nPairs > it.pair_cap ? 1 : 0);
+            o.total_logprob = lastTotal;
+            o.n_tracebacks = nTb;
+        }
+    }
+}
+
+}  // namespace cpecan

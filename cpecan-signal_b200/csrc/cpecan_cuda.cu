@@ -13,6 +13,7 @@
 
 #include "cpecan_cuda.h"
 #include "cpecan_kernels.cuh"
+#include "cpecan_align2.cuh"
 
 using namespace cpecan;
 
@@ -21,6 +22,11 @@ namespace {
 constexpr int KSLOTS = 4;                         // cells per thread
 constexpr int NBUCKET = 6;                        // G = 1, 2, 4, 8, 16, 32 warps per alignment
 constexpr int bucketG[NBUCKET] = { 1, 2, 4, 8, 16, 32 };
+
+// kernel generation 2: one warp per alignment, ring of N = 128 << bucket positions (power of two)
+constexpr int NCFG2 = 6;
+constexpr int CFG2_MARGIN = 40;                   // ring positions beyond the widest diagonal (window + look-ahead)
+inline int cfg2N(int b) { return 128 << b; }
 
 struct DevBuf {
     void *p = nullptr;
@@ -72,7 +78,9 @@ struct cpecan_ctx {
     DevBuf dItems, dOut, dRef, dRefOff, dEvSrc, dEvSrcOff, dAnchors, dScale, dCentre, dXp, dEv, dPairs, dOrder,
            dQueue, dScratch, dRowoff, dTotals, dCompact, dCompactOff;
     int64_t pairCapTotal = 0, totalsLen = 0;
-    Bucket buckets[NBUCKET];
+    Bucket buckets[NCFG2 > NBUCKET ? NCFG2 : NBUCKET];
+    int gen = 2;                 // kernel generation (CPECAN_KERNEL=1 selects the first kernel)
+    int occ2[NCFG2][2] = {};
     bool wantTotals = false;
     std::vector<int64_t> hTotOff;
     cpecan_timing timing{};
@@ -93,6 +101,24 @@ namespace {
 template <int G, bool SX> void launchAlign(const KernelArgs &a, int nCta, cudaStream_t s) {
     k_align<G, KSLOTS, SX><<<nCta, 32 * G, 0, s>>>(a);
 }
+cudaError_t prepCfg2(int cfg, bool sx) {
+    const int bytes = (int) align2_smem_bytes(cfg2N(cfg));
+    return sx ? cudaFuncSetAttribute(k_align2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)
+              : cudaFuncSetAttribute(k_align2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+int occCfg2(int cfg, bool sx) {
+    int nb = 0;
+    const size_t bytes = align2_smem_bytes(cfg2N(cfg));
+    if (sx) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_align2<true>, 32, bytes);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_align2<false>, 32, bytes);
+    return nb;
+}
+void launchCfg2(int cfg, bool sx, const KernelArgs2 &a, int nCta, cudaStream_t s) {
+    const size_t bytes = align2_smem_bytes(cfg2N(cfg));
+    if (sx) k_align2<true><<<nCta, 32, bytes, s>>>(a);
+    else k_align2<false><<<nCta, 32, bytes, s>>>(a);
+}
+
 template <int G> int occupancyOf(bool sx) {
     int nb = 0;
     if (sx) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_align<G, KSLOTS, true>, 32 * G, 0);
@@ -177,6 +203,13 @@ int cpecan_cuda_init(int device, cpecan_ctx **ctx_out) {
     }
     for (auto &e : ctx->ev) cudaEventCreate(&e);
     for (int b = 0; b < NBUCKET; b++) { ctx->occ[b][0] = occupancy(b, false); ctx->occ[b][1] = occupancy(b, true); }
+    for (int c = 0; c < NCFG2; c++)
+        for (int sx = 0; sx < 2; sx++) {
+            if (prepCfg2(c, sx != 0) != cudaSuccess) { cudaGetLastError(); ctx->occ2[c][sx] = 0; continue; }
+            ctx->occ2[c][sx] = occCfg2(c, sx != 0);
+        }
+    if (ctx->occ2[NCFG2 - 1][0] == 0) { prepCfg2(NCFG2 - 2, false); prepCfg2(NCFG2 - 2, true); }
+    if (const char *g = getenv("CPECAN_KERNEL")) ctx->gen = atoi(g) == 1 ? 1 : 2;
     *ctx_out = ctx;
     return CPECAN_OK;
 }
@@ -265,7 +298,7 @@ int cpecan_cuda_stage(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_param
         it.tot_off = ctx->wantTotals ? totTot : -1;
         ctx->hTotOff[i] = totTot;
         totTot += 3 * (lX + lY + 1);   // total, term 1, term 2 per diagonal
-        xpTot += lX + 1; evTot += lY + 1;
+        xpTot += lX + 2; evTot += lY + 1;
         maxLX = std::max(maxLX, (int) lX); maxLY = std::max(maxLY, (int) lY);
         const double sc = B->scale ? B->scale[5 * i] : 1.0, sh = B->scale ? B->scale[5 * i + 1] : 0.0;
         centre[i] = 68.0 * sc + sh;
@@ -330,15 +363,20 @@ int cpecan_cuda_stage(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_param
         cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); ctx->timing.plan_ms = ms;
     }
 
-    // ---- bucket by required warps per alignment, order largest first ----------------------------------------
+    // ---- bucket by the ring size an alignment needs, order largest first ---------------------------------------
+    const int nBuckets = ctx->gen == 2 ? NCFG2 : NBUCKET;
     for (auto &b : ctx->buckets) { b.order.clear(); b.nCta = 0; b.ringRows = 0; }
     int64_t cells = 0;
     for (int64_t i = 0; i < n; i++) {
         const ItemOut &o = ctx->hOut[i];
         cells += o.band_cells;
         int b = 0;
-        while (b < NBUCKET && 32 * bucketG[b] * KSLOTS - KSLOTS < o.max_width) b++;
-        if (b == NBUCKET) { ctx->err = "band wider than 4092 cells is not supported"; return CPECAN_ERR_BAND_TOO_WIDE; }
+        if (ctx->gen == 2) {
+            while (b < NCFG2 && (cfg2N(b) < o.max_width + CFG2_MARGIN || ctx->occ2[b][ctx->hasSX ? 1 : 0] == 0)) b++;
+        } else {
+            while (b < NBUCKET && 32 * bucketG[b] * KSLOTS - KSLOTS < o.max_width) b++;
+        }
+        if (b == nBuckets) { ctx->err = "band wider than the widest kernel instantiation"; return CPECAN_ERR_BAND_TOO_WIDE; }
         ctx->buckets[b].order.push_back((int) i);
         ctx->buckets[b].ringRows = std::max(ctx->buckets[b].ringRows, o.max_rows);
     }
@@ -346,24 +384,28 @@ int cpecan_cuda_stage(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_param
     size_t scratchFloats = 0, rowoffInts = 0, orderInts = 0;
     std::vector<int> orderAll;
     orderAll.reserve(n);
-    for (int b = 0; b < NBUCKET; b++) {
+    for (int b = 0; b < nBuckets; b++) {
         Bucket &bk = ctx->buckets[b];
         if (bk.order.empty()) continue;
         std::stable_sort(bk.order.begin(), bk.order.end(), [&](int a, int c) { return ctx->hOut[a].band_cells > ctx->hOut[c].band_cells; });
-        const int occ = std::max(1, ctx->occ[b][ctx->hasSX ? 1 : 0]);
+        const int sx = ctx->hasSX ? 1 : 0;
+        const int occ = std::max(1, ctx->gen == 2 ? ctx->occ2[b][sx] : ctx->occ[b][sx]);
+        const int warps = ctx->gen == 2 ? 1 : bucketG[b];
+        const int ringN = ctx->gen == 2 ? cfg2N(b) : 32 * bucketG[b] * KSLOTS;
         bk.nCta = (int) std::min<int64_t>((int64_t) bk.order.size(), (int64_t) ctx->prop.multiProcessorCount * occ);
-        bk.stride = (long long) bk.ringRows * 3 * 32 * bucketG[b] * KSLOTS;
+        // gen 2: float4 (M, X, Y, offset) per ring position and row; gen 1: 3 floats + per-thread offsets
+        bk.stride = ctx->gen == 2 ? (long long) bk.ringRows * ringN * 4 : (long long) bk.ringRows * 3 * ringN;
         bk.scratchOff = scratchFloats; scratchFloats += (size_t) bk.stride * bk.nCta;
-        bk.rowoffOff = rowoffInts; rowoffInts += (size_t) bk.ringRows * bk.nCta * 32 * bucketG[b];
+        bk.rowoffOff = rowoffInts; rowoffInts += ctx->gen == 2 ? 0 : (size_t) bk.ringRows * bk.nCta * 32 * warps;
         bk.orderOff = orderInts; orderInts += bk.order.size();
         orderAll.insert(orderAll.end(), bk.order.begin(), bk.order.end());
-        ctx->timing.warps_per_item = bucketG[b];
+        ctx->timing.warps_per_item = warps;
         ctx->timing.ctas = bk.nCta;
     }
     CK(ctx->dScratch.ensure(std::max<size_t>(1, scratchFloats) * sizeof(float)));
     CK(ctx->dRowoff.ensure(std::max<size_t>(1, rowoffInts) * sizeof(int)));
     CK(ctx->dOrder.ensure(std::max<size_t>(1, orderInts) * sizeof(int)));
-    CK(ctx->dQueue.ensure(NBUCKET * sizeof(int)));
+    CK(ctx->dQueue.ensure(16 * sizeof(int)));
     CK(cudaMemcpyAsync(ctx->dOrder.p, orderAll.data(), orderAll.size() * sizeof(int), cudaMemcpyHostToDevice, s));
     if (ctx->wantTotals) CK(ctx->dTotals.ensure(std::max<int64_t>(1, totTot) * sizeof(double)));
     CK(cudaStreamSynchronize(s));
@@ -376,16 +418,38 @@ int cpecan_cuda_run_staged(cpecan_ctx *ctx) {
     CK(cudaSetDevice(ctx->device));
     if (ctx->n == 0) return CPECAN_OK;
     cudaStream_t s = ctx->stream;
-    CK(cudaMemsetAsync(ctx->dQueue.p, 0, NBUCKET * sizeof(int), s));
+    CK(cudaMemsetAsync(ctx->dQueue.p, 0, 16 * sizeof(int), s));
     if (ctx->wantTotals) {
         // NaN fill (all-ones bit pattern is a NaN)
         CK(cudaMemsetAsync(ctx->dTotals.p, 0xff, ctx->totalsLen * sizeof(double), s));
     }
     CK(cudaEventRecord(ctx->ev[4], s));
     int launches = 0;
-    for (int b = 0; b < NBUCKET; b++) {
+    const int nBuckets = ctx->gen == 2 ? NCFG2 : NBUCKET;
+    for (int b = 0; b < nBuckets; b++) {
         Bucket &bk = ctx->buckets[b];
         if (bk.order.empty()) continue;
+        if (ctx->gen == 2) {
+            KernelArgs2 a;
+            a.items = ctx->dItems.as<Item>();
+            a.order = ctx->dOrder.as<int>() + bk.orderOff;
+            a.n_items = (int) bk.order.size();
+            a.queue = ctx->dQueue.as<int>() + b;
+            a.anchors = ctx->dAnchors.as<long long>();
+            a.xparams = ctx->dXp.as<float4>();
+            a.events = ctx->dEv.as<float2>();
+            a.scratch = reinterpret_cast<float4 *>(ctx->dScratch.as<float>() + bk.scratchOff);
+            a.scratch_stride = bk.stride / 4;
+            a.ring_rows = bk.ringRows;
+            a.ringN = cfg2N(b);
+            a.pairs = ctx->dPairs.as<int>();
+            a.out = ctx->dOut.as<ItemOut>();
+            a.totals = ctx->wantTotals ? ctx->dTotals.as<double>() : nullptr;
+            a.P = ctx->P;
+            launchCfg2(b, ctx->hasSX, a, bk.nCta, s);
+            launches++;
+            continue;
+        }
         KernelArgs a;
         a.items = ctx->dItems.as<Item>();
         a.order = ctx->dOrder.as<int>() + bk.orderOff;

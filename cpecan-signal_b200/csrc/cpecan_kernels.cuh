@@ -197,9 +197,10 @@ __global__ void k_prep_xparams3(const Item *items, const long long *ref_off, con
     if (scaled) { sc = scale[5 * i]; sh = scale[5 * i + 1]; var = scale[5 * i + 2]; scsd = scale[5 * i + 3]; varsd = scale[5 * i + 4]; }
     float4 *dst = out + 3 * it.xp_off;
     const float ninf = CP_NEG_INF;
-    for (int x = blockIdx.y * blockDim.x + threadIdx.x; x <= it.lX; x += gridDim.y * blockDim.x) {
+    // record lX + 1 is the all -inf dummy the second-generation kernel reads for columns beyond the matrix
+    for (int x = blockIdx.y * blockDim.x + threadIdx.x; x <= it.lX + 1; x += gridDim.y * blockDim.x) {
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = make_float4(ninf, 0.f, 0.f, 0.f), c = make_float4(0.f, ninf, ninf, 0.f);
-        const int k = x > 0 ? kmer_code(r + x - 1) : -1;
+        const int k = (x > 0 && x <= it.lX) ? kmer_code(r + x - 1) : -1;
         if (k >= 0) {
             const double *m = mt.match + 1 + 5 * k;
             double mu = m[0], sd = m[1], nu = m[2], tau = m[3], lam = m[4];
