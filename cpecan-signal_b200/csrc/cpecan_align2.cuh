@@ -28,8 +28,25 @@ namespace cpecan {
 
 #define CP_BIG 1.0e30f
 
-// max(x, y) + q(|x - y|) for |x - y| < 7.5, else max(x, y).  NaN (both -inf) and +inf differences fall to max.
-__device__ __forceinline__ float logadd2(float x, float y) {
+// Multiplier coefficients of the logAdd segments, kept in registers for the whole kernel (an FFMA takes only one
+// immediate; without this ptxas re-materialises the eight constants in every loop iteration).
+struct LaCoef { float a4, c4, a3, c3, a2, c2, a1, c1; };
+__device__ __forceinline__ LaCoef la_coef() {
+    LaCoef k;
+    asm volatile("mov.f32 %0, 0fB9F07885;" : "=f"(k.a4));
+    asm volatile("mov.f32 %0, 0fBD8DDAF8;" : "=f"(k.c4));
+    asm volatile("mov.f32 %0, 0fBB96E5CE;" : "=f"(k.a3));
+    asm volatile("mov.f32 %0, 0fBE9BAB98;" : "=f"(k.c3));
+    asm volatile("mov.f32 %0, 0fBC6E18FA;" : "=f"(k.a2));
+    asm volatile("mov.f32 %0, 0fBF011E08;" : "=f"(k.c2));
+    asm volatile("mov.f32 %0, 0fBC19343D;" : "=f"(k.a1));
+    asm volatile("mov.f32 %0, 0fBF004EA8;" : "=f"(k.c1));
+    return k;
+}
+
+// max(x, y) + q(|x - y|) for |x - y| < 7.5, else max(x, y); q = the reference's cubic segment minus the identity,
+// evaluated as (a t + b) t^2 + ((c - 1) t + d).  NaN (both -inf) and +inf differences fall through to max.
+__device__ __forceinline__ float logadd2(float x, float y, const LaCoef &k) {
     float r;
     asm("{\n\t"
         ".reg .pred p1, p2, p3, p5;\n\t"
@@ -42,18 +59,18 @@ __device__ __forceinline__ float logadd2(float x, float y) {
         "setp.le.f32 p1, a, 0f3F800000;\n\t"            // 1.0
         "setp.lt.f32 p5, a, 0f40F00000;\n\t"            // 7.5
         "mul.f32 a2, a, a;\n\t"
-        "fma.rn.f32 u, a, 0fB9F07885, 0f3C1EDBBF;\n\t"  // (4.5, 7.5)
-        "fma.rn.f32 v, a, 0fBD8DDAF8, 0f3E2C11EF;\n\t"
-        "@p3 fma.rn.f32 u, a, 0fBB96E5CE, 0f3D81E63C;\n\t"  // (2.5, 4.5]
-        "@p3 fma.rn.f32 v, a, 0fBE9BAB98, 0f3F03A75F;\n\t"
-        "@p2 fma.rn.f32 u, a, 0fBC6E18FA, 0f3E0F4D0A;\n\t"  // (1, 2.5]
-        "@p2 fma.rn.f32 v, a, 0fBF011E08, 0f3F313020;\n\t"
-        "@p1 fma.rn.f32 u, a, 0fBC19343D, 0f3E05CB9C;\n\t"  // [0, 1]
-        "@p1 fma.rn.f32 v, a, 0fBF004EA8, 0f3F3175C2;\n\t"
+        "fma.rn.f32 u, a, %3, 0f3C1EDBBF;\n\t"          // (4.5, 7.5)
+        "fma.rn.f32 v, a, %4, 0f3E2C11EF;\n\t"
+        "@p3 fma.rn.f32 u, a, %5, 0f3D81E63C;\n\t"      // (2.5, 4.5]
+        "@p3 fma.rn.f32 v, a, %6, 0f3F03A75F;\n\t"
+        "@p2 fma.rn.f32 u, a, %7, 0f3E0F4D0A;\n\t"      // (1, 2.5]
+        "@p2 fma.rn.f32 v, a, %8, 0f3F313020;\n\t"
+        "@p1 fma.rn.f32 u, a, %9, 0f3E05CB9C;\n\t"      // [0, 1]
+        "@p1 fma.rn.f32 v, a, %10, 0f3F3175C2;\n\t"
         "fma.rn.f32 u, u, a2, v;\n\t"
         "@p5 add.f32 %0, %0, u;\n\t"
         "}"
-        : "=f"(r) : "f"(x), "f"(y));
+        : "=f"(r) : "f"(x), "f"(y), "f"(k.a4), "f"(k.c4), "f"(k.a3), "f"(k.c3), "f"(k.a2), "f"(k.c2), "f"(k.a1), "f"(k.c1));
     return r;
 }
 
@@ -77,8 +94,14 @@ struct KernelArgs2 {
 
 __host__ __device__ inline size_t align2_smem_bytes(int ringN) { return (size_t) ringN * (2 * 16 + 2 * 4); }
 
-// left fold in ascending x over ring-positioned values: element i lives at (start + i) & (N - 1)
-__device__ __forceinline__ float warp_ordered_fold_ring(const float *buf, int start, int w, int NM) {
+// Left fold  acc = logadd(acc, v[0]), logadd(acc, v[1]), ...  in ascending x (the order of dpDiagonal_dotProduct,
+// impl/pairwiseAligner.c:587-597) over ring-positioned values: element i lives at (start + i) & (N - 1).
+// Exactly equal to the serial fold, at the cost of the few elements near the ridge only:
+//   * an element more than 7.5 below the running prefix maximum cannot change acc (acc >= prefix maximum);
+//   * an element at least 7.5 + 12 above the prefix maximum RESETS the fold: acc <= prefix maximum + ln(count) +
+//     count * 6e-4 (the cubic over-estimates by at most 5.5e-4 per step) < prefix maximum + 12 for count <= 4096, so
+//     logadd returns the element itself and everything before it is forgotten.
+__device__ __forceinline__ float warp_ordered_fold_ring(const float *buf, int start, int w, int NM, const LaCoef &k) {
     const int lane = threadIdx.x & 31;
     float acc = CP_NEG_INF, runmax = CP_NEG_INF;
     for (int base = 0; base < w; base += 32) {
@@ -89,12 +112,17 @@ __device__ __forceinline__ float warp_ordered_fold_ring(const float *buf, int st
         for (int o = 1; o < 32; o <<= 1) { float t = __shfl_up_sync(CP_FULL, m, o); if (lane >= o) m = fmaxf(m, t); }
         float excl = __shfl_up_sync(CP_FULL, m, 1);
         excl = lane == 0 ? runmax : fmaxf(excl, runmax);
-        const bool live = v > excl - 7.6f;     // anything further below the running maximum cannot change the fold
-        unsigned mask = __ballot_sync(CP_FULL, live);
+        unsigned mask = __ballot_sync(CP_FULL, v > excl - 7.6f);
+        const unsigned resets = __ballot_sync(CP_FULL, v >= excl + 19.5f);
+        if (resets) {
+            const int j = 31 - __clz(resets);
+            acc = __shfl_sync(CP_FULL, v, j);
+            mask &= j == 31 ? 0u : ~((2u << j) - 1u);
+        }
         while (mask) {
             const int b = __ffs(mask) - 1;
             mask &= mask - 1;
-            acc = logadd2(acc, __shfl_sync(CP_FULL, v, b));
+            acc = logadd2(acc, __shfl_sync(CP_FULL, v, b), k);
         }
         runmax = fmaxf(runmax, __shfl_sync(CP_FULL, m, 31));
     }
@@ -122,6 +150,8 @@ __global__ void __launch_bounds__(32) k_align2(const KernelArgs2 A) {
     float4 *rows = A.scratch + (long long) blockIdx.x * A.scratch_stride;
     const int R = A.ring_rows;
     const float4 NIENT = make_float4(NI, NI, NI, -CP_BIG);
+    const LaCoef K = la_coef();
+#define LA(a, b) logadd2((a), (b), K)
     const float tMC = P.tMC, tMX = P.tMX, tMY = P.tMY, tOX = P.tOX, tOY = P.tOY, tEX = P.tEX, tEY = P.tEY, tSX = P.tSX;
 
     for (;;) {
@@ -171,30 +201,57 @@ __global__ void __launch_bounds__(32) k_align2(const KernelArgs2 A) {
             int Dt = -1;
             bool atEnd = false;
             {
+                // The (diagonal, chunk) tasks are walked as ONE loop with the inputs of the next task (k-mer record,
+                // event) requested before the current one is computed, so global-load latency hides behind a full
+                // chunk of arithmetic, also across the step to the next diagonal.
                 int rowF = dcur % R;
-                while (true) {
-                    const int d = dcur + 1;
+                int d = dcur + 1;
+                {
                     const int plo = lo, phi = hi;
                     bw.range(d, lo, hi);
                     if (lo < plo || lo > plo + 1 || hi < phi || hi > phi + 1) status |= 4;
-                    rowF = rowF + 1 == R ? 0 : rowF + 1;
-                    float4 *frow = rows + (long long) rowF * N;
-                    const int cLo = max(lo - 1, 0) >> 5, cHi = min(hi + 1, lX) >> 5;
-                    for (int c = cHi; c >= cLo; c--) {               // descending x: in-place update of the d-2 entries
+                }
+                int cLo = max(lo - 1, 0) >> 5, c = min(hi + 1, lX) >> 5;
+                rowF = rowF + 1 == R ? 0 : rowF + 1;
+                float4 *frow = rows + (long long) rowF * N;
+                float4 npa, npb, npc;
+                float2 nev;
+                auto prefetch = [&](int dd, int cc) {
+                    const int x = (cc << 5) + lane;
+                    const int xx = min(x, lX + 1);
+                    npa = xp[3 * xx]; npb = xp[3 * xx + 1]; npc = xp[3 * xx + 2];
+                    nev = evp[min(max(dd - x, 0), lY)];
+                };
+                prefetch(d, c);
+                for (;;) {
+                    const float4 pa = npa, pb = npb, pc = npc;
+                    const float2 ev = nev;
+                    const bool last = c == cLo;
+                    int nd = d, nc = c - 1, nlo = lo, nhi = hi;
+                    bool stop = false;
+                    if (last) {
+                        const bool tbPoint = !unbanded && d >= tracedBackTo + P.minDiags && (hi - lo + 1) <= 2 * P.expansion + 1;
+                        stop = d == D || tbPoint;
+                        if (!stop) {
+                            nd = d + 1;
+                            bw.range(nd, nlo, nhi);
+                            if (nlo < lo || nlo > lo + 1 || nhi < hi || nhi > hi + 1) status |= 4;
+                            nc = min(nhi + 1, lX) >> 5;
+                        }
+                    }
+                    if (!stop) prefetch(nd, nc);
+                    {
                         const int x = (c << 5) + lane;
                         const int s = x & NM, sl = (x - 1) & NM;
                         const float4 own = A1[s], L = A1[sl], Mi = A2[sl];
-                        const int xx = min(x, lX + 1);
-                        const float4 pa = xp[3 * xx], pb = xp[3 * xx + 1], pc = xp[3 * xx + 2];
-                        const float2 ev = evp[min(max(d - x, 0), lY)];
                         const bool inb = x >= lo && x <= hi;
                         __syncwarp();
                         const float U = fmaxf(own.w, fmaxf(L.w, Mi.w));
                         // impl/stateMachine.c:1314-1333: transitions folded in code order, emission added once
-                        float tX = logadd2(L.x + tOX, L.y + tEX);
-                        if (HAS_SX) tX = logadd2(tX, L.z + tSX);
-                        float tM = logadd2(logadd2(Mi.x + tMC, Mi.y + tMX), Mi.z + tMY);
-                        float tY = logadd2(own.x + tOY, own.z + tEY);
+                        float tX = LA(L.x + tOX, L.y + tEX);
+                        if (HAS_SX) tX = LA(tX, L.z + tSX);
+                        float tM = LA(LA(Mi.x + tMC, Mi.y + tMX), Mi.z + tMY);
+                        float tY = LA(own.x + tOY, own.z + tEY);
                         const float dmM = ev.x - pa.x, dnM = ev.y - pa.z, dmY = ev.x - pb.y, dnY = ev.y - pb.w;
                         const float eM = fmaf(pa.y, dmM * dmM, fmaf(pa.w, dnM * dnM, pb.x));
                         const float eY = fmaf(pb.z, dmY * dmY, fmaf(pc.x, dnY * dnY, pc.y));
@@ -204,15 +261,20 @@ __global__ void __launch_bounds__(32) k_align2(const KernelArgs2 A) {
                         float cM = inb ? tM : NI, cX = inb ? tX : NI, cY = inb ? tY : NI, co = inb ? U : -CP_BIG;
                         rebase(cM, cX, cY, co);
                         const float4 e = make_float4(cM, cX, cY, co);
-                        A2[s] = e;
+                        A2[s] = e;                                   // descending x: in place over the d-2 entry
                         if (inb) frow[s] = e;
                         __syncwarp();
                     }
-                    { float4 *t = A1; A1 = A2; A2 = t; }
-                    dcur = d;
-                    atEnd = d == D;
-                    const bool tbPoint = !unbanded && d >= tracedBackTo + P.minDiags && (hi - lo + 1) <= 2 * P.expansion + 1;
-                    if (atEnd || tbPoint) { Dt = d; break; }
+                    if (last) {
+                        { float4 *t = A1; A1 = A2; A2 = t; }
+                        dcur = d;
+                        if (stop) { Dt = d; atEnd = d == D; break; }
+                        d = nd; lo = nlo; hi = nhi;
+                        cLo = max(lo - 1, 0) >> 5;
+                        rowF = rowF + 1 == R ? 0 : rowF + 1;
+                        frow = rows + (long long) rowF * N;
+                    }
+                    c = nc;
                 }
             }
 
@@ -250,17 +312,26 @@ __global__ void __launch_bounds__(32) k_align2(const KernelArgs2 A) {
                         const float4 own = A1[s], R1 = A1[sr], R2 = A2[sr];
                         U = fmaxf(own.w, fmaxf(R1.w, R2.w));
                         const float gm2 = R2.x + (R2.w - U), gx1 = R1.y + (R1.w - U), gy1 = own.z + (own.w - U);
-                        bM = logadd2(logadd2(gm2 + tMC, gy1 + tOY), gx1 + tOX);
-                        bX = logadd2(gm2 + tMX, gx1 + tEX);
-                        bY = logadd2(gm2 + tMY, gy1 + tEY);
-                        if (HAS_SX) bY = logadd2(bY, gx1 + tSX);
+                        bM = LA(LA(gm2 + tMC, gy1 + tOY), gx1 + tOX);
+                        bX = LA(gm2 + tMX, gx1 + tEX);
+                        bY = LA(gm2 + tMY, gy1 + tEY);
+                        if (HAS_SX) bY = LA(bY, gx1 + tSX);
                     };
                     // posterior of one cell + G = B + emission, re-based, back into the ring
-                    auto cellPost = [&](int x, int s, bool inb, float bM, float bX, float bY, float U) {
+                    float4 npa, npb, npc, nF;
+                    float2 nev;
+                    auto prefetchB = [&](int cc) {
+                        const int x = (cc << 5) + lane;
+                        const int xx = min(x, lX + 1);
+                        npa = xp[3 * xx]; npb = xp[3 * xx + 1]; npc = xp[3 * xx + 2];
+                        nev = evp[min(max(d - x, 0), lY)];
+                        nF = NIENT;
+                        if (post && x >= blo && x <= bhi) nF = frow[x & NM];
+                    };
+                    auto cellPost = [&](int x, int s, bool inb, float bM, float bX, float bY, float U, const float4 pa,
+                                        const float4 pb, const float4 pc, const float2 ev, const float4 F) {
                         const int y = d - x;
                         if (post) {
-                            float4 F = NIENT;
-                            if (inb) F = frow[s];
                             const float lp = (F.x + bM) + (((F.w + U) - totBase) - totSt);
                             float p = __expf(lp);
                             const bool ok = inb && x > 0 && y > 0 && p >= P.threshold;
@@ -275,9 +346,6 @@ __global__ void __launch_bounds__(32) k_align2(const KernelArgs2 A) {
                             }
                             nPairs += __popc(mask);
                         }
-                        const int xx = min(x, lX + 1);
-                        const float4 pa = xp[3 * xx], pb = xp[3 * xx + 1], pc = xp[3 * xx + 2];
-                        const float2 ev = evp[min(max(y, 0), lY)];
                         const float dmM = ev.x - pa.x, dnM = ev.y - pa.z, dmY = ev.x - pb.y, dnY = ev.y - pb.w;
                         const float eM = fmaf(pa.y, dmM * dmM, fmaf(pa.w, dnM * dnM, pb.x));
                         const float eY = fmaf(pb.z, dmY * dmY, fmaf(pc.x, dnY * dnY, pc.y));
@@ -287,13 +355,17 @@ __global__ void __launch_bounds__(32) k_align2(const KernelArgs2 A) {
                     };
 
                     if (!doTotal) {
+                        prefetchB(cLo);
                         for (int c = cLo; c <= cHi; c++) {             // ascending x: in-place update of the d+2 entries
                             const int x = (c << 5) + lane, s = x & NM;
                             const bool inb = x >= blo && x <= bhi;
+                            const float4 pa = npa, pb = npb, pc = npc, F = nF;
+                            const float2 ev = nev;
+                            if (c < cHi) prefetchB(c + 1);
                             float bM, bX, bY, U;
                             cellB(x, s, bM, bX, bY, U);
                             __syncwarp();
-                            cellPost(x, s, inb, bM, bX, bY, U);
+                            cellPost(x, s, inb, bM, bX, bY, U, pa, pb, pc, ev, F);
                             __syncwarp();
                         }
                     } else {
@@ -309,7 +381,7 @@ __global__ void __launch_bounds__(32) k_align2(const KernelArgs2 A) {
                             A2[s] = make_float4(inb ? bM : NI, inb ? bX : NI, inb ? bY : NI, inb ? U : -CP_BIG);
                             if (inb) {
                                 const float4 F = frow[s];
-                                const float c1 = logadd2(logadd2(F.x + bM, F.y + bX), F.z + bY);
+                                const float c1 = LA(LA(F.x + bM, F.y + bX), F.z + bY);
                                 const float us = F.w + U;
                                 sm_c1[s] = c1; sm_us[s] = us;
                                 if (c1 > -1e30f) lmax = max(lmax, (int) us + (int) floorf(c1));
@@ -320,7 +392,7 @@ __global__ void __launch_bounds__(32) k_align2(const KernelArgs2 A) {
                         const float fbase = base == CP_INT_MIN ? 0.f : (float) base;
                         for (int x = blo + lane; x <= bhi; x += 32) { const int s = x & NM; sm_c1[s] = sm_c1[s] + (sm_us[s] - fbase); }
                         __syncwarp();
-                        const float t1 = warp_ordered_fold_ring(sm_c1, blo & NM, bhi - blo + 1, NM);
+                        const float t1 = warp_ordered_fold_ring(sm_c1, blo & NM, bhi - blo + 1, NM, K);
                         float tot = t1, t2v = NI;
                         if (d < Dt && base != CP_INT_MIN) {
                             // term 2: matches jumping over diagonal d = a match-only forward step from F[d-1] into the
@@ -337,14 +409,14 @@ __global__ void __launch_bounds__(32) k_align2(const KernelArgs2 A) {
                                 if (x - 1 >= lm1 && x - 1 <= hm1) {
                                     const float4 F = fprev[(x - 1) & NM];
                                     const float4 Gn = A1[x & NM];
-                                    const float md = logadd2(logadd2(F.x + tMC, F.y + tMX), F.z + tMY);
+                                    const float md = LA(LA(F.x + tMC, F.y + tMX), F.z + tMY);
                                     val = (md + Gn.x) + ((F.w + Gn.w) - fbase);
                                 }
                                 sm_c1[x & NM] = val;
                             }
                             __syncwarp();
-                            t2v = warp_ordered_fold_ring(sm_c1, l1 & NM, h1 - l1 + 1, NM);
-                            tot = logadd2(t1, t2v);
+                            t2v = warp_ordered_fold_ring(sm_c1, l1 & NM, h1 - l1 + 1, NM, K);
+                            tot = LA(t1, t2v);
                         }
                         totSt = tot;
                         totBase = fbase;
@@ -359,8 +431,9 @@ __global__ void __launch_bounds__(32) k_align2(const KernelArgs2 A) {
                             const int x = (c << 5) + lane, s = x & NM;
                             const bool inb = x >= blo && x <= bhi;
                             const float4 b = A2[s];
+                            prefetchB(c);
                             __syncwarp();
-                            cellPost(x, s, inb, b.x, b.y, b.z, b.w);
+                            cellPost(x, s, inb, b.x, b.y, b.z, b.w, npa, npb, npc, nev, nF);
                             __syncwarp();
                         }
                     }
@@ -400,4 +473,5 @@ __global__ void __launch_bounds__(32) k_align2(const KernelArgs2 A) {
     }
 }
 
+#undef LA
 }  // namespace cpecan
