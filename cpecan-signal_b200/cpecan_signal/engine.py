@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(PKG_ROOT, "libcpecan_cuda.so")
+LIB_PATH = os.environ.get("CPECAN_LIB") or os.path.join(PKG_ROOT, "libcpecan_cuda.so")   # CPECAN_LIB: developer A/B builds
 
 SM_THREE_STATE = 2
 SM_VANILLA = 4

@@ -74,6 +74,8 @@ __device__ __forceinline__ float logadd2(float x, float y, const LaCoef &k) {
     return r;
 }
 
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+
 struct KernelArgs2 {
     const Item *items;
     const int *order;
@@ -136,8 +138,11 @@ __device__ __forceinline__ void rebase(float &a, float &b, float &c, float &off)
     a -= s; b -= s; c -= s; off += s;
 }
 
+#ifndef CP_MINB
+#define CP_MINB 16
+#endif
 template <bool HAS_SX>
-__global__ void __launch_bounds__(32) k_align2(const KernelArgs2 A) {
+__global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
     extern __shared__ __align__(16) unsigned char smraw[];
     const int N = A.ringN, NM = N - 1;
     float4 *ring = reinterpret_cast<float4 *>(smraw);             // 2 * N entries
@@ -271,6 +276,13 @@ __global__ void __launch_bounds__(32) k_align2(const KernelArgs2 A) {
                         if (stop) { Dt = d; atEnd = d == D; break; }
                         d = nd; lo = nlo; hi = nhi;
                         cLo = max(lo - 1, 0) >> 5;
+                        if ((d & 15) == 0) {
+                            // columns / events that enter the band during the next diagonals: first touch comes from
+                            // DRAM, so pull them into L2 well ahead (one lane stalling stalls the warp)
+                            const int px = hi + 32 + lane, py = (d - lo) + 32 + lane;
+                            if (px <= lX + 1) { prefetch_l2(xp + 3 * px); prefetch_l2(xp + 3 * px + 2); }
+                            if (py <= lY) prefetch_l2(evp + py);
+                        }
                         rowF = rowF + 1 == R ? 0 : rowF + 1;
                         frow = rows + (long long) rowF * N;
                     }
@@ -303,6 +315,17 @@ __global__ void __launch_bounds__(32) k_align2(const KernelArgs2 A) {
                     const int cLo = max(blo - 1, 0) >> 5, cHi = min(bhi + 1, lX) >> 5;
                     bool doTotal = false;
                     if (post) { doTotal = unbanded ? (d == Dt) : (count % P.totalEvery == 0); count++; }
+                    if (d - 2 > tracedBackTo && d - 2 <= tracedBackFrom) {
+                        // the forward cells of diagonal d-2 were written >= 1000 diagonals ago: DRAM -> L2 now
+                        const int rowP = rowB >= 2 ? rowB - 2 : rowB - 2 + R;
+                        const float4 *fp = rows + (long long) rowP * N;
+                        for (int c = max(cLo - 1, 0); c <= cHi; c++) prefetch_l2(fp + (((c << 5) + lane) & NM));
+                    }
+                    if ((d & 15) == 0) {
+                        const int px = blo - 32 - lane, py = (d - bhi) - 32 - lane;
+                        if (px >= 0) { prefetch_l2(xp + 3 * px); prefetch_l2(xp + 3 * px + 2); }
+                        if (py >= 1) prefetch_l2(evp + py);
+                    }
 
                     // B of one cell from the ring (pull form of impl/pairwiseAligner.c:378-383: first from diagonal
                     // d+2 as "middle", then d+1 in ascending x-y as "upper", then "lower"), in units U
