@@ -27,6 +27,7 @@
 namespace cpecan {
 
 #define CP_BIG 1.0e30f
+#define CP_POS_INF (__int_as_float(0x7f800000))
 
 // Multiplier coefficients of the logAdd segments, kept in registers for the whole kernel (an FFMA takes only one
 // immediate; without this ptxas re-materialises the eight constants in every loop iteration).
@@ -174,6 +175,7 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
         int nPairs = 0, status = 0, nTb = 0;
         double lastTotal = 0.0;
         const bool unbanded = P.mode == 2;
+        const float logThrLo = __logf(P.threshold) - 1e-3f;      // pre-filter; the exact test is p >= threshold
 
         if (D == 0) {
             if (lane == 0) { ItemOut &o = A.out[itemIdx]; o.n_pairs = 0; o.status = 0; o.total_logprob = 0.0; o.n_tracebacks = 0; }
@@ -216,23 +218,25 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                     bw.range(d, lo, hi);
                     if (lo < plo || lo > plo + 1 || hi < phi || hi > phi + 1) status |= 4;
                 }
-                int cLo = max(lo - 1, 0) >> 5, c = min(hi + 1, lX) >> 5;
+                // lanes are placed relative to the window [lo-1, hi+1] of the diagonal (the cells one outside the band
+                // are written as -inf for the neighbours that will read them): chunk j holds x = wlo + 32 j + lane
+                int wlo = max(lo - 1, 0), c = (min(hi + 1, lX) - wlo) >> 5;
                 rowF = rowF + 1 == R ? 0 : rowF + 1;
                 float4 *frow = rows + (long long) rowF * N;
                 float4 npa, npb, npc;
                 float2 nev;
-                auto prefetch = [&](int dd, int cc) {
-                    const int x = (cc << 5) + lane;
+                auto prefetch = [&](int dd, int xbase) {
+                    const int x = xbase + lane;
                     const int xx = min(x, lX + 1);
                     npa = xp[3 * xx]; npb = xp[3 * xx + 1]; npc = xp[3 * xx + 2];
                     nev = evp[min(max(dd - x, 0), lY)];
                 };
-                prefetch(d, c);
+                prefetch(d, wlo + (c << 5));
                 for (;;) {
                     const float4 pa = npa, pb = npb, pc = npc;
                     const float2 ev = nev;
-                    const bool last = c == cLo;
-                    int nd = d, nc = c - 1, nlo = lo, nhi = hi;
+                    const bool last = c == 0;
+                    int nd = d, nc = c - 1, nlo = lo, nhi = hi, nwlo = wlo;
                     bool stop = false;
                     if (last) {
                         const bool tbPoint = !unbanded && d >= tracedBackTo + P.minDiags && (hi - lo + 1) <= 2 * P.expansion + 1;
@@ -241,12 +245,13 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                             nd = d + 1;
                             bw.range(nd, nlo, nhi);
                             if (nlo < lo || nlo > lo + 1 || nhi < hi || nhi > hi + 1) status |= 4;
-                            nc = min(nhi + 1, lX) >> 5;
+                            nwlo = max(nlo - 1, 0);
+                            nc = (min(nhi + 1, lX) - nwlo) >> 5;
                         }
                     }
-                    if (!stop) prefetch(nd, nc);
+                    if (!stop) prefetch(nd, nwlo + (nc << 5));
                     {
-                        const int x = (c << 5) + lane;
+                        const int x = wlo + (c << 5) + lane;
                         const int s = x & NM, sl = (x - 1) & NM;
                         const float4 own = A1[s], L = A1[sl], Mi = A2[sl];
                         const bool inb = x >= lo && x <= hi;
@@ -260,10 +265,9 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                         const float dmM = ev.x - pa.x, dnM = ev.y - pa.z, dmY = ev.x - pb.y, dnY = ev.y - pb.w;
                         const float eM = fmaf(pa.y, dmM * dmM, fmaf(pa.w, dnM * dnM, pb.x));
                         const float eY = fmaf(pb.z, dmY * dmY, fmaf(pc.x, dnY * dnY, pc.y));
-                        tX += pc.z + (L.w - U);
-                        tM += eM + (Mi.w - U);
-                        tY += eY + (own.w - U);
-                        float cM = inb ? tM : NI, cX = inb ? tX : NI, cY = inb ? tY : NI, co = inb ? U : -CP_BIG;
+                        const float Um = inb ? U : CP_POS_INF;       // a cell outside the band comes out as -inf
+                        float cM = tM + (eM + (Mi.w - Um)), cX = tX + (pc.z + (L.w - Um)), cY = tY + (eY + (own.w - Um));
+                        float co = inb ? U : -CP_BIG;
                         rebase(cM, cX, cY, co);
                         const float4 e = make_float4(cM, cX, cY, co);
                         A2[s] = e;                                   // descending x: in place over the d-2 entry
@@ -274,8 +278,7 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                         { float4 *t = A1; A1 = A2; A2 = t; }
                         dcur = d;
                         if (stop) { Dt = d; atEnd = d == D; break; }
-                        d = nd; lo = nlo; hi = nhi;
-                        cLo = max(lo - 1, 0) >> 5;
+                        d = nd; lo = nlo; hi = nhi; wlo = nwlo;
                         if ((d & 15) == 0) {
                             // columns / events that enter the band during the next diagonals: first touch comes from
                             // DRAM, so pull them into L2 well ahead (one lane stalling stalls the warp)
@@ -312,14 +315,15 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                     }
                     const float4 *frow = rows + (long long) rowB * N;
                     const bool post = d <= tracedBackFrom;
-                    const int cLo = max(blo - 1, 0) >> 5, cHi = min(bhi + 1, lX) >> 5;
+                    const int wlo = max(blo - 1, 0), nch = ((min(bhi + 1, lX) - wlo) >> 5) + 1;
+                    const int plo = max(blo, 1), phi = min(bhi, d - 1);   // cells with x > 0 and y > 0 report posteriors
                     bool doTotal = false;
                     if (post) { doTotal = unbanded ? (d == Dt) : (count % P.totalEvery == 0); count++; }
                     if (d - 2 > tracedBackTo && d - 2 <= tracedBackFrom) {
                         // the forward cells of diagonal d-2 were written >= 1000 diagonals ago: DRAM -> L2 now
                         const int rowP = rowB >= 2 ? rowB - 2 : rowB - 2 + R;
                         const float4 *fp = rows + (long long) rowP * N;
-                        for (int c = max(cLo - 1, 0); c <= cHi; c++) prefetch_l2(fp + (((c << 5) + lane) & NM));
+                        for (int c = 0; c <= nch; c++) prefetch_l2(fp + ((max(wlo - 32, 0) + (c << 5) + lane) & NM));
                     }
                     if ((d & 15) == 0) {
                         const int px = blo - 32 - lane, py = (d - bhi) - 32 - lane;
@@ -329,12 +333,14 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
 
                     // B of one cell from the ring (pull form of impl/pairwiseAligner.c:378-383: first from diagonal
                     // d+2 as "middle", then d+1 in ascending x-y as "upper", then "lower"), in units U
-                    auto cellB = [&](int x, int s, float &bM, float &bX, float &bY, float &U) {
-                        if (d == Dt) { bM = endM; bX = endX; bY = endY; U = 0.f; return; }
+                    // a cell outside the band comes out as -inf (its inputs are converted to units +inf)
+                    auto cellB = [&](int x, int s, bool inb, float &bM, float &bX, float &bY, float &U) {
+                        if (d == Dt) { bM = inb ? endM : NI; bX = inb ? endX : NI; bY = inb ? endY : NI; U = 0.f; return; }
                         const int sr = (x + 1) & NM;
                         const float4 own = A1[s], R1 = A1[sr], R2 = A2[sr];
                         U = fmaxf(own.w, fmaxf(R1.w, R2.w));
-                        const float gm2 = R2.x + (R2.w - U), gx1 = R1.y + (R1.w - U), gy1 = own.z + (own.w - U);
+                        const float Um = inb ? U : CP_POS_INF;
+                        const float gm2 = R2.x + (R2.w - Um), gx1 = R1.y + (R1.w - Um), gy1 = own.z + (own.w - Um);
                         bM = LA(LA(gm2 + tMC, gy1 + tOY), gx1 + tOX);
                         bX = LA(gm2 + tMX, gx1 + tEX);
                         bY = LA(gm2 + tMY, gy1 + tEY);
@@ -344,7 +350,7 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                     float4 npa, npb, npc, nF;
                     float2 nev;
                     auto prefetchB = [&](int cc) {
-                        const int x = (cc << 5) + lane;
+                        const int x = wlo + (cc << 5) + lane;
                         const int xx = min(x, lX + 1);
                         npa = xp[3 * xx]; npb = xp[3 * xx + 1]; npc = xp[3 * xx + 2];
                         nev = evp[min(max(d - x, 0), lY)];
@@ -353,18 +359,19 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                     };
                     auto cellPost = [&](int x, int s, bool inb, float bM, float bX, float bY, float U, const float4 pa,
                                         const float4 pb, const float4 pc, const float2 ev, const float4 F) {
-                        const int y = d - x;
                         if (post) {
+                            // impl/pairwiseAligner.c:768-793; exp only for the cells that can reach the threshold
                             const float lp = (F.x + bM) + (((F.w + U) - totBase) - totSt);
-                            float p = __expf(lp);
-                            const bool ok = inb && x > 0 && y > 0 && p >= P.threshold;
-                            p = fminf(p, 1.0f);
+                            bool ok = x >= plo && x <= phi && lp >= logThrLo;
+                            float p = 0.f;
+                            if (ok) { p = __expf(lp); ok = p >= P.threshold; }
                             const unsigned mask = __ballot_sync(CP_FULL, ok);
                             if (ok) {
                                 const int pos = nPairs + __popc(mask & ((1u << lane) - 1u));
                                 if (pos < it.pair_cap) {
+                                    p = fminf(p, 1.0f);
                                     pairs[3 * pos] = P.dbgLogP ? __float_as_int(lp) : (int) floorf(p * 10000000.0f);
-                                    pairs[3 * pos + 1] = x - 1; pairs[3 * pos + 2] = y - 1;
+                                    pairs[3 * pos + 1] = x - 1; pairs[3 * pos + 2] = d - x - 1;
                                 }
                             }
                             nPairs += __popc(mask);
@@ -372,21 +379,21 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                         const float dmM = ev.x - pa.x, dnM = ev.y - pa.z, dmY = ev.x - pb.y, dnY = ev.y - pb.w;
                         const float eM = fmaf(pa.y, dmM * dmM, fmaf(pa.w, dnM * dnM, pb.x));
                         const float eY = fmaf(pb.z, dmY * dmY, fmaf(pc.x, dnY * dnY, pc.y));
-                        float gM = inb ? bM + eM : NI, gX = inb ? bX + pc.z : NI, gY = inb ? bY + eY : NI, go = inb ? U : -CP_BIG;
+                        float gM = bM + eM, gX = bX + pc.z, gY = bY + eY, go = inb ? U : -CP_BIG;   // b is -inf outside the band
                         rebase(gM, gX, gY, go);
                         A2[s] = make_float4(gM, gX, gY, go);
                     };
 
                     if (!doTotal) {
-                        prefetchB(cLo);
-                        for (int c = cLo; c <= cHi; c++) {             // ascending x: in-place update of the d+2 entries
-                            const int x = (c << 5) + lane, s = x & NM;
+                        prefetchB(0);
+                        for (int c = 0; c < nch; c++) {                // ascending x: in-place update of the d+2 entries
+                            const int x = wlo + (c << 5) + lane, s = x & NM;
                             const bool inb = x >= blo && x <= bhi;
                             const float4 pa = npa, pb = npb, pc = npc, F = nF;
                             const float2 ev = nev;
-                            if (c < cHi) prefetchB(c + 1);
+                            if (c + 1 < nch) prefetchB(c + 1);
                             float bM, bX, bY, U;
-                            cellB(x, s, bM, bX, bY, U);
+                            cellB(x, s, inb, bM, bX, bY, U);
                             __syncwarp();
                             cellPost(x, s, inb, bM, bX, bY, U, pa, pb, pc, ev, F);
                             __syncwarp();
@@ -395,13 +402,13 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                         // ---- totalProbability (impl/pairwiseAligner.c:736-754), recomputed every 10th posterior diagonal
                         // pass 1: B into the ring (units in .w), dot-product terms and their units aside
                         int lmax = CP_INT_MIN;
-                        for (int c = cLo; c <= cHi; c++) {
-                            const int x = (c << 5) + lane, s = x & NM;
+                        for (int c = 0; c < nch; c++) {
+                            const int x = wlo + (c << 5) + lane, s = x & NM;
                             const bool inb = x >= blo && x <= bhi;
                             float bM, bX, bY, U;
-                            cellB(x, s, bM, bX, bY, U);
+                            cellB(x, s, inb, bM, bX, bY, U);
                             __syncwarp();
-                            A2[s] = make_float4(inb ? bM : NI, inb ? bX : NI, inb ? bY : NI, inb ? U : -CP_BIG);
+                            A2[s] = make_float4(bM, bX, bY, inb ? U : -CP_BIG);
                             if (inb) {
                                 const float4 F = frow[s];
                                 const float c1 = LA(LA(F.x + bM, F.y + bX), F.z + bY);
@@ -450,8 +457,8 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                         }
                         __syncwarp();
                         // pass 2: posteriors and G from the parked B
-                        for (int c = cLo; c <= cHi; c++) {
-                            const int x = (c << 5) + lane, s = x & NM;
+                        for (int c = 0; c < nch; c++) {
+                            const int x = wlo + (c << 5) + lane, s = x & NM;
                             const bool inb = x >= blo && x <= bhi;
                             const float4 b = A2[s];
                             prefetchB(c);
