@@ -189,7 +189,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--reads-per-gpu", type=int, default=1536)
+    ap.add_argument("--reads-per-gpu", type=int, default=24576)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -216,7 +216,9 @@ def main():
     l1 = l3 = None
     from cpecan_signal import synth
     l1, _, l3 = synth.load_model_file(synth.TEMPLATE_MODEL)
-    for j, e in enumerate(EXPANSIONS):
+    order = sorted(range(3), key=lambda j: -EXPANSIONS[j])      # widest band first: its tail is filled by the others
+    for j in order:
+        e = EXPANSIONS[j]
         sub = reads[j::3]
         eng = Engine(local)
         mid = eng.upload_model(l1, l3, np.full(4096, -2.3025850929940455))
@@ -226,7 +228,7 @@ def main():
         cap = eng.default_pair_capacity(hb, per_event=3)
         outs.append((eng.pinned_empty(hb.n, RESULT_DTYPE), eng.pinned_empty((cap, 3), np.int32)))
         engines.append(eng); batches.append(hb)
-    params = [default_params(diagonalExpansion=e) for e in EXPANSIONS]
+    params = [default_params(diagonalExpansion=EXPANSIONS[j]) for j in order]
 
     def barrier():
         torch.cuda.synchronize()
@@ -252,9 +254,17 @@ def main():
     for eng, hb, p, o in zip(engines, batches, params, outs):
         eng.stage(hb, params=p, pair_cap=len(o[1]))
     cells_rank = sum(eng.timing()["band_cells"] for eng in engines)
-    for _ in range(args.warmup):
+    def resident_step():
+        """One pass of the hot path over the whole resident batch: the three expansions' kernels are enqueued
+        together (each context has its own streams) so that the GPU stays full through their tails."""
         for eng in engines:
-            eng.run_staged()
+            eng.run_staged_async()
+        for eng in engines:
+            eng.wait()
+        return max(eng.timing()["align_ms"] for eng in engines), sum(eng.timing()["kernel_launches"] for eng in engines)
+
+    for _ in range(args.warmup):
+        resident_step()
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
@@ -262,15 +272,14 @@ def main():
     t0 = time.perf_counter()
     kern_ms = 0.0
     launches = 0
+    l0 = sum(eng.timing()["kernel_launches"] for eng in engines)
     for _ in range(args.steps):
-        for eng in engines:
-            eng.run_staged()
-            tm = eng.timing()
-            kern_ms += tm["align_ms"]
+        span_ms, l1 = resident_step()
+        kern_ms += span_ms                # CUDA-event span of the step's k_align2 launches (they start together)
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
-    launches = len(engines) * args.steps
+    launches = l1 - l0
     wall = max_over_ranks(wall)
     kern_ms_max = max_over_ranks(kern_ms)
     cells_total = sum_over_ranks(float(cells_rank))
@@ -285,7 +294,7 @@ def main():
         n_pairs += int(res["n_pairs"].sum())
 
     # ---- end-to-end through the C-ABI with host buffers ---------------------------------------------------
-    for _ in range(2):
+    for _ in range(1):
         for eng, hb, p, o in zip(engines, batches, params, outs):
             eng.align_batch(hb, params=p, out=o)
     barrier()

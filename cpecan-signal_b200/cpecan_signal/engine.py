@@ -262,6 +262,12 @@ class Engine:
     def run_staged(self):
         self._check(self.lib.cpecan_cuda_run_staged(self.ctx), "run_staged")
 
+    def run_staged_async(self):
+        self._check(self.lib.cpecan_cuda_run_staged_async(self.ctx), "run_staged_async")
+
+    def wait(self):
+        self._check(self.lib.cpecan_cuda_wait(self.ctx), "wait")
+
     def fetch_staged(self):
         pairs = np.zeros((self._staged_cap, 3), dtype=np.int32)
         results = np.zeros(self._staged_n, dtype=RESULT_DTYPE)

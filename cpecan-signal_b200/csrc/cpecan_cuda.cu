@@ -61,6 +61,9 @@ struct cpecan_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {};
+    cudaStream_t bstream[8] = {};     // one stream per ring-size bucket: their kernels overlap, so one bucket's tail
+    cudaEvent_t bev[8] = {};          // of long alignments is filled by the next bucket's CTAs
+    bool running = false;
     cudaDeviceProp prop{};
     std::string err;
     std::mutex mu;
@@ -202,6 +205,8 @@ int cpecan_cuda_init(int device, cpecan_ctx **ctx_out) {
         return CPECAN_ERR_CUDA;
     }
     for (auto &e : ctx->ev) cudaEventCreate(&e);
+    for (auto &st : ctx->bstream) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    for (auto &e : ctx->bev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     for (int b = 0; b < NBUCKET; b++) { ctx->occ[b][0] = occupancy(b, false); ctx->occ[b][1] = occupancy(b, true); }
     for (int c = 0; c < NCFG2; c++)
         for (int sx = 0; sx < 2; sx++) {
@@ -224,6 +229,8 @@ void cpecan_cuda_destroy(cpecan_ctx *ctx) {
                        &ctx->dQueue, &ctx->dScratch, &ctx->dRowoff, &ctx->dTotals, &ctx->dCompact, &ctx->dCompactOff };
     for (auto *b : bufs) b->release();
     for (auto &e : ctx->ev) cudaEventDestroy(e);
+    for (auto &e : ctx->bev) cudaEventDestroy(e);
+    for (auto &st : ctx->bstream) cudaStreamDestroy(st);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -412,11 +419,12 @@ int cpecan_cuda_stage(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_param
     return CPECAN_OK;
 }
 
-int cpecan_cuda_run_staged(cpecan_ctx *ctx) {
+int cpecan_cuda_run_staged_async(cpecan_ctx *ctx) {
     if (!ctx) return CPECAN_ERR_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
     CK(cudaSetDevice(ctx->device));
     if (ctx->n == 0) return CPECAN_OK;
+    if (ctx->running) { ctx->err = "run_staged_async: the previous run was not waited for"; return CPECAN_ERR_ARG; }
     cudaStream_t s = ctx->stream;
     CK(cudaMemsetAsync(ctx->dQueue.p, 0, 16 * sizeof(int), s));
     if (ctx->wantTotals) {
@@ -446,7 +454,10 @@ int cpecan_cuda_run_staged(cpecan_ctx *ctx) {
             a.out = ctx->dOut.as<ItemOut>();
             a.totals = ctx->wantTotals ? ctx->dTotals.as<double>() : nullptr;
             a.P = ctx->P;
-            launchCfg2(b, ctx->hasSX, a, bk.nCta, s);
+            CK(cudaStreamWaitEvent(ctx->bstream[b], ctx->ev[4], 0));
+            launchCfg2(b, ctx->hasSX, a, bk.nCta, ctx->bstream[b]);
+            CK(cudaEventRecord(ctx->bev[b], ctx->bstream[b]));
+            CK(cudaStreamWaitEvent(s, ctx->bev[b], 0));
             launches++;
             continue;
         }
@@ -471,12 +482,27 @@ int cpecan_cuda_run_staged(cpecan_ctx *ctx) {
     }
     CK(cudaEventRecord(ctx->ev[5], s));
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(s));
+    ctx->timing.kernel_launches += launches;
+    ctx->running = true;
+    return CPECAN_OK;
+}
+
+int cpecan_cuda_wait(cpecan_ctx *ctx) {
+    if (!ctx) return CPECAN_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!ctx->running) return CPECAN_OK;
+    CK(cudaSetDevice(ctx->device));
+    ctx->running = false;
+    CK(cudaStreamSynchronize(ctx->stream));
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]);
     ctx->timing.align_ms = ms;
-    ctx->timing.kernel_launches += launches;
     return CPECAN_OK;
+}
+
+int cpecan_cuda_run_staged(cpecan_ctx *ctx) {
+    int rc = cpecan_cuda_run_staged_async(ctx);
+    return rc == CPECAN_OK ? cpecan_cuda_wait(ctx) : rc;
 }
 
 int cpecan_cuda_fetch_staged(cpecan_ctx *ctx, int32_t *pairs_out, cpecan_result *results) {

@@ -149,6 +149,10 @@ int cpecan_cuda_expectations_batch(cpecan_ctx *ctx, const cpecan_hmm *hmm, const
 int cpecan_cuda_stage(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *params, int32_t mode,
                       const cpecan_batch *batch, int64_t pair_cap_total);
 int cpecan_cuda_run_staged(cpecan_ctx *ctx);
+/* The same split in two, so that several contexts (e.g. one per band expansion) keep the GPU full together:
+ * run_staged_async() only enqueues, wait() blocks until the context's kernels are done and fills the timing. */
+int cpecan_cuda_run_staged_async(cpecan_ctx *ctx);
+int cpecan_cuda_wait(cpecan_ctx *ctx);
 int cpecan_cuda_fetch_staged(cpecan_ctx *ctx, int32_t *pairs_out, cpecan_result *results);
 
 /* Page-locked host buffers for callers that want asynchronous, full-rate host<->device copies. */
