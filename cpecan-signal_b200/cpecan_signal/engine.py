@@ -248,6 +248,33 @@ class Engine:
                 tl = [t[0] for t in tl]
         return results, pairs, tl
 
+    N_EXPECT = 9 + N_KMERS + 1
+
+    def expectations_batch(self, batch, hmm=None, params=None, out=None, pseudocount=0.0):
+        """getExpectationsUsingAnchors over a batch (reference impl/pairwiseAligner.c:1571-1591), summed on device.
+        Returns (expectations[9 + 4096 + 1], results): transitions row-major from*3+to, k-mer skip counts, likelihood;
+        the sums are ADDED to `out` (or to a fresh vector pre-filled with `pseudocount` in the count slots)."""
+        hmm = hmm or three_state_hmm()
+        params = params or default_params()
+        if out is None:
+            out = np.full(self.N_EXPECT, float(pseudocount), dtype=np.float64)
+            out[-1] = 0.0
+        results = np.zeros(batch.n, dtype=RESULT_DTYPE)
+        cb = batch.cstruct()
+        self._check(self.lib.cpecan_cuda_expectations_batch(self.ctx, C.byref(hmm), C.byref(params), C.byref(cb),
+                                                            out.ctypes.data_as(C.c_void_p),
+                                                            results.ctypes.data_as(C.c_void_p)), "expectations_batch")
+        return out, results
+
+    def expectations_device_ptr(self):
+        p = C.c_void_p()
+        self._check(self.lib.cpecan_cuda_expectations_device_ptr(self.ctx, C.byref(p)), "expectations_device_ptr")
+        return p.value
+
+    def fetch_expectations(self, out):
+        self._check(self.lib.cpecan_cuda_fetch_expectations(self.ctx, out.ctypes.data_as(C.c_void_p)), "fetch_expectations")
+        return out
+
     # device-resident variant (kernel-only timing)
     def stage(self, batch, hmm=None, params=None, mode=MODE_POSTERIOR, pair_cap=None):
         hmm = hmm or three_state_hmm()

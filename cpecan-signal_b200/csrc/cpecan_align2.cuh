@@ -92,6 +92,7 @@ struct KernelArgs2 {
     int *pairs;
     ItemOut *out;
     double *totals;
+    double *expect;               // EXPECT: 9 transition sums, 4096 k-mer skip sums, 1 likelihood (batch totals)
     DevParams P;
 };
 
@@ -142,7 +143,7 @@ __device__ __forceinline__ void rebase(float &a, float &b, float &c, float &off)
 #ifndef CP_MINB
 #define CP_MINB 16
 #endif
-template <bool HAS_SX>
+template <bool HAS_SX, bool EXPECT>
 __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
     extern __shared__ __align__(16) unsigned char smraw[];
     const int N = A.ringN, NM = N - 1;
@@ -175,7 +176,9 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
         int nPairs = 0, status = 0, nTb = 0;
         double lastTotal = 0.0;
         const bool unbanded = P.mode == 2;
-        const float logThrLo = __logf(P.threshold) - 1e-3f;      // pre-filter; the exact test is p >= threshold
+        const float logThrLo = __logf(P.threshold) - 1e-3f;
+        double eT[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };            // EXPECT: this lane's share of the transition sums
+        double eLik = 0.0;      // pre-filter; the exact test is p >= threshold
 
         if (D == 0) {
             if (lane == 0) { ItemOut &o = A.out[itemIdx]; o.n_pairs = 0; o.status = 0; o.total_logprob = 0.0; o.n_tracebacks = 0; }
@@ -331,6 +334,20 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                         if (py >= 1) prefetch_l2(evp + py);
                     }
 
+                    // E-step inputs: forward cells of the three predecessors live on diagonals d-1 and d-2
+                    int el1 = 0, eh1 = -1, el2 = 0, eh2 = -1;
+                    const float4 *frow1 = frow, *frow2 = frow;
+                    float aT[9] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
+                    if (EXPECT && post) {
+                        BandWalker be = bb;
+                        if (d >= 1) be.range(d - 1, el1, eh1);
+                        // the reference has freed the forward diagonals below tracedBackTo by now (impl/pairwiseAligner.c:
+                        // 971-985), so on the first diagonal of a later traceback the match predecessors are absent
+                        if (d >= 2 && d - 2 >= tracedBackTo) be.range(d - 2, el2, eh2);
+                        const int r1 = rowB == 0 ? R - 1 : rowB - 1, r2 = r1 == 0 ? R - 1 : r1 - 1;
+                        frow1 = rows + (long long) r1 * N; frow2 = rows + (long long) r2 * N;
+                    }
+
                     // B of one cell from the ring (pull form of impl/pairwiseAligner.c:378-383: first from diagonal
                     // d+2 as "middle", then d+1 in ascending x-y as "upper", then "lower"), in units U
                     // a cell outside the band comes out as -inf (its inputs are converted to units +inf)
@@ -359,6 +376,32 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                     };
                     auto cellPost = [&](int x, int s, bool inb, float bM, float bX, float bY, float U, const float4 pa,
                                         const float4 pb, const float4 pc, const float2 ev, const float4 F) {
+                        const float dmM = ev.x - pa.x, dnM = ev.y - pa.z, dmY = ev.x - pb.y, dnY = ev.y - pb.w;
+                        const float eM = fmaf(pa.y, dmM * dmM, fmaf(pa.w, dnM * dnM, pb.x));
+                        const float eY = fmaf(pb.z, dmY * dmY, fmaf(pc.x, dnY * dnY, pc.y));
+                        if (EXPECT) {
+                            if (post) {
+                                // diagonalCalculation_Expectations (impl/pairwiseAligner.c:841-863): for every transition
+                                // into this cell p = exp(F_pred[from] + B[to] + eP + tP - total) (:426-443)
+                                float4 FL = NIENT, FM = NIENT, FU = NIENT;
+                                if (inb) {
+                                    if (x - 1 >= el1 && x - 1 <= eh1) FL = frow1[(x - 1) & NM];
+                                    if (x - 1 >= el2 && x - 1 <= eh2) FM = frow2[(x - 1) & NM];
+                                    if (x >= el1 && x <= eh1) FU = frow1[s];
+                                }
+                                const float kX = (bX + pc.z) + (((FL.w + U) - totBase) - totSt);
+                                const float kM = (bM + eM) + (((FM.w + U) - totBase) - totSt);
+                                const float kY = (bY + eY) + (((FU.w + U) - totBase) - totSt);
+                                const float pMX = __expf(FL.x + tOX + kX), pXX = __expf(FL.y + tEX + kX);
+                                const float pYX = HAS_SX ? __expf(FL.z + tSX + kX) : 0.f;
+                                aT[1] += pMX; aT[4] += pXX; aT[7] += pYX;                 // from * 3 + to, to = X (1)
+                                aT[0] += __expf(FM.x + tMC + kM); aT[3] += __expf(FM.y + tMX + kM); aT[6] += __expf(FM.z + tMY + kM);
+                                aT[2] += __expf(FU.x + tOY + kY); aT[8] += __expf(FU.z + tEY + kY);
+                                const float pk = pMX + pXX + pYX;
+                                const int kmer = __float_as_int(pc.w);
+                                if (pk > 1e-13f && kmer >= 0) atomicAdd(A.expect + 9 + kmer, (double) pk);
+                            }
+                        } else
                         if (post) {
                             // impl/pairwiseAligner.c:768-793; exp only for the cells that can reach the threshold
                             const float lp = (F.x + bM) + (((F.w + U) - totBase) - totSt);
@@ -376,9 +419,6 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                             }
                             nPairs += __popc(mask);
                         }
-                        const float dmM = ev.x - pa.x, dnM = ev.y - pa.z, dmY = ev.x - pb.y, dnY = ev.y - pb.w;
-                        const float eM = fmaf(pa.y, dmM * dmM, fmaf(pa.w, dnM * dnM, pb.x));
-                        const float eY = fmaf(pb.z, dmY * dmY, fmaf(pc.x, dnY * dnY, pc.y));
                         float gM = bM + eM, gX = bX + pc.z, gY = bY + eY, go = inb ? U : -CP_BIG;   // b is -inf outside the band
                         rebase(gM, gX, gY, go);
                         A2[s] = make_float4(gM, gX, gY, go);
@@ -469,6 +509,11 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                     }
                     if (post) {
                         const double totAbs = (double) totSt + (double) totBase;
+                        if (EXPECT) {
+#pragma unroll
+                            for (int i = 0; i < 9; i++) eT[i] += (double) aT[i];
+                            eLik += totAbs;                       // "a hack": once per diagonal (:852-857)
+                        }
                         if (d == D) lastTotal = totAbs;
                         if (dbgTot != nullptr && lane == 0) dbgTot[d] = totAbs;
                     }
@@ -493,6 +538,16 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
             }
         }
 
+        if (EXPECT) {
+#pragma unroll
+            for (int i = 0; i < 9; i++) {
+                double v = eT[i];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(CP_FULL, v, o);
+                if (lane == 0) atomicAdd(A.expect + i, v);
+            }
+            if (lane == 0) atomicAdd(A.expect + 9 + 4096, eLik);
+        }
         if (lane == 0) {
             ItemOut &o = A.out[itemIdx];
             o.n_pairs = nPairs;

@@ -79,7 +79,7 @@ struct cpecan_ctx {
     std::vector<Item> hItems;
     std::vector<ItemOut> hOut;
     DevBuf dItems, dOut, dRef, dRefOff, dEvSrc, dEvSrcOff, dAnchors, dScale, dCentre, dXp, dEv, dPairs, dOrder,
-           dQueue, dScratch, dRowoff, dTotals, dCompact, dCompactOff;
+           dQueue, dScratch, dRowoff, dTotals, dCompact, dCompactOff, dExpect;
     int64_t pairCapTotal = 0, totalsLen = 0;
     Bucket buckets[NCFG2 > NBUCKET ? NCFG2 : NBUCKET];
     int gen = 2;                 // kernel generation (CPECAN_KERNEL=1 selects the first kernel)
@@ -104,22 +104,31 @@ namespace {
 template <int G, bool SX> void launchAlign(const KernelArgs &a, int nCta, cudaStream_t s) {
     k_align<G, KSLOTS, SX><<<nCta, 32 * G, 0, s>>>(a);
 }
+template <bool SX, bool EX> cudaError_t prepK2(int bytes) {
+    return cudaFuncSetAttribute(k_align2<SX, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
 cudaError_t prepCfg2(int cfg, bool sx) {
     const int bytes = (int) align2_smem_bytes(cfg2N(cfg));
-    return sx ? cudaFuncSetAttribute(k_align2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)
-              : cudaFuncSetAttribute(k_align2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaError_t e = sx ? prepK2<true, false>(bytes) : prepK2<false, false>(bytes);
+    if (e != cudaSuccess) return e;
+    return sx ? prepK2<true, true>(bytes) : prepK2<false, true>(bytes);
 }
 int occCfg2(int cfg, bool sx) {
     int nb = 0;
     const size_t bytes = align2_smem_bytes(cfg2N(cfg));
-    if (sx) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_align2<true>, 32, bytes);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_align2<false>, 32, bytes);
+    if (sx) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_align2<true, false>, 32, bytes);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_align2<false, false>, 32, bytes);
     return nb;
 }
-void launchCfg2(int cfg, bool sx, const KernelArgs2 &a, int nCta, cudaStream_t s) {
+void launchCfg2(int cfg, bool sx, bool expect, const KernelArgs2 &a, int nCta, cudaStream_t s) {
     const size_t bytes = align2_smem_bytes(cfg2N(cfg));
-    if (sx) k_align2<true><<<nCta, 32, bytes, s>>>(a);
-    else k_align2<false><<<nCta, 32, bytes, s>>>(a);
+    if (expect) {
+        if (sx) k_align2<true, true><<<nCta, 32, bytes, s>>>(a);
+        else k_align2<false, true><<<nCta, 32, bytes, s>>>(a);
+    } else {
+        if (sx) k_align2<true, false><<<nCta, 32, bytes, s>>>(a);
+        else k_align2<false, false><<<nCta, 32, bytes, s>>>(a);
+    }
 }
 
 template <int G> int occupancyOf(bool sx) {
@@ -226,7 +235,7 @@ void cpecan_cuda_destroy(cpecan_ctx *ctx) {
     for (auto &m : ctx->models) { cudaFree(m.match); cudaFree(m.gapy); cudaFree(m.gapx); }
     DevBuf *bufs[] = { &ctx->dModels, &ctx->dItems, &ctx->dOut, &ctx->dRef, &ctx->dRefOff, &ctx->dEvSrc, &ctx->dEvSrcOff,
                        &ctx->dAnchors, &ctx->dScale, &ctx->dCentre, &ctx->dXp, &ctx->dEv, &ctx->dPairs, &ctx->dOrder,
-                       &ctx->dQueue, &ctx->dScratch, &ctx->dRowoff, &ctx->dTotals, &ctx->dCompact, &ctx->dCompactOff };
+                       &ctx->dQueue, &ctx->dScratch, &ctx->dRowoff, &ctx->dTotals, &ctx->dCompact, &ctx->dCompactOff, &ctx->dExpect };
     for (auto *b : bufs) b->release();
     for (auto &e : ctx->ev) cudaEventDestroy(e);
     for (auto &e : ctx->bev) cudaEventDestroy(e);
@@ -427,6 +436,11 @@ int cpecan_cuda_run_staged_async(cpecan_ctx *ctx) {
     if (ctx->running) { ctx->err = "run_staged_async: the previous run was not waited for"; return CPECAN_ERR_ARG; }
     cudaStream_t s = ctx->stream;
     CK(cudaMemsetAsync(ctx->dQueue.p, 0, 16 * sizeof(int), s));
+    CK(ctx->dExpect.ensure(CPECAN_N_EXPECT * sizeof(double)));
+    if (ctx->mode == CPECAN_MODE_EXPECTATION) {
+        if (ctx->gen != 2) { ctx->err = "expectations need kernel generation 2"; return CPECAN_ERR_ARG; }
+        CK(cudaMemsetAsync(ctx->dExpect.p, 0, CPECAN_N_EXPECT * sizeof(double), s));
+    }
     if (ctx->wantTotals) {
         // NaN fill (all-ones bit pattern is a NaN)
         CK(cudaMemsetAsync(ctx->dTotals.p, 0xff, ctx->totalsLen * sizeof(double), s));
@@ -455,7 +469,8 @@ int cpecan_cuda_run_staged_async(cpecan_ctx *ctx) {
             a.totals = ctx->wantTotals ? ctx->dTotals.as<double>() : nullptr;
             a.P = ctx->P;
             CK(cudaStreamWaitEvent(ctx->bstream[b], ctx->ev[4], 0));
-            launchCfg2(b, ctx->hasSX, a, bk.nCta, ctx->bstream[b]);
+            a.expect = ctx->dExpect.as<double>();
+            launchCfg2(b, ctx->hasSX, ctx->mode == CPECAN_MODE_EXPECTATION, a, bk.nCta, ctx->bstream[b]);
             CK(cudaEventRecord(ctx->bev[b], ctx->bstream[b]));
             CK(cudaStreamWaitEvent(s, ctx->bev[b], 0));
             launches++;
@@ -572,11 +587,38 @@ int cpecan_cuda_align_batch(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan
     return rc;
 }
 
-int cpecan_cuda_expectations_batch(cpecan_ctx *ctx, const cpecan_hmm *, const cpecan_params *, const cpecan_batch *,
-                                   double *, cpecan_result *) {
+int cpecan_cuda_expectations_batch(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *params,
+                                   const cpecan_batch *batch, double *expectations_out, cpecan_result *results) {
     if (!ctx) return CPECAN_ERR_CUDA;
-    ctx->err = "expectations_batch: not implemented yet";
-    return CPECAN_ERR_ARG;
+    if (!expectations_out || !results) { ctx->err = "expectations_batch: null output"; return CPECAN_ERR_ARG; }
+    ctx->wantTotals = false;
+    int rc = cpecan_cuda_stage(ctx, hmm, params, CPECAN_MODE_EXPECTATION, batch, 0);
+    if (rc == CPECAN_OK) rc = cpecan_cuda_run_staged(ctx);
+    if (rc == CPECAN_OK) rc = cpecan_cuda_fetch_staged(ctx, nullptr, results);
+    if (rc == CPECAN_OK && ctx->n > 0) rc = cpecan_cuda_fetch_expectations(ctx, expectations_out);
+    return rc;
+}
+
+int cpecan_cuda_fetch_expectations(cpecan_ctx *ctx, double *expectations_out) {
+    if (!ctx || !expectations_out) return CPECAN_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->mode != CPECAN_MODE_EXPECTATION) { ctx->err = "fetch_expectations: the staged batch is not in expectation mode"; return CPECAN_ERR_ARG; }
+    std::vector<double> tmp(CPECAN_N_EXPECT);
+    CK(cudaMemcpyAsync(tmp.data(), ctx->dExpect.p, CPECAN_N_EXPECT * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < CPECAN_N_EXPECT; i++) expectations_out[i] += tmp[i];
+    ctx->timing.d2h_bytes += CPECAN_N_EXPECT * 8;
+    return CPECAN_OK;
+}
+
+int cpecan_cuda_expectations_device_ptr(cpecan_ctx *ctx, double **dev_ptr_out) {
+    if (!ctx || !dev_ptr_out) return CPECAN_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->dExpect.ensure(CPECAN_N_EXPECT * sizeof(double)));
+    *dev_ptr_out = ctx->dExpect.as<double>();
+    return CPECAN_OK;
 }
 
 void *cpecan_cuda_host_alloc(cpecan_ctx *ctx, int64_t bytes) {

@@ -180,7 +180,7 @@ __device__ __forceinline__ int kmer_code(const char *s) {   // impl/stateMachine
 // x-parameter record, 12 floats per matrix column x (sequence index x-1), three-state machine:
 //   [0] mu_m - c0   [1] -1/(2 sd_m^2)   [2] nu_m   [3] -1/(2 tau_m^2)
 //   [4] K_m         [5] mu_y - c0       [6] -1/(2 sd_y^2)   [7] nu_y
-//   [8] -1/(2 tau_y^2)   [9] K_y        [10] gap-X emission (log)   [11] unused
+//   [8] -1/(2 tau_y^2)   [9] K_y        [10] gap-X emission (log)   [11] k-mer index as int bits (-1: none)
 // so that  match(x, ev) = K_m + c1 (m - mu)^2 + c2 (n - nu)^2  (two log-Gaussians, impl/stateMachine.c:333-343,
 // 595-629) and likewise for the gap-Y ("extra event") table, which the reference never scales (:631-651).
 // x = 0 (sequence index -1) reads the literal "n" in the reference => every emission is LOG_ZERO.
@@ -199,7 +199,7 @@ __global__ void k_prep_xparams3(const Item *items, const long long *ref_off, con
     const float ninf = CP_NEG_INF;
     // record lX + 1 is the all -inf dummy the second-generation kernel reads for columns beyond the matrix
     for (int x = blockIdx.y * blockDim.x + threadIdx.x; x <= it.lX + 1; x += gridDim.y * blockDim.x) {
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = make_float4(ninf, 0.f, 0.f, 0.f), c = make_float4(0.f, ninf, ninf, 0.f);
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = make_float4(ninf, 0.f, 0.f, 0.f), c = make_float4(0.f, ninf, ninf, __int_as_float(-1));
         const int k = (x > 0 && x <= it.lX) ? kmer_code(r + x - 1) : -1;
         if (k >= 0) {
             const double *m = mt.match + 1 + 5 * k;
@@ -219,6 +219,7 @@ __global__ void k_prep_xparams3(const Item *items, const long long *ref_off, con
                 c.y = (float) (-2.0 * 0.91893853320467267 - log(sdy) - log(tauy));
             }
             c.z = (float) mt.gapx[k];
+            c.w = __int_as_float(k);
         }
         dst[3 * x] = a; dst[3 * x + 1] = b; dst[3 * x + 2] = c;
     }

@@ -141,8 +141,14 @@ int cpecan_cuda_align_batch(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan
 /* Baum-Welch expectations for a batch (getExpectationsUsingAnchors, impl/pairwiseAligner.c:1571-1591), summed over
  * the batch on device.  expectations_out: threeState 9 + 4096 + 1 doubles (transitions row-major from*3+to, k-mer
  * skip counts, likelihood); vanilla 60 + 1.  Values are ADDED to what the buffer already holds (pseudocounts). */
+#define CPECAN_N_EXPECT (9 + 4096 + 1)
 int cpecan_cuda_expectations_batch(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *params,
                                    const cpecan_batch *batch, double *expectations_out, cpecan_result *results);
+/* The same in steps, for the EM driver: stage(mode = CPECAN_MODE_EXPECTATION) + run_staged() leave the batch sums in a
+ * device buffer of CPECAN_N_EXPECT doubles; expectations_device_ptr() exposes it so that the caller can all-reduce it
+ * in place across GPUs (NCCL over NVLink) before fetch_expectations() ADDS it to a host vector. */
+int cpecan_cuda_fetch_expectations(cpecan_ctx *ctx, double *expectations_out);
+int cpecan_cuda_expectations_device_ptr(cpecan_ctx *ctx, double **dev_ptr_out);
 
 /* Device-resident variant used to measure kernel-only throughput: stage() copies and prepares a batch in HBM once,
  * run_staged() re-runs plan + align kernels on it (results stay on device), fetch_staged() copies results back. */

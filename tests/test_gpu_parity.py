@@ -107,3 +107,55 @@ def test_batch_mixed_widths_vs_oracle(engine, template_tables):
         stats = parity.compare_pairs(item_pairs(res, pairs, i), want)
         parity.compare_totals(totals[i], wtot)
         print(i, stats)
+
+
+# ------------------------------------------------------------------------------------------ E-step (expectations)
+EXP_RTOL = 2e-4      # FP32 device path vs the reference's doubles; sums of ~1e5 terms
+
+
+def _check_expectations(got, want):
+    assert got.shape == want.shape == (9 + 4096 + 1,)
+    np.testing.assert_allclose(got[:9], want[:9], rtol=EXP_RTOL, atol=2e-6)
+    np.testing.assert_allclose(got[9:-1], want[9:-1], rtol=EXP_RTOL, atol=2e-6)
+    assert abs(got[-1] - want[-1]) <= 1e-4 * abs(want[-1])
+
+
+@pytest.mark.parametrize("cfg,e,ragged", [("e20_r00", 20, (0, 0)), ("e50_r11", 50, (1, 1))])
+def test_fixture_expectations(engine, zymo, template_tables, cfg, e, ragged):
+    """getExpectationsUsingAnchors on the reference's fixture read (golden from the unmodified reference, pseudocount
+    1e-4 as vanillaAlign.c:675-676)."""
+    from cpecan_signal import default_params
+    rd = zymo["read"]
+    batch = _three_state_batch(engine, template_tables, [zymo["ref"]], [rd["template_events"]],
+                               [zymo["anchors_template"]], [rd["template_params"]], [ragged])
+    got, res = engine.expectations_batch(batch, params=default_params(diagonalExpansion=e), pseudocount=1e-4)
+    assert res[0]["status"] == 0
+    _check_expectations(got, zymo["three_expectations_" + cfg])
+
+
+def test_synthetic_expectations_batch_sum(engine, syn_golden, template_tables):
+    """A batch's expectations are the sum of its reads' (the device accumulates over the batch)."""
+    from cpecan_signal import default_params, synth
+    tags = ["s0", "s1", "s3"]                       # same expansion groups are not required: one call per tag, then a joint call
+    want_sum = None
+    for tag in tags:
+        idx, lX, e, r0, r1, every, mind = (int(v) for v in syn_golden[tag + "_meta"])
+        r = synth.make_read(template_tables[0], idx, lX=lX, anchor_every=every)
+        batch = _three_state_batch(engine, template_tables, [r.ref], [r.events], [r.anchors], [r.scale5], [(r0, r1)])
+        got, res = engine.expectations_batch(batch, params=default_params(diagonalExpansion=e, minDiagsBetweenTraceBack=mind),
+                                             pseudocount=1e-4)
+        assert res[0]["status"] == 0
+        _check_expectations(got, syn_golden[tag + "_expect"])
+    # two reads with identical parameters in ONE call
+    import oracleshim as O
+    l1, l2, l3 = template_tables
+    reads = [synth.make_read(l1, 300 + i, lX=500) for i in range(3)]
+    batch = _three_state_batch(engine, template_tables, [r.ref for r in reads], [r.events for r in reads],
+                               [r.anchors for r in reads], [r.scale5 for r in reads], [(1, 1)] * 3)
+    got, res = engine.expectations_batch(batch, params=default_params(diagonalExpansion=30), pseudocount=0.0)
+    want = np.zeros(9 + 4096 + 1)
+    for r in reads:
+        m = O.Model(O.THREE_STATE, tables=(l1, l2, l3), scale5=r.scale5)
+        want += O.expectations(m, r.ref, r.events, r.anchors, params=O.default_params(diagonalExpansion=30), ragged=(1, 1),
+                               pseudocount=0.0)
+    _check_expectations(got, want)
