@@ -1,0 +1,172 @@
+"""Baum-Welch training driver for the signal pair-HMM: the batched, multi-GPU sibling of the reference's
+scripts/trainModels.py loop (:244-330) and of its expectation container (impl/continuousHmm.c, scripts/nanoporeLib.py
+:985-1054).
+
+One EM iteration = E-step over this rank's shard of the reads on its GPU (Engine.expectations, summed on device) ->
+ONE all-reduce of the 4106-double expectation vector across ranks (NCCL over NVLink on GPUs; gloo in the CPU tests) ->
+the same normalisation on every rank -> rank 0 writes the .hmm file in the reference's format -> every rank reloads it
+(the reference feeds the 6-decimal text file back with -y/-z, so the rounding of "%f" is part of the M-step)."""
+import math
+import os
+
+import numpy as np
+
+N_KMERS = 4096
+N_EXPECT = 9 + N_KMERS + 1
+THREE_STATE = 2
+M, X, Y = 0, 1, 2
+
+
+class ContinuousPairHmm:
+    """Expectations of the three-state machine: 3x3 transitions (row-major from*3+to), 4096 k-mer skip counts and the
+    likelihood (reference inc/continuousHmm.h:7-25)."""
+
+    def __init__(self, pseudocount=0.0):
+        # hmmContinuous_getEmptyHmm(type, pseudocount, ...) puts the pseudocount in every slot (vanillaAlign.c:675-676)
+        self.transitions = np.full(9, float(pseudocount))
+        self.kmer_skip_probs = np.full(N_KMERS, float(pseudocount))
+        self.likelihood = 0.0
+        self.running_likelihoods = []
+
+    # -- accumulation (continuousPairHmm_addTo*; nanoporeLib.py add_expectations_file) ---------------------------
+    def add_expectations(self, vec):
+        vec = np.asarray(vec, dtype=np.float64)
+        if vec.shape != (N_EXPECT,):
+            raise ValueError("expectation vector must have %d entries" % N_EXPECT)
+        if np.isnan(vec[:9]).any():            # the reference writes header-only files for these and skips them
+            return False
+        self.transitions += vec[:9]
+        self.kmer_skip_probs += vec[9:9 + N_KMERS]
+        self.likelihood += float(vec[-1])
+        return True
+
+    def vector(self):
+        return np.concatenate([self.transitions, self.kmer_skip_probs, [self.likelihood]])
+
+    # -- continuousPairHmm_normalize (impl/continuousHmm.c:173-190, hmmDiscrete_normalize2 impl/discreteHmm.c:125-137)
+    def normalize(self):
+        t = self.transitions.reshape(3, 3)
+        self.transitions = (t / t.sum(axis=1, keepdims=True)).reshape(9)
+        self.kmer_skip_probs = self.kmer_skip_probs / self.kmer_skip_probs.sum()
+
+    # -- text format of continuousPairHmm_writeToFile (impl/continuousHmm.c:234-271) -------------------------------
+    def write(self, path):
+        with open(path, "w") as fh:
+            fh.write("%d\t%d\t%d\t\n" % (THREE_STATE, 3, N_KMERS))
+            if not np.isnan(self.transitions).any():           # hmmContinuous_checkTransitions: header only on NaN
+                fh.write("".join("%f\t" % v for v in self.transitions))
+                fh.write("%f\n" % self.likelihood)
+                fh.write("".join("%f\t" % v for v in self.kmer_skip_probs))
+                fh.write("\n")
+
+    @classmethod
+    def load(cls, path):
+        """continuousPairHmm_loadFromFile (impl/continuousHmm.c:273-370): same checks, same errors (as exceptions)."""
+        with open(path) as fh:
+            head = fh.readline().split()
+            if len(head) < 3:
+                raise ValueError("%s: bad header" % path)
+            typ, n_states, n_sym = int(head[0]), int(head[1]), int(head[2])
+            if typ != THREE_STATE or n_states != 3 or n_sym != N_KMERS:
+                raise ValueError("%s: not a three-state 6-mer HMM (type %d, %d states, %d symbols)" % (path, typ, n_states, n_sym))
+            line1 = fh.readline().split()
+            if len(line1) != 10:
+                raise ValueError("Incorrect number of transitions in the input HMM file %s, got %d instead of 10" % (path, len(line1)))
+            line2 = fh.readline().split()
+            if len(line2) != N_KMERS:
+                raise ValueError("Incorrect number of emissions in the input HMM file %s, got %d instead of %d" % (path, len(line2), N_KMERS))
+        h = cls()
+        h.transitions = np.array(line1[:9], dtype=np.float64)
+        h.likelihood = float(line1[9])
+        h.kmer_skip_probs = np.array(line2, dtype=np.float64)
+        return h
+
+    # -- continuousPairHmm_loadTransitionsAndKmerGapProbs (impl/continuousHmm.c:206-232) ----------------------------
+    def state_machine_params(self):
+        """(transitions[9] in StateMachine3 field order, gapX[4096] log-probabilities) as the DP will use them."""
+        t = self.transitions.reshape(3, 3)
+        with np.errstate(divide="ignore"):
+            trans = np.array([
+                math.log(t[M, M]) if t[M, M] > 0 else -np.inf,      # MATCH_CONTINUE
+                math.log(t[X, M]) if t[X, M] > 0 else -np.inf,      # MATCH_FROM_GAP_X
+                math.log(t[Y, M]) if t[Y, M] > 0 else -np.inf,      # MATCH_FROM_GAP_Y
+                math.log(t[M, X]) if t[M, X] > 0 else -np.inf,      # GAP_OPEN_X
+                math.log(t[M, Y]) if t[M, Y] > 0 else -np.inf,      # GAP_OPEN_Y
+                math.log(1.0 - t[X, M]) if t[X, M] < 1 else -np.inf,  # GAP_EXTEND_X = log(1 - P(X->M))
+                math.log(t[Y, Y]) if t[Y, Y] > 0 else -np.inf,      # GAP_EXTEND_Y
+                math.log(t[Y, X]) if t[Y, X] > 0 else -np.inf,      # GAP_SWITCH_TO_X
+                -np.inf,                                            # GAP_SWITCH_TO_Y = LOG_ZERO
+            ])
+            gapx = np.log(self.kmer_skip_probs)
+        return trans, gapx
+
+
+def shard_by_cells(cells, world):
+    """Partition of reads over ranks balanced by band cells: longest-processing-time greedy.
+    Returns a list of index arrays (sorted), one per rank; every read appears exactly once."""
+    cells = np.asarray(cells, dtype=np.int64)
+    order = np.argsort(-cells, kind="stable")
+    load = np.zeros(world, dtype=np.int64)
+    parts = [[] for _ in range(world)]
+    for i in order:
+        r = int(np.argmin(load))
+        parts[r].append(int(i))
+        load[r] += cells[i]
+    return [np.array(sorted(p), dtype=np.int64) for p in parts]
+
+
+def allreduce_sum(vec, group_ok):
+    """Sum of a float64 vector over all ranks (in place for torch tensors).  vec: numpy array (CPU, gloo) or a CUDA
+    tensor viewing the engine's device accumulator (NCCL)."""
+    if not group_ok:
+        return vec
+    import torch
+    import torch.distributed as dist
+    if isinstance(vec, np.ndarray):
+        t = torch.from_numpy(vec)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return vec
+    dist.all_reduce(vec, op=dist.ReduceOp.SUM)
+    return vec
+
+
+class _DevView:
+    """__cuda_array_interface__ wrapper so torch can all-reduce the engine's device buffer in place."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+def gpu_estep(engine, batch, hmm, params, distributed):
+    """E-step of this rank's shard on its GPU; the batch sums are all-reduced IN PLACE in the device accumulator
+    (the kernel's atomics and the NCCL collective share one buffer), then fetched once."""
+    import torch
+    engine.stage(batch, hmm=hmm, params=params, mode=1, pair_cap=1)
+    engine.run_staged()
+    if distributed:
+        view = torch.as_tensor(_DevView(engine.expectations_device_ptr(), N_EXPECT), device="cuda")
+        allreduce_sum(view, True)
+        torch.cuda.synchronize()
+    out = np.zeros(N_EXPECT)
+    engine.fetch_expectations(out)
+    return out
+
+
+def em_iteration(model, estep_sum, n_reads_total, hmm_path, rank=0, pseudocount=1e-4, barrier=None):
+    """M-step shared by every rank.  estep_sum: the all-reduced expectation vector of the iteration.  Mirrors
+    add_and_norm_expectations (scripts/trainModels.py:126-135): the model object carries its (normalised) values into
+    the next iteration's sum, every read contributes the pseudocount of its own expectation file, likelihood restarts
+    at zero, then normalise, write, remember the likelihood."""
+    model.likelihood = 0.0
+    vec = np.array(estep_sum, dtype=np.float64, copy=True)
+    vec[:9 + N_KMERS] += pseudocount * n_reads_total
+    model.add_expectations(vec)
+    model.normalize()
+    if rank == 0:
+        tmp = hmm_path + ".tmp"
+        model.write(tmp)
+        os.replace(tmp, hmm_path)
+    if barrier is not None:
+        barrier()
+    model.running_likelihoods.append(model.likelihood)
+    return ContinuousPairHmm.load(hmm_path)        # what the next E-step sees: the 6-decimal file, as with -y / -z

@@ -175,6 +175,11 @@ class Engine:
                                                       C.c_int32(gapx.size), C.byref(mid)), "upload_model")
         return mid.value
 
+    def update_model(self, model_id, match=None, gapy=None, gapx=None):
+        arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in (match, gapy, gapx)]
+        ptrs = [None if a is None else a.ctypes.data_as(C.c_void_p) for a in arrs]
+        self._check(self.lib.cpecan_cuda_update_model(self.ctx, C.c_int32(model_id), *ptrs), "update_model")
+
     def device_info(self):
         sm, clk, mem = C.c_int32(), C.c_int32(), C.c_int64()
         self._check(self.lib.cpecan_cuda_device_info(self.ctx, C.byref(sm), C.byref(clk), C.byref(mem)), "device_info")

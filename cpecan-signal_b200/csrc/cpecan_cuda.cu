@@ -266,6 +266,21 @@ int cpecan_cuda_upload_model(cpecan_ctx *ctx, const double *match, const double 
     return CPECAN_OK;
 }
 
+int cpecan_cuda_update_model(cpecan_ctx *ctx, int32_t model_id, const double *match, const double *gapy,
+                             const double *gapx) {
+    if (!ctx) return CPECAN_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (model_id < 0 || model_id >= (int32_t) ctx->models.size()) { ctx->err = "update_model: bad model id"; return CPECAN_ERR_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const size_t tbl = (1 + 4096 * 5) * sizeof(double);
+    Model &m = ctx->models[model_id];
+    if (match) CK(cudaMemcpy(m.match, match, tbl, cudaMemcpyHostToDevice));
+    if (gapy) CK(cudaMemcpy(m.gapy, gapy, tbl, cudaMemcpyHostToDevice));
+    if (gapx) CK(cudaMemcpy(m.gapx, gapx, m.n_gapx * sizeof(double), cudaMemcpyHostToDevice));
+    return CPECAN_OK;
+}
+
 int cpecan_cuda_stage(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *params, int32_t mode,
                       const cpecan_batch *B, int64_t pair_cap_total) {
     if (!ctx || !hmm || !params || !B || B->n_items < 0) return CPECAN_ERR_ARG;

@@ -122,6 +122,11 @@ const char *cpecan_cuda_last_error(cpecan_ctx *ctx);
 int cpecan_cuda_upload_model(cpecan_ctx *ctx, const double *match, const double *gapy, const double *gapx,
                              int32_t n_gapx, int32_t *model_id_out);
 
+/* Overwrite tables of an uploaded model in place (NULL = keep): what the M-step loaders do to a live StateMachine
+ * (continuousPairHmm_loadTransitionsAndKmerGapProbs rewrites EMISSION_GAP_X_PROBS, impl/continuousHmm.c:206-232). */
+int cpecan_cuda_update_model(cpecan_ctx *ctx, int32_t model_id, const double *match, const double *gapy,
+                             const double *gapx);
+
 /* Posterior match probabilities for a batch.
  *   pairs_out   int32 triples (score, x, y), score = floor(p * 1e7) (PAIR_ALIGNMENT_PROB_1), x / y sequence
  *               coordinates local to the item; pair_cap_total = capacity of pairs_out in triples.  Item i gets a

@@ -82,6 +82,8 @@ def main():
     out["tiny_vanilla_pairs"] = pairs
     print("tiny", len(out["tiny_three_pairs"]), len(pairs))
     np.savez_compressed(os.path.join(GOLDEN, "zymo_golden.npz"), **out)
+    # the expectation FILE as the reference's own writer lays it out (continuousPairHmm_writeToFile)
+    R.write_pair_hmm(out["three_expectations_e20_r00"], os.path.join(GOLDEN, "zymo_three_e20.expectations"))
 
     # ---- seeded synthetic reads (small, so the committed file stays small) -------------------------------------
     match = synth.load_model_file(T_MODEL)[0]

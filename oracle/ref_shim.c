@@ -324,3 +324,36 @@ int64_t ref_load_npread(const char *npReadFile, int64_t *dims3, double *params10
     nanopore_nanoporeReadDestruct(np);
     return 0;
 }
+
+/* ---- expectation container (impl/continuousHmm.c): file format, normalisation, M-step load --------------------- */
+
+/* Fills a threeState ContinuousPairHmm from exp[4106] (9 transitions, 4096 k-mer skips, likelihood), optionally
+ * normalises it (continuousPairHmm_normalize) and writes it with the reference's own writer. */
+int64_t ref_write_pair_hmm(const double *exp, int normalize, const char *path) {
+    Hmm *hmm = hmmContinuous_getEmptyHmm(threeState, 0.0, 0.0);
+    ContinuousPairHmm *cp = (ContinuousPairHmm *) hmm;
+    for (int i = 0; i < 9; i++) cp->transitions[i] = exp[i];
+    for (int i = 0; i < NUM_OF_KMERS; i++) cp->individualKmerGapProbs[i] = exp[9 + i];
+    hmm->likelihood = exp[9 + NUM_OF_KMERS];
+    if (normalize) hmmContinuous_normalize(hmm, threeState);
+    hmmContinuous_writeToFile(path, hmm, threeState);
+    hmmContinuous_destruct(hmm, threeState);
+    return 0;
+}
+
+/* Loads an .hmm file with the reference's loader into a strawMan state machine (hmmContinuous_loadSignalHmm ->
+ * continuousPairHmm_loadTransitionsAndKmerGapProbs) and returns what the DP will see: the 9 transitions in
+ * StateMachine3 field order and the 4096 gap-X emissions. */
+int64_t ref_load_pair_hmm(const char *hmmPath, const char *modelFile, double *trans9, double *gapX4096) {
+    StateMachine *sM = getStrawManStateMachine3(modelFile);
+    hmmContinuous_loadSignalHmm(hmmPath, sM, threeState);
+    StateMachine3 *s3 = (StateMachine3 *) sM;
+    trans9[0] = s3->TRANSITION_MATCH_CONTINUE; trans9[1] = s3->TRANSITION_MATCH_FROM_GAP_X;
+    trans9[2] = s3->TRANSITION_MATCH_FROM_GAP_Y; trans9[3] = s3->TRANSITION_GAP_OPEN_X;
+    trans9[4] = s3->TRANSITION_GAP_OPEN_Y; trans9[5] = s3->TRANSITION_GAP_EXTEND_X;
+    trans9[6] = s3->TRANSITION_GAP_EXTEND_Y; trans9[7] = s3->TRANSITION_GAP_SWITCH_TO_X;
+    trans9[8] = s3->TRANSITION_GAP_SWITCH_TO_Y;
+    for (int i = 0; i < NUM_OF_KMERS; i++) gapX4096[i] = sM->EMISSION_GAP_X_PROBS[i];
+    freeStateMachine(sM);
+    return 0;
+}

@@ -170,3 +170,18 @@ def fixture_anchors(ref_seq, npread_file, strand=0):
     n = lib().ref_fixture_anchors(ref_seq.encode(), npread_file.encode(), int(strand), _iptr(out),
                                   C.c_int64(len(out)), C.byref(raw))
     return out[:n].copy(), raw.value
+
+
+def write_pair_hmm(exp, path, normalize=False):
+    """continuousPairHmm_writeToFile (after continuousPairHmm_normalize when asked) on a 4106-vector."""
+    exp = np.ascontiguousarray(exp, dtype=np.float64)
+    assert exp.size == 9 + 4096 + 1
+    lib().ref_write_pair_hmm(_dptr(exp), int(bool(normalize)), path.encode())
+
+
+def load_pair_hmm(hmm_path, model_file):
+    """hmmContinuous_loadSignalHmm into a strawMan machine: (transitions[9] in StateMachine3 order, gapX[4096])."""
+    t = np.zeros(9)
+    g = np.zeros(4096)
+    lib().ref_load_pair_hmm(hmm_path.encode(), model_file.encode(), _dptr(t), _dptr(g))
+    return t, g

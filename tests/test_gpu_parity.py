@@ -116,7 +116,8 @@ EXP_RTOL = 2e-4      # FP32 device path vs the reference's doubles; sums of ~1e5
 def _check_expectations(got, want):
     assert got.shape == want.shape == (9 + 4096 + 1,)
     np.testing.assert_allclose(got[:9], want[:9], rtol=EXP_RTOL, atol=2e-6)
-    np.testing.assert_allclose(got[9:-1], want[9:-1], rtol=EXP_RTOL, atol=2e-6)
+    # a k-mer's skip count is a sum of a few posteriors, each within the 1e-4 posterior tolerance of north_star
+    np.testing.assert_allclose(got[9:-1], want[9:-1], rtol=EXP_RTOL, atol=1e-4)
     assert abs(got[-1] - want[-1]) <= 1e-4 * abs(want[-1])
 
 
@@ -159,3 +160,37 @@ def test_synthetic_expectations_batch_sum(engine, syn_golden, template_tables):
         want += O.expectations(m, r.ref, r.events, r.anchors, params=O.default_params(diagonalExpansion=30), ragged=(1, 1),
                                pseudocount=0.0)
     _check_expectations(got, want)
+
+
+def test_em_iterations_vs_oracle(engine, template_tables, tmp_path):
+    """Two Baum-Welch iterations on the GPU (E-step on device, M-step + .hmm round trip on the host) against the same
+    loop with the oracle as the E-step: trained transitions, k-mer skip probabilities and likelihoods agree."""
+    import oracleshim as O
+    from cpecan_signal import HostBatch, default_params, em, synth, three_state_hmm
+    l1, l2, l3 = template_tables
+    reads = [synth.make_read(l1, 800 + i, lX=300 + 50 * (i % 3)) for i in range(6)]
+    e = 30
+    mid = engine.upload_model(l1, l3, np.full(4096, -2.3025850929940455))
+    batch = HostBatch([r.ref for r in reads], [r.events for r in reads], [r.anchors for r in reads],
+                      model_ids=[mid] * len(reads), scales=[r.scale5 for r in reads], ragged=[(1, 1)] * len(reads))
+    gm, om = em.ContinuousPairHmm(), em.ContinuousPairHmm()
+    g_trans = o_trans = None
+    g_gapx = o_gapx = None
+    for it in range(2):
+        hmm = three_state_hmm(g_trans)
+        if g_gapx is not None:
+            engine.update_model(mid, gapx=g_gapx)
+        gvec = em.gpu_estep(engine, batch, hmm, default_params(diagonalExpansion=e), distributed=False)
+        ovec = np.zeros(em.N_EXPECT)
+        for r in reads:
+            m = O.Model(O.THREE_STATE, tables=(l1, l2, l3), scale5=r.scale5, transitions=o_trans, gap_x=o_gapx)
+            ovec += O.expectations(m, r.ref, r.events, r.anchors, params=O.default_params(diagonalExpansion=e),
+                                   ragged=(1, 1), pseudocount=0.0)
+        _check_expectations(gvec, ovec)
+        gl = em.em_iteration(gm, gvec, len(reads), str(tmp_path / "g.hmm"))
+        ol = em.em_iteration(om, ovec, len(reads), str(tmp_path / "o.hmm"))
+        np.testing.assert_allclose(gl.transitions, ol.transitions, atol=3e-6)
+        np.testing.assert_allclose(gl.kmer_skip_probs, ol.kmer_skip_probs, atol=3e-6)
+        g_trans, g_gapx = gl.state_machine_params()
+        o_trans, o_gapx = ol.state_machine_params()
+    assert abs(gm.running_likelihoods[-1] - om.running_likelihoods[-1]) <= 1e-4 * abs(om.running_likelihoods[-1])
