@@ -183,6 +183,91 @@ def reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+# ----------------------------------------------------------------------------------------------- EM (config 5)
+def em_arm(args):
+    """BASELINE config 5: Baum-Welch iterations over a resident batch.  One step = E-step of this rank's reads
+    (expectation kernels, sums in a device buffer) + ONE NCCL all-reduce of the 4106 doubles in place + the M-step
+    (normalise, rank 0 writes the reference-format .hmm, every rank reloads it) + re-derivation of the per-column
+    parameters on device.  Reads are sharded over ranks by band cells (weak scaling: B reads per GPU)."""
+    import tempfile
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from cpecan_signal import Engine, HostBatch, default_params, em, synth, three_state_hmm
+    B = min(args.reads_per_gpu, 8192)
+    e = 64
+    reads = generate_reads(B, 50_000_000 + rank * 1_000_000, procs=max(1, min(32, (os.cpu_count() or 1) // max(1, world))))
+    l1, _, l3 = synth.load_model_file(synth.TEMPLATE_MODEL)
+    eng = Engine(local)
+    mid = eng.upload_model(l1, l3, np.full(4096, -2.3025850929940455))
+    hb = HostBatch([r.ref for r in reads], [r.events for r in reads], [r.anchors for r in reads],
+                   model_ids=[mid] * B, scales=[r.scale5 for r in reads], ragged=[(1, 1)] * B)
+    params = default_params(diagonalExpansion=e)
+    hmm = three_state_hmm()
+    eng.stage(hb, hmm=hmm, params=params, mode=1, pair_cap=1)
+    cells_rank = eng.timing()["band_cells"]
+    view = torch.as_tensor(em._DevView(eng.expectations_device_ptr(), em.N_EXPECT), device="cuda")
+    model = em.ContinuousPairHmm()
+    td = tempfile.mkdtemp()
+    path = [os.path.join(td, "template_trained.hmm")]
+    if world > 1:
+        dist.broadcast_object_list(path, src=0)
+    hmm_path = path[0]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def step():
+        nonlocal hmm
+        eng.run_staged()
+        if world > 1:
+            dist.all_reduce(view, op=dist.ReduceOp.SUM)
+            torch.cuda.synchronize()
+        vec = np.zeros(em.N_EXPECT)
+        eng.fetch_expectations(vec)
+        loaded = em.em_iteration(model, vec, B * world, hmm_path, rank=rank, barrier=barrier if world > 1 else None)
+        trans, gapx = loaded.state_machine_params()
+        eng.update_model(mid, gapx=gapx)
+        hmm = three_state_hmm(trans)
+        eng.restage_model(hmm)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    barrier()
+    wall = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([wall, float(cells_rank)], dtype=torch.float64, device="cuda")
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        wall, cells_total = float(tmax[0]), float(t[1])
+    else:
+        cells_total = float(cells_rank)
+    if rank == 0:
+        print(json.dumps({
+            "metric": "em_iteration_gcups", "value": 2.0 * cells_total * args.steps / wall / 1e9, "unit": "GCUPS",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "reads_per_s": B * world * args.steps / wall,
+            "config": {"workload": "C5: Baum-Welch iteration (E-step kernels + all-reduce of 4106 doubles + M-step), "
+                                   "synthetic reads lX~6700 x lY~8000, e=64, three-state", "reads_per_gpu": B,
+                       "allreduce_bytes": em.N_EXPECT * 8, "collective": "nccl all_reduce in place on the device accumulator"
+                       if world > 1 else "none (1 rank)"},
+            "likelihoods": [float(v) for v in model.running_likelihoods[-3:]]}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ----------------------------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -192,10 +277,16 @@ def main():
     ap.add_argument("--reads-per-gpu", type=int, default=24576)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="posterior", choices=["posterior", "em"],
+                    help="posterior = BASELINE config 3/4 (default, the headline); em = config 5, one Baum-Welch "
+                         "iteration per step (E-step kernels + NCCL all-reduce + M-step)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
         reference_arm(args)
+        return
+    if args.workload == "em":
+        em_arm(args)
         return
 
     import torch

@@ -294,6 +294,9 @@ class Engine:
     def run_staged(self):
         self._check(self.lib.cpecan_cuda_run_staged(self.ctx), "run_staged")
 
+    def restage_model(self, hmm):
+        self._check(self.lib.cpecan_cuda_restage_model(self.ctx, C.byref(hmm)), "restage_model")
+
     def run_staged_async(self):
         self._check(self.lib.cpecan_cuda_run_staged_async(self.ctx), "run_staged_async")
 

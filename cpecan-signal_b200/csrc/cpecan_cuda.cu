@@ -82,6 +82,8 @@ struct cpecan_ctx {
            dQueue, dScratch, dRowoff, dTotals, dCompact, dCompactOff, dExpect;
     int64_t pairCapTotal = 0, totalsLen = 0;
     Bucket buckets[NCFG2 > NBUCKET ? NCFG2 : NBUCKET];
+    int stagedMaxLX = 0;
+    bool stagedScaled = false;
     int gen = 2;                 // kernel generation (CPECAN_KERNEL=1 selects the first kernel)
     int occ2[NCFG2][2] = {};
     bool wantTotals = false;
@@ -373,6 +375,7 @@ int cpecan_cuda_stage(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_param
         dim3 ge((unsigned) n, (unsigned) std::min(64, (maxLY + 256) / 256 + 1));
         k_prep_events<<<ge, 256, 0, s>>>(ctx->dItems.as<Item>(), ctx->dEvSrcOff.as<long long>(), ctx->dEvSrc.as<double>(),
                                         ctx->dCentre.as<double>(), ctx->dEv.as<float2>());
+        ctx->stagedMaxLX = maxLX; ctx->stagedScaled = dScale != nullptr;
         dim3 gx((unsigned) n, (unsigned) std::min(64, (maxLX + 256) / 256 + 1));
         k_prep_xparams3<<<gx, 256, 0, s>>>(ctx->dItems.as<Item>(), ctx->dRefOff.as<long long>(), ctx->dRef.as<char>(),
                                           ctx->dModels.as<ModelTables>(), dScale, ctx->dCentre.as<double>(), ctx->dXp.as<float4>());
@@ -439,6 +442,32 @@ int cpecan_cuda_stage(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_param
     CK(ctx->dQueue.ensure(16 * sizeof(int)));
     CK(cudaMemcpyAsync(ctx->dOrder.p, orderAll.data(), orderAll.size() * sizeof(int), cudaMemcpyHostToDevice, s));
     if (ctx->wantTotals) CK(ctx->dTotals.ensure(std::max<int64_t>(1, totTot) * sizeof(double)));
+    CK(cudaStreamSynchronize(s));
+    return CPECAN_OK;
+}
+
+int cpecan_cuda_restage_model(cpecan_ctx *ctx, const cpecan_hmm *hmm) {
+    if (!ctx || !hmm) return CPECAN_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->running) { ctx->err = "restage_model: a run is in flight"; return CPECAN_ERR_ARG; }
+    if (hmm->sm_type != CPECAN_SM_THREE_STATE) { ctx->err = "only the three-state machine is implemented on device"; return CPECAN_ERR_ARG; }
+    if (ctx->n == 0) return CPECAN_OK;
+    DevParams &P = ctx->P;
+    const double *t = hmm->transitions;
+    P.tMC = (float) t[0]; P.tMX = (float) t[1]; P.tMY = (float) t[2]; P.tOX = (float) t[3]; P.tOY = (float) t[4];
+    P.tEX = (float) t[5]; P.tEY = (float) t[6]; P.tSX = (float) t[7]; P.tSY = (float) t[8];
+    P.endv[0] = (float) t[0]; P.endv[1] = (float) t[1]; P.endv[2] = (float) t[2];
+    P.rendv[0] = (float) ((t[3] + t[4]) / 2.0); P.rendv[1] = (float) t[5]; P.rendv[2] = (float) t[6];
+    ctx->hasSX = !(std::isinf(t[7]) && t[7] < 0);
+    P.hasSX = ctx->hasSX;
+    cudaStream_t s = ctx->stream;
+    dim3 gx((unsigned) ctx->n, (unsigned) std::min(64, (ctx->stagedMaxLX + 256) / 256 + 1));
+    k_prep_xparams3<<<gx, 256, 0, s>>>(ctx->dItems.as<Item>(), ctx->dRefOff.as<long long>(), ctx->dRef.as<char>(),
+                                      ctx->dModels.as<ModelTables>(), ctx->stagedScaled ? ctx->dScale.as<double>() : nullptr,
+                                      ctx->dCentre.as<double>(), ctx->dXp.as<float4>());
+    ctx->timing.kernel_launches += 1;
+    CK(cudaGetLastError());
     CK(cudaStreamSynchronize(s));
     return CPECAN_OK;
 }

@@ -160,6 +160,9 @@ int cpecan_cuda_expectations_device_ptr(cpecan_ctx *ctx, double **dev_ptr_out);
 int cpecan_cuda_stage(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *params, int32_t mode,
                       const cpecan_batch *batch, int64_t pair_cap_total);
 int cpecan_cuda_run_staged(cpecan_ctx *ctx);
+/* New transitions / updated model tables for the batch that is already staged (the M-step between two E-steps of a
+ * resident batch): re-derives the per-column parameter records on device, no host<->device copy of the reads. */
+int cpecan_cuda_restage_model(cpecan_ctx *ctx, const cpecan_hmm *hmm);
 /* The same split in two, so that several contexts (e.g. one per band expansion) keep the GPU full together:
  * run_staged_async() only enqueues, wait() blocks until the context's kernels are done and fills the timing. */
 int cpecan_cuda_run_staged_async(cpecan_ctx *ctx);
