@@ -54,6 +54,35 @@ def three_state_hmm(transitions=None):
     return h
 
 
+# stateMachine3Vanilla_construct (reference impl/stateMachine.c:1575-1579) and the strand defaults (:1291-1303, float
+# literals there): TRANSITION_M_TO_Y_NOT_X, TRANSITION_E_TO_E, then the three DEFAULT_END_* log-probabilities
+VANILLA_END = (-0.23552123624314988, -1.6269694202638481, -4.3187242127300092)
+VANILLA_STRAND = {None: (0.17, float(np.float32(0.55))),
+                  "template": (float(np.float32(0.17)), float(np.float32(0.55))),
+                  "complement": (float(np.float32(0.14)), float(np.float32(0.49)))}
+
+
+def vanilla_hmm(strand=None, m_to_y_not_x=None, e_to_e=None):
+    """StateMachine3Vanilla: strand = None (constructor values), "template" or "complement"
+    (stateMachine3Vanilla_setStrandTransitionsToDefaults)."""
+    h = Hmm()
+    h.sm_type = SM_VANILLA
+    mty, ete = VANILLA_STRAND[strand]
+    h.vanilla[0] = mty if m_to_y_not_x is None else float(m_to_y_not_x)
+    h.vanilla[1] = ete if e_to_e is None else float(e_to_e)
+    for i in range(3):
+        h.vanilla[2 + i] = VANILLA_END[i]
+    return h
+
+
+def vanilla_gapx(skip_bins):
+    """The 30 skip bins of a .model file as EMISSION_GAP_X_PROBS holds them for the vanilla machine: beta in [0, 30),
+    alpha in [30, 60) (emissions_signal_loadPoreModel, impl/stateMachine.c:282-294)."""
+    b = np.ascontiguousarray(skip_bins, dtype=np.float64)
+    assert b.size == 30
+    return np.concatenate([b, b])
+
+
 class Batch(C.Structure):
     _fields_ = [("n_items", C.c_int64), ("ref", C.c_void_p), ("ref_off", C.c_void_p), ("events", C.c_void_p),
                 ("ev_off", C.c_void_p), ("anchors", C.c_void_p), ("anchor_off", C.c_void_p),
@@ -254,6 +283,7 @@ class Engine:
         return results, pairs, tl
 
     N_EXPECT = 9 + N_KMERS + 1
+    N_EXPECT_VANILLA = 60 + 1
 
     def expectations_batch(self, batch, hmm=None, params=None, out=None, pseudocount=0.0):
         """getExpectationsUsingAnchors over a batch (reference impl/pairwiseAligner.c:1571-1591), summed on device.
@@ -262,7 +292,8 @@ class Engine:
         hmm = hmm or three_state_hmm()
         params = params or default_params()
         if out is None:
-            out = np.full(self.N_EXPECT, float(pseudocount), dtype=np.float64)
+            out = np.full(self.N_EXPECT_VANILLA if hmm.sm_type == SM_VANILLA else self.N_EXPECT, float(pseudocount),
+                          dtype=np.float64)
             out[-1] = 0.0
         results = np.zeros(batch.n, dtype=RESULT_DTYPE)
         cb = batch.cstruct()

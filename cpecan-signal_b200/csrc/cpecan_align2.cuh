@@ -83,8 +83,8 @@ struct KernelArgs2 {
     int n_items;
     int *queue;
     const long long *anchors;
-    const float4 *xparams;        // 3 float4 per matrix column x = 0 .. lX+1 (the last record is the all -inf dummy)
-    const float2 *events;
+    const float4 *xparams;        // 4 float4 per matrix column x = 0 .. lX+1 (the last record is the all -inf dummy)
+    const float4 *events;
     float4 *scratch;              // per warp: ring of forward rows, N float4 (M, X, Y, offset) each
     long long scratch_stride;     // float4 per warp
     int ring_rows;
@@ -143,7 +143,8 @@ __device__ __forceinline__ void rebase(float &a, float &b, float &c, float &off)
 #ifndef CP_MINB
 #define CP_MINB 16
 #endif
-template <bool HAS_SX, bool EXPECT>
+// MACH: 0 = three-state (strawMan) machine, 1 = vanilla machine (per-column transitions, inverse-Gaussian noise term)
+template <int MACH, bool HAS_SX, bool EXPECT>
 __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
     extern __shared__ __align__(16) unsigned char smraw[];
     const int N = A.ringN, NM = N - 1;
@@ -159,7 +160,16 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
     const float4 NIENT = make_float4(NI, NI, NI, -CP_BIG);
     const LaCoef K = la_coef();
 #define LA(a, b) logadd2((a), (b), K)
-    const float tMC = P.tMC, tMX = P.tMX, tMY = P.tMY, tOX = P.tOX, tOY = P.tOY, tEX = P.tEX, tEY = P.tEY, tSX = P.tSX;
+    // three-state: global transitions; vanilla: M->X, X->X, M->M, X->M, M->Y come from the column records
+    const float gMC = P.tMC, gMX = P.tMX, gOX = P.tOX, gOY = P.tOY, gEX = P.tEX, tSX = P.tSX;
+    const float tMY = MACH ? P.vYM : P.tMY, tEY = MACH ? P.vYY : P.tEY;
+    // emission of the match (Y = false) or extra-event (Y = true) state from a column record and an event record
+    auto emit = [](const float4 pa, const float4 pb, const float4 pc, const float4 ev, bool Y) -> float {
+        const float dm = ev.x - (Y ? pb.y : pa.x), dn = ev.y - (Y ? pb.w : pa.z);
+        const float c1 = Y ? pb.z : pa.y, q = Y ? pc.x : pa.w, k0 = Y ? pc.y : pb.x;
+        if (MACH) return fmaf(c1, dm * dm, fmaf(q * ev.z, dn * dn, k0)) + ev.w;
+        return fmaf(c1, dm * dm, fmaf(q, dn * dn, k0));
+    };
 
     for (;;) {
         int qi = 0;
@@ -169,8 +179,8 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
         const int itemIdx = A.order[qi];
         const Item it = A.items[itemIdx];
         const int lX = it.lX, lY = it.lY, D = lX + lY;
-        const float4 *xp = A.xparams + 3 * it.xp_off;
-        const float2 *evp = A.events + it.ev_off;
+        const float4 *xp = A.xparams + 4 * it.xp_off;
+        const float4 *evp = A.events + it.ev_off;
         int *pairs = A.pairs + 3 * it.pair_off;
         double *dbgTot = (A.totals != nullptr && it.tot_off >= 0) ? A.totals + it.tot_off : nullptr;
         int nPairs = 0, status = 0, nTb = 0;
@@ -226,18 +236,17 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                 int wlo = max(lo - 1, 0), c = (min(hi + 1, lX) - wlo) >> 5;
                 rowF = rowF + 1 == R ? 0 : rowF + 1;
                 float4 *frow = rows + (long long) rowF * N;
-                float4 npa, npb, npc;
-                float2 nev;
+                float4 npa, npb, npc, npd, nev;
                 auto prefetch = [&](int dd, int xbase) {
                     const int x = xbase + lane;
                     const int xx = min(x, lX + 1);
-                    npa = xp[3 * xx]; npb = xp[3 * xx + 1]; npc = xp[3 * xx + 2];
+                    npa = xp[4 * xx]; npb = xp[4 * xx + 1]; npc = xp[4 * xx + 2];
+                    if (MACH) npd = xp[4 * xx + 3];
                     nev = evp[min(max(dd - x, 0), lY)];
                 };
                 prefetch(d, wlo + (c << 5));
                 for (;;) {
-                    const float4 pa = npa, pb = npb, pc = npc;
-                    const float2 ev = nev;
+                    const float4 pa = npa, pb = npb, pc = npc, pd = npd, ev = nev;
                     const bool last = c == 0;
                     int nd = d, nc = c - 1, nlo = lo, nhi = hi, nwlo = wlo;
                     bool stop = false;
@@ -261,15 +270,17 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                         __syncwarp();
                         const float U = fmaxf(own.w, fmaxf(L.w, Mi.w));
                         // impl/stateMachine.c:1314-1333: transitions folded in code order, emission added once
+                        // (vanilla: impl/stateMachine.c:1368-1409, the transitions are those of THIS column)
+                        const float tOX = MACH ? pd.x : gOX, tEX = MACH ? pd.y : gEX, tMC = MACH ? pd.z : gMC,
+                                    tMX = MACH ? pd.w : gMX, tOY = MACH ? pc.z : gOY;
                         float tX = LA(L.x + tOX, L.y + tEX);
                         if (HAS_SX) tX = LA(tX, L.z + tSX);
                         float tM = LA(LA(Mi.x + tMC, Mi.y + tMX), Mi.z + tMY);
                         float tY = LA(own.x + tOY, own.z + tEY);
-                        const float dmM = ev.x - pa.x, dnM = ev.y - pa.z, dmY = ev.x - pb.y, dnY = ev.y - pb.w;
-                        const float eM = fmaf(pa.y, dmM * dmM, fmaf(pa.w, dnM * dnM, pb.x));
-                        const float eY = fmaf(pb.z, dmY * dmY, fmaf(pc.x, dnY * dnY, pc.y));
+                        const float eM = emit(pa, pb, pc, ev, false), eY = emit(pa, pb, pc, ev, true);
+                        const float eX = MACH ? 0.f : pc.z;
                         const float Um = inb ? U : CP_POS_INF;       // a cell outside the band comes out as -inf
-                        float cM = tM + (eM + (Mi.w - Um)), cX = tX + (pc.z + (L.w - Um)), cY = tY + (eY + (own.w - Um));
+                        float cM = tM + (eM + (Mi.w - Um)), cX = tX + (eX + (L.w - Um)), cY = tY + (eY + (own.w - Um));
                         float co = inb ? U : -CP_BIG;
                         rebase(cM, cX, cY, co);
                         const float4 e = make_float4(cM, cX, cY, co);
@@ -286,7 +297,7 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                             // columns / events that enter the band during the next diagonals: first touch comes from
                             // DRAM, so pull them into L2 well ahead (one lane stalling stalls the warp)
                             const int px = hi + 32 + lane, py = (d - lo) + 32 + lane;
-                            if (px <= lX + 1) { prefetch_l2(xp + 3 * px); prefetch_l2(xp + 3 * px + 2); }
+                            if (px <= lX + 1) { prefetch_l2(xp + 4 * px); prefetch_l2(xp + 4 * px + 2); }
                             if (py <= lY) prefetch_l2(evp + py);
                         }
                         rowF = rowF + 1 == R ? 0 : rowF + 1;
@@ -330,7 +341,7 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                     }
                     if ((d & 15) == 0) {
                         const int px = blo - 32 - lane, py = (d - bhi) - 32 - lane;
-                        if (px >= 0) { prefetch_l2(xp + 3 * px); prefetch_l2(xp + 3 * px + 2); }
+                        if (px >= 0) { prefetch_l2(xp + 4 * px); prefetch_l2(xp + 4 * px + 2); }
                         if (py >= 1) prefetch_l2(evp + py);
                     }
 
@@ -351,8 +362,12 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                     // B of one cell from the ring (pull form of impl/pairwiseAligner.c:378-383: first from diagonal
                     // d+2 as "middle", then d+1 in ascending x-y as "upper", then "lower"), in units U
                     // a cell outside the band comes out as -inf (its inputs are converted to units +inf)
-                    auto cellB = [&](int x, int s, bool inb, float &bM, float &bX, float &bY, float &U) {
+                    // (vanilla: the transitions INTO a successor cell are those of the successor's column: pdR = record d
+                    // of column x+1; M->Y uses this column's log a_my)
+                    auto cellB = [&](int x, int s, bool inb, const float4 pdR, float myLog, float &bM, float &bX, float &bY, float &U) {
                         if (d == Dt) { bM = inb ? endM : NI; bX = inb ? endX : NI; bY = inb ? endY : NI; U = 0.f; return; }
+                        const float tOX = MACH ? pdR.x : gOX, tEX = MACH ? pdR.y : gEX, tMC = MACH ? pdR.z : gMC,
+                                    tMX = MACH ? pdR.w : gMX, tOY = MACH ? myLog : gOY;
                         const int sr = (x + 1) & NM;
                         const float4 own = A1[s], R1 = A1[sr], R2 = A2[sr];
                         U = fmaxf(own.w, fmaxf(R1.w, R2.w));
@@ -364,21 +379,20 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                         if (HAS_SX) bY = LA(bY, gx1 + tSX);
                     };
                     // posterior of one cell + G = B + emission, re-based, back into the ring
-                    float4 npa, npb, npc, nF;
-                    float2 nev;
+                    float4 npa, npb, npc, npdR, nF, nev;
                     auto prefetchB = [&](int cc) {
                         const int x = wlo + (cc << 5) + lane;
                         const int xx = min(x, lX + 1);
-                        npa = xp[3 * xx]; npb = xp[3 * xx + 1]; npc = xp[3 * xx + 2];
+                        npa = xp[4 * xx]; npb = xp[4 * xx + 1]; npc = xp[4 * xx + 2];
+                        if (MACH) npdR = xp[4 * min(x + 1, lX + 1) + 3];
                         nev = evp[min(max(d - x, 0), lY)];
                         nF = NIENT;
                         if (post && x >= blo && x <= bhi) nF = frow[x & NM];
                     };
                     auto cellPost = [&](int x, int s, bool inb, float bM, float bX, float bY, float U, const float4 pa,
-                                        const float4 pb, const float4 pc, const float2 ev, const float4 F) {
-                        const float dmM = ev.x - pa.x, dnM = ev.y - pa.z, dmY = ev.x - pb.y, dnY = ev.y - pb.w;
-                        const float eM = fmaf(pa.y, dmM * dmM, fmaf(pa.w, dnM * dnM, pb.x));
-                        const float eY = fmaf(pb.z, dmY * dmY, fmaf(pc.x, dnY * dnY, pc.y));
+                                        const float4 pb, const float4 pc, const float4 ev, const float4 F) {
+                        const float eM = emit(pa, pb, pc, ev, false), eY = emit(pa, pb, pc, ev, true);
+                        const float eX = MACH ? 0.f : pc.z;
                         if (EXPECT) {
                             if (post) {
                                 // diagonalCalculation_Expectations (impl/pairwiseAligner.c:841-863): for every transition
@@ -389,17 +403,30 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                                     if (x - 1 >= el2 && x - 1 <= eh2) FM = frow2[(x - 1) & NM];
                                     if (x >= el1 && x <= eh1) FU = frow1[s];
                                 }
-                                const float kX = (bX + pc.z) + (((FL.w + U) - totBase) - totSt);
-                                const float kM = (bM + eM) + (((FM.w + U) - totBase) - totSt);
-                                const float kY = (bY + eY) + (((FU.w + U) - totBase) - totSt);
+                                float4 pdo = NIENT;
+                                if (MACH) pdo = xp[4 * min(x, lX + 1) + 3];
+                                const float tOX = MACH ? pdo.x : gOX, tEX = MACH ? pdo.y : gEX, tMC = MACH ? pdo.z : gMC,
+                                            tMX = MACH ? pdo.w : gMX, tOY = MACH ? pc.z : gOY;
+                                const float kX = (bX + eX) + (((FL.w + U) - totBase) - totSt);
                                 const float pMX = __expf(FL.x + tOX + kX), pXX = __expf(FL.y + tEX + kX);
-                                const float pYX = HAS_SX ? __expf(FL.z + tSX + kX) : 0.f;
-                                aT[1] += pMX; aT[4] += pXX; aT[7] += pYX;                 // from * 3 + to, to = X (1)
-                                aT[0] += __expf(FM.x + tMC + kM); aT[3] += __expf(FM.y + tMX + kM); aT[6] += __expf(FM.z + tMY + kM);
-                                aT[2] += __expf(FU.x + tOY + kY); aT[8] += __expf(FU.z + tEY + kY);
-                                const float pk = pMX + pXX + pYX;
-                                const int kmer = __float_as_int(pc.w);
-                                if (pk > 1e-13f && kmer >= 0) atomicAdd(A.expect + 9 + kmer, (double) pk);
+                                if (MACH) {
+                                    // cell_signal_updateBetaAndAlphaProb (impl/pairwiseAligner.c:478-498): skip bins only
+                                    const int bin = __float_as_int(pc.w);
+                                    if (bin >= 0) {
+                                        if (pMX > 1e-13f) atomicAdd(A.expect + bin, (double) pMX);
+                                        if (pXX > 1e-13f) atomicAdd(A.expect + 30 + bin, (double) pXX);
+                                    }
+                                } else {
+                                    const float kM = (bM + eM) + (((FM.w + U) - totBase) - totSt);
+                                    const float kY = (bY + eY) + (((FU.w + U) - totBase) - totSt);
+                                    const float pYX = HAS_SX ? __expf(FL.z + tSX + kX) : 0.f;
+                                    aT[1] += pMX; aT[4] += pXX; aT[7] += pYX;             // from * 3 + to, to = X (1)
+                                    aT[0] += __expf(FM.x + tMC + kM); aT[3] += __expf(FM.y + tMX + kM); aT[6] += __expf(FM.z + tMY + kM);
+                                    aT[2] += __expf(FU.x + tOY + kY); aT[8] += __expf(FU.z + tEY + kY);
+                                    const float pk = pMX + pXX + pYX;
+                                    const int kmer = __float_as_int(pc.w);
+                                    if (pk > 1e-13f && kmer >= 0) atomicAdd(A.expect + 9 + kmer, (double) pk);
+                                }
                             }
                         } else
                         if (post) {
@@ -419,7 +446,7 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                             }
                             nPairs += __popc(mask);
                         }
-                        float gM = bM + eM, gX = bX + pc.z, gY = bY + eY, go = inb ? U : -CP_BIG;   // b is -inf outside the band
+                        float gM = bM + eM, gX = bX + eX, gY = bY + eY, go = inb ? U : -CP_BIG;   // b is -inf outside the band
                         rebase(gM, gX, gY, go);
                         A2[s] = make_float4(gM, gX, gY, go);
                     };
@@ -429,11 +456,10 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                         for (int c = 0; c < nch; c++) {                // ascending x: in-place update of the d+2 entries
                             const int x = wlo + (c << 5) + lane, s = x & NM;
                             const bool inb = x >= blo && x <= bhi;
-                            const float4 pa = npa, pb = npb, pc = npc, F = nF;
-                            const float2 ev = nev;
+                            const float4 pa = npa, pb = npb, pc = npc, pdR = npdR, F = nF, ev = nev;
                             if (c + 1 < nch) prefetchB(c + 1);
                             float bM, bX, bY, U;
-                            cellB(x, s, inb, bM, bX, bY, U);
+                            cellB(x, s, inb, pdR, pc.z, bM, bX, bY, U);
                             __syncwarp();
                             cellPost(x, s, inb, bM, bX, bY, U, pa, pb, pc, ev, F);
                             __syncwarp();
@@ -446,7 +472,10 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                             const int x = wlo + (c << 5) + lane, s = x & NM;
                             const bool inb = x >= blo && x <= bhi;
                             float bM, bX, bY, U;
-                            cellB(x, s, inb, bM, bX, bY, U);
+                            float4 pdR = NIENT;
+                            float myLog = 0.f;
+                            if (MACH) { pdR = xp[4 * min(x + 1, lX + 1) + 3]; myLog = xp[4 * min(x, lX + 1) + 2].z; }
+                            cellB(x, s, inb, pdR, myLog, bM, bX, bY, U);
                             __syncwarp();
                             A2[s] = make_float4(bM, bX, bY, inb ? U : -CP_BIG);
                             if (inb) {
@@ -479,7 +508,9 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                                 if (x - 1 >= lm1 && x - 1 <= hm1) {
                                     const float4 F = fprev[(x - 1) & NM];
                                     const float4 Gn = A1[x & NM];
-                                    const float md = LA(LA(F.x + tMC, F.y + tMX), F.z + tMY);
+                                    float4 pdx = NIENT;
+                                    if (MACH) pdx = xp[4 * min(x, lX + 1) + 3];
+                                    const float md = LA(LA(F.x + (MACH ? pdx.z : gMC), F.y + (MACH ? pdx.w : gMX)), F.z + tMY);
                                     val = (md + Gn.x) + ((F.w + Gn.w) - fbase);
                                 }
                                 sm_c1[x & NM] = val;
@@ -540,13 +571,13 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
 
         if (EXPECT) {
 #pragma unroll
-            for (int i = 0; i < 9; i++) {
+            for (int i = 0; i < (MACH ? 0 : 9); i++) {
                 double v = eT[i];
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(CP_FULL, v, o);
                 if (lane == 0) atomicAdd(A.expect + i, v);
             }
-            if (lane == 0) atomicAdd(A.expect + 9 + 4096, eLik);
+            if (lane == 0) atomicAdd(A.expect + (MACH ? 60 : 9 + 4096), eLik);
         }
         if (lane == 0) {
             ItemOut &o = A.out[itemIdx];

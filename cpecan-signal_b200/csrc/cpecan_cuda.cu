@@ -1,5 +1,5 @@
 // cpecan_cuda.cu -- host side of the C-ABI declared in include/cpecan_cuda.h: context, staging, kernel launches.
-// All device work runs on the engine's own stream; timings come from CUDA events on that stream.
+// All device work runs on the context's own streams; timings come from CUDA events on those streams.
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cmath>
@@ -19,11 +19,7 @@ using namespace cpecan;
 
 namespace {
 
-constexpr int KSLOTS = 4;                         // cells per thread
-constexpr int NBUCKET = 6;                        // G = 1, 2, 4, 8, 16, 32 warps per alignment
-constexpr int bucketG[NBUCKET] = { 1, 2, 4, 8, 16, 32 };
-
-// kernel generation 2: one warp per alignment, ring of N = 128 << bucket positions (power of two)
+// one warp per alignment; ring of N = 128 << bucket positions (power of two) in shared memory
 constexpr int NCFG2 = 6;
 constexpr int CFG2_MARGIN = 40;                   // ring positions beyond the widest diagonal (window + look-ahead)
 inline int cfg2N(int b) { return 128 << b; }
@@ -49,9 +45,8 @@ struct Model { double *match = nullptr, *gapy = nullptr, *gapx = nullptr; int n_
 struct Bucket {
     std::vector<int> order;      // item indices, largest first
     int nCta = 0, ringRows = 0;
-    long long stride = 0;        // floats per CTA
-    size_t scratchOff = 0;       // floats into the scratch buffer
-    size_t rowoffOff = 0;        // ints into the rowoff buffer
+    long long stride = 0;        // float4 per CTA
+    size_t scratchOff = 0;       // float4 into the scratch buffer
     size_t orderOff = 0;         // ints into the order buffer
 };
 
@@ -74,22 +69,22 @@ struct cpecan_ctx {
     // staged batch
     int64_t n = 0;
     int mode = 0;
+    int machine = 0;             // 0 three-state, 1 vanilla
+    double mToYNotX = 0.0;
     DevParams P{};
     bool hasSX = false;
     std::vector<Item> hItems;
     std::vector<ItemOut> hOut;
     DevBuf dItems, dOut, dRef, dRefOff, dEvSrc, dEvSrcOff, dAnchors, dScale, dCentre, dXp, dEv, dPairs, dOrder,
-           dQueue, dScratch, dRowoff, dTotals, dCompact, dCompactOff, dExpect;
+           dQueue, dScratch, dTotals, dCompact, dCompactOff, dExpect;
     int64_t pairCapTotal = 0, totalsLen = 0;
-    Bucket buckets[NCFG2 > NBUCKET ? NCFG2 : NBUCKET];
+    Bucket buckets[NCFG2];
     int stagedMaxLX = 0;
     bool stagedScaled = false;
-    int gen = 2;                 // kernel generation (CPECAN_KERNEL=1 selects the first kernel)
-    int occ2[NCFG2][2] = {};
+    int occ2[NCFG2][2][2] = {};  // [bucket][machine][hasSX]
     bool wantTotals = false;
     std::vector<int64_t> hTotOff;
     cpecan_timing timing{};
-    int occ[NBUCKET][2] = {};
 };
 
 namespace {
@@ -103,61 +98,33 @@ namespace {
         }                                                                                          \
     } while (0)
 
-template <int G, bool SX> void launchAlign(const KernelArgs &a, int nCta, cudaStream_t s) {
-    k_align<G, KSLOTS, SX><<<nCta, 32 * G, 0, s>>>(a);
+// k_align2<MACH, HAS_SX, EXPECT>: dispatch over the instantiations (the vanilla machine has no Y->X transition)
+template <typename F> auto dispatchK2(int mach, bool sx, bool ex, F f) {
+    if (mach) return ex ? f(k_align2<1, false, true>) : f(k_align2<1, false, false>);
+    if (sx) return ex ? f(k_align2<0, true, true>) : f(k_align2<0, true, false>);
+    return ex ? f(k_align2<0, false, true>) : f(k_align2<0, false, false>);
 }
-template <bool SX, bool EX> cudaError_t prepK2(int bytes) {
-    return cudaFuncSetAttribute(k_align2<SX, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-}
-cudaError_t prepCfg2(int cfg, bool sx) {
+cudaError_t prepCfg2(int cfg) {
     const int bytes = (int) align2_smem_bytes(cfg2N(cfg));
-    cudaError_t e = sx ? prepK2<true, false>(bytes) : prepK2<false, false>(bytes);
-    if (e != cudaSuccess) return e;
-    return sx ? prepK2<true, true>(bytes) : prepK2<false, true>(bytes);
+    for (int mach = 0; mach < 2; mach++)
+        for (int sx = 0; sx < 2; sx++)
+            for (int ex = 0; ex < 2; ex++) {
+                cudaError_t e = dispatchK2(mach, sx != 0, ex != 0, [&](auto k) {
+                    return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); });
+                if (e != cudaSuccess) return e;
+            }
+    return cudaSuccess;
 }
-int occCfg2(int cfg, bool sx) {
-    int nb = 0;
+int occCfg2(int cfg, int mach, bool sx) {
     const size_t bytes = align2_smem_bytes(cfg2N(cfg));
-    if (sx) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_align2<true, false>, 32, bytes);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_align2<false, false>, 32, bytes);
-    return nb;
+    return dispatchK2(mach, sx, false, [&](auto k) {
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, 32, bytes);
+        return nb; });
 }
-void launchCfg2(int cfg, bool sx, bool expect, const KernelArgs2 &a, int nCta, cudaStream_t s) {
+void launchCfg2(int cfg, int mach, bool sx, bool expect, const KernelArgs2 &a, int nCta, cudaStream_t s) {
     const size_t bytes = align2_smem_bytes(cfg2N(cfg));
-    if (expect) {
-        if (sx) k_align2<true, true><<<nCta, 32, bytes, s>>>(a);
-        else k_align2<false, true><<<nCta, 32, bytes, s>>>(a);
-    } else {
-        if (sx) k_align2<true, false><<<nCta, 32, bytes, s>>>(a);
-        else k_align2<false, false><<<nCta, 32, bytes, s>>>(a);
-    }
-}
-
-template <int G> int occupancyOf(bool sx) {
-    int nb = 0;
-    if (sx) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_align<G, KSLOTS, true>, 32 * G, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_align<G, KSLOTS, false>, 32 * G, 0);
-    return nb;
-}
-int occupancy(int b, bool sx) {
-    switch (b) {
-        case 0: return occupancyOf<1>(sx);
-        case 1: return occupancyOf<2>(sx);
-        case 2: return occupancyOf<4>(sx);
-        case 3: return occupancyOf<8>(sx);
-        case 4: return occupancyOf<16>(sx);
-        default: return occupancyOf<32>(sx);
-    }
-}
-void launchBucket(int b, bool sx, const KernelArgs &a, int nCta, cudaStream_t s) {
-    switch (b) {
-        case 0: sx ? launchAlign<1, true>(a, nCta, s) : launchAlign<1, false>(a, nCta, s); break;
-        case 1: sx ? launchAlign<2, true>(a, nCta, s) : launchAlign<2, false>(a, nCta, s); break;
-        case 2: sx ? launchAlign<4, true>(a, nCta, s) : launchAlign<4, false>(a, nCta, s); break;
-        case 3: sx ? launchAlign<8, true>(a, nCta, s) : launchAlign<8, false>(a, nCta, s); break;
-        case 4: sx ? launchAlign<16, true>(a, nCta, s) : launchAlign<16, false>(a, nCta, s); break;
-        default: sx ? launchAlign<32, true>(a, nCta, s) : launchAlign<32, false>(a, nCta, s); break;
-    }
+    dispatchK2(mach, sx, expect, [&](auto k) { k<<<nCta, 32, bytes, s>>>(a); return 0; });
 }
 
 __global__ void k_compact(const Item *items, const ItemOut *out, const long long *dstOff, int n, const int *src, int *dst) {
@@ -170,33 +137,69 @@ __global__ void k_compact(const Item *items, const ItemOut *out, const long long
     for (int j = threadIdx.x; j < 3 * np; j += blockDim.x) d[j] = s[j];
 }
 
+// transitions and state vectors of the machine (everything but the banding parameters)
+int fillMachine(cpecan_ctx *ctx, const cpecan_hmm *hmm) {
+    DevParams &P = ctx->P;
+    const float NI = -INFINITY;
+    P.startv[0] = 0.f; P.startv[1] = NI; P.startv[2] = NI;                 // impl/stateMachine.c:1168-1172
+    P.rstartv[0] = NI; P.rstartv[1] = 0.f; P.rstartv[2] = 0.f;             // :1174-1177
+    if (hmm->sm_type == CPECAN_SM_THREE_STATE) {
+        const double *t = hmm->transitions;
+        P.tMC = (float) t[0]; P.tMX = (float) t[1]; P.tMY = (float) t[2]; P.tOX = (float) t[3]; P.tOY = (float) t[4];
+        P.tEX = (float) t[5]; P.tEY = (float) t[6]; P.tSX = (float) t[7]; P.tSY = (float) t[8];
+        P.endv[0] = (float) t[0]; P.endv[1] = (float) t[1]; P.endv[2] = (float) t[2];           // :1179-1192
+        P.rendv[0] = (float) ((t[3] + t[4]) / 2.0); P.rendv[1] = (float) t[5]; P.rendv[2] = (float) t[6];  // :1194-1207
+        ctx->hasSX = !(std::isinf(t[7]) && t[7] < 0);
+        ctx->machine = 0;
+        P.vYM = P.vYY = 0.f;
+    } else if (hmm->sm_type == CPECAN_SM_VANILLA) {
+        // stateMachine3Vanilla: per-column transitions come from the skip bins (impl/stateMachine.c:1368-1409); here
+        // only the two global ones and the end vectors (:1209-1235)
+        const double *v = hmm->vanilla;
+        const double a_yy = v[1];
+        P.vYY = (float) std::log(a_yy);
+        P.vYM = (float) std::log(1.0 - a_yy);
+        P.tMC = P.tMX = P.tMY = P.tOX = P.tOY = P.tEX = P.tEY = 0.f; P.tSX = P.tSY = NI;
+        P.endv[0] = (float) v[2]; P.endv[1] = (float) v[3]; P.endv[2] = (float) v[4];
+        P.rendv[0] = (float) ((v[3] + v[4]) / 2.0); P.rendv[1] = (float) v[3]; P.rendv[2] = (float) v[4];
+        ctx->hasSX = false;
+        ctx->machine = 1;
+        ctx->mToYNotX = v[0];
+    } else {
+        ctx->err = "state machine type not implemented on device (threeState = 2 and vanilla = 4 are)";
+        return CPECAN_ERR_ARG;
+    }
+    P.machine = ctx->machine;
+    P.hasSX = ctx->hasSX;
+    return CPECAN_OK;
+}
+
 int fillDevParams(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *p, int mode) {
-    if (hmm->sm_type != CPECAN_SM_THREE_STATE) { ctx->err = "only the three-state machine is implemented on device"; return CPECAN_ERR_ARG; }
     if (p->diagonalExpansion < 0 || p->diagonalExpansion % 2 != 0 || p->traceBackDiagonals < 1 ||
         p->minDiagsBetweenTraceBack < 2 || p->traceBackDiagonals + 1 >= p->minDiagsBetweenTraceBack) {
         ctx->err = "invalid banding parameters (see impl/pairwiseAligner.c:880-884 of the reference)";
         return CPECAN_ERR_ARG;
     }
+    int rc = fillMachine(ctx, hmm);
+    if (rc != CPECAN_OK) return rc;
     DevParams &P = ctx->P;
-    const double *t = hmm->transitions;
-    P.tMC = (float) t[0]; P.tMX = (float) t[1]; P.tMY = (float) t[2]; P.tOX = (float) t[3]; P.tOY = (float) t[4];
-    P.tEX = (float) t[5]; P.tEY = (float) t[6]; P.tSX = (float) t[7]; P.tSY = (float) t[8];
-    const float NI = -INFINITY;
-    P.startv[0] = 0.f; P.startv[1] = NI; P.startv[2] = NI;                 // impl/stateMachine.c:1168-1172
-    P.rstartv[0] = NI; P.rstartv[1] = 0.f; P.rstartv[2] = 0.f;             // :1174-1177
-    P.endv[0] = (float) t[0]; P.endv[1] = (float) t[1]; P.endv[2] = (float) t[2];           // :1179-1192
-    P.rendv[0] = (float) ((t[3] + t[4]) / 2.0); P.rendv[1] = (float) t[5]; P.rendv[2] = (float) t[6];  // :1194-1207
     P.threshold = (float) p->threshold;
     P.minDiags = (int) p->minDiagsBetweenTraceBack;
     P.tbDiags = (int) p->traceBackDiagonals;
     P.expansion = (int) p->diagonalExpansion;
     P.totalEvery = 10;
-    P.rebaseEvery = 8;
+    P.rebaseEvery = 1;
     P.mode = mode;
-    ctx->hasSX = !(std::isinf(t[7]) && t[7] < 0);
-    P.hasSX = ctx->hasSX;
     P.dbgLogP = getenv("CPECAN_DEBUG_LOGP") ? atoi(getenv("CPECAN_DEBUG_LOGP")) : 0;
     return CPECAN_OK;
+}
+
+void launchPrepX(cpecan_ctx *ctx, cudaStream_t s) {
+    dim3 gx((unsigned) ctx->n, (unsigned) std::min(64, (ctx->stagedMaxLX + 256) / 256 + 1));
+    k_prep_xparams<<<gx, 256, 0, s>>>(ctx->dItems.as<Item>(), ctx->dRefOff.as<long long>(), ctx->dRef.as<char>(),
+                                     ctx->dModels.as<ModelTables>(), ctx->stagedScaled ? ctx->dScale.as<double>() : nullptr,
+                                     ctx->dCentre.as<double>(), ctx->dXp.as<float4>(), ctx->machine, ctx->mToYNotX);
+    ctx->timing.kernel_launches += 1;
 }
 
 }  // namespace
@@ -218,14 +221,11 @@ int cpecan_cuda_init(int device, cpecan_ctx **ctx_out) {
     for (auto &e : ctx->ev) cudaEventCreate(&e);
     for (auto &st : ctx->bstream) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
     for (auto &e : ctx->bev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-    for (int b = 0; b < NBUCKET; b++) { ctx->occ[b][0] = occupancy(b, false); ctx->occ[b][1] = occupancy(b, true); }
-    for (int c = 0; c < NCFG2; c++)
-        for (int sx = 0; sx < 2; sx++) {
-            if (prepCfg2(c, sx != 0) != cudaSuccess) { cudaGetLastError(); ctx->occ2[c][sx] = 0; continue; }
-            ctx->occ2[c][sx] = occCfg2(c, sx != 0);
-        }
-    if (ctx->occ2[NCFG2 - 1][0] == 0) { prepCfg2(NCFG2 - 2, false); prepCfg2(NCFG2 - 2, true); }
-    if (const char *g = getenv("CPECAN_KERNEL")) ctx->gen = atoi(g) == 1 ? 1 : 2;
+    for (int c = 0; c < NCFG2; c++) {
+        if (prepCfg2(c) != cudaSuccess) { cudaGetLastError(); break; }      // ring too large for this device's shared memory
+        for (int mach = 0; mach < 2; mach++)
+            for (int sx = 0; sx < 2; sx++) ctx->occ2[c][mach][sx] = occCfg2(c, mach, sx != 0);
+    }
     *ctx_out = ctx;
     return CPECAN_OK;
 }
@@ -237,7 +237,7 @@ void cpecan_cuda_destroy(cpecan_ctx *ctx) {
     for (auto &m : ctx->models) { cudaFree(m.match); cudaFree(m.gapy); cudaFree(m.gapx); }
     DevBuf *bufs[] = { &ctx->dModels, &ctx->dItems, &ctx->dOut, &ctx->dRef, &ctx->dRefOff, &ctx->dEvSrc, &ctx->dEvSrcOff,
                        &ctx->dAnchors, &ctx->dScale, &ctx->dCentre, &ctx->dXp, &ctx->dEv, &ctx->dPairs, &ctx->dOrder,
-                       &ctx->dQueue, &ctx->dScratch, &ctx->dRowoff, &ctx->dTotals, &ctx->dCompact, &ctx->dCompactOff, &ctx->dExpect };
+                       &ctx->dQueue, &ctx->dScratch, &ctx->dTotals, &ctx->dCompact, &ctx->dCompactOff, &ctx->dExpect };
     for (auto *b : bufs) b->release();
     for (auto &e : ctx->ev) cudaEventDestroy(e);
     for (auto &e : ctx->bev) cudaEventDestroy(e);
@@ -288,6 +288,7 @@ int cpecan_cuda_stage(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_param
     if (!ctx || !hmm || !params || !B || B->n_items < 0) return CPECAN_ERR_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
     CK(cudaSetDevice(ctx->device));
+    if (ctx->running) { ctx->err = "stage: a run is in flight"; return CPECAN_ERR_ARG; }
     int rc = fillDevParams(ctx, hmm, params, mode);
     if (rc != CPECAN_OK) return rc;
     const int64_t n = B->n_items;
@@ -296,6 +297,7 @@ int cpecan_cuda_stage(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_param
     ctx->timing = cpecan_timing{};
     if (n == 0) return CPECAN_OK;
     cudaStream_t s = ctx->stream;
+    const int needGapx = ctx->machine ? 60 : 4096;
 
     if (ctx->modelsDirty) {
         std::vector<ModelTables> mt(ctx->models.size());
@@ -319,6 +321,10 @@ int cpecan_cuda_stage(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_param
         const int64_t refLen = B->ref_off[i + 1] - B->ref_off[i];
         const int64_t lX = refLen >= 5 ? refLen - 5 : 0, lY = B->ev_off[i + 1] - B->ev_off[i];
         if (B->model_id[i] < 0 || B->model_id[i] >= (int) ctx->models.size()) { ctx->err = "bad model id"; return CPECAN_ERR_ARG; }
+        if (ctx->models[B->model_id[i]].n_gapx < needGapx) {
+            ctx->err = "model has too few gap-X entries for this state machine (threeState: 4096 log-probabilities, vanilla: 60 skip bins)";
+            return CPECAN_ERR_ARG;
+        }
         it.xp_off = xpTot; it.ev_off = evTot; it.an_off = B->anchor_off[i];
         it.lX = (int) lX; it.lY = (int) lY; it.nA = (int) (B->anchor_off[i + 1] - B->anchor_off[i]);
         it.flags = B->ragged ? B->ragged[i] : 0;
@@ -351,8 +357,8 @@ int cpecan_cuda_stage(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_param
     CK(ctx->dEvSrcOff.ensure((n + 1) * sizeof(long long)));
     CK(ctx->dAnchors.ensure(std::max<int64_t>(1, nAn) * 2 * sizeof(long long)));
     CK(ctx->dCentre.ensure(n * sizeof(double)));
-    CK(ctx->dXp.ensure(xpTot * 3 * sizeof(float4)));
-    CK(ctx->dEv.ensure(evTot * sizeof(float2)));
+    CK(ctx->dXp.ensure(xpTot * 4 * sizeof(float4)));
+    CK(ctx->dEv.ensure(evTot * sizeof(float4)));
     CK(ctx->dPairs.ensure(std::max<long long>(1, pairTot) * 3 * sizeof(int)));
     CK(cudaMemcpyAsync(ctx->dItems.p, ctx->hItems.data(), n * sizeof(Item), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->dRef.p, B->ref, refBytes, cudaMemcpyHostToDevice, s));
@@ -361,12 +367,13 @@ int cpecan_cuda_stage(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_param
     CK(cudaMemcpyAsync(ctx->dEvSrcOff.p, B->ev_off, (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, s));
     if (nAn) CK(cudaMemcpyAsync(ctx->dAnchors.p, B->anchors, nAn * 2 * sizeof(long long), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->dCentre.p, centre.data(), n * sizeof(double), cudaMemcpyHostToDevice, s));
-    const double *dScale = nullptr;
+    ctx->stagedScaled = false;
     if (B->scale) {
         CK(ctx->dScale.ensure(n * 5 * sizeof(double)));
         CK(cudaMemcpyAsync(ctx->dScale.p, B->scale, n * 5 * sizeof(double), cudaMemcpyHostToDevice, s));
-        dScale = ctx->dScale.as<double>();
+        ctx->stagedScaled = true;
     }
+    ctx->stagedMaxLX = maxLX;
     ctx->timing.h2d_bytes = n * (int64_t) sizeof(Item) + refBytes + 2 * (n + 1) * 8 + nEv * 24 + nAn * 16 + n * 8 + (B->scale ? n * 40 : 0);
     CK(cudaEventRecord(ctx->ev[1], s));
 
@@ -374,12 +381,9 @@ int cpecan_cuda_stage(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_param
     {
         dim3 ge((unsigned) n, (unsigned) std::min(64, (maxLY + 256) / 256 + 1));
         k_prep_events<<<ge, 256, 0, s>>>(ctx->dItems.as<Item>(), ctx->dEvSrcOff.as<long long>(), ctx->dEvSrc.as<double>(),
-                                        ctx->dCentre.as<double>(), ctx->dEv.as<float2>());
-        ctx->stagedMaxLX = maxLX; ctx->stagedScaled = dScale != nullptr;
-        dim3 gx((unsigned) n, (unsigned) std::min(64, (maxLX + 256) / 256 + 1));
-        k_prep_xparams3<<<gx, 256, 0, s>>>(ctx->dItems.as<Item>(), ctx->dRefOff.as<long long>(), ctx->dRef.as<char>(),
-                                          ctx->dModels.as<ModelTables>(), dScale, ctx->dCentre.as<double>(), ctx->dXp.as<float4>());
-        ctx->timing.kernel_launches += 2;
+                                        ctx->dCentre.as<double>(), ctx->dEv.as<float4>());
+        ctx->timing.kernel_launches += 1;
+        launchPrepX(ctx, s);
     }
     CK(cudaEventRecord(ctx->ev[2], s));
 
@@ -398,48 +402,39 @@ int cpecan_cuda_stage(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_param
     }
 
     // ---- bucket by the ring size an alignment needs, order largest first ---------------------------------------
-    const int nBuckets = ctx->gen == 2 ? NCFG2 : NBUCKET;
     for (auto &b : ctx->buckets) { b.order.clear(); b.nCta = 0; b.ringRows = 0; }
+    const int sx = ctx->hasSX ? 1 : 0;
     int64_t cells = 0;
     for (int64_t i = 0; i < n; i++) {
         const ItemOut &o = ctx->hOut[i];
         cells += o.band_cells;
         int b = 0;
-        if (ctx->gen == 2) {
-            while (b < NCFG2 && (cfg2N(b) < o.max_width + CFG2_MARGIN || ctx->occ2[b][ctx->hasSX ? 1 : 0] == 0)) b++;
-        } else {
-            while (b < NBUCKET && 32 * bucketG[b] * KSLOTS - KSLOTS < o.max_width) b++;
-        }
-        if (b == nBuckets) { ctx->err = "band wider than the widest kernel instantiation"; return CPECAN_ERR_BAND_TOO_WIDE; }
+        while (b < NCFG2 && (cfg2N(b) < o.max_width + CFG2_MARGIN || ctx->occ2[b][ctx->machine][sx] == 0)) b++;
+        if (b == NCFG2) { ctx->err = "band wider than the widest ring this device's shared memory holds"; return CPECAN_ERR_BAND_TOO_WIDE; }
         ctx->buckets[b].order.push_back((int) i);
         ctx->buckets[b].ringRows = std::max(ctx->buckets[b].ringRows, o.max_rows);
     }
     ctx->timing.band_cells = cells;
-    size_t scratchFloats = 0, rowoffInts = 0, orderInts = 0;
+    size_t scratch4 = 0, orderInts = 0;
     std::vector<int> orderAll;
     orderAll.reserve(n);
-    for (int b = 0; b < nBuckets; b++) {
+    for (int b = 0; b < NCFG2; b++) {
         Bucket &bk = ctx->buckets[b];
         if (bk.order.empty()) continue;
         std::stable_sort(bk.order.begin(), bk.order.end(), [&](int a, int c) { return ctx->hOut[a].band_cells > ctx->hOut[c].band_cells; });
-        const int sx = ctx->hasSX ? 1 : 0;
-        const int occ = std::max(1, ctx->gen == 2 ? ctx->occ2[b][sx] : ctx->occ[b][sx]);
-        const int warps = ctx->gen == 2 ? 1 : bucketG[b];
-        const int ringN = ctx->gen == 2 ? cfg2N(b) : 32 * bucketG[b] * KSLOTS;
+        const int occ = std::max(1, ctx->occ2[b][ctx->machine][sx]);
         bk.nCta = (int) std::min<int64_t>((int64_t) bk.order.size(), (int64_t) ctx->prop.multiProcessorCount * occ);
-        // gen 2: float4 (M, X, Y, offset) per ring position and row; gen 1: 3 floats + per-thread offsets
-        bk.stride = ctx->gen == 2 ? (long long) bk.ringRows * ringN * 4 : (long long) bk.ringRows * 3 * ringN;
-        bk.scratchOff = scratchFloats; scratchFloats += (size_t) bk.stride * bk.nCta;
-        bk.rowoffOff = rowoffInts; rowoffInts += ctx->gen == 2 ? 0 : (size_t) bk.ringRows * bk.nCta * 32 * warps;
+        bk.stride = (long long) bk.ringRows * cfg2N(b);           // float4 (M, X, Y, offset) per ring position and row
+        bk.scratchOff = scratch4; scratch4 += (size_t) bk.stride * bk.nCta;
         bk.orderOff = orderInts; orderInts += bk.order.size();
         orderAll.insert(orderAll.end(), bk.order.begin(), bk.order.end());
-        ctx->timing.warps_per_item = warps;
+        ctx->timing.warps_per_item = 1;
         ctx->timing.ctas = bk.nCta;
     }
-    CK(ctx->dScratch.ensure(std::max<size_t>(1, scratchFloats) * sizeof(float)));
-    CK(ctx->dRowoff.ensure(std::max<size_t>(1, rowoffInts) * sizeof(int)));
+    CK(ctx->dScratch.ensure(std::max<size_t>(1, scratch4) * sizeof(float4)));
     CK(ctx->dOrder.ensure(std::max<size_t>(1, orderInts) * sizeof(int)));
     CK(ctx->dQueue.ensure(16 * sizeof(int)));
+    CK(ctx->dExpect.ensure(CPECAN_N_EXPECT * sizeof(double)));
     CK(cudaMemcpyAsync(ctx->dOrder.p, orderAll.data(), orderAll.size() * sizeof(int), cudaMemcpyHostToDevice, s));
     if (ctx->wantTotals) CK(ctx->dTotals.ensure(std::max<int64_t>(1, totTot) * sizeof(double)));
     CK(cudaStreamSynchronize(s));
@@ -451,24 +446,14 @@ int cpecan_cuda_restage_model(cpecan_ctx *ctx, const cpecan_hmm *hmm) {
     std::lock_guard<std::mutex> lk(ctx->mu);
     CK(cudaSetDevice(ctx->device));
     if (ctx->running) { ctx->err = "restage_model: a run is in flight"; return CPECAN_ERR_ARG; }
-    if (hmm->sm_type != CPECAN_SM_THREE_STATE) { ctx->err = "only the three-state machine is implemented on device"; return CPECAN_ERR_ARG; }
+    const int machineBefore = ctx->machine;
+    int rc = fillMachine(ctx, hmm);
+    if (rc != CPECAN_OK) return rc;
     if (ctx->n == 0) return CPECAN_OK;
-    DevParams &P = ctx->P;
-    const double *t = hmm->transitions;
-    P.tMC = (float) t[0]; P.tMX = (float) t[1]; P.tMY = (float) t[2]; P.tOX = (float) t[3]; P.tOY = (float) t[4];
-    P.tEX = (float) t[5]; P.tEY = (float) t[6]; P.tSX = (float) t[7]; P.tSY = (float) t[8];
-    P.endv[0] = (float) t[0]; P.endv[1] = (float) t[1]; P.endv[2] = (float) t[2];
-    P.rendv[0] = (float) ((t[3] + t[4]) / 2.0); P.rendv[1] = (float) t[5]; P.rendv[2] = (float) t[6];
-    ctx->hasSX = !(std::isinf(t[7]) && t[7] < 0);
-    P.hasSX = ctx->hasSX;
-    cudaStream_t s = ctx->stream;
-    dim3 gx((unsigned) ctx->n, (unsigned) std::min(64, (ctx->stagedMaxLX + 256) / 256 + 1));
-    k_prep_xparams3<<<gx, 256, 0, s>>>(ctx->dItems.as<Item>(), ctx->dRefOff.as<long long>(), ctx->dRef.as<char>(),
-                                      ctx->dModels.as<ModelTables>(), ctx->stagedScaled ? ctx->dScale.as<double>() : nullptr,
-                                      ctx->dCentre.as<double>(), ctx->dXp.as<float4>());
-    ctx->timing.kernel_launches += 1;
+    if (ctx->machine != machineBefore) { ctx->err = "restage_model: the staged batch was prepared for the other state machine"; return CPECAN_ERR_ARG; }
+    launchPrepX(ctx, ctx->stream);
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(s));
+    CK(cudaStreamSynchronize(ctx->stream));
     return CPECAN_OK;
 }
 
@@ -480,63 +465,34 @@ int cpecan_cuda_run_staged_async(cpecan_ctx *ctx) {
     if (ctx->running) { ctx->err = "run_staged_async: the previous run was not waited for"; return CPECAN_ERR_ARG; }
     cudaStream_t s = ctx->stream;
     CK(cudaMemsetAsync(ctx->dQueue.p, 0, 16 * sizeof(int), s));
-    CK(ctx->dExpect.ensure(CPECAN_N_EXPECT * sizeof(double)));
-    if (ctx->mode == CPECAN_MODE_EXPECTATION) {
-        if (ctx->gen != 2) { ctx->err = "expectations need kernel generation 2"; return CPECAN_ERR_ARG; }
-        CK(cudaMemsetAsync(ctx->dExpect.p, 0, CPECAN_N_EXPECT * sizeof(double), s));
-    }
-    if (ctx->wantTotals) {
-        // NaN fill (all-ones bit pattern is a NaN)
-        CK(cudaMemsetAsync(ctx->dTotals.p, 0xff, ctx->totalsLen * sizeof(double), s));
-    }
+    if (ctx->mode == CPECAN_MODE_EXPECTATION) CK(cudaMemsetAsync(ctx->dExpect.p, 0, CPECAN_N_EXPECT * sizeof(double), s));
+    if (ctx->wantTotals) CK(cudaMemsetAsync(ctx->dTotals.p, 0xff, ctx->totalsLen * sizeof(double), s));   // all-ones = NaN
     CK(cudaEventRecord(ctx->ev[4], s));
     int launches = 0;
-    const int nBuckets = ctx->gen == 2 ? NCFG2 : NBUCKET;
-    for (int b = 0; b < nBuckets; b++) {
+    for (int b = 0; b < NCFG2; b++) {
         Bucket &bk = ctx->buckets[b];
         if (bk.order.empty()) continue;
-        if (ctx->gen == 2) {
-            KernelArgs2 a;
-            a.items = ctx->dItems.as<Item>();
-            a.order = ctx->dOrder.as<int>() + bk.orderOff;
-            a.n_items = (int) bk.order.size();
-            a.queue = ctx->dQueue.as<int>() + b;
-            a.anchors = ctx->dAnchors.as<long long>();
-            a.xparams = ctx->dXp.as<float4>();
-            a.events = ctx->dEv.as<float2>();
-            a.scratch = reinterpret_cast<float4 *>(ctx->dScratch.as<float>() + bk.scratchOff);
-            a.scratch_stride = bk.stride / 4;
-            a.ring_rows = bk.ringRows;
-            a.ringN = cfg2N(b);
-            a.pairs = ctx->dPairs.as<int>();
-            a.out = ctx->dOut.as<ItemOut>();
-            a.totals = ctx->wantTotals ? ctx->dTotals.as<double>() : nullptr;
-            a.P = ctx->P;
-            CK(cudaStreamWaitEvent(ctx->bstream[b], ctx->ev[4], 0));
-            a.expect = ctx->dExpect.as<double>();
-            launchCfg2(b, ctx->hasSX, ctx->mode == CPECAN_MODE_EXPECTATION, a, bk.nCta, ctx->bstream[b]);
-            CK(cudaEventRecord(ctx->bev[b], ctx->bstream[b]));
-            CK(cudaStreamWaitEvent(s, ctx->bev[b], 0));
-            launches++;
-            continue;
-        }
-        KernelArgs a;
+        KernelArgs2 a;
         a.items = ctx->dItems.as<Item>();
         a.order = ctx->dOrder.as<int>() + bk.orderOff;
         a.n_items = (int) bk.order.size();
         a.queue = ctx->dQueue.as<int>() + b;
         a.anchors = ctx->dAnchors.as<long long>();
         a.xparams = ctx->dXp.as<float4>();
-        a.events = ctx->dEv.as<float2>();
-        a.scratch = ctx->dScratch.as<float>() + bk.scratchOff;
-        a.scratch_off = ctx->dRowoff.as<int>() + bk.rowoffOff;
+        a.events = ctx->dEv.as<float4>();
+        a.scratch = ctx->dScratch.as<float4>() + bk.scratchOff;
         a.scratch_stride = bk.stride;
         a.ring_rows = bk.ringRows;
+        a.ringN = cfg2N(b);
         a.pairs = ctx->dPairs.as<int>();
         a.out = ctx->dOut.as<ItemOut>();
         a.totals = ctx->wantTotals ? ctx->dTotals.as<double>() : nullptr;
+        a.expect = ctx->dExpect.as<double>();
         a.P = ctx->P;
-        launchBucket(b, ctx->hasSX, a, bk.nCta, s);
+        CK(cudaStreamWaitEvent(ctx->bstream[b], ctx->ev[4], 0));
+        launchCfg2(b, ctx->machine, ctx->hasSX, ctx->mode == CPECAN_MODE_EXPECTATION, a, bk.nCta, ctx->bstream[b]);
+        CK(cudaEventRecord(ctx->bev[b], ctx->bstream[b]));
+        CK(cudaStreamWaitEvent(s, ctx->bev[b], 0));
         launches++;
     }
     CK(cudaEventRecord(ctx->ev[5], s));
@@ -648,11 +604,12 @@ int cpecan_cuda_fetch_expectations(cpecan_ctx *ctx, double *expectations_out) {
     std::lock_guard<std::mutex> lk(ctx->mu);
     CK(cudaSetDevice(ctx->device));
     if (ctx->mode != CPECAN_MODE_EXPECTATION) { ctx->err = "fetch_expectations: the staged batch is not in expectation mode"; return CPECAN_ERR_ARG; }
-    std::vector<double> tmp(CPECAN_N_EXPECT);
-    CK(cudaMemcpyAsync(tmp.data(), ctx->dExpect.p, CPECAN_N_EXPECT * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    const int len = ctx->machine ? CPECAN_N_EXPECT_VANILLA : CPECAN_N_EXPECT;
+    std::vector<double> tmp(len);
+    CK(cudaMemcpyAsync(tmp.data(), ctx->dExpect.p, len * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    for (int i = 0; i < CPECAN_N_EXPECT; i++) expectations_out[i] += tmp[i];
-    ctx->timing.d2h_bytes += CPECAN_N_EXPECT * 8;
+    for (int i = 0; i < len; i++) expectations_out[i] += tmp[i];
+    ctx->timing.d2h_bytes += len * 8;
     return CPECAN_OK;
 }
 

@@ -146,7 +146,8 @@ int cpecan_cuda_align_batch(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan
 /* Baum-Welch expectations for a batch (getExpectationsUsingAnchors, impl/pairwiseAligner.c:1571-1591), summed over
  * the batch on device.  expectations_out: threeState 9 + 4096 + 1 doubles (transitions row-major from*3+to, k-mer
  * skip counts, likelihood); vanilla 60 + 1.  Values are ADDED to what the buffer already holds (pseudocounts). */
-#define CPECAN_N_EXPECT (9 + 4096 + 1)
+#define CPECAN_N_EXPECT (9 + 4096 + 1)   /* threeState: transitions, k-mer skip counts, likelihood */
+#define CPECAN_N_EXPECT_VANILLA (60 + 1)  /* vanilla: 30 beta + 30 alpha skip-bin counts, likelihood */
 int cpecan_cuda_expectations_batch(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *params,
                                    const cpecan_batch *batch, double *expectations_out, cpecan_result *results);
 /* The same in steps, for the EM driver: stage(mode = CPECAN_MODE_EXPECTATION) + run_staged() leave the batch sums in a

@@ -194,3 +194,93 @@ def test_em_iterations_vs_oracle(engine, template_tables, tmp_path):
         g_trans, g_gapx = gl.state_machine_params()
         o_trans, o_gapx = ol.state_machine_params()
     assert abs(gm.running_likelihoods[-1] - om.running_likelihoods[-1]) <= 1e-4 * abs(om.running_likelihoods[-1])
+
+
+# ------------------------------------------------------------------------------------------ vanilla state machine
+def _vanilla_batch(eng, tables, refs, events, anchors, scales, ragged):
+    from cpecan_signal import HostBatch, vanilla_gapx
+    l1, l2, l3 = tables
+    mid = eng.upload_model(l1, l3, vanilla_gapx(l2))
+    return HostBatch(refs, events, anchors, model_ids=[mid] * len(refs), scales=scales, ragged=ragged)
+
+
+@pytest.mark.parametrize("tag,e,ragged,count", [("vanilla_e20_r00", 20, (0, 0), 999), ("vanilla_e50_r11", 50, (1, 1), None)])
+def test_fixture_banded_vanilla(engine, zymo, template_tables, tag, e, ragged, count):
+    """stateMachine3Vanilla on the fixture read: 999 aligned pairs banded (tests/signalPairwiseTest.c:1250-1310)."""
+    from cpecan_signal import default_params, vanilla_hmm
+    from cpecan_signal.engine import item_pairs
+    rd = zymo["read"]
+    batch = _vanilla_batch(engine, template_tables, [zymo["ref"]], [rd["template_events"]],
+                           [zymo["anchors_template"]], [rd["template_params"]], [ragged])
+    res, pairs, totals = engine.align_batch(batch, hmm=vanilla_hmm("template"), params=default_params(diagonalExpansion=e),
+                                            want_totals=True)
+    assert res[0]["status"] == 0
+    got = item_pairs(res, pairs, 0)
+    stats = parity.compare_pairs(got, zymo[tag + "_pairs"])
+    worst_total = parity.compare_totals(totals[0], zymo[tag + "_totals"])
+    print(tag, stats, worst_total)
+    if count is not None:
+        assert abs(stats["n_got"] - count) <= 2
+
+
+def test_fixture_unbanded_vanilla(engine, zymo, template_tables):
+    """getAlignedPairsWithoutBanding, vanilla: 953 pairs (tests/signalPairwiseTest.c:1296-1303)."""
+    from cpecan_signal import vanilla_hmm
+    from cpecan_signal.engine import MODE_UNBANDED, item_pairs
+    rd = zymo["read"]
+    batch = _vanilla_batch(engine, template_tables, [zymo["ref"]], [rd["template_events"]], [np.zeros((0, 2))],
+                           [rd["template_params"]], [(0, 0)])
+    res, pairs, _ = engine.align_batch(batch, hmm=vanilla_hmm("template"), mode=MODE_UNBANDED)
+    assert res[0]["status"] == 0
+    stats = parity.compare_pairs(item_pairs(res, pairs, 0), zymo["vanilla_unbanded_pairs"])
+    assert abs(res[0]["total_logprob"] - float(zymo["vanilla_unbanded_total"])) <= 1e-4 * abs(float(zymo["vanilla_unbanded_total"]))
+    assert abs(stats["n_got"] - 953) <= 2
+
+
+def test_tiny_known_answer_vanilla(engine, zymo, template_tables):
+    """tests/signalPairwiseTest.c:795-897: exactly 5 pairs {(2,0),(3,3),(5,4),(6,5),(7,6)} at threshold 0.5."""
+    from cpecan_signal import default_params, vanilla_hmm
+    from cpecan_signal.engine import MODE_UNBANDED, item_pairs
+    ev = np.array([58.743435, 0.887833, 0.0571, 53.604965, 0.816836, 0.0571, 58.432015, 0.735143, 0.0571,
+                   63.684352, 0.795437, 0.0571, 58.921430, 0.812959, 0.0571, 59.895882, 0.740952, 0.0571,
+                   61.684303, 0.722332, 0.0571]).reshape(-1, 3)
+    batch = _vanilla_batch(engine, template_tables, ["ACGATACGGACAT"], [ev], [np.zeros((0, 2))], None, [(0, 0)])
+    res, pairs, _ = engine.align_batch(batch, hmm=vanilla_hmm(None), params=default_params(threshold=0.5), mode=MODE_UNBANDED)
+    got = item_pairs(res, pairs, 0)
+    assert {(int(x), int(y)) for _, x, y in got} == {(2, 0), (3, 3), (5, 4), (6, 5), (7, 6)}
+    parity.compare_pairs(got, zymo["tiny_vanilla_pairs"], threshold=0.5)
+
+
+@pytest.mark.parametrize("cfg,e,ragged", [("e20_r00", 20, (0, 0)), ("e50_r11", 50, (1, 1))])
+def test_fixture_expectations_vanilla(engine, zymo, template_tables, cfg, e, ragged):
+    """Vanilla E-step: 30 beta + 30 alpha skip-bin counts and the likelihood (impl/pairwiseAligner.c:478-498)."""
+    from cpecan_signal import default_params, vanilla_hmm
+    rd = zymo["read"]
+    batch = _vanilla_batch(engine, template_tables, [zymo["ref"]], [rd["template_events"]],
+                           [zymo["anchors_template"]], [rd["template_params"]], [ragged])
+    got, res = engine.expectations_batch(batch, hmm=vanilla_hmm("template"), params=default_params(diagonalExpansion=e),
+                                         pseudocount=1e-4)
+    want = zymo["vanilla_expectations_" + cfg]
+    assert res[0]["status"] == 0 and got.shape == want.shape == (61,)
+    np.testing.assert_allclose(got[:60], want[:60], rtol=EXP_RTOL, atol=1e-4)
+    assert abs(got[-1] - want[-1]) <= 1e-4 * abs(want[-1])
+
+
+def test_vanilla_synthetic_vs_oracle(engine, template_tables):
+    """Seeded synthetic reads with inverse-Gaussian noise through the vanilla machine, batch of mixed sizes."""
+    import oracleshim as O
+    from cpecan_signal import default_params, synth, vanilla_hmm
+    from cpecan_signal.engine import item_pairs
+    l1, l2, l3 = template_tables
+    reads = [synth.make_read(l1, 900 + i, lX=lx, noise_dist="wald") for i, lx in enumerate([300, 1200, 500])]
+    e = 40
+    batch = _vanilla_batch(engine, template_tables, [r.ref for r in reads], [r.events for r in reads],
+                           [r.anchors for r in reads], [r.scale5 for r in reads], [(1, 1)] * len(reads))
+    res, pairs, totals = engine.align_batch(batch, hmm=vanilla_hmm("complement"), params=default_params(diagonalExpansion=e),
+                                            want_totals=True)
+    for i, r in enumerate(reads):
+        m = O.Model(O.VANILLA, tables=(l1, l2, l3), scale5=r.scale5, strand=1)
+        want, wtot = O.align_banded(m, r.ref, r.events, r.anchors, params=O.default_params(diagonalExpansion=e),
+                                    ragged=(1, 1), want_totals=True)
+        assert res[i]["status"] == 0
+        print(i, parity.compare_pairs(item_pairs(res, pairs, i), want), parity.compare_totals(totals[i], wtot))
