@@ -1,0 +1,272 @@
+/*
+ * cpecan_host.h -- the reference's C API for the signal hot path, re-declared for libcpecan_host.so.
+ *
+ * This is the drop-in boundary on the CALLER's side: same names, argument meaning, struct layouts
+ * and error behaviour as the reference's cPecanLib.a for this path, so that vanillaAlign.c and the CuTest suites link
+ * against it unchanged.  Every entry point cites the reference declaration it replaces.  The DP itself runs in
+ * libcpecan_cuda.so (include/cpecan_cuda.h); there is NO CPU fallback: getAlignedPairsUsingAnchors and friends abort
+ * (st_errAbort semantics: message + abort) when no CUDA device is usable.
+ *
+ * sonLib is an un-vendored dependency of the reference (include.mk:2); the few container types the API exposes
+ * (stList, stIntTuple) are provided here with the sonLib function names.
+ */
+#ifndef CPECAN_HOST_H_
+#define CPECAN_HOST_H_
+
+#include <stdbool.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------- sonLib subset (stList / stIntTuple) */
+typedef struct _stList stList;
+typedef int64_t stIntTuple;                                  /* sonLib: an int64 array whose slot 0 is the length */
+stList *stList_construct(void);
+stList *stList_construct3(int64_t size, void (*destructElement)(void *));
+void stList_destruct(stList *list);
+int64_t stList_length(stList *list);
+void *stList_get(stList *list, int64_t index);
+void stList_set(stList *list, int64_t index, void *item);
+void stList_append(stList *list, void *item);
+void *stList_pop(stList *list);
+void stList_sort(stList *list, int (*cmpFn)(const void *a, const void *b));
+void stList_setDestructor(stList *list, void (*destructElement)(void *));
+stIntTuple *stIntTuple_construct2(int64_t a, int64_t b);
+stIntTuple *stIntTuple_construct3(int64_t a, int64_t b, int64_t c);
+stIntTuple *stIntTuple_construct4(int64_t a, int64_t b, int64_t c, int64_t d);
+void stIntTuple_destruct(stIntTuple *t);
+int64_t stIntTuple_get(stIntTuple *t, int64_t index);
+int64_t stIntTuple_length(stIntTuple *t);
+int stIntTuple_cmpFn(const void *a, const void *b);
+int stIntTuple_equalsFn(const void *a, const void *b);
+void st_errAbort(const char *format, ...);                   /* message on stderr + abort() */
+
+/* ---------------------------------------------------------------- inc/pairwiseAligner.h */
+#define PAIR_ALIGNMENT_PROB_1 10000000                       /* inc/pairwiseAligner.h:26 */
+#define LOG_ZERO (-INFINITY)
+
+typedef enum { nucleotide = 0, kmer = 1, event = 2 } SequenceType;            /* :29-33 */
+
+typedef struct _sequence Sequence;                                             /* :35-42 */
+struct _sequence {
+    int64_t length;
+    void *elements;
+    void *(*get)(void *elements, int64_t index);
+    Sequence *(*sliceFcn)(Sequence *, int64_t, int64_t);
+};
+Sequence *sequence_construct(int64_t length, void *elements, void *(*getFcn)(void *, int64_t));             /* :50 */
+Sequence *sequence_construct2(int64_t length, void *elements, void *(*getFcn)(void *, int64_t),
+                              Sequence *(*sliceFcn)(Sequence *, int64_t, int64_t));                         /* :52-53 */
+Sequence *sequence_sliceNucleotideSequence2(Sequence *inputSequence, int64_t start, int64_t sliceLength);   /* :59 */
+Sequence *sequence_sliceEventSequence2(Sequence *inputSequence, int64_t start, int64_t sliceLength);        /* :61 */
+void sequence_sequenceDestroy(Sequence *seq);                                                               /* :63 */
+void *sequence_getKmer(void *elements, int64_t index);                                                      /* :67 */
+void *sequence_getKmer2(void *elements, int64_t index);                                                     /* :70 */
+void *sequence_getEvent(void *elements, int64_t index);                                                     /* :75 */
+int64_t sequence_correctSeqLength(int64_t length, SequenceType type);                                       /* :77 */
+
+typedef struct _pairwiseAlignmentBandingParameters {                                                        /* :80-91 */
+    double threshold;
+    int64_t minDiagsBetweenTraceBack;
+    int64_t traceBackDiagonals;
+    int64_t diagonalExpansion;
+    int64_t constraintDiagonalTrim;
+    int64_t anchorMatrixBiggerThanThis;
+    int64_t repeatMaskMatrixBiggerThanThis;
+    int64_t splitMatrixBiggerThanThis;
+    bool alignAmbiguityCharacters;
+    float gapGamma;
+} PairwiseAlignmentParameters;
+PairwiseAlignmentParameters *pairwiseAlignmentBandingParameters_construct(void);                            /* :93 */
+void pairwiseAlignmentBandingParameters_destruct(PairwiseAlignmentParameters *p);                           /* :95 */
+
+typedef struct _diagonal { int64_t xay, xmyL, xmyR; } Diagonal;                                             /* :139-143 */
+Diagonal diagonal_construct(int64_t xay, int64_t xmyL, int64_t xmyR);   /* aborts on odd parity / xmyL > xmyR */
+int64_t diagonal_getXay(Diagonal diagonal);
+int64_t diagonal_getMinXmy(Diagonal diagonal);
+int64_t diagonal_getMaxXmy(Diagonal diagonal);
+int64_t diagonal_getWidth(Diagonal diagonal);
+int64_t diagonal_getXCoordinate(int64_t xay, int64_t xmy);
+int64_t diagonal_getYCoordinate(int64_t xay, int64_t xmy);
+int64_t diagonal_equals(Diagonal diagonal1, Diagonal diagonal2);
+
+typedef struct _band Band;                                                                                  /* :165-171 */
+Band *band_construct(stList *anchorPairs, int64_t lX, int64_t lY, int64_t expansion);
+void band_destruct(Band *band);
+typedef struct _bandIterator BandIterator;                                                                  /* :175-185 */
+BandIterator *bandIterator_construct(Band *band);
+void bandIterator_destruct(BandIterator *bandIterator);
+BandIterator *bandIterator_clone(BandIterator *bandIterator);
+Diagonal bandIterator_getNext(BandIterator *bandIterator);
+Diagonal bandIterator_getPrevious(BandIterator *bandIterator);
+
+double logAdd(double x, double y);                                                                          /* :191 */
+
+typedef struct _stateMachine StateMachine;
+typedef struct _hmm Hmm;
+typedef struct _dpMatrix DpMatrix;                            /* opaque: the forward/backward matrices live on the GPU */
+
+/* The two per-diagonal callbacks select the work mode by pointer identity; calling them directly
+ * aborts -- the diagonals are never materialised on the host. */
+void diagonalCalculationPosteriorMatchProbs(StateMachine *sM, int64_t xay, DpMatrix *forwardDpMatrix,       /* :246-249 */
+                                            DpMatrix *backwardDpMatrix, Sequence *sX, Sequence *sY,
+                                            double totalProbability, PairwiseAlignmentParameters *p, void *extraArgs);
+void diagonalCalculation_Expectations(StateMachine *sM, int64_t xay, DpMatrix *forwardDpMatrix,             /* :260-264 */
+                                      DpMatrix *backwardDpMatrix, Sequence *sX, Sequence *sY,
+                                      double totalProbability, PairwiseAlignmentParameters *p, void *extraArgs);
+
+stList *getAlignedPairsUsingAnchors(StateMachine *sM, Sequence *SsX, Sequence *SsY, stList *anchorPairs,    /* :288-296 */
+                                    PairwiseAlignmentParameters *p,
+                                    void (*diagonalPosteriorProbFn)(StateMachine *, int64_t, DpMatrix *, DpMatrix *,
+                                                                    Sequence *, Sequence *, double,
+                                                                    PairwiseAlignmentParameters *, void *),
+                                    bool alignmentHasRaggedLeftEnd, bool alignmentHasRaggedRightEnd);
+stList *getAlignedPairsWithoutBanding(StateMachine *sM, void *cX, void *cY, int64_t lX, int64_t lY,          /* :279-286 */
+                                      PairwiseAlignmentParameters *p,
+                                      void *(*getXFcn)(void *, int64_t), void *(*getYFcn)(void *, int64_t),
+                                      void (*diagonalPosteriorProbFn)(StateMachine *, int64_t, DpMatrix *, DpMatrix *,
+                                                                      Sequence *, Sequence *, double,
+                                                                      PairwiseAlignmentParameters *, void *),
+                                      bool alignmentHasRaggedLeftEnd, bool alignmentHasRaggedRightEnd);
+void getExpectationsUsingAnchors(StateMachine *sM, Hmm *hmmExpectations, Sequence *SsX, Sequence *SsY,      /* :299-311 */
+                                 stList *anchorPairs, PairwiseAlignmentParameters *p,
+                                 void (*diagonalCalcExpectationFcn)(StateMachine *, int64_t, DpMatrix *, DpMatrix *,
+                                                                    Sequence *, Sequence *, double,
+                                                                    PairwiseAlignmentParameters *, void *),
+                                 bool alignmentHasRaggedLeftEnd, bool alignmentHasRaggedRightEnd);
+
+int sortByXPlusYCoordinate(const void *i, const void *j);                                                   /* :316 */
+int sortByXPlusYCoordinate2(const void *i, const void *j);                                                  /* :318 */
+stList *filterToRemoveOverlap(stList *overlappingPairs);                                                    /* :324 */
+stList *getSplitPoints(stList *anchorPairs, int64_t lX, int64_t lY, int64_t maxMatrixSize,                  /* :328-329 */
+                       bool alignmentHasRaggedLeftEnd, bool alignmentHasRaggedRightEnd);
+
+/* ---------------------------------------------------------------- inc/stateMachine.h */
+#define KMER_LENGTH 6                                         /* inc/emissionMatrix.h:4-5 */
+#define NUM_OF_KMERS 4096
+#define MODEL_PARAMS 5
+
+typedef enum { fiveState = 0, fiveStateAsymmetric = 1, threeState = 2, threeStateAsymmetric = 3, vanilla = 4,
+               echelon = 5, fourState = 6, threeStateHdp = 7 } StateMachineType;                            /* :20-29 */
+typedef enum { match = 0, shortGapX = 1, shortGapY = 2, longGapX = 3, longGapY = 4 } State;                 /* :31-33 */
+#ifdef __cplusplus
+typedef enum _strand { template_ = 0, complement = 1 } Strand;   /* `template` is reserved in C++ (:35-38) */
+#else
+typedef enum _strand { template = 0, complement = 1 } Strand;
+#endif
+
+struct _hmm {                                                                                               /* :47-74 */
+    double likelihood;
+    StateMachineType type;
+    int64_t stateNumber;
+    int64_t symbolSetSize;
+    int64_t matrixSize;
+    void (*addToTransitionExpectationFcn)(Hmm *hmm, int64_t from, int64_t to, double p);
+    void (*setTransitionFcn)(Hmm *hmm, int64_t from, int64_t to, double p);
+    double (*getTransitionsExpFcn)(Hmm *hmm, int64_t from, int64_t to);
+    void (*addToEmissionExpectationFcn)(Hmm *hmm, int64_t state, int64_t x, int64_t y, double p);
+    void (*setEmissionExpectationFcn)(Hmm *hmm, int64_t state, int64_t x, int64_t y, double p);
+    double (*getEmissionExpFcn)(Hmm *hmm, int64_t state, int64_t x, int64_t y);
+    int64_t (*getElementIndexFcn)(void *);
+};
+
+struct _stateMachine {                                                                                      /* :76-102 */
+    StateMachineType type;
+    int64_t stateNumber;
+    int64_t matchState;
+    int64_t parameterSetSize;
+    double *EMISSION_MATCH_PROBS;
+    double *EMISSION_GAP_X_PROBS;
+    double *EMISSION_GAP_Y_PROBS;
+    double (*startStateProb)(StateMachine *sM, int64_t state);
+    double (*endStateProb)(StateMachine *sM, int64_t state);
+    double (*raggedEndStateProb)(StateMachine *sM, int64_t state);
+    double (*raggedStartStateProb)(StateMachine *sM, int64_t state);
+    void (*cellCalculate)(StateMachine *sM, double *current, double *lower, double *middle, double *upper, void *cX,
+                          void *cY, void (*doTransition)(double *, double *, int64_t, int64_t, double, double, void *),
+                          void *extraArgs);                   /* aborts: the cells are computed on the GPU */
+    void (*cellCalculateUpdateExpectations)(double *fromCells, double *toCells, int64_t from, int64_t to, double eP,
+                                            double tP, void *extraArgs);
+};
+
+typedef struct _StateMachine3 {                                                                             /* :176-195 */
+    StateMachine model;
+    double TRANSITION_MATCH_CONTINUE;
+    double TRANSITION_MATCH_FROM_GAP_X;
+    double TRANSITION_MATCH_FROM_GAP_Y;
+    double TRANSITION_GAP_OPEN_X;
+    double TRANSITION_GAP_OPEN_Y;
+    double TRANSITION_GAP_EXTEND_X;
+    double TRANSITION_GAP_EXTEND_Y;
+    double TRANSITION_GAP_SWITCH_TO_X;
+    double TRANSITION_GAP_SWITCH_TO_Y;
+    double (*getXGapProbFcn)(const double *emissionXGapProbs, void *i);
+    double (*getYGapProbFcn)(const double *emissionYGapProbs, void *x, void *y);
+    double (*getMatchProbFcn)(const double *emissionMatchProbs, void *x, void *y);
+} StateMachine3;
+
+typedef struct _StateMachine3vanilla {                                                                      /* :217-231 */
+    StateMachine model;
+    double TRANSITION_M_TO_Y_NOT_X;
+    double TRANSITION_E_TO_E;
+    double DEFAULT_END_MATCH_PROB;
+    double DEFAULT_END_FROM_X_PROB;
+    double DEFAULT_END_FROM_Y_PROB;
+    double (*getKmerSkipProb)(StateMachine *sM, void *kmerList, bool getAlpha);
+    double (*getScaledMatchProbFcn)(const double *scaledEventModel, void *kmer, void *event);
+    double (*getMatchProbFcn)(const double *eventModel, void *kmer, void *event);
+} StateMachine3Vanilla;
+
+StateMachine *getStrawManStateMachine3(const char *modelFile);                                              /* :368 */
+StateMachine *getSignalStateMachine3Vanilla(const char *modelFile);                                         /* :374 */
+void emissions_signal_scaleModel(StateMachine *sM, double scale, double shift, double var, double scale_sd,
+                                 double var_sd);                                                            /* :341-342 */
+void stateMachine3_setTransitionsToNanoporeDefaults(StateMachine *sM);
+void stateMachine3Vanilla_setStrandTransitionsToDefaults(StateMachine *sM, Strand strand);                  /* :383 */
+int64_t emissions_discrete_getKmerIndex(void *kmer);                                                        /* :305 */
+void stateMachine_destruct(StateMachine *stateMachine);                                                     /* :387 */
+
+/* ---------------------------------------------------------------- inc/continuousHmm.h */
+Hmm *hmmContinuous_getEmptyHmm(StateMachineType type, double pseudocount, double threshold);                /* :107 */
+void hmmContinuous_normalize(Hmm *hmm, StateMachineType type);                                              /* :113 */
+void hmmContinuous_writeToFile(const char *outFile, Hmm *hmm, StateMachineType type);                       /* :116 */
+void hmmContinuous_loadSignalHmm(const char *hmmFile, StateMachine *sM, StateMachineType type);             /* :104 */
+void hmmContinuous_destruct(Hmm *hmm, StateMachineType type);                                               /* :119 */
+void vanillaHmm_implantMatchModelsintoHmm(StateMachine *sM, Hmm *hmm);                                      /* :87 */
+
+/* ---------------------------------------------------------------- inc/nanopore.h */
+#define NB_EVENT_PARAMS 3
+typedef struct _nanoporeReadAdjustmentParameters { double scale, shift, var, scale_sd, var_sd; } NanoporeReadAdjustmentParameters;
+typedef struct _nanoporeRead {                                                                              /* :14-29 */
+    int64_t readLength;
+    int64_t nbTemplateEvents;
+    int64_t nbComplementEvents;
+    NanoporeReadAdjustmentParameters templateParams;
+    NanoporeReadAdjustmentParameters complementParams;
+    char *twoDread;
+    int64_t *templateEventMap;
+    double *templateEvents;
+    int64_t *complementEventMap;
+    double *complementEvents;
+    bool scaled;
+} NanoporeRead;
+NanoporeRead *nanopore_loadNanoporeReadFromFile(const char *nanoporeReadFile);                              /* :31 */
+stList *nanopore_remapAnchorPairs(stList *anchorPairs, int64_t *eventMap);                                  /* :33 */
+stList *nanopore_remapAnchorPairsWithOffset(stList *unmappedPairs, int64_t *eventMap, int64_t mapOffset);   /* :35 */
+void nanopore_nanoporeReadDestruct(NanoporeRead *npRead);                                                   /* :39 */
+
+/* ---------------------------------------------------------------- additive: batching and device selection */
+/* Many (read, reference) pairs in one call: what N calls of getAlignedPairsUsingAnchors return, computed as one GPU
+ * batch.  All arrays have n entries; result[i] is a new stList owned by the caller. */
+void getAlignedPairsUsingAnchorsBatch(int64_t n, StateMachine **sMs, Sequence **sXs, Sequence **sYs, stList **anchorPairs,
+                                      PairwiseAlignmentParameters *p, bool raggedLeft, bool raggedRight, stList **results);
+/* Device for this process (default: $CPECAN_DEVICE or 0); must be called before the first alignment. */
+void cpecan_host_set_device(int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
