@@ -75,6 +75,12 @@ __device__ __forceinline__ float logadd2(float x, float y, const LaCoef &k) {
     return r;
 }
 
+// Keeps all four components of a prefetched record live until the point of use.  Without it ptxas re-uses a component
+// the arithmetic never reads (e.g. the k-mer index) as a scratch register while the LDG.128 is still in flight, and the
+// write-after-write scoreboard wait on that one register serialises the warp behind the load (ncu: 18 % of all samples
+// sat on the first integer instruction after the prefetch).
+__device__ __forceinline__ void keep_live(const float4 &v) { asm volatile("" :: "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)); }
+
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 
 struct KernelArgs2 {
@@ -96,7 +102,7 @@ struct KernelArgs2 {
     DevParams P;
 };
 
-__host__ __device__ inline size_t align2_smem_bytes(int ringN) { return (size_t) ringN * (2 * 16 + 2 * 4); }
+__host__ __device__ inline size_t align2_smem_bytes(int ringN) { return (size_t) ringN * (2 * 16); }
 
 // Left fold  acc = logadd(acc, v[0]), logadd(acc, v[1]), ...  in ascending x (the order of dpDiagonal_dotProduct,
 // impl/pairwiseAligner.c:587-597) over ring-positioned values: element i lives at (start + i) & (N - 1).
@@ -149,14 +155,17 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
     extern __shared__ __align__(16) unsigned char smraw[];
     const int N = A.ringN, NM = N - 1;
     float4 *ring = reinterpret_cast<float4 *>(smraw);             // 2 * N entries
-    float *sm_c1 = reinterpret_cast<float *>(ring + 2 * N);       // N
-    float *sm_us = sm_c1 + N;                                     // N
 
     const int lane = threadIdx.x;
     const DevParams &P = A.P;
     const float NI = CP_NEG_INF;
     float4 *rows = A.scratch + (long long) blockIdx.x * A.scratch_stride;
     const int R = A.ring_rows;
+    // dot-product terms of the total-probability diagonals (1 in 10): kept in the warp's global scratch (one extra
+    // row behind the forward rows), not in shared memory -- every KB of shared memory per warp is a KB less L1 for
+    // the column records and events the warps stream
+    float *sm_c1 = reinterpret_cast<float *>(rows + (long long) R * N);
+    float *sm_us = sm_c1 + N;
     const float4 NIENT = make_float4(NI, NI, NI, -CP_BIG);
     const LaCoef K = la_coef();
 #define LA(a, b) logadd2((a), (b), K)
@@ -179,7 +188,9 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
         const int itemIdx = A.order[qi];
         const Item it = A.items[itemIdx];
         const int lX = it.lX, lY = it.lY, D = lX + lY;
-        const float4 *xp = A.xparams + 4 * it.xp_off;
+        // the four planes (a, b, c, d) of the column records, each lX + 2 float4 long: neighbouring lanes read
+        // neighbouring 16-byte records, so a warp's LDG.128 touches 4-5 cache lines instead of 16
+        const float4 *xpA = A.xparams + 4 * it.xp_off, *xpB = xpA + (lX + 2), *xpC = xpB + (lX + 2), *xpD = xpC + (lX + 2);
         const float4 *evp = A.events + it.ev_off;
         int *pairs = A.pairs + 3 * it.pair_off;
         double *dbgTot = (A.totals != nullptr && it.tot_off >= 0) ? A.totals + it.tot_off : nullptr;
@@ -233,19 +244,21 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                 }
                 // lanes are placed relative to the window [lo-1, hi+1] of the diagonal (the cells one outside the band
                 // are written as -inf for the neighbours that will read them): chunk j holds x = wlo + 32 j + lane
-                int wlo = max(lo - 1, 0), c = (min(hi + 1, lX) - wlo) >> 5;
+                int wlo = max(lo - 1, 0) & ~7, c = (min(hi + 1, lX) - wlo) >> 5;     // 8-lane aligned: own LDS/STS.128 conflict free
                 rowF = rowF + 1 == R ? 0 : rowF + 1;
                 float4 *frow = rows + (long long) rowF * N;
                 float4 npa, npb, npc, npd, nev;
                 auto prefetch = [&](int dd, int xbase) {
                     const int x = xbase + lane;
                     const int xx = min(x, lX + 1);
-                    npa = xp[4 * xx]; npb = xp[4 * xx + 1]; npc = xp[4 * xx + 2];
-                    if (MACH) npd = xp[4 * xx + 3];
+                    npa = xpA[xx]; npb = xpB[xx]; npc = xpC[xx];
+                    if (MACH) npd = xpD[xx];
                     nev = evp[min(max(dd - x, 0), lY)];
                 };
                 prefetch(d, wlo + (c << 5));
                 for (;;) {
+                    keep_live(npa); keep_live(npb); keep_live(npc); keep_live(nev);
+                    if (MACH) keep_live(npd);
                     const float4 pa = npa, pb = npb, pc = npc, pd = npd, ev = nev;
                     const bool last = c == 0;
                     int nd = d, nc = c - 1, nlo = lo, nhi = hi, nwlo = wlo;
@@ -257,17 +270,17 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                             nd = d + 1;
                             bw.range(nd, nlo, nhi);
                             if (nlo < lo || nlo > lo + 1 || nhi < hi || nhi > hi + 1) status |= 4;
-                            nwlo = max(nlo - 1, 0);
+                            nwlo = max(nlo - 1, 0) & ~7;
                             nc = (min(nhi + 1, lX) - nwlo) >> 5;
                         }
                     }
-                    if (!stop) prefetch(nd, nwlo + (nc << 5));
                     {
                         const int x = wlo + (c << 5) + lane;
                         const int s = x & NM, sl = (x - 1) & NM;
                         const float4 own = A1[s], L = A1[sl], Mi = A2[sl];
                         const bool inb = x >= lo && x <= hi;
                         __syncwarp();
+                        prefetch(nd, nwlo + (max(nc, 0) << 5));      // inputs of the next task (harmless clamped addresses at the stop)
                         const float U = fmaxf(own.w, fmaxf(L.w, Mi.w));
                         // impl/stateMachine.c:1314-1333: transitions folded in code order, emission added once
                         // (vanilla: impl/stateMachine.c:1368-1409, the transitions are those of THIS column)
@@ -297,7 +310,7 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                             // columns / events that enter the band during the next diagonals: first touch comes from
                             // DRAM, so pull them into L2 well ahead (one lane stalling stalls the warp)
                             const int px = hi + 32 + lane, py = (d - lo) + 32 + lane;
-                            if (px <= lX + 1) { prefetch_l2(xp + 4 * px); prefetch_l2(xp + 4 * px + 2); }
+                            if (px <= lX + 1) { prefetch_l2(xpA + px); prefetch_l2(xpB + px); prefetch_l2(xpC + px); if (MACH) prefetch_l2(xpD + px); }
                             if (py <= lY) prefetch_l2(evp + py);
                         }
                         rowF = rowF + 1 == R ? 0 : rowF + 1;
@@ -329,7 +342,7 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                     }
                     const float4 *frow = rows + (long long) rowB * N;
                     const bool post = d <= tracedBackFrom;
-                    const int wlo = max(blo - 1, 0), nch = ((min(bhi + 1, lX) - wlo) >> 5) + 1;
+                    const int wlo = max(blo - 1, 0) & ~7, nch = ((min(bhi + 1, lX) - wlo) >> 5) + 1;
                     const int plo = max(blo, 1), phi = min(bhi, d - 1);   // cells with x > 0 and y > 0 report posteriors
                     bool doTotal = false;
                     if (post) { doTotal = unbanded ? (d == Dt) : (count % P.totalEvery == 0); count++; }
@@ -341,7 +354,7 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                     }
                     if ((d & 15) == 0) {
                         const int px = blo - 32 - lane, py = (d - bhi) - 32 - lane;
-                        if (px >= 0) { prefetch_l2(xp + 4 * px); prefetch_l2(xp + 4 * px + 2); }
+                        if (px >= 0) { prefetch_l2(xpA + px); prefetch_l2(xpB + px); prefetch_l2(xpC + px); if (MACH) prefetch_l2(xpD + px); }
                         if (py >= 1) prefetch_l2(evp + py);
                     }
 
@@ -383,8 +396,8 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                     auto prefetchB = [&](int cc) {
                         const int x = wlo + (cc << 5) + lane;
                         const int xx = min(x, lX + 1);
-                        npa = xp[4 * xx]; npb = xp[4 * xx + 1]; npc = xp[4 * xx + 2];
-                        if (MACH) npdR = xp[4 * min(x + 1, lX + 1) + 3];
+                        npa = xpA[xx]; npb = xpB[xx]; npc = xpC[xx];
+                        if (MACH) npdR = xpD[min(x + 1, lX + 1)];
                         nev = evp[min(max(d - x, 0), lY)];
                         nF = NIENT;
                         if (post && x >= blo && x <= bhi) nF = frow[x & NM];
@@ -404,7 +417,7 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                                     if (x >= el1 && x <= eh1) FU = frow1[s];
                                 }
                                 float4 pdo = NIENT;
-                                if (MACH) pdo = xp[4 * min(x, lX + 1) + 3];
+                                if (MACH) pdo = xpD[min(x, lX + 1)];
                                 const float tOX = MACH ? pdo.x : gOX, tEX = MACH ? pdo.y : gEX, tMC = MACH ? pdo.z : gMC,
                                             tMX = MACH ? pdo.w : gMX, tOY = MACH ? pc.z : gOY;
                                 const float kX = (bX + eX) + (((FL.w + U) - totBase) - totSt);
@@ -456,6 +469,8 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                         for (int c = 0; c < nch; c++) {                // ascending x: in-place update of the d+2 entries
                             const int x = wlo + (c << 5) + lane, s = x & NM;
                             const bool inb = x >= blo && x <= bhi;
+                            keep_live(npa); keep_live(npb); keep_live(npc); keep_live(nev); keep_live(nF);
+                            if (MACH) keep_live(npdR);
                             const float4 pa = npa, pb = npb, pc = npc, pdR = npdR, F = nF, ev = nev;
                             if (c + 1 < nch) prefetchB(c + 1);
                             float bM, bX, bY, U;
@@ -474,7 +489,7 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                             float bM, bX, bY, U;
                             float4 pdR = NIENT;
                             float myLog = 0.f;
-                            if (MACH) { pdR = xp[4 * min(x + 1, lX + 1) + 3]; myLog = xp[4 * min(x, lX + 1) + 2].z; }
+                            if (MACH) { pdR = xpD[min(x + 1, lX + 1)]; myLog = xpC[min(x, lX + 1)].z; }
                             cellB(x, s, inb, pdR, myLog, bM, bX, bY, U);
                             __syncwarp();
                             A2[s] = make_float4(bM, bX, bY, inb ? U : -CP_BIG);
@@ -509,7 +524,7 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                                     const float4 F = fprev[(x - 1) & NM];
                                     const float4 Gn = A1[x & NM];
                                     float4 pdx = NIENT;
-                                    if (MACH) pdx = xp[4 * min(x, lX + 1) + 3];
+                                    if (MACH) pdx = xpD[min(x, lX + 1)];
                                     const float md = LA(LA(F.x + (MACH ? pdx.z : gMC), F.y + (MACH ? pdx.w : gMX)), F.z + tMY);
                                     val = (md + Gn.x) + ((F.w + Gn.w) - fbase);
                                 }

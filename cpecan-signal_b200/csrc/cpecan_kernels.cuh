@@ -168,8 +168,8 @@ __device__ __forceinline__ int kmer_code(const char *s) {   // impl/stateMachine
     return v;
 }
 
-// x-parameter record: 4 float4 per matrix column x (sequence index x-1); records 0 .. lX+1, the last one the all
-// -inf dummy read for columns beyond the matrix.
+// x-parameter record: 4 float4 per matrix column x (sequence index x-1), stored as four PLANES of lX + 2 float4 per
+// item (a[0..lX+1], b[..], c[..], d[..]); record lX+1 is the all -inf dummy read for columns beyond the matrix.
 //   a = (mu_m - c0, -1/(2 sd_m^2), nu_m, q_m)      b = (K_m, mu_y - c0, -1/(2 sd_y^2), nu_y)
 //   c = (q_y, K_y, gap-X emission | log a_my, k-mer index | skip bin as int bits)
 //   d = vanilla only: (log a_mx, log a_xx, log a_mm, log a_xm)
@@ -246,7 +246,8 @@ __global__ void k_prep_xparams(const Item *items, const long long *ref_off, cons
             c.z = (float) log(a_my);
             c.w = __int_as_float((int) bin);
         }
-        dst[4 * x] = a; dst[4 * x + 1] = b; dst[4 * x + 2] = c; dst[4 * x + 3] = d;
+        const int plane = it.lX + 2;          // four planes per item: lanes of a warp read neighbouring records of one plane
+        dst[x] = a; dst[plane + x] = b; dst[2 * plane + x] = c; dst[3 * plane + x] = d;
     }
 }
 
