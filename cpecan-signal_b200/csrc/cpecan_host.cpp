@@ -629,6 +629,9 @@ void getAlignedPairsUsingAnchorsBatch(int64_t n, StateMachine **sMs, Sequence **
         int64_t j = i;
         for (; j < n && sameHmm(hmm, hmmOf(sMs[j])); j++) {
             checkSequences(sMs[j], sXs[j], sYs[j]);
+            // A negative length happens in the reference's own pipeline (vanillaAlign.c:645-651 slices the complement
+            // events with a DECREASING event map); the reference then walks a degenerate band and reports no pair.
+            if (sXs[j]->length < 0 || sYs[j]->length < 0) continue;
             addRead(f, j, modelIdLocked(ctx, sMs[j]), sXs[j], sYs[j], anchorPairs[j], p, raggedLeft, raggedRight);
         }
         runPosterior(ctx, hmm, prm, CPECAN_MODE_POSTERIOR, f, results);
@@ -686,6 +689,7 @@ void getExpectationsUsingAnchors(StateMachine *sM, Hmm *hmmExpectations, Sequenc
     std::lock_guard<std::mutex> lk(gMu);
     cpecan_ctx *ctx = gpuLocked();
     checkSequences(sM, SsX, SsY);
+    if (SsX->length < 0 || SsY->length < 0) return;   // degenerate input (see getAlignedPairsUsingAnchorsBatch): nothing is added
     Flat f;
     addRead(f, 0, modelIdLocked(ctx, sM), SsX, SsY, anchorPairs, p, alignmentHasRaggedLeftEnd, alignmentHasRaggedRightEnd);
     if (f.n() == 0) return;

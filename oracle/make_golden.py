@@ -120,5 +120,36 @@ def main():
     np.savez_compressed(os.path.join(GOLDEN, "synthetic_golden.npz"), **syn)
 
 
+def vanilla_align_goldens():
+    """tests/golden/vanillaAlign/*: outputs of the UNMODIFIED reference CLI (oracle/_ref/vanillaAlign, `make -C oracle
+    vanillaAlign lastz`) on the fixture 2D read.  The guide cigar comes from the reference's vendored lastz."""
+    import shutil
+    import subprocess
+    import tempfile
+    ref_dir = os.path.join(HERE, "_ref")
+    out_dir = os.path.join(GOLDEN, "vanillaAlign")
+    os.makedirs(out_dir, exist_ok=True)
+    ref = open(os.path.join(GOLDEN, "ZymoRef.txt")).readline().strip()
+    read = open(os.path.join(GOLDEN, "ZymoC_ch_1_file1.npRead")).read().split("\n")[1].strip()
+    with tempfile.TemporaryDirectory() as td:
+        open(os.path.join(td, "ref.fa"), "w").write(">ZymoRef\n%s\n" % ref)
+        open(os.path.join(td, "read.fa"), "w").write(">read\n%s\n" % read)
+        cigar = subprocess.run([os.path.join(ref_dir, "cPecanLastz"), "--format=cigar", "ref.fa", "read.fa"], cwd=td,
+                               capture_output=True, text=True, check=True).stdout.split("\n")[0] + "\n"
+        open(os.path.join(out_dir, "guide.cigar"), "w").write(cigar)
+        base = ["-T", T_MODEL, "-C", C_MODEL, "-L", "readA", "-q", os.path.join(GOLDEN, "ZymoC_ch_1_file1.npRead"),
+                "-r", os.path.join(GOLDEN, "ZymoRef.txt")]
+        for tag, flag in (("s", ["-s"]), ("v", [])):
+            tsv = os.path.join(td, "out_%s.tsv" % tag)
+            r = subprocess.run([os.path.join(ref_dir, "vanillaAlign")] + flag + base + ["-u", tsv], input=cigar,
+                               capture_output=True, text=True, check=True)
+            open(os.path.join(out_dir, "stdout_%s.txt" % tag), "w").write(r.stdout)
+            shutil.copy(tsv, os.path.join(out_dir, "out_%s.tsv" % tag))
+        subprocess.run([os.path.join(ref_dir, "vanillaAlign"), "-s"] + base +
+                       ["-t", os.path.join(out_dir, "t_s.exp"), "-c", os.path.join(out_dir, "c_s.exp")], input=cigar,
+                       capture_output=True, text=True, check=True)
+
+
 if __name__ == "__main__":
     main()
+    vanilla_align_goldens()

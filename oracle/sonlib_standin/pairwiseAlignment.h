@@ -36,5 +36,9 @@ struct PairwiseAlignment {
 
 struct PairwiseAlignment *cigarRead(FILE *fileHandle);
 void destructPairwiseAlignment(struct PairwiseAlignment *pA);
+void checkPairwiseAlignment(struct PairwiseAlignment *pA);
+/* sonLib string helpers the reference's vanillaAlign.c calls (it reaches sonLib.h only through this header) */
+char *stString_reverseComplementString(const char *s);
+char *stString_replace(const char *s, const char *what, const char *with);
 
 #endif

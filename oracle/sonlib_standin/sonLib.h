@@ -71,6 +71,9 @@ char *stString_copy(const char *s);
 char *stString_getSubString(const char *s, int64_t start, int64_t length);
 stList *stString_split(const char *s);
 char *stFile_getLineFromFile(FILE *f);
+/* used by the reference's vanillaAlign.c only (oracle/vanilla_align_stubs.c) */
+char *stString_reverseComplementString(const char *s);
+char *stString_replace(const char *s, const char *what, const char *with);
 
 /* exceptions: the hot path throws only from diagonal_construct on invalid coordinates */
 void stThrowNew(const char *id, const char *fmt, ...);
