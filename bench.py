@@ -35,6 +35,11 @@ sys.path.insert(0, os.path.join(ROOT, "cpecan-signal_b200"))
 EXPANSIONS = (64, 128, 256)
 LX = 6700
 HBM_BYTES_PER_CELL = 25.0       # forward cell written + read once (24 B) + inputs/outputs (<1 B)
+# DRAM bytes per band cell of k_align2 from the ncu --set full capture committed under profiles/
+# (r1_ncu_k_align2_e64_summary.txt: dram__bytes_read.sum 129.0 GB + dram__bytes_write.sum 75.6 GB for one launch over
+# ~4.6e9 band cells -- 75.6 GB of predicated 16-byte forward-cell stores): 16 B written + 28 B read per band cell
+# (forward rows are float4 (M, X, Y, offset); the L2 prefetch of forward rows fetches whole 512-byte chunks)
+DRAM_BYTES_PER_CELL_NCU = 44.0
 ISSUE_OPS_PER_CELL = 165.0
 METRIC = "banded_fwd_bwd_posterior_gcups"
 
@@ -449,7 +454,10 @@ def main():
         "gpu_launches_e2e": int(e2e_launches),
         "kernel_ms_per_step": kern_ms_max / args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved_gbs / hbm_peak,
+                     "traffic": DRAM_BYTES_PER_CELL_NCU * cells_rank / len(engines),   # bytes per launch (ncu, see above)
+                     "algorithmic_bytes_per_launch": HBM_BYTES_PER_CELL * cells_rank / len(engines),
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_band_cell": HBM_BYTES_PER_CELL},
         "roofline_issue": {"bound": "fp32_issue", "achieved": issue_ach / 1e12, "peak": issue_peak / 1e12,
                            "unit": "Tissue-op/s", "frac": issue_ach / issue_peak,
