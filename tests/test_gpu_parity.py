@@ -284,3 +284,41 @@ def test_vanilla_synthetic_vs_oracle(engine, template_tables):
                                     ragged=(1, 1), want_totals=True)
         assert res[i]["status"] == 0
         print(i, parity.compare_pairs(item_pairs(res, pairs, i), want), parity.compare_totals(totals[i], wtot))
+
+
+def test_split_regions_as_items(engine, syn_golden, template_tables):
+    """An anchor gap above splitMatrixBiggerThanThis: the regions of getSplitPoints become work items with ragged
+    ends on the cut sides, and their pairs, shifted back and reversed per region, are what
+    getAlignedPairsUsingAnchors returns (impl/pairwiseAligner.c:1356-1422, 1447-1454)."""
+    import oracleshim as O
+    from cpecan_signal import default_params, synth
+    from cpecan_signal.engine import item_pairs
+    idx, lX, e, r0, r1, every, mind, split = (int(v) for v in syn_golden["split_meta"])
+    lo, hi = (int(v) for v in syn_golden["split_keep_lo_hi"])
+    r = synth.make_read(template_tables[0], idx, lX=lX, anchor_every=every)
+    anchors = r.anchors[(r.anchors[:, 0] < lo) | (r.anchors[:, 0] > hi)]
+    regions = O.split_points(anchors, r.lX, r.lY, split, r0, r1)
+    assert len(regions) == 2
+    refs, evs, ans, rag = [], [], [], []
+    j = 0
+    for i, (x1, y1, x2, y2) in enumerate(regions):
+        refs.append(r.ref[x1:x2 + 5])
+        evs.append(r.events[y1:y2])
+        sub = []
+        while j < len(anchors) and anchors[j, 0] + anchors[j, 1] < x2 + y2:
+            sub.append((anchors[j, 0] - x1, anchors[j, 1] - y1)); j += 1
+        ans.append(np.array(sub, dtype=np.int64).reshape(-1, 2))
+        rag.append((r0 or i > 0, r1 or i < len(regions) - 1))
+    batch = _three_state_batch(engine, template_tables, refs, evs, ans, [r.scale5] * len(regions), rag)
+    res, pairs, _ = engine.align_batch(batch, params=default_params(diagonalExpansion=e))
+    got = []
+    for i, (x1, y1, x2, y2) in enumerate(regions):
+        assert res[i]["status"] == 0
+        p = parity.reverse_regions(item_pairs(res, pairs, i)).astype(np.int64)
+        p[:, 1] += x1; p[:, 2] += y1
+        got.append(p)
+    got = np.concatenate(got)
+    stats = parity.compare_pairs(got, syn_golden["split_pairs"])
+    print(stats)
+    if stats["n_got"] == stats["n_want"]:
+        assert np.array_equal(got[:, 1:], syn_golden["split_pairs"][:, 1:])
