@@ -322,3 +322,31 @@ def test_split_regions_as_items(engine, syn_golden, template_tables):
     print(stats)
     if stats["n_got"] == stats["n_want"]:
         assert np.array_equal(got[:, 1:], syn_golden["split_pairs"][:, 1:])
+
+
+def test_argument_errors_are_reported(engine, template_tables):
+    """Integer status + message, never an abort: odd expansion (not representable by the device band walker), a model
+    with too few gap-X entries for the machine, an unknown state-machine type."""
+    from cpecan_signal import EngineError, HostBatch, default_params, synth, vanilla_hmm
+    from cpecan_signal.engine import Hmm
+    l1, l2, l3 = template_tables
+    r = synth.make_read(l1, 7, lX=200)
+    mid = engine.upload_model(l1, l3, np.full(4096, -2.3025850929940455))
+    hb = HostBatch([r.ref], [r.events], [r.anchors], model_ids=[mid], scales=[r.scale5], ragged=[(1, 1)])
+    with pytest.raises(EngineError, match="banding parameters"):
+        engine.align_batch(hb, params=default_params(diagonalExpansion=21))
+    mid60 = engine.upload_model(l1, l3, np.full(60, 0.1))
+    hb60 = HostBatch([r.ref], [r.events], [r.anchors], model_ids=[mid60], scales=[r.scale5], ragged=[(1, 1)])
+    with pytest.raises(EngineError, match="gap-X"):
+        engine.align_batch(hb60)                                   # three-state needs 4096 entries
+    engine.align_batch(hb60, hmm=vanilla_hmm("template"))          # vanilla is fine with 60
+    bad = Hmm()
+    bad.sm_type = 6                                                # fourState: not implemented on device
+    with pytest.raises(EngineError, match="not implemented"):
+        engine.align_batch(hb, hmm=bad)
+    # empty batch and an item without events are legal
+    res, pairs, _ = engine.align_batch(HostBatch([], [], []))
+    assert len(res) == 0
+    hb0 = HostBatch([r.ref], [np.zeros((0, 3))], [np.zeros((0, 2))], model_ids=[mid], scales=[r.scale5], ragged=[(1, 1)])
+    res, pairs, _ = engine.align_batch(hb0)
+    assert res[0]["status"] == 0 and res[0]["n_pairs"] == 0

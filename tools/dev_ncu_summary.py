@@ -1,5 +1,5 @@
 """Developer helper (not a test): summarise an .ncu-rep (raw + source pages) the way profiles/*.txt are written.
-   python tests/dev_ncu_summary.py gpurun_out/x.ncu-rep"""
+   python tools/dev_ncu_summary.py gpurun_out/x.ncu-rep"""
 import csv
 import io
 import subprocess

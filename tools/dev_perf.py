@@ -1,5 +1,5 @@
 """Developer perf probe (not a test): kernel-only timing of one expansion; the command ncu captures.
-   python tests/dev_perf.py --e 64 --n 1776 --reps 3 [--lx 6700]"""
+   python tools/dev_perf.py --e 64 --n 1776 --reps 3 [--lx 6700]"""
 import argparse
 import os
 import sys
