@@ -83,6 +83,10 @@ __device__ __forceinline__ void keep_live(const float4 &v) { asm volatile("" :: 
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 
+// column records + event of one (diagonal, chunk) task, as loaded for this lane
+struct FwdRec { float4 a, b, c, d, ev; };
+struct BwdRec { float4 a, b, c, dR, ev, F; };
+
 struct KernelArgs2 {
     const Item *items;
     const int *order;
@@ -95,6 +99,7 @@ struct KernelArgs2 {
     long long scratch_stride;     // float4 per warp
     int ring_rows;
     int ringN;                    // ring positions (power of two)
+    int zero;                     // always 0, but only the host knows (see the register prefetch in k_align2)
     int *pairs;
     ItemOut *out;
     double *totals;
@@ -247,19 +252,27 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                 int wlo = max(lo - 1, 0) & ~7, c = (min(hi + 1, lX) - wlo) >> 5;     // 8-lane aligned: own LDS/STS.128 conflict free
                 rowF = rowF + 1 == R ? 0 : rowF + 1;
                 float4 *frow = rows + (long long) rowF * N;
-                float4 npa, npb, npc, npd, nev;
-                auto prefetch = [&](int dd, int xbase) {
+                // Register prefetch: the records of task i+1 are loaded into r1 while task i computes on r0.  Two things
+                // keep the loads a whole iteration ahead of their use (ncu, before: 2 x 11 % of all samples on the waits):
+                //   * they are issued before the warp barrier -- ptxas does not move loads across it, and left to itself
+                //     it sinks them to the end of the iteration (shorter live ranges under the 128-register cap);
+                //   * ptxas gives ALL of them the same scoreboard, a counter, so the first touch of the CURRENT records
+                //     waits for every load in flight.  The address of the new loads therefore depends (vacuously) on the
+                //     current record: the wait then comes before the loads are issued, when nothing is in flight.
+                //     (Unrolling by two with swapped register sets has the same scoreboard problem and its larger body
+                //     falls out of the 6 KB L0 instruction cache: no_instruction stalls 0.24 -> 0.81 per issue.)
+                FwdRec r0, r1;
+                auto prefetch = [&](FwdRec &r, int dd, int xbase, int big) {
                     const int x = xbase + lane;
-                    const int xx = min(x, lX + 1);
-                    npa = xpA[xx]; npb = xpB[xx]; npc = xpC[xx];
-                    if (MACH) npd = xpD[xx];
-                    nev = evp[min(max(dd - x, 0), lY)];
+                    const int xx = min(min(x, lX + 1), big);
+                    r.a = xpA[xx]; r.b = xpB[xx]; r.c = xpC[xx];
+                    if (MACH) r.d = xpD[xx];
+                    r.ev = evp[min(max(dd - x, 0), lY)];
                 };
-                prefetch(d, wlo + (c << 5));
-                for (;;) {
-                    keep_live(npa); keep_live(npb); keep_live(npc); keep_live(nev);
-                    if (MACH) keep_live(npd);
-                    const float4 pa = npa, pb = npb, pc = npc, pd = npd, ev = nev;
+                // one (diagonal, chunk) task; true when the sweep ends
+                int late = 0;        // bits of the last value a task computes
+                auto fstep = [&](const FwdRec &cur, FwdRec &nxt) -> bool {
+                    const float4 pa = cur.a, pb = cur.b, pc = cur.c, pd = cur.d, ev = cur.ev;
                     const bool last = c == 0;
                     int nd = d, nc = c - 1, nlo = lo, nhi = hi, nwlo = wlo;
                     bool stop = false;
@@ -277,10 +290,13 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                     {
                         const int x = wlo + (c << 5) + lane;
                         const int s = x & NM, sl = (x - 1) & NM;
+                        // inputs of the next task (harmless clamped addresses at the stop); "big" >= 2^30 never clamps.
+                        // It also makes pc.w (the k-mer index, otherwise read by the E-step only) a live register: ptxas
+                        // would re-use a dead one while the LDG.128 is in flight (write-after-write stall)
+                        prefetch(nxt, nd, nwlo + (max(nc, 0) << 5), (__float_as_int(pc.w) & 0x7fffffff) | 0x40000000);
                         const float4 own = A1[s], L = A1[sl], Mi = A2[sl];
                         const bool inb = x >= lo && x <= hi;
                         __syncwarp();
-                        prefetch(nd, nwlo + (max(nc, 0) << 5));      // inputs of the next task (harmless clamped addresses at the stop)
                         const float U = fmaxf(own.w, fmaxf(L.w, Mi.w));
                         // impl/stateMachine.c:1314-1333: transitions folded in code order, emission added once
                         // (vanilla: impl/stateMachine.c:1368-1409, the transitions are those of THIS column)
@@ -297,6 +313,7 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                         float co = inb ? U : -CP_BIG;
                         rebase(cM, cX, cY, co);
                         const float4 e = make_float4(cM, cX, cY, co);
+                        late = __float_as_int(co);
                         A2[s] = e;                                   // descending x: in place over the d-2 entry
                         if (inb) frow[s] = e;
                         __syncwarp();
@@ -304,7 +321,7 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                     if (last) {
                         { float4 *t = A1; A1 = A2; A2 = t; }
                         dcur = d;
-                        if (stop) { Dt = d; atEnd = d == D; break; }
+                        if (stop) { Dt = d; atEnd = d == D; return true; }
                         d = nd; lo = nlo; hi = nhi; wlo = nwlo;
                         if ((d & 15) == 0) {
                             // columns / events that enter the band during the next diagonals: first touch comes from
@@ -317,6 +334,16 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                         frow = rows + (long long) rowF * N;
                     }
                     c = nc;
+                    return false;
+                };
+                prefetch(r0, d, wlo + (c << 5), 0x40000000);
+                for (;;) {
+                    if (fstep(r0, r1)) break;
+                    r0 = r1;
+                    //   * pc.w has its last use early in the task, and ptxas then copies the freshly loaded value into
+                    //     its register right behind the load (and waits).  Its copy is therefore tied (one LOP3 instead
+                    //     of the MOV) to the last value the task computes: (late & 0) ^ w.
+                    r0.c.w = __int_as_float((late & A.zero) ^ __float_as_int(r1.c.w));
                 }
             }
 
@@ -392,18 +419,18 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                         if (HAS_SX) bY = LA(bY, gx1 + tSX);
                     };
                     // posterior of one cell + G = B + emission, re-based, back into the ring
-                    float4 npa, npb, npc, npdR, nF, nev;
-                    auto prefetchB = [&](int cc) {
+                    BwdRec q0, q1;
+                    auto prefetchB = [&](BwdRec &q, int cc, int big) {
                         const int x = wlo + (cc << 5) + lane;
-                        const int xx = min(x, lX + 1);
-                        npa = xpA[xx]; npb = xpB[xx]; npc = xpC[xx];
-                        if (MACH) npdR = xpD[min(x + 1, lX + 1)];
-                        nev = evp[min(max(d - x, 0), lY)];
-                        nF = NIENT;
-                        if (post && x >= blo && x <= bhi) nF = frow[x & NM];
+                        const int xx = min(min(x, lX + 1), big);
+                        q.a = xpA[xx]; q.b = xpB[xx]; q.c = xpC[xx];
+                        if (MACH) q.dR = xpD[min(min(x + 1, lX + 1), big)];
+                        q.ev = evp[min(max(d - x, 0), lY)];
+                        q.F = NIENT;
+                        if (post && x >= blo && x <= bhi) q.F = frow[x & NM];
                     };
                     auto cellPost = [&](int x, int s, bool inb, float bM, float bX, float bY, float U, const float4 pa,
-                                        const float4 pb, const float4 pc, const float4 ev, const float4 F) {
+                                        const float4 pb, const float4 pc, const float4 ev, const float4 F) -> int {
                         const float eM = emit(pa, pb, pc, ev, false), eY = emit(pa, pb, pc, ev, true);
                         const float eX = MACH ? 0.f : pc.z;
                         if (EXPECT) {
@@ -462,22 +489,24 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                         float gM = bM + eM, gX = bX + eX, gY = bY + eY, go = inb ? U : -CP_BIG;   // b is -inf outside the band
                         rebase(gM, gX, gY, go);
                         A2[s] = make_float4(gM, gX, gY, go);
+                        return __float_as_int(go);
                     };
 
                     if (!doTotal) {
-                        prefetchB(0);
+                        prefetchB(q0, 0, 0x40000000);
                         for (int c = 0; c < nch; c++) {                // ascending x: in-place update of the d+2 entries
                             const int x = wlo + (c << 5) + lane, s = x & NM;
                             const bool inb = x >= blo && x <= bhi;
-                            keep_live(npa); keep_live(npb); keep_live(npc); keep_live(nev); keep_live(nF);
-                            if (MACH) keep_live(npdR);
-                            const float4 pa = npa, pb = npb, pc = npc, pdR = npdR, F = nF, ev = nev;
-                            if (c + 1 < nch) prefetchB(c + 1);
+                            const float4 pa = q0.a, pb = q0.b, pc = q0.c, pdR = q0.dR, F = q0.F, ev = q0.ev;
+                            // register prefetch of the next chunk as in the forward sweep (after the last chunk: again this one)
+                            prefetchB(q1, min(c + 1, nch - 1), (__float_as_int(pc.w) & 0x7fffffff) | 0x40000000);
                             float bM, bX, bY, U;
                             cellB(x, s, inb, pdR, pc.z, bM, bX, bY, U);
                             __syncwarp();
-                            cellPost(x, s, inb, bM, bX, bY, U, pa, pb, pc, ev, F);
+                            const int late = cellPost(x, s, inb, bM, bX, bY, U, pa, pb, pc, ev, F);
                             __syncwarp();
+                            q0 = q1;
+                            q0.c.w = __int_as_float((late & A.zero) ^ __float_as_int(q1.c.w));
                         }
                     } else {
                         // ---- totalProbability (impl/pairwiseAligner.c:736-754), recomputed every 10th posterior diagonal
@@ -547,9 +576,9 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                             const int x = wlo + (c << 5) + lane, s = x & NM;
                             const bool inb = x >= blo && x <= bhi;
                             const float4 b = A2[s];
-                            prefetchB(c);
+                            prefetchB(q0, c, 0x40000000);
                             __syncwarp();
-                            cellPost(x, s, inb, b.x, b.y, b.z, b.w, npa, npb, npc, nev, nF);
+                            cellPost(x, s, inb, b.x, b.y, b.z, b.w, q0.a, q0.b, q0.c, q0.ev, q0.F);
                             __syncwarp();
                         }
                     }

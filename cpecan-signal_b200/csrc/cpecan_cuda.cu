@@ -485,6 +485,7 @@ int cpecan_cuda_run_staged_async(cpecan_ctx *ctx) {
         a.scratch_stride = bk.stride;
         a.ring_rows = bk.ringRows;
         a.ringN = cfg2N(b);
+        a.zero = 0;
         a.pairs = ctx->dPairs.as<int>();
         a.out = ctx->dOut.as<ItemOut>();
         a.totals = ctx->wantTotals ? ctx->dTotals.as<double>() : nullptr;

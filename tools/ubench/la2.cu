@@ -1,0 +1,34 @@
+#include <cuda_runtime.h>
+struct Args { float *out; const float *in; int n; unsigned long long lak[8]; };
+__device__ __forceinline__ float logadd2p(float x, float y, const Args &A) {
+    float r;
+    asm("{\n\t"
+        ".reg .pred p1, p2, p3, p5;\n\t"
+        ".reg .f32 d, a, a2, u, v;\n\t"
+        ".reg .b64 aa, uv;\n\t"
+        "sub.f32 d, %1, %2;\n\t"
+        "abs.f32 a, d;\n\t"
+        "max.f32 %0, %1, %2;\n\t"
+        "setp.le.f32 p3, a, 0f40900000;\n\t"
+        "setp.le.f32 p2, a, 0f40200000;\n\t"
+        "setp.le.f32 p1, a, 0f3F800000;\n\t"
+        "setp.lt.f32 p5, a, 0f40F00000;\n\t"
+        "mul.f32 a2, a, a;\n\t"
+        "mov.b64 aa, {a, a};\n\t"
+        "fma.rn.f32x2 uv, aa, %3, %4;\n\t"
+        "@p3 fma.rn.f32x2 uv, aa, %5, %6;\n\t"
+        "@p2 fma.rn.f32x2 uv, aa, %7, %8;\n\t"
+        "@p1 fma.rn.f32x2 uv, aa, %9, %10;\n\t"
+        "mov.b64 {u, v}, uv;\n\t"
+        "fma.rn.f32 u, u, a2, v;\n\t"
+        "@p5 add.f32 %0, %0, u;\n\t"
+        "}"
+        : "=f"(r) : "f"(x), "f"(y), "l"(A.lak[0]), "l"(A.lak[1]), "l"(A.lak[2]), "l"(A.lak[3]), "l"(A.lak[4]), "l"(A.lak[5]), "l"(A.lak[6]), "l"(A.lak[7]));
+    return r;
+}
+__global__ void k(const Args A) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float acc = A.in[i];
+    for (int j = 0; j < A.n; j++) acc = logadd2p(acc, A.in[i + j], A);
+    A.out[i] = acc;
+}
