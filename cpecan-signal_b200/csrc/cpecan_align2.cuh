@@ -373,6 +373,18 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                     const int plo = max(blo, 1), phi = min(bhi, d - 1);   // cells with x > 0 and y > 0 report posteriors
                     bool doTotal = false;
                     if (post) { doTotal = unbanded ? (d == Dt) : (count % P.totalEvery == 0); count++; }
+                    BwdRec q0, q1;
+                    auto prefetchB = [&](BwdRec &q, int cc, int big) {
+                        const int x = wlo + (cc << 5) + lane;
+                        const int xx = min(min(x, lX + 1), big);
+                        q.a = xpA[xx]; q.b = xpB[xx]; q.c = xpC[xx];
+                        if (MACH) q.dR = xpD[min(min(x + 1, lX + 1), big)];
+                        q.ev = evp[min(max(d - x, 0), lY)];
+                        q.F = NIENT;
+                        if (post && x >= blo && x <= bhi) q.F = frow[x & NM];
+                    };
+                    // the first chunk's records are requested here, ahead of the per-diagonal bookkeeping below
+                    if (!doTotal) prefetchB(q0, 0, 0x40000000);
                     if (d - 2 > tracedBackTo && d - 2 <= tracedBackFrom) {
                         // the forward cells of diagonal d-2 were written >= 1000 diagonals ago: DRAM -> L2 now
                         const int rowP = rowB >= 2 ? rowB - 2 : rowB - 2 + R;
@@ -419,16 +431,6 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                         if (HAS_SX) bY = LA(bY, gx1 + tSX);
                     };
                     // posterior of one cell + G = B + emission, re-based, back into the ring
-                    BwdRec q0, q1;
-                    auto prefetchB = [&](BwdRec &q, int cc, int big) {
-                        const int x = wlo + (cc << 5) + lane;
-                        const int xx = min(min(x, lX + 1), big);
-                        q.a = xpA[xx]; q.b = xpB[xx]; q.c = xpC[xx];
-                        if (MACH) q.dR = xpD[min(min(x + 1, lX + 1), big)];
-                        q.ev = evp[min(max(d - x, 0), lY)];
-                        q.F = NIENT;
-                        if (post && x >= blo && x <= bhi) q.F = frow[x & NM];
-                    };
                     auto cellPost = [&](int x, int s, bool inb, float bM, float bX, float bY, float U, const float4 pa,
                                         const float4 pb, const float4 pc, const float4 ev, const float4 F) -> int {
                         const float eM = emit(pa, pb, pc, ev, false), eY = emit(pa, pb, pc, ev, true);
@@ -493,7 +495,6 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                     };
 
                     if (!doTotal) {
-                        prefetchB(q0, 0, 0x40000000);
                         for (int c = 0; c < nch; c++) {                // ascending x: in-place update of the d+2 entries
                             const int x = wlo + (c << 5) + lane, s = x & NM;
                             const bool inb = x >= blo && x <= bhi;
