@@ -252,27 +252,39 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                 int wlo = max(lo - 1, 0) & ~7, c = (min(hi + 1, lX) - wlo) >> 5;     // 8-lane aligned: own LDS/STS.128 conflict free
                 rowF = rowF + 1 == R ? 0 : rowF + 1;
                 float4 *frow = rows + (long long) rowF * N;
-                // Register prefetch: the records of task i+1 are loaded into r1 while task i computes on r0.  Two things
-                // keep the loads a whole iteration ahead of their use (ncu, before: 2 x 11 % of all samples on the waits):
+                // Software pipeline over the tasks: the column records and the event of task i+1 are requested at the
+                // top of task i and consumed at its END, where they are reduced to the emissions (and, vanilla, the
+                // transitions) of task i+1 -- 3 to 8 values carried over instead of 14 to 22 record registers, and no
+                // register copies.  What keeps the loads a whole task ahead of their use:
                 //   * they are issued before the warp barrier -- ptxas does not move loads across it, and left to itself
                 //     it sinks them to the end of the iteration (shorter live ranges under the 128-register cap);
-                //   * ptxas gives ALL of them the same scoreboard, a counter, so the first touch of the CURRENT records
-                //     waits for every load in flight.  The address of the new loads therefore depends (vacuously) on the
-                //     current record: the wait then comes before the loads are issued, when nothing is in flight.
-                //     (Unrolling by two with swapped register sets has the same scoreboard problem and its larger body
-                //     falls out of the 6 KB L0 instruction cache: no_instruction stalls 0.24 -> 0.81 per issue.)
-                FwdRec r0, r1;
-                auto prefetch = [&](FwdRec &r, int dd, int xbase, int big) {
+                //   * nothing is in flight when they are issued (ptxas gives all of them the same scoreboard, a counter,
+                //     so a wait for an older load would wait for these too);
+                //   * every component of a record is read (a dead one -- the k-mer index, an E-step input -- is OR-ed
+                //     in under a mask only the host knows to be zero), else ptxas re-uses its register while the
+                //     LDG.128 is in flight and the write-after-write hazard waits out the load.
+                // (Tried and measured worse: register double buffering, 14 MOVs per task and ptxas places the copy of an
+                // early-dying component right behind the load; the same unrolled by two, whose body falls out of the
+                // instruction caches, no_instruction 0.24 -> 0.81 per issue; prefetch.global.L1 + late loads, -4 %.)
+                FwdRec r;
+                auto load = [&](int dd, int xbase) {
                     const int x = xbase + lane;
-                    const int xx = min(min(x, lX + 1), big);
+                    const int xx = min(x, lX + 1);
                     r.a = xpA[xx]; r.b = xpB[xx]; r.c = xpC[xx];
                     if (MACH) r.d = xpD[xx];
                     r.ev = evp[min(max(dd - x, 0), lY)];
                 };
+                struct { float eM, eY, eX, tOX, tEX, tMC, tMX, tOY; } E;
+                auto reduce = [&]() {
+                    E.eM = emit(r.a, r.b, r.c, r.ev, false); E.eY = emit(r.a, r.b, r.c, r.ev, true);
+                    const float cz = __int_as_float(__float_as_int(r.c.z) | (__float_as_int(r.c.w) & A.zero));
+                    E.eX = MACH ? 0.f : cz;
+                    // impl/stateMachine.c:1368-1409: the vanilla transitions are those of THIS column
+                    E.tOX = MACH ? r.d.x : gOX; E.tEX = MACH ? r.d.y : gEX; E.tMC = MACH ? r.d.z : gMC;
+                    E.tMX = MACH ? r.d.w : gMX; E.tOY = MACH ? cz : gOY;
+                };
                 // one (diagonal, chunk) task; true when the sweep ends
-                int late = 0;        // bits of the last value a task computes
-                auto fstep = [&](const FwdRec &cur, FwdRec &nxt) -> bool {
-                    const float4 pa = cur.a, pb = cur.b, pc = cur.c, pd = cur.d, ev = cur.ev;
+                auto fstep = [&]() -> bool {
                     const bool last = c == 0;
                     int nd = d, nc = c - 1, nlo = lo, nhi = hi, nwlo = wlo;
                     bool stop = false;
@@ -290,33 +302,25 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                     {
                         const int x = wlo + (c << 5) + lane;
                         const int s = x & NM, sl = (x - 1) & NM;
-                        // inputs of the next task (harmless clamped addresses at the stop); "big" >= 2^30 never clamps.
-                        // It also makes pc.w (the k-mer index, otherwise read by the E-step only) a live register: ptxas
-                        // would re-use a dead one while the LDG.128 is in flight (write-after-write stall)
-                        prefetch(nxt, nd, nwlo + (max(nc, 0) << 5), (__float_as_int(pc.w) & 0x7fffffff) | 0x40000000);
+                        load(nd, nwlo + (max(nc, 0) << 5));          // next task (harmless clamped addresses at the stop)
                         const float4 own = A1[s], L = A1[sl], Mi = A2[sl];
                         const bool inb = x >= lo && x <= hi;
                         __syncwarp();
                         const float U = fmaxf(own.w, fmaxf(L.w, Mi.w));
                         // impl/stateMachine.c:1314-1333: transitions folded in code order, emission added once
-                        // (vanilla: impl/stateMachine.c:1368-1409, the transitions are those of THIS column)
-                        const float tOX = MACH ? pd.x : gOX, tEX = MACH ? pd.y : gEX, tMC = MACH ? pd.z : gMC,
-                                    tMX = MACH ? pd.w : gMX, tOY = MACH ? pc.z : gOY;
-                        float tX = LA(L.x + tOX, L.y + tEX);
+                        float tX = LA(L.x + E.tOX, L.y + E.tEX);
                         if (HAS_SX) tX = LA(tX, L.z + tSX);
-                        float tM = LA(LA(Mi.x + tMC, Mi.y + tMX), Mi.z + tMY);
-                        float tY = LA(own.x + tOY, own.z + tEY);
-                        const float eM = emit(pa, pb, pc, ev, false), eY = emit(pa, pb, pc, ev, true);
-                        const float eX = MACH ? 0.f : pc.z;
+                        float tM = LA(LA(Mi.x + E.tMC, Mi.y + E.tMX), Mi.z + tMY);
+                        float tY = LA(own.x + E.tOY, own.z + tEY);
                         const float Um = inb ? U : CP_POS_INF;       // a cell outside the band comes out as -inf
-                        float cM = tM + (eM + (Mi.w - Um)), cX = tX + (eX + (L.w - Um)), cY = tY + (eY + (own.w - Um));
+                        float cM = tM + (E.eM + (Mi.w - Um)), cX = tX + (E.eX + (L.w - Um)), cY = tY + (E.eY + (own.w - Um));
                         float co = inb ? U : -CP_BIG;
                         rebase(cM, cX, cY, co);
                         const float4 e = make_float4(cM, cX, cY, co);
-                        late = __float_as_int(co);
                         A2[s] = e;                                   // descending x: in place over the d-2 entry
                         if (inb) frow[s] = e;
                         __syncwarp();
+                        reduce();
                     }
                     if (last) {
                         { float4 *t = A1; A1 = A2; A2 = t; }
@@ -336,15 +340,9 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                     c = nc;
                     return false;
                 };
-                prefetch(r0, d, wlo + (c << 5), 0x40000000);
-                for (;;) {
-                    if (fstep(r0, r1)) break;
-                    r0 = r1;
-                    //   * pc.w has its last use early in the task, and ptxas then copies the freshly loaded value into
-                    //     its register right behind the load (and waits).  Its copy is therefore tied (one LOP3 instead
-                    //     of the MOV) to the last value the task computes: (late & 0) ^ w.
-                    r0.c.w = __int_as_float((late & A.zero) ^ __float_as_int(r1.c.w));
-                }
+                load(d, wlo + (c << 5));
+                reduce();
+                while (!fstep()) { }
             }
 
             // =============================== traceback ===================================================
