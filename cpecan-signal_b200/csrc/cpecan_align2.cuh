@@ -371,18 +371,30 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                     const int plo = max(blo, 1), phi = min(bhi, d - 1);   // cells with x > 0 and y > 0 report posteriors
                     bool doTotal = false;
                     if (post) { doTotal = unbanded ? (d == Dt) : (count % P.totalEvery == 0); count++; }
-                    BwdRec q0, q1;
-                    auto prefetchB = [&](BwdRec &q, int cc, int big) {
+                    // The same software pipeline as in the forward sweep: the records of the next chunk are requested at
+                    // the top of a chunk and reduced at its end to what the cell needs (emissions, the forward cell's match
+                    // value and units, the k-mer index for the E-step, the vanilla transitions).
+                    BwdRec q;
+                    struct { float eM, eY, eX, Fx, Fw, tOX, tEX, tMC, tMX, myLog; int kw; } G;
+                    auto loadB = [&](int cc) {
                         const int x = wlo + (cc << 5) + lane;
-                        const int xx = min(min(x, lX + 1), big);
+                        const int xx = min(x, lX + 1);
                         q.a = xpA[xx]; q.b = xpB[xx]; q.c = xpC[xx];
-                        if (MACH) q.dR = xpD[min(min(x + 1, lX + 1), big)];
+                        if (MACH) q.dR = xpD[min(x + 1, lX + 1)];
                         q.ev = evp[min(max(d - x, 0), lY)];
                         q.F = NIENT;
                         if (post && x >= blo && x <= bhi) q.F = frow[x & NM];
                     };
+                    auto reduceB = [&]() {
+                        G.eM = emit(q.a, q.b, q.c, q.ev, false); G.eY = emit(q.a, q.b, q.c, q.ev, true);
+                        G.kw = __float_as_int(q.c.w);
+                        const float cz = EXPECT ? q.c.z : __int_as_float(__float_as_int(q.c.z) | (G.kw & A.zero));   // see the forward sweep
+                        G.eX = MACH ? 0.f : cz; G.myLog = cz;
+                        G.tOX = MACH ? q.dR.x : 0.f; G.tEX = MACH ? q.dR.y : 0.f; G.tMC = MACH ? q.dR.z : 0.f; G.tMX = MACH ? q.dR.w : 0.f;
+                        G.Fx = q.F.x; G.Fw = q.F.w;
+                    };
                     // the first chunk's records are requested here, ahead of the per-diagonal bookkeeping below
-                    if (!doTotal) prefetchB(q0, 0, 0x40000000);
+                    if (!doTotal) loadB(0);
                     if (d - 2 > tracedBackTo && d - 2 <= tracedBackFrom) {
                         // the forward cells of diagonal d-2 were written >= 1000 diagonals ago: DRAM -> L2 now
                         const int rowP = rowB >= 2 ? rowB - 2 : rowB - 2 + R;
@@ -429,10 +441,8 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                         if (HAS_SX) bY = LA(bY, gx1 + tSX);
                     };
                     // posterior of one cell + G = B + emission, re-based, back into the ring
-                    auto cellPost = [&](int x, int s, bool inb, float bM, float bX, float bY, float U, const float4 pa,
-                                        const float4 pb, const float4 pc, const float4 ev, const float4 F) -> int {
-                        const float eM = emit(pa, pb, pc, ev, false), eY = emit(pa, pb, pc, ev, true);
-                        const float eX = MACH ? 0.f : pc.z;
+                    auto cellPost = [&](int x, int s, bool inb, float bM, float bX, float bY, float U, float eM, float eY,
+                                        float eX, float Fx, float Fw, float myLog, int kw) {
                         if (EXPECT) {
                             if (post) {
                                 // diagonalCalculation_Expectations (impl/pairwiseAligner.c:841-863): for every transition
@@ -446,12 +456,12 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                                 float4 pdo = NIENT;
                                 if (MACH) pdo = xpD[min(x, lX + 1)];
                                 const float tOX = MACH ? pdo.x : gOX, tEX = MACH ? pdo.y : gEX, tMC = MACH ? pdo.z : gMC,
-                                            tMX = MACH ? pdo.w : gMX, tOY = MACH ? pc.z : gOY;
+                                            tMX = MACH ? pdo.w : gMX, tOY = MACH ? myLog : gOY;
                                 const float kX = (bX + eX) + (((FL.w + U) - totBase) - totSt);
                                 const float pMX = __expf(FL.x + tOX + kX), pXX = __expf(FL.y + tEX + kX);
                                 if (MACH) {
                                     // cell_signal_updateBetaAndAlphaProb (impl/pairwiseAligner.c:478-498): skip bins only
-                                    const int bin = __float_as_int(pc.w);
+                                    const int bin = kw;
                                     if (bin >= 0) {
                                         if (pMX > 1e-13f) atomicAdd(A.expect + bin, (double) pMX);
                                         if (pXX > 1e-13f) atomicAdd(A.expect + 30 + bin, (double) pXX);
@@ -464,14 +474,14 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                                     aT[0] += __expf(FM.x + tMC + kM); aT[3] += __expf(FM.y + tMX + kM); aT[6] += __expf(FM.z + tMY + kM);
                                     aT[2] += __expf(FU.x + tOY + kY); aT[8] += __expf(FU.z + tEY + kY);
                                     const float pk = pMX + pXX + pYX;
-                                    const int kmer = __float_as_int(pc.w);
+                                    const int kmer = kw;
                                     if (pk > 1e-13f && kmer >= 0) atomicAdd(A.expect + 9 + kmer, (double) pk);
                                 }
                             }
                         } else
                         if (post) {
                             // impl/pairwiseAligner.c:768-793; exp only for the cells that can reach the threshold
-                            const float lp = (F.x + bM) + (((F.w + U) - totBase) - totSt);
+                            const float lp = (Fx + bM) + (((Fw + U) - totBase) - totSt);
                             bool ok = x >= plo && x <= phi && lp >= logThrLo;
                             float p = 0.f;
                             if (ok) { p = __expf(lp); ok = p >= P.threshold; }
@@ -489,23 +499,21 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                         float gM = bM + eM, gX = bX + eX, gY = bY + eY, go = inb ? U : -CP_BIG;   // b is -inf outside the band
                         rebase(gM, gX, gY, go);
                         A2[s] = make_float4(gM, gX, gY, go);
-                        return __float_as_int(go);
                     };
 
                     if (!doTotal) {
+                        reduceB();
                         for (int c = 0; c < nch; c++) {                // ascending x: in-place update of the d+2 entries
                             const int x = wlo + (c << 5) + lane, s = x & NM;
                             const bool inb = x >= blo && x <= bhi;
-                            const float4 pa = q0.a, pb = q0.b, pc = q0.c, pdR = q0.dR, F = q0.F, ev = q0.ev;
-                            // register prefetch of the next chunk as in the forward sweep (after the last chunk: again this one)
-                            prefetchB(q1, min(c + 1, nch - 1), (__float_as_int(pc.w) & 0x7fffffff) | 0x40000000);
+                            const auto cur = G;
+                            loadB(min(c + 1, nch - 1));                // the next chunk (after the last one: again this one)
                             float bM, bX, bY, U;
-                            cellB(x, s, inb, pdR, pc.z, bM, bX, bY, U);
+                            cellB(x, s, inb, make_float4(cur.tOX, cur.tEX, cur.tMC, cur.tMX), cur.myLog, bM, bX, bY, U);
                             __syncwarp();
-                            const int late = cellPost(x, s, inb, bM, bX, bY, U, pa, pb, pc, ev, F);
+                            cellPost(x, s, inb, bM, bX, bY, U, cur.eM, cur.eY, cur.eX, cur.Fx, cur.Fw, cur.myLog, cur.kw);
                             __syncwarp();
-                            q0 = q1;
-                            q0.c.w = __int_as_float((late & A.zero) ^ __float_as_int(q1.c.w));
+                            reduceB();
                         }
                     } else {
                         // ---- totalProbability (impl/pairwiseAligner.c:736-754), recomputed every 10th posterior diagonal
@@ -575,9 +583,10 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                             const int x = wlo + (c << 5) + lane, s = x & NM;
                             const bool inb = x >= blo && x <= bhi;
                             const float4 b = A2[s];
-                            prefetchB(q0, c, 0x40000000);
+                            loadB(c);
+                            reduceB();
                             __syncwarp();
-                            cellPost(x, s, inb, b.x, b.y, b.z, b.w, q0.a, q0.b, q0.c, q0.ev, q0.F);
+                            cellPost(x, s, inb, b.x, b.y, b.z, b.w, G.eM, G.eY, G.eX, G.Fx, G.Fw, G.myLog, G.kw);
                             __syncwarp();
                         }
                     }
