@@ -47,7 +47,7 @@ __device__ __forceinline__ LaCoef la_coef() {
 
 // max(x, y) + q(|x - y|) for |x - y| < 7.5, else max(x, y); q = the reference's cubic segment minus the identity,
 // evaluated as (a t + b) t^2 + ((c - 1) t + d).  NaN (both -inf) and +inf differences fall through to max.
-__device__ __forceinline__ float logadd2(float x, float y, const LaCoef &k) {
+__device__ __forceinline__ float logadd2p(float x, float y, const LaCoef &k) {
     float r;
     asm("{\n\t"
         ".reg .pred p1, p2, p3, p5;\n\t"
@@ -72,6 +72,53 @@ __device__ __forceinline__ float logadd2(float x, float y, const LaCoef &k) {
         "@p5 add.f32 %0, %0, u;\n\t"
         "}"
         : "=f"(r) : "f"(x), "f"(y), "f"(k.a4), "f"(k.c4), "f"(k.a3), "f"(k.c3), "f"(k.a2), "f"(k.c2), "f"(k.a1), "f"(k.c1));
+    return r;
+}
+
+// logAdd coefficient table in shared memory: entry i serves |x - y| in ((i - 1) / 2, i / 2] -- the reference's segment
+// bounds 1, 2.5, 4.5 and the cut-off 7.5 are all multiples of 1/2 and closed on the right, as ceil(2 |x - y|) is.
+// An entry holds (a, b, c - 1, d) of the segment's cubic a t^3 + b t^2 + c t + d; entry 16 (beyond the cut-off) is zero.
+#define CP_LAT_ENTRIES 17
+#define CP_LAT_BYTES 288
+__device__ __forceinline__ void la_table_init(float4 *tbl, int lane) {
+    if (lane < CP_LAT_ENTRIES) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lane <= 2) v = make_float4(__int_as_float(0xBC19343D), __int_as_float(0x3E05CB9C), __int_as_float(0xBF004EA8), __int_as_float(0x3F3175C2));
+        else if (lane <= 5) v = make_float4(__int_as_float(0xBC6E18FA), __int_as_float(0x3E0F4D0A), __int_as_float(0xBF011E08), __int_as_float(0x3F313020));
+        else if (lane <= 9) v = make_float4(__int_as_float(0xBB96E5CE), __int_as_float(0x3D81E63C), __int_as_float(0xBE9BAB98), __int_as_float(0x3F03A75F));
+        else if (lane <= 15) v = make_float4(__int_as_float(0xB9F07885), __int_as_float(0x3C1EDBBF), __int_as_float(0xBD8DDAF8), __int_as_float(0x3E2C11EF));
+        tbl[lane] = v;
+    }
+}
+
+// max(x, y) + q(|x - y|) for |x - y| < 7.5, else max(x, y); q = the reference's cubic segment (impl/pairwiseAligner.c:
+// 235-255) minus the identity, evaluated as (a t + b) t^2 + ((c - 1) t + d) with the segment's coefficients fetched by
+// one LDS.128 (13 instructions; selecting them with predicated immediate FFMAs took 19, with a tree of selects more).
+// NaN (both -inf) and +inf differences fall through to max: cvt gives 0 / INT_MAX for them and the add is predicated.
+__device__ __forceinline__ float logadd2(float x, float y, unsigned tbl) {
+    float r;
+    asm("{\n\t"
+        ".reg .pred p5;\n\t"
+        ".reg .f32 d, a, a2, t, c3, c2, c1, c0, u, v;\n\t"
+        ".reg .s32 i;\n\t"
+        ".reg .u32 ad;\n\t"
+        "sub.f32 d, %1, %2;\n\t"
+        "abs.f32 a, d;\n\t"
+        "max.f32 %0, %1, %2;\n\t"
+        "setp.lt.f32 p5, a, 0f40F00000;\n\t"            // 7.5
+        "add.f32 t, a, a;\n\t"
+        "cvt.rpi.s32.f32 i, t;\n\t"
+        "min.s32 i, i, 16;\n\t"
+        "shl.b32 ad, i, 4;\n\t"
+        "add.u32 ad, ad, %3;\n\t"
+        "ld.shared.v4.f32 {c3, c2, c1, c0}, [ad];\n\t"
+        "mul.f32 a2, a, a;\n\t"
+        "fma.rn.f32 u, a, c3, c2;\n\t"
+        "fma.rn.f32 v, a, c1, c0;\n\t"
+        "fma.rn.f32 u, u, a2, v;\n\t"
+        "@p5 add.f32 %0, %0, u;\n\t"
+        "}"
+        : "=f"(r) : "f"(x), "f"(y), "r"(tbl));
     return r;
 }
 
@@ -107,7 +154,7 @@ struct KernelArgs2 {
     DevParams P;
 };
 
-__host__ __device__ inline size_t align2_smem_bytes(int ringN) { return (size_t) ringN * (2 * 16); }
+__host__ __device__ inline size_t align2_smem_bytes(int ringN) { return (size_t) ringN * (2 * 16) + CP_LAT_BYTES; }
 
 // Left fold  acc = logadd(acc, v[0]), logadd(acc, v[1]), ...  in ascending x (the order of dpDiagonal_dotProduct,
 // impl/pairwiseAligner.c:587-597) over ring-positioned values: element i lives at (start + i) & (N - 1).
@@ -116,7 +163,7 @@ __host__ __device__ inline size_t align2_smem_bytes(int ringN) { return (size_t)
 //   * an element at least 7.5 + 12 above the prefix maximum RESETS the fold: acc <= prefix maximum + ln(count) +
 //     count * 6e-4 (the cubic over-estimates by at most 5.5e-4 per step) < prefix maximum + 12 for count <= 4096, so
 //     logadd returns the element itself and everything before it is forgotten.
-__device__ __forceinline__ float warp_ordered_fold_ring(const float *buf, int start, int w, int NM, const LaCoef &k) {
+__device__ __forceinline__ float warp_ordered_fold_ring(const float *buf, int start, int w, int NM, unsigned k) {
     const int lane = threadIdx.x & 31;
     float acc = CP_NEG_INF, runmax = CP_NEG_INF;
     for (int base = 0; base < w; base += 32) {
@@ -172,8 +219,13 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
     float *sm_c1 = reinterpret_cast<float *>(rows + (long long) R * N);
     float *sm_us = sm_c1 + N;
     const float4 NIENT = make_float4(NI, NI, NI, -CP_BIG);
-    const LaCoef K = la_coef();
+    // logAdd coefficient table behind the ring
+    la_table_init(ring + 2 * N, threadIdx.x);
+    __syncwarp();
+    const unsigned K = (unsigned) __cvta_generic_to_shared(ring + 2 * N);
 #define LA(a, b) logadd2((a), (b), K)
+    const LaCoef KP = la_coef();
+#define LAP(a, b) logadd2p((a), (b), KP)
     // three-state: global transitions; vanilla: M->X, X->X, M->M, X->M, M->Y come from the column records
     const float gMC = P.tMC, gMX = P.tMX, gOX = P.tOX, gOY = P.tOY, gEX = P.tEX, tSX = P.tSX;
     const float tMY = MACH ? P.vYM : P.tMY, tEY = MACH ? P.vYY : P.tEY;
@@ -310,7 +362,7 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                         // impl/stateMachine.c:1314-1333: transitions folded in code order, emission added once
                         float tX = LA(L.x + E.tOX, L.y + E.tEX);
                         if (HAS_SX) tX = LA(tX, L.z + tSX);
-                        float tM = LA(LA(Mi.x + E.tMC, Mi.y + E.tMX), Mi.z + tMY);
+                        float tM = LAP(LAP(Mi.x + E.tMC, Mi.y + E.tMX), Mi.z + tMY);
                         float tY = LA(own.x + E.tOY, own.z + tEY);
                         const float Um = inb ? U : CP_POS_INF;       // a cell outside the band comes out as -inf
                         float cM = tM + (E.eM + (Mi.w - Um)), cX = tX + (E.eX + (L.w - Um)), cY = tY + (E.eY + (own.w - Um));
@@ -435,7 +487,7 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                         U = fmaxf(own.w, fmaxf(R1.w, R2.w));
                         const float Um = inb ? U : CP_POS_INF;
                         const float gm2 = R2.x + (R2.w - Um), gx1 = R1.y + (R1.w - Um), gy1 = own.z + (own.w - Um);
-                        bM = LA(LA(gm2 + tMC, gy1 + tOY), gx1 + tOX);
+                        bM = LAP(LAP(gm2 + tMC, gy1 + tOY), gx1 + tOX);
                         bX = LA(gm2 + tMX, gx1 + tEX);
                         bY = LA(gm2 + tMY, gy1 + tEY);
                         if (HAS_SX) bY = LA(bY, gx1 + tSX);
