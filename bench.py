@@ -381,7 +381,7 @@ def main():
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
-    launches = l1 - l0
+    launches = sum_over_ranks(float(l1 - l0))            # whole job, like value
     wall = max_over_ranks(wall)
     kern_ms_max = max_over_ranks(kern_ms)
     cells_total = sum_over_ranks(float(cells_rank))
@@ -421,6 +421,7 @@ def main():
     barrier()
     e2e_wall = max_over_ranks(time.perf_counter() - t0)
     e2e_gcups = 2.0 * cells_total * args.steps / e2e_wall / 1e9
+    h2d, d2h, e2e_launches = sum_over_ranks(float(h2d)), sum_over_ranks(float(d2h)), sum_over_ranks(float(e2e_launches))   # whole job
     pool.shutdown()
 
     if rank != 0:
