@@ -279,8 +279,13 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--reads-per-gpu", type=int, default=24576)
+    ap.add_argument("--reads-per-gpu", type=int, default=99999,
+                    help="reads per GPU and step; the default is BASELINE config 3's 100k-read batch (divisible by the 3 expansions)")
+    ap.add_argument("--unique-reads", type=int, default=12288,
+                    help="distinct synthetic reads generated per rank (2.7 ms of host time each); the batch tiles them, every "
+                         "copy with its own host and device buffers")
     ap.add_argument("--impl", default="b200")
+    ap.add_argument("--pairs-per-event", type=float, default=2.0, help="capacity of the aligned-pair buffers (the batch yields ~1.1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="posterior", choices=["posterior", "em"],
                     help="posterior = BASELINE config 3/4 (default, the headline); em = config 5, one Baum-Welch "
@@ -307,7 +312,9 @@ def main():
     from cpecan_signal.engine import RESULT_DTYPE
 
     B = args.reads_per_gpu - args.reads_per_gpu % 3
-    reads = generate_reads(B, rank * 1_000_000, procs=max(1, min(32, (os.cpu_count() or 1) // max(1, world))))
+    n_unique = min(B, max(3, args.unique_reads - args.unique_reads % 3))
+    reads = generate_reads(n_unique, rank * 1_000_000, procs=max(1, min(32, (os.cpu_count() or 1) // max(1, world))))
+    reads = [reads[i % n_unique] for i in range(B)]          # n_unique is a multiple of 3: a read keeps its expansion
     engines, batches, outs = [], [], []
     l1 = l3 = None
     from cpecan_signal import synth
@@ -321,10 +328,12 @@ def main():
         hb = HostBatch([r.ref for r in sub], [r.events for r in sub], [r.anchors for r in sub],
                        model_ids=[mid] * len(sub), scales=[r.scale5 for r in sub], ragged=[(1, 1)] * len(sub))
         eng.pin_batch(hb)
-        cap = eng.default_pair_capacity(hb, per_event=2)      # ~1.1 aligned pairs per event at threshold 0.01
+        cap = eng.default_pair_capacity(hb, per_event=args.pairs_per_event)      # ~1.1 aligned pairs per event at threshold 0.01
         outs.append((eng.pinned_empty(hb.n, RESULT_DTYPE), eng.pinned_empty((cap, 3), np.int32)))
         engines.append(eng); batches.append(hb)
     params = [default_params(diagonalExpansion=EXPANSIONS[j]) for j in order]
+    _free, _tot = torch.cuda.mem_get_info()
+    print("rank %d: %d reads (%d distinct) pinned; device memory before staging: %.1f of %.1f GB free" % (rank, B, n_unique, _free / 1e9, _tot / 1e9), file=sys.stderr, flush=True)
     # host memory: at 8 ranks per box keep only the pinned batches and the small sample the CPU baseline needs
     n_keep = max(3, min(3 * (os.cpu_count() or 1), 192, B))
     n_keep -= n_keep % 3
@@ -356,6 +365,8 @@ def main():
     for eng, hb, p, o in zip(engines, batches, params, outs):
         eng.stage(hb, params=p, pair_cap=len(o[1]))
     cells_rank = sum(eng.timing()["band_cells"] for eng in engines)
+    _free, _tot = torch.cuda.mem_get_info()
+    print("rank %d: batch staged; device memory: %.1f of %.1f GB free" % (rank, _free / 1e9, _tot / 1e9), file=sys.stderr, flush=True)
     def resident_step():
         """One pass of the hot path over the whole resident batch: the three expansions' kernels are enqueued
         together (each context has its own streams) so that the GPU stays full through their tails."""
@@ -451,7 +462,7 @@ def main():
         "reads_per_s": reads_total * args.steps / wall, "band_cells_per_s": cells_total * args.steps / wall,
         "config": {"workload": "C3: batched synthetic reads lX~6700 x lY~8000 events, 6-mer template model, anchors "
                                "every 50 k-mers, expansions 64/128/256 evenly, three-state, threshold 0.01, ragged (1,1)",
-                   "reads_per_gpu": B, "reads_total": int(reads_total), "band_cells_per_step": int(cells_total),
+                   "reads_per_gpu": B, "distinct_reads_per_gpu": n_unique, "reads_total": int(reads_total), "band_cells_per_step": int(cells_total),
                    "aligned_pairs_rank0": n_pairs, "sharding": "reads partitioned over ranks, no collective",
                    "l2": "inputs + forward spill per step >> 126 MB L2 (no flush needed)"},
         "e2e": {"value": e2e_gcups, "unit": "GCUPS", "h2d_bytes_per_step": int(h2d / args.steps),

@@ -245,9 +245,9 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
         const int itemIdx = A.order[qi];
         const Item it = A.items[itemIdx];
         const int lX = it.lX, lY = it.lY, D = lX + lY;
-        // the four planes (a, b, c, d) of the column records, each lX + 2 float4 long: neighbouring lanes read
+        // the planes (a, b, c and, vanilla, d) of the column records, each lX + 2 float4 long: neighbouring lanes read
         // neighbouring 16-byte records, so a warp's LDG.128 touches 4-5 cache lines instead of 16
-        const float4 *xpA = A.xparams + 4 * it.xp_off, *xpB = xpA + (lX + 2), *xpC = xpB + (lX + 2), *xpD = xpC + (lX + 2);
+        const float4 *xpA = A.xparams + (MACH ? 4 : 3) * it.xp_off, *xpB = xpA + (lX + 2), *xpC = xpB + (lX + 2), *xpD = xpC + (lX + 2);
         const float4 *evp = A.events + it.ev_off;
         int *pairs = A.pairs + 3 * it.pair_off;
         double *dbgTot = (A.totals != nullptr && it.tot_off >= 0) ? A.totals + it.tot_off : nullptr;

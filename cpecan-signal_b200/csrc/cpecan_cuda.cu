@@ -31,7 +31,7 @@ struct DevBuf {
         if (bytes <= cap) return cudaSuccess;
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
-        size_t want = bytes + bytes / 8 + 256;
+        size_t want = bytes + std::min<size_t>(bytes / 8, (size_t) 64 << 20) + 256;   // growth slack, bounded: the big buffers are tens of GB
         cudaError_t e = cudaMalloc(&p, want);
         if (e == cudaSuccess) cap = want;
         return e;
@@ -357,7 +357,7 @@ int cpecan_cuda_stage(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_param
     CK(ctx->dEvSrcOff.ensure((n + 1) * sizeof(long long)));
     CK(ctx->dAnchors.ensure(std::max<int64_t>(1, nAn) * 2 * sizeof(long long)));
     CK(ctx->dCentre.ensure(n * sizeof(double)));
-    CK(ctx->dXp.ensure(xpTot * 4 * sizeof(float4)));
+    CK(ctx->dXp.ensure(xpTot * (ctx->machine ? 4 : 3) * sizeof(float4)));
     CK(ctx->dEv.ensure(evTot * sizeof(float4)));
     CK(ctx->dPairs.ensure(std::max<long long>(1, pairTot) * 3 * sizeof(int)));
     CK(cudaMemcpyAsync(ctx->dItems.p, ctx->hItems.data(), n * sizeof(Item), cudaMemcpyHostToDevice, s));
@@ -548,12 +548,16 @@ int cpecan_cuda_fetch_staged(cpecan_ctx *ctx, int32_t *pairs_out, cpecan_result 
     ctx->timing.d2h_bytes = n * (int64_t) sizeof(ItemOut);
     if (pairs_out && dst[n] > 0) {
         CK(ctx->dCompactOff.ensure((n + 1) * sizeof(long long)));
-        CK(ctx->dCompact.ensure(dst[n] * 3 * sizeof(int)));
+        // the packed copy goes into the raw-event staging buffer when it fits: that one is dead once the batch is
+        // prepared (24 B per event against ~13 B of aligned pairs), and a 100k-read batch has no 10 GB to spare
+        const size_t packedBytes = (size_t) dst[n] * 3 * sizeof(int);
+        int *packed = ctx->dEvSrc.as<int>();
+        if (packedBytes > ctx->dEvSrc.cap) { CK(ctx->dCompact.ensure(packedBytes)); packed = ctx->dCompact.as<int>(); }
         CK(cudaMemcpyAsync(ctx->dCompactOff.p, dst.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, s));
         k_compact<<<(unsigned) n, 128, 0, s>>>(ctx->dItems.as<Item>(), ctx->dOut.as<ItemOut>(), ctx->dCompactOff.as<long long>(), (int) n,
-                                              ctx->dPairs.as<int>(), ctx->dCompact.as<int>());
+                                              ctx->dPairs.as<int>(), packed);
         ctx->timing.kernel_launches += 1;
-        CK(cudaMemcpyAsync(pairs_out, ctx->dCompact.p, dst[n] * 3 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(pairs_out, packed, packedBytes, cudaMemcpyDeviceToHost, s));
         ctx->timing.d2h_bytes += dst[n] * 12;
     }
     CK(cudaEventRecord(ctx->ev[7], s));

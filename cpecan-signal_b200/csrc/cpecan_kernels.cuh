@@ -192,7 +192,7 @@ __global__ void k_prep_xparams(const Item *items, const long long *ref_off, cons
     double sc = 1, sh = 0, var = 1, scsd = 1, varsd = 1;
     const bool scaled = scale != nullptr;
     if (scaled) { sc = scale[5 * i]; sh = scale[5 * i + 1]; var = scale[5 * i + 2]; scsd = scale[5 * i + 3]; varsd = scale[5 * i + 4]; }
-    float4 *dst = out + 4 * it.xp_off;
+    float4 *dst = out + (machine ? 4 : 3) * it.xp_off;      // the fourth plane (per-column transitions) is the vanilla machine's
     const float ninf = CP_NEG_INF;
     const double HL2PI = 0.91893853320467267;
     for (int x = blockIdx.y * blockDim.x + threadIdx.x; x <= it.lX + 1; x += gridDim.y * blockDim.x) {
@@ -246,8 +246,9 @@ __global__ void k_prep_xparams(const Item *items, const long long *ref_off, cons
             c.z = (float) log(a_my);
             c.w = __int_as_float((int) bin);
         }
-        const int plane = it.lX + 2;          // four planes per item: lanes of a warp read neighbouring records of one plane
-        dst[x] = a; dst[plane + x] = b; dst[2 * plane + x] = c; dst[3 * plane + x] = d;
+        const int plane = it.lX + 2;          // planes per item: lanes of a warp read neighbouring records of one plane
+        dst[x] = a; dst[plane + x] = b; dst[2 * plane + x] = c;
+        if (machine) dst[3 * plane + x] = d;
     }
 }
 
