@@ -163,12 +163,15 @@ __host__ __device__ inline size_t align2_smem_bytes(int ringN) { return (size_t)
 //   * an element at least 7.5 + 12 above the prefix maximum RESETS the fold: acc <= prefix maximum + ln(count) +
 //     count * 6e-4 (the cubic over-estimates by at most 5.5e-4 per step) < prefix maximum + 12 for count <= 4096, so
 //     logadd returns the element itself and everything before it is forgotten.
-__device__ __forceinline__ float warp_ordered_fold_ring(const float *buf, int start, int w, int NM, unsigned k) {
+// With us != nullptr element i is buf[i] + (us[i] - fbase): the terms are stored in their own units and brought to the
+// common base here.
+__device__ __forceinline__ float warp_ordered_fold_ring(const float *buf, const float *us, float fbase, int start, int w, int NM, unsigned k) {
     const int lane = threadIdx.x & 31;
     float acc = CP_NEG_INF, runmax = CP_NEG_INF;
     for (int base = 0; base < w; base += 32) {
         const int idx = base + lane;
-        const float v = idx < w ? buf[(start + idx) & NM] : CP_NEG_INF;
+        float v = CP_NEG_INF;
+        if (idx < w) { const int p = (start + idx) & NM; v = buf[p]; if (us != nullptr) v = v + (us[p] - fbase); }
         float m = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { float t = __shfl_up_sync(CP_FULL, m, o); if (lane >= o) m = fmaxf(m, t); }
@@ -571,9 +574,12 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                         // ---- totalProbability (impl/pairwiseAligner.c:736-754), recomputed every 10th posterior diagonal
                         // pass 1: B into the ring (units in .w), dot-product terms and their units aside
                         int lmax = CP_INT_MIN;
+                        float4 Fn = frow[(wlo + lane) & NM];           // forward cell of chunk 0 (used inside the band only)
                         for (int c = 0; c < nch; c++) {
                             const int x = wlo + (c << 5) + lane, s = x & NM;
                             const bool inb = x >= blo && x <= bhi;
+                            const float4 F = Fn;
+                            Fn = frow[(x + (c + 1 < nch ? 32 : 0)) & NM];                  // next chunk's, a chunk ahead of its use
                             float bM, bX, bY, U;
                             float4 pdR = NIENT;
                             float myLog = 0.f;
@@ -582,7 +588,6 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                             __syncwarp();
                             A2[s] = make_float4(bM, bX, bY, inb ? U : -CP_BIG);
                             if (inb) {
-                                const float4 F = frow[s];
                                 const float c1 = LA(LA(F.x + bM, F.y + bX), F.z + bY);
                                 const float us = F.w + U;
                                 sm_c1[s] = c1; sm_us[s] = us;
@@ -590,11 +595,10 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                             }
                             __syncwarp();
                         }
+                        loadB(0);                                      // pass 2's first chunk: in flight during the folds
                         const int base = __reduce_max_sync(CP_FULL, lmax);
                         const float fbase = base == CP_INT_MIN ? 0.f : (float) base;
-                        for (int x = blo + lane; x <= bhi; x += 32) { const int s = x & NM; sm_c1[s] = sm_c1[s] + (sm_us[s] - fbase); }
-                        __syncwarp();
-                        const float t1 = warp_ordered_fold_ring(sm_c1, blo & NM, bhi - blo + 1, NM, K);
+                        const float t1 = warp_ordered_fold_ring(sm_c1, sm_us, fbase, blo & NM, bhi - blo + 1, NM, K);
                         float tot = t1, t2v = NI;
                         if (d < Dt && base != CP_INT_MIN) {
                             // term 2: matches jumping over diagonal d = a match-only forward step from F[d-1] into the
@@ -606,10 +610,12 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                             const int rowM = rowB == 0 ? R - 1 : rowB - 1;
                             const float4 *fprev = rows + (long long) rowM * N;
                             __syncwarp();
+                            float4 Fp = fprev[(l1 + lane - 1) & NM];
                             for (int x = l1 + lane; x <= h1; x += 32) {
                                 float val = NI;
+                                const float4 F = Fp;
+                                Fp = fprev[(x + 31) & NM];             // the next round's, a round ahead of its use
                                 if (x - 1 >= lm1 && x - 1 <= hm1) {
-                                    const float4 F = fprev[(x - 1) & NM];
                                     const float4 Gn = A1[x & NM];
                                     float4 pdx = NIENT;
                                     if (MACH) pdx = xpD[min(x, lX + 1)];
@@ -619,7 +625,7 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                                 sm_c1[x & NM] = val;
                             }
                             __syncwarp();
-                            t2v = warp_ordered_fold_ring(sm_c1, l1 & NM, h1 - l1 + 1, NM, K);
+                            t2v = warp_ordered_fold_ring(sm_c1, nullptr, 0.f, l1 & NM, h1 - l1 + 1, NM, K);
                             tot = LA(t1, t2v);
                         }
                         totSt = tot;
@@ -631,15 +637,17 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                         }
                         __syncwarp();
                         // pass 2: posteriors and G from the parked B
+                        reduceB();
                         for (int c = 0; c < nch; c++) {
                             const int x = wlo + (c << 5) + lane, s = x & NM;
                             const bool inb = x >= blo && x <= bhi;
                             const float4 b = A2[s];
-                            loadB(c);
+                            const auto cur = G;
+                            loadB(min(c + 1, nch - 1));
+                            __syncwarp();
+                            cellPost(x, s, inb, b.x, b.y, b.z, b.w, cur.eM, cur.eY, cur.eX, cur.Fx, cur.Fw, cur.myLog, cur.kw);
+                            __syncwarp();
                             reduceB();
-                            __syncwarp();
-                            cellPost(x, s, inb, b.x, b.y, b.z, b.w, G.eM, G.eY, G.eX, G.Fx, G.Fw, G.myLog, G.kw);
-                            __syncwarp();
                         }
                     }
                     if (post) {
