@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
             const float *endv = (atEnd && (it.flags & 2)) ? P.rendv : P.endv;
             const float endM = endv[0], endX = endv[1], endY = endv[2];
             float totSt = NI, totBase = 0.f;
-            int count = 0;
+            int tillTotal = 0;
             {
                 int rowB = Dt % R;
                 for (int d = Dt; d > tracedBackTo; d--) {
@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                     const int wlo = max(blo - 1, 0) & ~7, nch = ((min(bhi + 1, lX) - wlo) >> 5) + 1;
                     const int plo = max(blo, 1), phi = min(bhi, d - 1);   // cells with x > 0 and y > 0 report posteriors
                     bool doTotal = false;
-                    if (post) { doTotal = unbanded ? (d == Dt) : (count % P.totalEvery == 0); count++; }
+                    if (post) { doTotal = unbanded ? (d == Dt) : (tillTotal == 0); tillTotal = tillTotal == 0 ? P.totalEvery - 1 : tillTotal - 1; }   // every totalEvery-th posterior diagonal, from the first
                     // The same software pipeline as in the forward sweep: the records of the next chunk are requested at
                     // the top of a chunk and reduced at its end to what the cell needs (emissions, the forward cell's match
                     // value and units, the k-mer index for the E-step, the vanilla transitions).
@@ -454,7 +454,9 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                         // the forward cells of diagonal d-2 were written >= 1000 diagonals ago: DRAM -> L2 now
                         const int rowP = rowB >= 2 ? rowB - 2 : rowB - 2 + R;
                         const float4 *fp = rows + (long long) rowP * N;
-                        for (int c = 0; c <= nch; c++) prefetch_l2(fp + ((max(wlo - 32, 0) + (c << 5) + lane) & NM));
+                        // one lane per 128-byte line (8 cells): a single instruction covers 256 cells of the window
+                        const int p0 = max(wlo - 32, 0), pw = (nch + 1) << 5;
+                        for (int o = lane << 3; o < pw; o += 256) prefetch_l2(fp + ((p0 + o) & NM));
                     }
                     if ((d & 15) == 0) {
                         const int px = blo - 32 - lane, py = (d - bhi) - 32 - lane;
