@@ -1,11 +1,16 @@
 """Baum-Welch training driver for the signal pair-HMM: the batched, multi-GPU sibling of the reference's
-scripts/trainModels.py loop (:244-330) and of its expectation container (impl/continuousHmm.c, scripts/nanoporeLib.py
-:985-1054).
+scripts/trainModels.py loop (:244-330) and of its expectation containers (impl/continuousHmm.c; scripts/nanoporeLib.py
+:985-1054 ContinuousPairHmm, :1159-1225 ConditionalSignalHmm).
 
 One EM iteration = E-step over this rank's shard of the reads on its GPU (Engine.expectations, summed on device) ->
-ONE all-reduce of the 4106-double expectation vector across ranks (NCCL over NVLink on GPUs; gloo in the CPU tests) ->
-the same normalisation on every rank -> rank 0 writes the .hmm file in the reference's format -> every rank reloads it
-(the reference feeds the 6-decimal text file back with -y/-z, so the rounding of "%f" is part of the M-step)."""
+ONE all-reduce of the expectation vector (4106 doubles three-state, 61 vanilla) across ranks (NCCL over NVLink on GPUs;
+gloo in the CPU tests) -> the same normalisation on every rank -> rank 0 writes the .hmm file the way trainModels.py does
+(nanoporeLib's writers: Python-2 str() of every float, 12 significant digits) -> every rank reloads it, as the next
+round of vanillaAlign does with -y / -z, so the text round trip is part of the M-step.
+
+Where the batch differs from the reference's loop: the reference sums per-read expectation FILES, which vanillaAlign
+writes with "%f" (6 decimals, impl/continuousHmm.c:234-271); here the per-read sums never leave the device and are
+added in FP64.  `write()` still produces that C format byte for byte (it is what `cpecanAlign -t/-c` emits)."""
 import math
 import os
 
@@ -13,8 +18,26 @@ import numpy as np
 
 N_KMERS = 4096
 N_EXPECT = 9 + N_KMERS + 1
+N_BINS = 60
+N_EXPECT_VANILLA = N_BINS + 1
+MODEL_PARAMS = 5
 THREE_STATE = 2
+VANILLA = 4
 M, X, Y = 0, 1, 2
+
+
+def py2_str(x):
+    """str(float) of the Python 2 the reference's scripts run under: '%.12g', with '.0' appended when the result
+    looks like an integer (PyFloat_STR_PRECISION = 12, format_float_short's Py_DTSF_ADD_DOT_0)."""
+    x = float(x)
+    if math.isnan(x):
+        return "nan"
+    if math.isinf(x):
+        return "inf" if x > 0 else "-inf"
+    s = "%.12g" % x
+    if "." not in s and "e" not in s:
+        s += ".0"
+    return s
 
 
 class ContinuousPairHmm:
@@ -59,6 +82,15 @@ class ContinuousPairHmm:
                 fh.write("".join("%f\t" % v for v in self.kmer_skip_probs))
                 fh.write("\n")
 
+    # -- text format of nanoporeLib.ContinuousPairHmm.write (scripts/nanoporeLib.py:1027-1054): the trained model -----
+    def write_trained(self, path):
+        with open(path, "w") as fh:
+            fh.write("2\t%d\t%d\n" % (3, N_KMERS))
+            fh.write("".join(py2_str(v) + "\t" for v in self.transitions))
+            fh.write(py2_str(self.likelihood) + "\n")
+            fh.write("".join(py2_str(v) + "\t" for v in self.kmer_skip_probs))
+            fh.write("\n")
+
     @classmethod
     def load(cls, path):
         """continuousPairHmm_loadFromFile (impl/continuousHmm.c:273-370): same checks, same errors (as exceptions)."""
@@ -101,6 +133,107 @@ class ContinuousPairHmm:
         return trans, gapx
 
 
+class ConditionalSignalHmm:
+    """Expectations of the vanilla machine: 60 skip bins -- beta (M->X) in 0..29, alpha (X->X) in 30..59 -- and the
+    likelihood; the two match-model lines ride along unused (reference inc/continuousHmm.h VanillaHmm;
+    scripts/nanoporeLib.py:1159-1225)."""
+
+    def __init__(self, pseudocount=0.0, match_model=None, scaled_match_model=None):
+        self.kmer_skip_bins = np.full(N_BINS, float(pseudocount))
+        n = 1 + N_KMERS * MODEL_PARAMS
+        self.match_model = np.zeros(n) if match_model is None else np.asarray(match_model, dtype=np.float64)
+        self.scaled_match_model = np.zeros(n) if scaled_match_model is None else np.asarray(scaled_match_model, dtype=np.float64)
+        self.likelihood = 0.0
+        self.running_likelihoods = []
+
+    def add_expectations(self, vec):
+        vec = np.asarray(vec, dtype=np.float64)
+        if vec.shape != (N_EXPECT_VANILLA,):
+            raise ValueError("expectation vector must have %d entries" % N_EXPECT_VANILLA)
+        if np.isnan(vec[:N_BINS]).any():
+            return False
+        self.kmer_skip_bins += vec[:N_BINS]
+        self.likelihood += float(vec[-1])      # nanoporeLib assigns the LAST file's value (:1183); one sum per batch here
+        return True
+
+    def vector(self):
+        return np.concatenate([self.kmer_skip_bins, [self.likelihood]])
+
+    def normalize(self):
+        """nanoporeLib.ConditionalSignalHmm.normalize (:1188-1197): alpha and beta separately -- the C container
+        normalises all 60 jointly and says so itself ("this is wrong", impl/continuousHmm.c:424-433); the training
+        loop uses the Python one."""
+        self.kmer_skip_bins[:30] = self.kmer_skip_bins[:30] / self.kmer_skip_bins[:30].sum()
+        self.kmer_skip_bins[30:] = self.kmer_skip_bins[30:] / self.kmer_skip_bins[30:].sum()
+
+    def normalize_joint(self):
+        """vanillaHmm_normalizeKmerSkipBins (impl/continuousHmm.c:424-433)."""
+        self.kmer_skip_bins = self.kmer_skip_bins / self.kmer_skip_bins.sum()
+
+    # -- vanillaHmm_writeToFile (impl/continuousHmm.c:477-517): what vanillaAlign / cpecanAlign -t/-c emit ---------------
+    def write(self, path):
+        with open(path, "w") as fh:
+            fh.write("%d\t%d\t%d\t\n" % (VANILLA, 3, N_KMERS))
+            if not np.isnan(self.kmer_skip_bins).any():
+                fh.write("".join("%f\t" % v for v in self.kmer_skip_bins))
+                fh.write("%f\n" % self.likelihood)
+                fh.write("".join("%f\t" % v for v in self.match_model) + "\n")
+                fh.write("".join("%f\t" % v for v in self.scaled_match_model) + "\n")
+
+    # -- nanoporeLib.ConditionalSignalHmm.write (:1199-1225): the trained model ----------------------------------------
+    def write_trained(self, path):
+        with open(path, "w") as fh:
+            fh.write("4\t%d\t%d\n" % (3, N_KMERS))
+            fh.write("".join(py2_str(v) + "\t" for v in self.kmer_skip_bins))
+            fh.write(py2_str(self.likelihood) + "\n")
+            fh.write("".join(py2_str(v) + "\t" for v in self.match_model) + "\n")
+            fh.write("".join(py2_str(v) + "\t" for v in self.scaled_match_model) + "\n")
+
+    @classmethod
+    def load(cls, path):
+        """vanillaHmm_loadFromFile (impl/continuousHmm.c:519-628): type 4, 3 states, 61 numbers on line 1, the two
+        model lines of 1 + 4096 * 5 numbers."""
+        with open(path) as fh:
+            head = fh.readline().split()
+            if len(head) < 3:
+                raise ValueError("%s: bad header" % path)
+            typ, n_states, n_sym = int(float(head[0])), int(float(head[1])), int(float(head[2]))
+            if typ != VANILLA or n_states != 3 or n_sym != N_KMERS:
+                raise ValueError("%s: not a vanilla 6-mer HMM (type %d, %d states, %d symbols)" % (path, typ, n_states, n_sym))
+            line1 = fh.readline().split()
+            if len(line1) != N_EXPECT_VANILLA:
+                raise ValueError("Incorrect number of skip bins in the input HMM file %s, got %d instead of %d" % (path, len(line1), N_EXPECT_VANILLA))
+            n = 1 + N_KMERS * MODEL_PARAMS
+            line2, line3 = fh.readline().split(), fh.readline().split()
+            if len(line2) != n or len(line3) != n:
+                raise ValueError("Incorrect number of match-model parameters in the input HMM file %s" % path)
+        h = cls(match_model=np.array(line2, dtype=np.float64), scaled_match_model=np.array(line3, dtype=np.float64))
+        h.kmer_skip_bins = np.array(line1[:N_BINS], dtype=np.float64)
+        h.likelihood = float(line1[N_BINS])
+        return h
+
+    def state_machine_params(self):
+        """vanillaHmm_loadKmerSkipBinExpectations (impl/continuousHmm.c:457-466): the 60 bins go into
+        EMISSION_GAP_X_PROBS as probabilities (the vanilla cell takes their logs itself); no transitions change."""
+        return None, self.kmer_skip_bins.copy()
+
+
+def cull_training_reads(read_lengths, training_amount, rng=None):
+    """cull_training_files (scripts/trainModels.py:78-104) over reads already in memory: shuffle, then take reads until
+    their cumulative 2D-read length reaches training_amount (the read that crosses the mark is included).  Returns
+    the chosen indices in draw order; every rank that passes the same seeded rng draws the same set."""
+    n = len(read_lengths)
+    order = np.arange(n)
+    (rng or np.random.default_rng()).shuffle(order)
+    total, out = 0, []
+    for i in order:
+        out.append(int(i))
+        total += int(read_lengths[i])
+        if total >= training_amount:
+            break
+    return np.array(out, dtype=np.int64)
+
+
 def shard_by_cells(cells, world):
     """Partition of reads over ranks balanced by band cells: longest-processing-time greedy.
     Returns a list of index arrays (sorted), one per rank; every read appears exactly once."""
@@ -139,15 +272,17 @@ class _DevView:
 
 def gpu_estep(engine, batch, hmm, params, distributed):
     """E-step of this rank's shard on its GPU; the batch sums are all-reduced IN PLACE in the device accumulator
-    (the kernel's atomics and the NCCL collective share one buffer), then fetched once."""
+    (the kernel's atomics and the NCCL collective share one buffer), then fetched once.  The vector has 4106 entries
+    for the three-state machine and 61 for the vanilla one (hmm.sm_type)."""
     import torch
+    n = N_EXPECT_VANILLA if hmm is not None and int(hmm.sm_type) == VANILLA else N_EXPECT
     engine.stage(batch, hmm=hmm, params=params, mode=1, pair_cap=1)
     engine.run_staged()
     if distributed:
-        view = torch.as_tensor(_DevView(engine.expectations_device_ptr(), N_EXPECT), device="cuda")
+        view = torch.as_tensor(_DevView(engine.expectations_device_ptr(), n), device="cuda")
         allreduce_sum(view, True)
         torch.cuda.synchronize()
-    out = np.zeros(N_EXPECT)
+    out = np.zeros(n)
     engine.fetch_expectations(out)
     return out
 
@@ -159,14 +294,14 @@ def em_iteration(model, estep_sum, n_reads_total, hmm_path, rank=0, pseudocount=
     at zero, then normalise, write, remember the likelihood."""
     model.likelihood = 0.0
     vec = np.array(estep_sum, dtype=np.float64, copy=True)
-    vec[:9 + N_KMERS] += pseudocount * n_reads_total
+    vec[:-1] += pseudocount * n_reads_total
     model.add_expectations(vec)
     model.normalize()
     if rank == 0:
         tmp = hmm_path + ".tmp"
-        model.write(tmp)
+        model.write_trained(tmp)
         os.replace(tmp, hmm_path)
     if barrier is not None:
         barrier()
     model.running_likelihoods.append(model.likelihood)
-    return ContinuousPairHmm.load(hmm_path)        # what the next E-step sees: the 6-decimal file, as with -y / -z
+    return type(model).load(hmm_path)        # what the next E-step sees: the text file, as with -y / -z

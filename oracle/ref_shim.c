@@ -357,3 +357,30 @@ int64_t ref_load_pair_hmm(const char *hmmPath, const char *modelFile, double *tr
     freeStateMachine(sM);
     return 0;
 }
+
+/* The same for the vanilla container: bins[61] (60 skip bins + likelihood) and the two model lines taken from the
+ * vanilla state machine built from modelFile (vanillaHmm_implantMatchModelsintoHmm); optionally normalised with the
+ * reference's own (joint) vanillaHmm_normalizeKmerSkipBins; written with vanillaHmm_writeToFile. */
+int64_t ref_write_vanilla_hmm(const double *bins, int normalize, const char *modelFile, const char *path) {
+    StateMachine *sM = getSignalStateMachine3Vanilla(modelFile);
+    Hmm *hmm = hmmContinuous_getEmptyHmm(vanilla, 0.0, 0.0);
+    VanillaHmm *vh = (VanillaHmm *) hmm;
+    for (int i = 0; i < 60; i++) vh->kmerSkipBins[i] = bins[i];
+    hmm->likelihood = bins[60];
+    vanillaHmm_implantMatchModelsintoHmm(sM, hmm);
+    if (normalize) hmmContinuous_normalize(hmm, vanilla);
+    hmmContinuous_writeToFile(path, hmm, vanilla);
+    hmmContinuous_destruct(hmm, vanilla);
+    freeStateMachine(sM);
+    return 0;
+}
+
+/* Loads a vanilla .hmm file with the reference's loader (hmmContinuous_loadSignalHmm -> vanillaHmm_loadKmerSkipBin
+ * Expectations) and returns the 60 skip-bin entries of EMISSION_GAP_X_PROBS the DP will see. */
+int64_t ref_load_vanilla_hmm(const char *hmmPath, const char *modelFile, double *bins60) {
+    StateMachine *sM = getSignalStateMachine3Vanilla(modelFile);
+    hmmContinuous_loadSignalHmm(hmmPath, sM, vanilla);
+    for (int i = 0; i < 60; i++) bins60[i] = sM->EMISSION_GAP_X_PROBS[i];
+    freeStateMachine(sM);
+    return 0;
+}

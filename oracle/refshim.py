@@ -185,3 +185,18 @@ def load_pair_hmm(hmm_path, model_file):
     g = np.zeros(4096)
     lib().ref_load_pair_hmm(hmm_path.encode(), model_file.encode(), _dptr(t), _dptr(g))
     return t, g
+
+
+def write_vanilla_hmm(bins61, model_file, path, normalize=False):
+    """vanillaHmm_writeToFile (after the reference's joint vanillaHmm_normalizeKmerSkipBins when asked) on 60 bins +
+    likelihood; the two model lines are those of the vanilla machine built from model_file."""
+    bins61 = np.ascontiguousarray(bins61, dtype=np.float64)
+    assert bins61.size == 61
+    lib().ref_write_vanilla_hmm(_dptr(bins61), int(bool(normalize)), model_file.encode(), path.encode())
+
+
+def load_vanilla_hmm(hmm_path, model_file):
+    """hmmContinuous_loadSignalHmm into a vanilla machine: the 60 skip-bin probabilities the DP will see."""
+    b = np.zeros(60)
+    lib().ref_load_vanilla_hmm(hmm_path.encode(), model_file.encode(), _dptr(b))
+    return b

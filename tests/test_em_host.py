@@ -56,6 +56,95 @@ def test_container_against_live_reference(zymo, tmp_path):
         assert np.array_equal(t, t_ref) and np.array_equal(g, g_ref)
 
 
+def test_py2_str_known_values():
+    """str(float) of Python 2 (12 significant digits, '.0' for integers): the number format of the trained-model files
+    scripts/nanoporeLib.py writes."""
+    for x, want in [(0.1, "0.1"), (1.0 / 3.0, "0.333333333333"), (1.0, "1.0"), (1e-05, "1e-05"), (0.000244140625, "0.000244140625"),
+                    (123456789012345.0, "1.23456789012e+14"), (-2.5, "-2.5"), (1e16, "1e+16"), (0.0, "0.0"),
+                    (2.0 / 3.0, "0.666666666667"), (100.0, "100.0"), (float("-inf"), "-inf")]:
+        assert em.py2_str(x) == want
+
+
+def test_trained_model_file_round_trip(zymo, tmp_path):
+    """The file the M-step writes (trainModels.py format) keeps 12 significant digits and is read back by the same
+    loader as the C format."""
+    m = _model_from(zymo["three_expectations_e20_r00"])
+    m.normalize()
+    path = str(tmp_path / "t.hmm")
+    m.write_trained(path)
+    lines = open(path).read().split("\n")
+    assert lines[0] == "2\t3\t4096" and len(lines[1].split("\t")) == 10 and len(lines[2].split("\t")) == 4097
+    back = em.ContinuousPairHmm.load(path)
+    np.testing.assert_allclose(back.transitions, m.transitions, rtol=1e-11)
+    np.testing.assert_allclose(back.kmer_skip_probs, m.kmer_skip_probs, rtol=1e-11)
+    if R.available():      # and by the reference's own loader, into the state machine
+        t_ref, g_ref = R.load_pair_hmm(path, synth.TEMPLATE_MODEL)
+        t, g = back.state_machine_params()
+        assert np.array_equal(t, t_ref) and np.array_equal(g, g_ref)
+
+
+def test_vanilla_container(tmp_path):
+    """ConditionalSignalHmm: alpha / beta normalised separately (nanoporeLib.py:1188-1197), files in both formats."""
+    rng = np.random.default_rng(5)
+    vec = np.concatenate([rng.uniform(0.5, 20.0, 60), [-12345.678]])
+    m = em.ConditionalSignalHmm(pseudocount=1e-4)
+    assert m.add_expectations(vec)
+    np.testing.assert_allclose(m.kmer_skip_bins, vec[:60] + 1e-4)
+    raw = m.kmer_skip_bins.copy()
+    m.normalize()
+    np.testing.assert_allclose(m.kmer_skip_bins[:30], raw[:30] / raw[:30].sum(), rtol=1e-15)
+    np.testing.assert_allclose(m.kmer_skip_bins[30:], raw[30:] / raw[30:].sum(), rtol=1e-15)
+    assert abs(m.kmer_skip_bins[:30].sum() - 1) < 1e-12 and abs(m.kmer_skip_bins[30:].sum() - 1) < 1e-12
+    p = str(tmp_path / "v.hmm")
+    m.write_trained(p)
+    back = em.ConditionalSignalHmm.load(p)
+    np.testing.assert_allclose(back.kmer_skip_bins, m.kmer_skip_bins, rtol=1e-11)
+    assert back.likelihood == pytest.approx(-12345.678)
+    assert not em.ConditionalSignalHmm().add_expectations(np.full(61, np.nan))
+    with pytest.raises(ValueError):
+        em.ContinuousPairHmm.load(p)                       # a vanilla file is not a three-state one
+    with pytest.raises(ValueError):
+        em.ConditionalSignalHmm().add_expectations(np.zeros(4106))
+
+
+@pytest.mark.skipif(not R.available(), reason="oracle/_ref not built")
+def test_vanilla_container_against_live_reference(tmp_path):
+    """C-format writer byte for byte against vanillaHmm_writeToFile (raw and after the C container's joint
+    normalisation); both of our file formats through the reference's loader into the vanilla state machine."""
+    rng = np.random.default_rng(6)
+    vec = np.concatenate([rng.uniform(0.01, 5.0, 60), [-4321.5]])
+    l1, l2, l3 = synth.load_model_file(synth.TEMPLATE_MODEL)
+    ref_raw, ref_norm, mine = str(tmp_path / "r.hmm"), str(tmp_path / "rn.hmm"), str(tmp_path / "m.hmm")
+    R.write_vanilla_hmm(vec, synth.TEMPLATE_MODEL, ref_raw)
+    R.write_vanilla_hmm(vec, synth.TEMPLATE_MODEL, ref_norm, normalize=True)
+    m = em.ConditionalSignalHmm(match_model=l1, scaled_match_model=l3)     # implantMatchModels: MATCH and GAP_Y tables
+    m.add_expectations(vec)
+    m.write(mine)
+    assert open(mine).read() == open(ref_raw).read()
+    j = em.ConditionalSignalHmm(match_model=l1, scaled_match_model=l3)
+    j.add_expectations(vec)
+    j.normalize_joint()
+    j.write(mine)
+    assert open(mine).read() == open(ref_norm).read()
+    m.normalize()
+    for writer in (m.write, m.write_trained):
+        writer(mine)
+        bins = R.load_vanilla_hmm(mine, synth.TEMPLATE_MODEL)
+        want = em.ConditionalSignalHmm.load(mine).state_machine_params()[1]
+        assert np.array_equal(bins, want)
+
+
+def test_cull_training_reads():
+    """trainModels.py's culling rule: shuffled, cumulative length up to and including the read that crosses the mark."""
+    lengths = np.array([500, 1200, 800, 300, 2500, 700])
+    got = em.cull_training_reads(lengths, 2000, rng=np.random.default_rng(3))
+    again = em.cull_training_reads(lengths, 2000, rng=np.random.default_rng(3))
+    assert np.array_equal(got, again) and len(set(got.tolist())) == len(got)
+    csum = np.cumsum(lengths[got])
+    assert csum[-1] >= 2000 and (len(got) == 1 or csum[-2] < 2000)
+    assert len(em.cull_training_reads(lengths, 10 ** 9, rng=np.random.default_rng(1))) == len(lengths)    # not enough data: all
+
+
 def test_load_errors(tmp_path):
     p = tmp_path / "bad.hmm"
     p.write_text("2\t3\t4096\t\n0.1\t0.2\n\n")

@@ -286,6 +286,41 @@ def test_vanilla_synthetic_vs_oracle(engine, template_tables):
         print(i, parity.compare_pairs(item_pairs(res, pairs, i), want), parity.compare_totals(totals[i], wtot))
 
 
+def test_em_iterations_vanilla_vs_oracle(engine, template_tables, tmp_path):
+    """Two training iterations of the vanilla machine (trainModels.py with stateMachineType vanilla): E-step on the GPU
+    (60 skip-bin sums + likelihood), ConditionalSignalHmm M-step with alpha / beta normalised separately, trained file
+    round trip, the new bins uploaded as EMISSION_GAP_X_PROBS -- against the same loop with the oracle as the E-step."""
+    import oracleshim as O
+    from cpecan_signal import default_params, em, synth, vanilla_gapx, vanilla_hmm
+    l1, l2, l3 = template_tables
+    reads = [synth.make_read(l1, 950 + i, lX=350 + 60 * (i % 3), noise_dist="wald") for i in range(5)]
+    e = 30
+    batch = _vanilla_batch(engine, template_tables, [r.ref for r in reads], [r.events for r in reads],
+                           [r.anchors for r in reads], [r.scale5 for r in reads], [(1, 1)] * len(reads))
+    mid = int(batch.model_id[0])
+    gm = em.ConditionalSignalHmm(match_model=l1, scaled_match_model=l3)
+    om = em.ConditionalSignalHmm(match_model=l1, scaled_match_model=l3)
+    g_bins = o_bins = None
+    for it in range(2):
+        if g_bins is not None:
+            engine.update_model(mid, gapx=g_bins)
+        gvec = em.gpu_estep(engine, batch, vanilla_hmm("template"), default_params(diagonalExpansion=e), distributed=False)
+        assert gvec.shape == (em.N_EXPECT_VANILLA,)
+        ovec = np.zeros(em.N_EXPECT_VANILLA)
+        for r in reads:
+            m = O.Model(O.VANILLA, tables=(l1, l2, l3), scale5=r.scale5, strand=0, gap_x=o_bins)
+            ovec += O.expectations(m, r.ref, r.events, r.anchors, params=O.default_params(diagonalExpansion=e),
+                                   ragged=(1, 1), pseudocount=0.0)
+        np.testing.assert_allclose(gvec[:60], ovec[:60], rtol=EXP_RTOL, atol=1e-4)
+        assert abs(gvec[-1] - ovec[-1]) <= 1e-4 * abs(ovec[-1])
+        gl = em.em_iteration(gm, gvec, len(reads), str(tmp_path / "gv.hmm"))
+        ol = em.em_iteration(om, ovec, len(reads), str(tmp_path / "ov.hmm"))
+        assert abs(gl.kmer_skip_bins[:30].sum() - 1) < 1e-9 and abs(gl.kmer_skip_bins[30:].sum() - 1) < 1e-9
+        np.testing.assert_allclose(gl.kmer_skip_bins, ol.kmer_skip_bins, atol=2e-5)
+        g_bins, o_bins = gl.state_machine_params()[1], ol.state_machine_params()[1]
+    assert abs(gm.running_likelihoods[-1] - om.running_likelihoods[-1]) <= 1e-4 * abs(om.running_likelihoods[-1])
+
+
 def test_split_regions_as_items(engine, syn_golden, template_tables):
     """An anchor gap above splitMatrixBiggerThanThis: the regions of getSplitPoints become work items with ragged
     ends on the cut sides, and their pairs, shifted back and reversed per region, are what
