@@ -109,6 +109,62 @@ def test_batch_mixed_widths_vs_oracle(engine, template_tables):
         print(i, stats)
 
 
+def test_c3_shape_batch_properties(engine, template_tables):
+    """BASELINE config 3's shape (lX ~ 6700, ~8000 events, expansions 64 / 128 / 256, ~14 tracebacks per read) at a
+    batch of several hundred reads, through properties that do not need the oracle -- plus the oracle on one read per
+    expansion.  Every read appears twice, in different places of the batch: the copies must agree bit for bit, and a
+    second run of the whole batch must reproduce the first (the result does not depend on which resident warp, which
+    shared-memory ring size bucket or which neighbours a read gets).  The posteriors of one event over all reference
+    positions sum to at most 1 (+ tolerance).  (The same over the events of one reference position does NOT hold in the
+    reference either: an intermediate traceback is seeded with the end vector on its last diagonal, and the 41
+    overlap diagonals do not always absorb that, so a position can be matched with probability ~1 on two diagonals
+    45 apart -- 277 positions of the first read here.)"""
+    import oracleshim as O
+    from cpecan_signal import default_params, synth
+    from cpecan_signal.engine import item_pairs
+    l1, l2, l3 = template_tables
+    uniq = [synth.make_read(l1, 4000 + i, lX=6700) for i in range(48)]
+    for e in (64, 128, 256):
+        reads = (uniq + uniq[::-1]) * 2                                  # 192 items, every read 4 times
+        batch = _three_state_batch(engine, template_tables, [r.ref for r in reads], [r.events for r in reads],
+                                   [r.anchors for r in reads], [r.scale5 for r in reads], [(1, 1)] * len(reads))
+        prm = default_params(diagonalExpansion=e)
+        res, pairs, _ = engine.align_batch(batch, params=prm)
+        res2, pairs2, _ = engine.align_batch(batch, params=prm)
+        assert (res["status"] == 0).all()
+        assert np.array_equal(res["n_pairs"], res2["n_pairs"]) and np.array_equal(pairs, pairs2)
+        assert np.array_equal(res["total_logprob"], res2["total_logprob"])
+        n = len(uniq)
+        for i in range(n):
+            a = item_pairs(res, pairs, i)
+            for j in (2 * n - 1 - i, 2 * n + i, 4 * n - 1 - i):
+                assert np.array_equal(a, item_pairs(res, pairs, j)), "copies of read %d differ (items %d, %d)" % (i, i, j)
+                assert res["total_logprob"][i] == res["total_logprob"][j]
+            r = uniq[i]
+            assert res["n_tracebacks"][i] >= 10 and res["band_cells"][i] > 6700 * e // 2
+            assert a[:, 0].min() >= 100000 and a[:, 0].max() <= 10000000
+            assert a[:, 1].min() >= 0 and a[:, 1].max() < r.lX and a[:, 2].min() >= 0 and a[:, 2].max() < r.lY
+            key = a[:, 1].astype(np.int64) * (r.lY + 1) + a[:, 2]
+            assert len(np.unique(key)) == len(key)                       # one posterior per (x, y)
+            # traceback order: inside one traceback diagonals descending and x ascending inside a diagonal; the
+            # tracebacks follow each other towards the end of the matrix
+            dgl = (a[:, 1] + a[:, 2]).astype(np.int64)
+            dd = np.diff(dgl)
+            ups = np.flatnonzero(dd > 0)
+            assert len(ups) <= res["n_tracebacks"][i] - 1
+            assert (np.diff(a[:, 1])[dd == 0] > 0).all()
+            seg_max = np.maximum.accumulate(dgl)
+            assert (dgl[ups + 1] > seg_max[ups]).all()
+            py = np.bincount(a[:, 2], weights=a[:, 0] / 1e7, minlength=r.lY)
+            assert py.max() <= 1.0 + 1e-2
+            assert np.isfinite(res["total_logprob"][i]) and -80000 < res["total_logprob"][i] < -5000
+        k = {64: 0, 128: 1, 256: 2}[e]
+        r = uniq[k]
+        m = O.Model(O.THREE_STATE, tables=(l1, l2, l3), scale5=r.scale5)
+        want, _ = O.align_banded(m, r.ref, r.events, r.anchors, params=O.default_params(diagonalExpansion=e), ragged=(1, 1))
+        print(e, parity.compare_pairs(item_pairs(res, pairs, k), want))
+
+
 # ------------------------------------------------------------------------------------------ E-step (expectations)
 EXP_RTOL = 2e-4      # FP32 device path vs the reference's doubles; sums of ~1e5 terms
 
