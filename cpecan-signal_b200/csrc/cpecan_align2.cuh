@@ -1,25 +1,29 @@
-// cpecan_align2.cuh -- second-generation sm_100a kernel for the banded signal pair-HMM (three-state machine).
+// cpecan_align2.cuh -- the sm_100a kernel for the banded signal pair-HMM (three-state and vanilla machines):
+// forward sweep, periodic traceback (backward values, local totals, posteriors or E-step sums), one launch per batch
+// and ring-size bucket.  Reference: impl/pairwiseAligner.c:870-1006 (schedule), :681-795 and :841-863 (diagonal
+// calculations), impl/stateMachine.c:1305-1334 and :1368-1409 (cell bodies).
 //
-// Same semantics as k_align (cpecan_kernels.cuh; reference impl/pairwiseAligner.c:870-1006, :714-795 and
-// impl/stateMachine.c:1305-1334) with a mapping chosen from the ncu profiles of the first kernel (profiles/r1_*):
-// lanes outside the ragged band, ALU-pipe selects inside logAdd and per-diagonal CTA barriers were its losses, and a
-// register-resident variant of this kernel (K unrolled register rows per warp) was instruction-cache bound.
+// The mapping comes out of the ncu profiles kept under profiles/ (a CTA per alignment with x-owned register rows lost
+// 60 % of its lanes outside the ragged band and sat on block barriers; a register-resident variant of this kernel was
+// instruction-cache bound):
 //
 //   * ONE WARP per alignment, no block barriers.  The reference positions x are cut into CHUNKS of 32 consecutive x
-//     (lane = x mod 32).  Per diagonal the warp loops (a run-time loop, one copy of the code) over just the chunks
-//     that intersect the band, so the cost of a diagonal follows the band width, not the widest diagonal of the read.
+//     placed relative to the band of the diagonal.  Per diagonal the warp loops (a run-time loop, one copy of the
+//     code) over just the chunks that intersect the band, so the cost of a diagonal follows its band width.
 //   * All per-cell state lives in a shared-memory ring of N positions (x mod N), two float4 (M, X, Y, offset) per
 //     position: the values of diagonals d-1 and d-2.  A cell reads its own and its neighbour's entries (LDS.128) and
 //     writes the new value over its own d-2 entry; walking the chunks in DESCENDING x on the way forward (ASCENDING
-//     on the way back) makes that in-place update safe, so two buffers suffice.  The k-mer side of the emissions is
-//     streamed from L1 (3 x LDG.128 per cell update, each record re-read ~W times while its column is in the band).
+//     on the way back) makes that in-place update safe, so two buffers suffice.
+//   * The k-mer side of the emissions (3 or 4 float4 column records) and the event are streamed from L1/L2 through a
+//     software pipeline over the (diagonal, chunk) tasks: requested at the top of task i, reduced at its end to the
+//     3 - 8 values task i+1 needs (see the forward sweep for why the loads stay a whole task ahead).
 //   * Every cell carries its own offset (an integer stored as float): values are FP32 relative to it.  logAdd is
 //     translation invariant, so a cell is computed in the units U = max(own, neighbours' offsets) and re-based to
 //     its own maximum afterwards; nothing is lost at log-probabilities of -40 000 and nothing depends on where in
 //     the diagonal the probability mass sits.
 //   * logAdd: the reference's 4-segment cubic and 7.5 cut-off (impl/pairwiseAligner.c:235-255) as max + q(|x-y|),
-//     q = cubic - identity, the segment chosen by predicated immediate-operand FFMAs (FMA pipe) instead of a tree of
-//     selects (ALU pipe, half rate).
+//     q = cubic - identity; on the dependent chain the segment is chosen by predicated immediate-operand FFMAs, off
+//     the chain its coefficients come from a shared-memory table with one LDS.128 (bit-identical results).
 //   * Aligned pairs leave in the reference's order for free: the backward walk visits x ascending inside a diagonal.
 #pragma once
 #include "cpecan_kernels.cuh"
@@ -121,12 +125,6 @@ __device__ __forceinline__ float logadd2(float x, float y, unsigned tbl) {
         : "=f"(r) : "f"(x), "f"(y), "r"(tbl));
     return r;
 }
-
-// Keeps all four components of a prefetched record live until the point of use.  Without it ptxas re-uses a component
-// the arithmetic never reads (e.g. the k-mer index) as a scratch register while the LDG.128 is still in flight, and the
-// write-after-write scoreboard wait on that one register serialises the warp behind the load (ncu: 18 % of all samples
-// sat on the first integer instruction after the prefetch).
-__device__ __forceinline__ void keep_live(const float4 &v) { asm volatile("" :: "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)); }
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 
