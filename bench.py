@@ -285,6 +285,9 @@ def main():
                     help="distinct synthetic reads generated per rank (2.7 ms of host time each); the batch tiles them, every "
                          "copy with its own host and device buffers")
     ap.add_argument("--impl", default="b200")
+    ap.add_argument("--e2e-subbatches", type=int, default=8,
+                    help="end-to-end leg: the reads of one expansion are streamed in this many sub-batches through two "
+                         "contexts, so that one's copies run under the other's kernels")
     ap.add_argument("--pairs-per-event", type=float, default=2.0, help="capacity of the aligned-pair buffers (the batch yields ~1.1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="posterior", choices=["posterior", "em"],
@@ -319,7 +322,10 @@ def main():
     l1 = l3 = None
     from cpecan_signal import synth
     l1, _, l3 = synth.load_model_file(synth.TEMPLATE_MODEL)
+    tbl_match, tbl_gapy = l1, l3
     order = sorted(range(3), key=lambda j: -EXPANSIONS[j])      # widest band first: its tail is filled by the others
+    SUB = max(1, args.e2e_subbatches)
+    host = Engine(local)                    # owns the page-locked host memory of both legs (stages nothing itself)
     for j in order:
         e = EXPANSIONS[j]
         sub = reads[j::3]
@@ -327,9 +333,10 @@ def main():
         mid = eng.upload_model(l1, l3, np.full(4096, -2.3025850929940455))
         hb = HostBatch([r.ref for r in sub], [r.events for r in sub], [r.anchors for r in sub],
                        model_ids=[mid] * len(sub), scales=[r.scale5 for r in sub], ragged=[(1, 1)] * len(sub))
-        eng.pin_batch(hb)
-        cap = eng.default_pair_capacity(hb, per_event=args.pairs_per_event)      # ~1.1 aligned pairs per event at threshold 0.01
-        outs.append((eng.pinned_empty(hb.n, RESULT_DTYPE), eng.pinned_empty((cap, 3), np.int32)))
+        host.pin_batch(hb)
+        # ~1.1 aligned pairs per event at threshold 0.01; room for the per-sub-batch rounding of the end-to-end leg
+        cap = eng.default_pair_capacity(hb, per_event=args.pairs_per_event) + 2048 * SUB
+        outs.append((host.pinned_empty(hb.n, RESULT_DTYPE), host.pinned_empty((cap, 3), np.int32)))
         engines.append(eng); batches.append(hb)
     params = [default_params(diagonalExpansion=EXPANSIONS[j]) for j in order]
     _free, _tot = torch.cuda.mem_get_info()
@@ -406,34 +413,66 @@ def main():
         assert int((res["status"] != 0).sum()) == 0, "non-zero item status"
         n_pairs += int(res["n_pairs"].sum())
 
+    info = engines[0].device_info()
+
     # ---- end-to-end through the C-ABI with host buffers ---------------------------------------------------
-    # One blocking align_batch call per expansion (H2D of the pinned host batch, staging kernels, plan, alignment
-    # kernels, D2H of the aligned pairs), issued from three host threads as a caller with several batches in hand
-    # would: ctypes drops the GIL, so one context's copies overlap another context's kernels.
+    # The same batch, streamed: the reads of an expansion go through the C-ABI in SUB sub-batches, alternately through
+    # two contexts, one blocking align_batch call each (H2D of the pinned host sub-batch, staging kernels, plan,
+    # alignment kernels, D2H of the aligned pairs) issued from one host thread per context.  ctypes drops the GIL, so a
+    # context's copies run under the other contexts' kernels; each context keeps half the resident warps
+    # (CPECAN_OCC_CAP) so that the forward-row rings of the six fit where the three resident ones did.
     from concurrent.futures import ThreadPoolExecutor
-    pool = ThreadPoolExecutor(max_workers=len(engines))
+    for eng in engines:
+        eng.close()                        # the resident batch leaves the device; the pinned host copies stay (host)
+    os.environ["CPECAN_OCC_CAP"] = "8"
+    lanes = []                             # per context: (engine, [(sub-batch, params, (results, pairs))])
+    for hb, p, o in zip(batches, params, outs):
+        bounds = np.linspace(0, hb.n, SUB + 1).astype(np.int64)
+        pair = []
+        for _ in range(min(2, SUB)):
+            eng = Engine(local)
+            eng.upload_model(tbl_match, tbl_gapy, np.full(4096, -2.3025850929940455))
+            pair.append((eng, []))
+        off = 0
+        for k in range(SUB):
+            sb = hb.view(int(bounds[k]), int(bounds[k + 1]))
+            cap_k = Engine.default_pair_capacity(sb, per_event=args.pairs_per_event)
+            assert off + cap_k <= len(o[1])
+            pair[k % len(pair)][1].append((sb, p, (o[0][int(bounds[k]):int(bounds[k + 1])], o[1][off:off + cap_k])))
+            off += cap_k
+        lanes += pair
+    pool = ThreadPoolExecutor(max_workers=len(lanes))
+    counters = [[0, 0, 0] for _ in lanes]
+
+    def run_lane(i):
+        eng, tasks = lanes[i]
+        for sb, p, o in tasks:
+            eng.align_batch(sb, None, p, 0, None, False, o)
+            tm = eng.timing()
+            counters[i][0] += tm["h2d_bytes"]; counters[i][1] += tm["d2h_bytes"]; counters[i][2] += tm["kernel_launches"]
 
     def e2e_step():
-        futs = [pool.submit(eng.align_batch, hb, None, p, 0, None, False, o)
-                for eng, hb, p, o in zip(engines, batches, params, outs)]
-        for f in futs:
+        for f in [pool.submit(run_lane, i) for i in range(len(lanes))]:
             f.result()
 
     e2e_step()
+    for eng, tasks in lanes:               # the streamed results are the resident ones
+        for sb, p, o in tasks:
+            assert int((o[0]["status"] != 0).sum()) == 0, "non-zero item status (end-to-end leg)"
+    assert sum(int(o[0]["n_pairs"].sum()) for eng, tasks in lanes for sb, p, o in tasks) == n_pairs
     barrier()
+    counters = [[0, 0, 0] for _ in lanes]
     t0 = time.perf_counter()
-    h2d = d2h = 0
-    e2e_launches = 0
     for _ in range(args.steps):
         e2e_step()
-        for eng in engines:
-            tm = eng.timing()
-            h2d += tm["h2d_bytes"]; d2h += tm["d2h_bytes"]; e2e_launches += tm["kernel_launches"]
     barrier()
     e2e_wall = max_over_ranks(time.perf_counter() - t0)
     e2e_gcups = 2.0 * cells_total * args.steps / e2e_wall / 1e9
-    h2d, d2h, e2e_launches = sum_over_ranks(float(h2d)), sum_over_ranks(float(d2h)), sum_over_ranks(float(e2e_launches))   # whole job
+    h2d, d2h, e2e_launches = (sum_over_ranks(float(sum(c[i] for c in counters))) for i in range(3))   # whole job
     pool.shutdown()
+    for eng, _ in lanes:
+        eng.close()
+    host.close()
 
     if rank != 0:
         if world > 1:
@@ -448,7 +487,6 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured" if "hbm_gbs" in peaks else "fallback"
-    info = engines[0].device_info()
     kern_s = kern_ms / 1e3                                   # this rank's kernels
     cells_steps = cells_rank * args.steps
     achieved_gbs = HBM_BYTES_PER_CELL * cells_steps / kern_s / 1e9
@@ -467,7 +505,8 @@ def main():
                    "l2": "inputs + forward spill per step >> 126 MB L2 (no flush needed)"},
         "e2e": {"value": e2e_gcups, "unit": "GCUPS", "h2d_bytes_per_step": int(h2d / args.steps),
                 "d2h_bytes_per_step": int(d2h / args.steps), "ms_per_step": e2e_wall / args.steps * 1e3,
-                "reads_per_s": reads_total * args.steps / e2e_wall},
+                "reads_per_s": reads_total * args.steps / e2e_wall,
+                "streaming": "%d sub-batches per expansion through %d contexts per GPU" % (SUB, len(lanes))},
         "gpu_launches": int(launches),
         "gpu_launches_e2e": int(e2e_launches),
         "kernel_ms_per_step": kern_ms_max / args.steps,

@@ -143,6 +143,22 @@ class HostBatch:
         self.ragged = np.zeros(n, dtype=np.uint8) if ragged is None else np.ascontiguousarray(
             [(int(a) & 1) | ((int(b) & 1) << 1) for a, b in ragged], dtype=np.uint8)
 
+    def view(self, i0, i1):
+        """Items [i0, i1) as a batch of their own WITHOUT copying the big arrays (views keep page-locked memory
+        page-locked); only the small offset arrays are rebased."""
+        v = HostBatch.__new__(HostBatch)
+        v.n = int(i1 - i0)
+        v.ref_off = np.ascontiguousarray(self.ref_off[i0:i1 + 1] - self.ref_off[i0])
+        v.ev_off = np.ascontiguousarray(self.ev_off[i0:i1 + 1] - self.ev_off[i0])
+        v.anchor_off = np.ascontiguousarray(self.anchor_off[i0:i1 + 1] - self.anchor_off[i0])
+        v.ref = self.ref[int(self.ref_off[i0]):max(int(self.ref_off[i1]), int(self.ref_off[i0]) + 1)]
+        v.events = self.events[int(self.ev_off[i0]):max(int(self.ev_off[i1]), int(self.ev_off[i0]) + 1)]
+        v.anchors = self.anchors[int(self.anchor_off[i0]):max(int(self.anchor_off[i1]), int(self.anchor_off[i0]) + 1)]
+        v.model_id = self.model_id[i0:i1]
+        v.scale = None if self.scale is None else self.scale[i0:i1]
+        v.ragged = self.ragged[i0:i1]
+        return v
+
     @property
     def lX(self):
         return np.maximum(np.diff(self.ref_off) - 5, 0)

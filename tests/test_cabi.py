@@ -51,3 +51,27 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".c", ".cpp")):
                 txt = open(os.path.join(d, f), errors="ignore").read()
                 assert "oracleshim" not in txt and "refshim" not in txt and "libcpecan_oracle" not in txt, f
+
+
+def test_host_batch_view_matches_a_fresh_batch():
+    """HostBatch.view (the sub-batches bench.py streams) describes the same items as a batch built from them."""
+    import numpy as np
+    from cpecan_signal import HostBatch
+    rng = np.random.default_rng(0)
+    refs = ["ACGTACGTAC" * (2 + i) for i in range(6)]
+    events = [rng.normal(size=(5 + 3 * i, 3)) for i in range(6)]
+    anchors = [np.array([[j, j] for j in range(i)], dtype=np.int64).reshape(-1, 2) for i in range(6)]
+    scales = [rng.normal(size=5) for _ in range(6)]
+    ragged = [(i & 1, (i >> 1) & 1) for i in range(6)]
+    full = HostBatch(refs, events, anchors, model_ids=list(range(6)), scales=scales, ragged=ragged)
+    for i0, i1 in ((0, 6), (1, 4), (5, 6), (0, 1)):
+        v = full.view(i0, i1)
+        w = HostBatch(refs[i0:i1], events[i0:i1], anchors[i0:i1], model_ids=list(range(i0, i1)), scales=scales[i0:i1],
+                      ragged=ragged[i0:i1])
+        assert v.n == w.n
+        for name in ("ref_off", "ev_off", "anchor_off", "model_id", "scale", "ragged"):
+            assert np.array_equal(getattr(v, name), getattr(w, name)), name
+        assert np.array_equal(v.ref[:v.ref_off[-1]], w.ref[:w.ref_off[-1]])
+        assert np.array_equal(v.events[:v.ev_off[-1]], w.events[:w.ev_off[-1]])
+        assert np.array_equal(v.anchors[:v.anchor_off[-1]], w.anchors[:w.anchor_off[-1]])
+        assert v.events.base is not None                      # a view, not a copy
