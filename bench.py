@@ -11,7 +11,8 @@ across ranks with no data-path collective (weak scaling: B reads per GPU).
 
   value      GCUPS = 2 * band cells / time / 1e9 with the batch resident in HBM (kernels only)
   e2e        the same metric through the C-ABI call with HOST buffers: H2D of the batch, preparation, plan, kernels
-             and D2H of the aligned pairs all inside the timed region
+             and D2H of the aligned pairs all inside the timed region; the batch is streamed in sub-batches through
+             two contexts per expansion so that one context's copies run under the others' kernels
   roofline   HBM bytes (25 B per band cell) / kernel time against MEASURED_PEAKS.json, plus the FP32
              issue-rate roofline SURVEY.md 8(d) defines (165 issue-ops per band cell)
   cpu_baseline / --impl reference
