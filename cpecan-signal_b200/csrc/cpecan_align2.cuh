@@ -155,21 +155,20 @@ struct KernelArgs2 {
 __host__ __device__ inline size_t align2_smem_bytes(int ringN) { return (size_t) ringN * (2 * 16) + CP_LAT_BYTES; }
 
 // Left fold  acc = logadd(acc, v[0]), logadd(acc, v[1]), ...  in ascending x (the order of dpDiagonal_dotProduct,
-// impl/pairwiseAligner.c:587-597) over ring-positioned values: element i lives at (start + i) & (N - 1).
+// impl/pairwiseAligner.c:587-597), fed 32 consecutive elements (one per lane, -inf where there is none) at a time,
+// straight from the registers of the pass that produces them.
 // Exactly equal to the serial fold, at the cost of the few elements near the ridge only:
 //   * an element more than 7.5 below the running prefix maximum cannot change acc (acc >= prefix maximum);
 //   * an element at least 7.5 + 12 above the prefix maximum RESETS the fold: acc <= prefix maximum + ln(count) +
 //     count * 6e-4 (the cubic over-estimates by at most 5.5e-4 per step) < prefix maximum + 12 for count <= 4096, so
 //     logadd returns the element itself and everything before it is forgotten.
-// With us != nullptr element i is buf[i] + (us[i] - fbase): the terms are stored in their own units and brought to the
-// common base here.
-__device__ __forceinline__ float warp_ordered_fold_ring(const float *buf, const float *us, float fbase, int start, int w, int NM, unsigned k) {
-    const int lane = threadIdx.x & 31;
-    float acc = CP_NEG_INF, runmax = CP_NEG_INF;
-    for (int base = 0; base < w; base += 32) {
-        const int idx = base + lane;
-        float v = CP_NEG_INF;
-        if (idx < w) { const int p = (start + idx) & NM; v = buf[p]; if (us != nullptr) v = v + (us[p] - fbase); }
+struct OrderedFold {
+    float acc, runmax;
+    int base;                              // integer units of acc (block_units)
+    __device__ __forceinline__ void reset() { acc = CP_NEG_INF; runmax = CP_NEG_INF; base = CP_INT_MIN; }
+
+    __device__ __forceinline__ void block(float v, unsigned k) {
+        const int lane = threadIdx.x & 31;
         float m = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { float t = __shfl_up_sync(CP_FULL, m, o); if (lane >= o) m = fmaxf(m, t); }
@@ -189,8 +188,21 @@ __device__ __forceinline__ float warp_ordered_fold_ring(const float *buf, const 
         }
         runmax = fmaxf(runmax, __shfl_sync(CP_FULL, m, 31));
     }
-    return acc;
-}
+
+    // Elements c1 in their own integer units us (floats holding integers).  The fold keeps its accumulator in the
+    // units of the largest element seen so far -- an exact integer shift when a block raises it -- so the values near
+    // the ridge stay small whatever the offsets of the cells are, and nothing has to be parked until the diagonal's
+    // maximum is known.
+    __device__ __forceinline__ void block_units(float c1, float us, bool valid, unsigned k) {
+        valid = valid && c1 > -1e30f;
+        const int cm = __reduce_max_sync(CP_FULL, valid ? (int) us + (int) floorf(c1) : CP_INT_MIN);
+        if (cm > base) {
+            if (base != CP_INT_MIN) { const float sh = (float) (base - cm); acc += sh; runmax += sh; }
+            base = cm;
+        }
+        block(valid ? c1 + (us - (float) base) : CP_NEG_INF, k);
+    }
+};
 
 // re-base a cell to its own maximum (integer shift, exact); a cell that is all -inf drifts down by 64 per step
 __device__ __forceinline__ void rebase(float &a, float &b, float &c, float &off) {
@@ -214,11 +226,6 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
     const float NI = CP_NEG_INF;
     float4 *rows = A.scratch + (long long) blockIdx.x * A.scratch_stride;
     const int R = A.ring_rows;
-    // dot-product terms of the total-probability diagonals (1 in 10): kept in the warp's global scratch (one extra
-    // row behind the forward rows), not in shared memory -- every KB of shared memory per warp is a KB less L1 for
-    // the column records and events the warps stream
-    float *sm_c1 = reinterpret_cast<float *>(rows + (long long) R * N);
-    float *sm_us = sm_c1 + N;
     const float4 NIENT = make_float4(NI, NI, NI, -CP_BIG);
     // logAdd coefficient table behind the ring
     la_table_init(ring + 2 * N, threadIdx.x);
@@ -573,7 +580,8 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                     } else {
                         // ---- totalProbability (impl/pairwiseAligner.c:736-754), recomputed every 10th posterior diagonal
                         // pass 1: B into the ring (units in .w), dot-product terms and their units aside
-                        int lmax = CP_INT_MIN;
+                        OrderedFold fold1;
+                        fold1.reset();
                         float4 Fn = frow[(wlo + lane) & NM];           // forward cell of chunk 0 (used inside the band only)
                         for (int c = 0; c < nch; c++) {
                             const int x = wlo + (c << 5) + lane, s = x & NM;
@@ -587,18 +595,16 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                             cellB(x, s, inb, pdR, myLog, bM, bX, bY, U);
                             __syncwarp();
                             A2[s] = make_float4(bM, bX, bY, inb ? U : -CP_BIG);
-                            if (inb) {
-                                const float c1 = LA(LA(F.x + bM, F.y + bX), F.z + bY);
-                                const float us = F.w + U;
-                                sm_c1[s] = c1; sm_us[s] = us;
-                                if (c1 > -1e30f) lmax = max(lmax, (int) us + (int) floorf(c1));
-                            }
+                            // dot product of F and B over the diagonal, folded as the cells come (ascending x)
+                            float c1 = NI, us = 0.f;
+                            if (inb) { c1 = LA(LA(F.x + bM, F.y + bX), F.z + bY); us = F.w + U; }
+                            fold1.block_units(c1, us, inb, K);
                             __syncwarp();
                         }
-                        loadB(0);                                      // pass 2's first chunk: in flight during the folds
-                        const int base = __reduce_max_sync(CP_FULL, lmax);
+                        loadB(0);                                      // pass 2's first chunk: in flight during the second term
+                        const int base = fold1.base;
                         const float fbase = base == CP_INT_MIN ? 0.f : (float) base;
-                        const float t1 = warp_ordered_fold_ring(sm_c1, sm_us, fbase, blo & NM, bhi - blo + 1, NM, K);
+                        const float t1 = fold1.acc;
                         float tot = t1, t2v = NI;
                         if (d < Dt && base != CP_INT_MIN) {
                             // term 2: matches jumping over diagonal d = a match-only forward step from F[d-1] into the
@@ -609,23 +615,24 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                             b2w.range(d - 1, lm1, hm1);
                             const int rowM = rowB == 0 ? R - 1 : rowB - 1;
                             const float4 *fprev = rows + (long long) rowM * N;
-                            __syncwarp();
+                            OrderedFold fold2;
+                            fold2.reset();
                             float4 Fp = fprev[(l1 + lane - 1) & NM];
-                            for (int x = l1 + lane; x <= h1; x += 32) {
+                            for (int xb = l1; xb <= h1; xb += 32) {
+                                const int x = xb + lane;
                                 float val = NI;
                                 const float4 F = Fp;
                                 Fp = fprev[(x + 31) & NM];             // the next round's, a round ahead of its use
-                                if (x - 1 >= lm1 && x - 1 <= hm1) {
+                                if (x <= h1 && x - 1 >= lm1 && x - 1 <= hm1) {
                                     const float4 Gn = A1[x & NM];
                                     float4 pdx = NIENT;
                                     if (MACH) pdx = xpD[min(x, lX + 1)];
                                     const float md = LA(LA(F.x + (MACH ? pdx.z : gMC), F.y + (MACH ? pdx.w : gMX)), F.z + tMY);
                                     val = (md + Gn.x) + ((F.w + Gn.w) - fbase);
                                 }
-                                sm_c1[x & NM] = val;
+                                fold2.block(val, K);
                             }
-                            __syncwarp();
-                            t2v = warp_ordered_fold_ring(sm_c1, nullptr, 0.f, l1 & NM, h1 - l1 + 1, NM, K);
+                            t2v = fold2.acc;
                             tot = LA(t1, t2v);
                         }
                         totSt = tot;
