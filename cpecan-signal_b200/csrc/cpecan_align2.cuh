@@ -657,7 +657,7 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                             reduceB();
                         }
                     }
-                    if (post) {
+                    if (post && (EXPECT || d == D || dbgTot != nullptr)) {     // FP64 only where somebody reads it
                         const double totAbs = (double) totSt + (double) totBase;
                         if (EXPECT) {
 #pragma unroll
