@@ -425,7 +425,7 @@ int cpecan_cuda_stage(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_param
         int occ = std::max(1, ctx->occ2[b][ctx->machine][sx]);
         if (const char *capEnv = getenv("CPECAN_OCC_CAP")) occ = std::max(1, std::min(occ, atoi(capEnv)));   // tuning knob: resident warps per SM
         bk.nCta = (int) std::min<int64_t>((int64_t) bk.order.size(), (int64_t) ctx->prop.multiProcessorCount * occ);
-        bk.stride = (long long) (bk.ringRows + 1) * cfg2N(b);     // float4 (M, X, Y, offset) per ring position and row, + 1 work row
+        bk.stride = (long long) bk.ringRows * cfg2N(b);           // float4 (M, X, Y, offset) per ring position and row
         bk.scratchOff = scratch4; scratch4 += (size_t) bk.stride * bk.nCta;
         bk.orderOff = orderInts; orderInts += bk.order.size();
         orderAll.insert(orderAll.end(), bk.order.begin(), bk.order.end());
