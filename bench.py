@@ -421,17 +421,17 @@ def main():
     # two contexts, one blocking align_batch call each (H2D of the pinned host sub-batch, staging kernels, plan,
     # alignment kernels, D2H of the aligned pairs) issued from one host thread per context.  ctypes drops the GIL, so a
     # context's copies run under the other contexts' kernels; each context keeps half the resident warps
-    # (CPECAN_OCC_CAP) so that the forward-row rings of the six fit where the three resident ones did.
+    # (cpecan_cuda_set_resident_warps) so that the forward-row rings of the six fit where the three resident ones did.
     from concurrent.futures import ThreadPoolExecutor
     for eng in engines:
         eng.close()                        # the resident batch leaves the device; the pinned host copies stay (host)
-    os.environ["CPECAN_OCC_CAP"] = "8"
     lanes = []                             # per context: (engine, [(sub-batch, params, (results, pairs))])
     for hb, p, o in zip(batches, params, outs):
         bounds = np.linspace(0, hb.n, SUB + 1).astype(np.int64)
         pair = []
         for _ in range(min(2, SUB)):
             eng = Engine(local)
+            eng.set_resident_warps(8)
             eng.upload_model(tbl_match, tbl_gapy, np.full(4096, -2.3025850929940455))
             pair.append((eng, []))
         off = 0

@@ -225,6 +225,10 @@ class Engine:
         ptrs = [None if a is None else a.ctypes.data_as(C.c_void_p) for a in arrs]
         self._check(self.lib.cpecan_cuda_update_model(self.ctx, C.c_int32(model_id), *ptrs), "update_model")
 
+    def set_resident_warps(self, warps_per_sm):
+        """At most this many resident alignment warps per SM for the batches staged from now on (0 = all that fit)."""
+        self._check(self.lib.cpecan_cuda_set_resident_warps(self.ctx, C.c_int32(int(warps_per_sm))), "set_resident_warps")
+
     def device_info(self):
         sm, clk, mem = C.c_int32(), C.c_int32(), C.c_int64()
         self._check(self.lib.cpecan_cuda_device_info(self.ctx, C.byref(sm), C.byref(clk), C.byref(mem)), "device_info")

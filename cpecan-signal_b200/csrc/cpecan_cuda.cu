@@ -82,6 +82,7 @@ struct cpecan_ctx {
     int stagedMaxLX = 0;
     bool stagedScaled = false;
     int occ2[NCFG2][2][2] = {};  // [bucket][machine][hasSX]
+    int occCap = 0;              // resident warps per SM this context may take (0 = all that fit)
     bool wantTotals = false;
     std::vector<int64_t> hTotOff;
     cpecan_timing timing{};
@@ -423,7 +424,7 @@ int cpecan_cuda_stage(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_param
         if (bk.order.empty()) continue;
         std::stable_sort(bk.order.begin(), bk.order.end(), [&](int a, int c) { return ctx->hOut[a].band_cells > ctx->hOut[c].band_cells; });
         int occ = std::max(1, ctx->occ2[b][ctx->machine][sx]);
-        if (const char *capEnv = getenv("CPECAN_OCC_CAP")) occ = std::max(1, std::min(occ, atoi(capEnv)));   // tuning knob: resident warps per SM
+        if (ctx->occCap > 0) occ = std::min(occ, ctx->occCap);       // cpecan_cuda_set_resident_warps
         bk.nCta = (int) std::min<int64_t>((int64_t) bk.order.size(), (int64_t) ctx->prop.multiProcessorCount * occ);
         bk.stride = (long long) bk.ringRows * cfg2N(b);           // float4 (M, X, Y, offset) per ring position and row
         bk.scratchOff = scratch4; scratch4 += (size_t) bk.stride * bk.nCta;
@@ -638,6 +639,14 @@ void *cpecan_cuda_host_alloc(cpecan_ctx *ctx, int64_t bytes) {
 
 void cpecan_cuda_host_free(cpecan_ctx *ctx, void *p) {
     if (ctx && p) { cudaSetDevice(ctx->device); cudaFreeHost(p); }
+}
+
+int cpecan_cuda_set_resident_warps(cpecan_ctx *ctx, int32_t warps_per_sm) {
+    if (!ctx) return CPECAN_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (warps_per_sm < 0) { ctx->err = "set_resident_warps: negative"; return CPECAN_ERR_ARG; }
+    ctx->occCap = warps_per_sm;
+    return CPECAN_OK;
 }
 
 int cpecan_cuda_get_timing(cpecan_ctx *ctx, cpecan_timing *out) {

@@ -174,6 +174,11 @@ int cpecan_cuda_fetch_staged(cpecan_ctx *ctx, int32_t *pairs_out, cpecan_result 
 void *cpecan_cuda_host_alloc(cpecan_ctx *ctx, int64_t bytes);
 void cpecan_cuda_host_free(cpecan_ctx *ctx, void *p);
 
+/* Share of the device one context takes: at most `warps_per_sm` resident alignment warps per SM for the batches staged
+ * afterwards (0 = as many as fit, the default).  Callers that stream sub-batches through several contexts at once give
+ * each a share, so that the forward-row rings (sized by the resident warps) of all of them fit in HBM. */
+int cpecan_cuda_set_resident_warps(cpecan_ctx *ctx, int32_t warps_per_sm);
+
 int cpecan_cuda_get_timing(cpecan_ctx *ctx, cpecan_timing *out);
 int cpecan_cuda_device_info(cpecan_ctx *ctx, int32_t *sm_count, int32_t *clock_khz, int64_t *hbm_bytes);
 
