@@ -109,6 +109,40 @@ def test_batch_mixed_widths_vs_oracle(engine, template_tables):
         print(i, stats)
 
 
+def test_edge_shapes_vs_oracle(engine, template_tables):
+    """Degenerate shapes in one batch: no anchors at all (the band is the whole matrix), a single anchor, anchors in the
+    corners, one k-mer against one event, more events than a band of the given expansion can follow, every ragged
+    combination."""
+    import oracleshim as O
+    from cpecan_signal import default_params, synth
+    from cpecan_signal.engine import item_pairs
+    l1, l2, l3 = template_tables
+    base = [synth.make_read(l1, 600 + i, lX=lx) for i, lx in enumerate([120, 200, 90, 150, 60, 260])]
+    refs = [r.ref for r in base]
+    events = [r.events for r in base]
+    anchors = [np.zeros((0, 2), np.int64),                       # none
+               base[1].anchors[:1],                              # one
+               np.array([[0, 0], [base[2].lX - 1, base[2].lY - 1]], dtype=np.int64),   # the corners
+               base[3].anchors,
+               base[4].anchors,
+               base[5].anchors[::2]]
+    refs.append(base[0].ref[:6]); events.append(base[0].events[:1]); anchors.append(np.zeros((0, 2), np.int64))   # 1 x 1
+    refs.append(base[1].ref[:40]); events.append(base[1].events[:150]); anchors.append(np.zeros((0, 2), np.int64))  # lY >> lX
+    scales = [r.scale5 for r in base] + [base[0].scale5, base[1].scale5]
+    ragged = [(0, 0), (1, 0), (0, 1), (1, 1), (0, 0), (1, 1), (0, 0), (1, 1)]
+    e = 20
+    batch = _three_state_batch(engine, template_tables, refs, events, anchors, scales, ragged)
+    res, pairs, totals = engine.align_batch(batch, params=default_params(diagonalExpansion=e), want_totals=True)
+    for i in range(len(refs)):
+        m = O.Model(O.THREE_STATE, tables=(l1, l2, l3), scale5=scales[i])
+        want, wtot = O.align_banded(m, refs[i], events[i], anchors[i], params=O.default_params(diagonalExpansion=e),
+                                    ragged=ragged[i], want_totals=True)
+        assert res[i]["status"] == 0, i
+        stats = parity.compare_pairs(item_pairs(res, pairs, i), want)
+        parity.compare_totals(totals[i], wtot)
+        print(i, stats)
+
+
 def test_c3_shape_batch_properties(engine, template_tables):
     """BASELINE config 3's shape (lX ~ 6700, ~8000 events, expansions 64 / 128 / 256, ~14 tracebacks per read) at a
     batch of several hundred reads, through properties that do not need the oracle -- plus the oracle on one read per
