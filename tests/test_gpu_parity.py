@@ -469,6 +469,11 @@ def test_argument_errors_are_reported(engine, template_tables):
     bad.sm_type = 6                                                # fourState: not implemented on device
     with pytest.raises(EngineError, match="not implemented"):
         engine.align_batch(hb, hmm=bad)
+    # a band wider than the widest shared-memory ring (a long read without anchors): refused, not mis-computed
+    big = synth.make_read(l1, 8, lX=6000)
+    hbw = HostBatch([big.ref], [big.events], [np.zeros((0, 2), np.int64)], model_ids=[mid], scales=[big.scale5], ragged=[(1, 1)])
+    with pytest.raises(EngineError, match="band wider"):
+        engine.align_batch(hbw)
     # empty batch and an item without events are legal
     res, pairs, _ = engine.align_batch(HostBatch([], [], []))
     assert len(res) == 0
