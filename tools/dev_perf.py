@@ -20,16 +20,19 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--lx", type=int, default=6700)
     ap.add_argument("--unique", type=int, default=0, help="generate only this many distinct reads and tile them")
+    ap.add_argument("--machine", default="three", choices=["three", "vanilla"])
     a = ap.parse_args()
     nu = a.unique or a.n
     reads = generate_reads(nu, 5_000_000, lX=a.lx)
     reads = [reads[i % nu] for i in range(a.n)]
-    l1, _, l3 = synth.load_model_file(synth.TEMPLATE_MODEL)
+    l1, l2, l3 = synth.load_model_file(synth.TEMPLATE_MODEL)
     eng = Engine(0)
-    mid = eng.upload_model(l1, l3, np.full(4096, -2.3025850929940455))
+    from cpecan_signal import vanilla_gapx, vanilla_hmm
+    hmm = vanilla_hmm("template") if a.machine == "vanilla" else None
+    mid = eng.upload_model(l1, l3, vanilla_gapx(l2) if a.machine == "vanilla" else np.full(4096, -2.3025850929940455))
     hb = HostBatch([r.ref for r in reads], [r.events for r in reads], [r.anchors for r in reads],
                    model_ids=[mid] * len(reads), scales=[r.scale5 for r in reads], ragged=[(1, 1)] * len(reads))
-    eng.stage(hb, params=default_params(diagonalExpansion=a.e), pair_cap=eng.default_pair_capacity(hb, 3))
+    eng.stage(hb, hmm=hmm, params=default_params(diagonalExpansion=a.e), pair_cap=eng.default_pair_capacity(hb, 3))
     cells = eng.timing()["band_cells"]
     for i in range(a.reps):
         eng.run_staged()
