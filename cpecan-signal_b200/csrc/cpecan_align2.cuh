@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                 }
                 // lanes are placed relative to the window [lo-1, hi+1] of the diagonal (the cells one outside the band
                 // are written as -inf for the neighbours that will read them): chunk j holds x = wlo + 32 j + lane
-                int wlo = max(lo - 1, 0) & ~7, c = (min(hi + 1, lX) - wlo) >> 5;     // 8-lane aligned: own LDS/STS.128 conflict free
+                int wlo = max(lo - 1, 0), c = (min(hi + 1, lX) - wlo) >> 5;     // any start: 8 consecutive float4 are 32 distinct banks
                 rowF = rowF + 1 == R ? 0 : rowF + 1;
                 float4 *frow = rows + (long long) rowF * N;
                 // Software pipeline over the tasks: the column records and the event of task i+1 are requested at the
@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                             nd = d + 1;
                             bw.range(nd, nlo, nhi);
                             if (nlo < lo || nlo > lo + 1 || nhi < hi || nhi > hi + 1) status |= 4;
-                            nwlo = max(nlo - 1, 0) & ~7;
+                            nwlo = max(nlo - 1, 0);
                             nc = (min(nhi + 1, lX) - nwlo) >> 5;
                         }
                     }
@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(32, CP_MINB) k_align2(const KernelArgs2 A) {
                     }
                     const float4 *frow = rows + (long long) rowB * N;
                     const bool post = d <= tracedBackFrom;
-                    const int wlo = max(blo - 1, 0) & ~7, nch = ((min(bhi + 1, lX) - wlo) >> 5) + 1;
+                    const int wlo = max(blo - 1, 0), nch = ((min(bhi + 1, lX) - wlo) >> 5) + 1;
                     const int plo = max(blo, 1), phi = min(bhi, d - 1);   // cells with x > 0 and y > 0 report posteriors
                     bool doTotal = false;
                     if (post) { doTotal = unbanded ? (d == Dt) : (tillTotal == 0); tillTotal = tillTotal == 0 ? P.totalEvery - 1 : tillTotal - 1; }   // every totalEvery-th posterior diagonal, from the first
