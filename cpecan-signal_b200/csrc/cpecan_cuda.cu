@@ -83,6 +83,7 @@ struct cpecan_ctx {
     bool stagedScaled = false;
     int occ2[NCFG2][2][2] = {};  // [bucket][machine][hasSX]
     int occCap = 0;              // resident warps per SM this context may take (0 = all that fit)
+    cudaEvent_t evBlock = nullptr;   // cudaEventBlockingSync: host threads sleep while they wait (several contexts per process)
     bool wantTotals = false;
     std::vector<int64_t> hTotOff;
     cpecan_timing timing{};
@@ -98,6 +99,13 @@ namespace {
             return CPECAN_ERR_CUDA;                                                                \
         }                                                                                          \
     } while (0)
+
+// Waits for a stream without spinning: a caller that streams sub-batches through several contexts has one host thread
+// per context, and most of them are waiting at any time.
+static cudaError_t waitStream(cpecan_ctx *ctx, cudaStream_t s) {
+    cudaError_t e = cudaEventRecord(ctx->evBlock, s);
+    return e != cudaSuccess ? e : cudaEventSynchronize(ctx->evBlock);
+}
 
 // k_align2<MACH, HAS_SX, EXPECT>: dispatch over the instantiations (the vanilla machine has no Y->X transition)
 template <typename F> auto dispatchK2(int mach, bool sx, bool ex, F f) {
@@ -222,6 +230,7 @@ int cpecan_cuda_init(int device, cpecan_ctx **ctx_out) {
     for (auto &e : ctx->ev) cudaEventCreate(&e);
     for (auto &st : ctx->bstream) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
     for (auto &e : ctx->bev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->evBlock, cudaEventBlockingSync | cudaEventDisableTiming);
     for (int c = 0; c < NCFG2; c++) {
         if (prepCfg2(c) != cudaSuccess) { cudaGetLastError(); break; }      // ring too large for this device's shared memory
         for (int mach = 0; mach < 2; mach++)
@@ -242,6 +251,7 @@ void cpecan_cuda_destroy(cpecan_ctx *ctx) {
     for (auto *b : bufs) b->release();
     for (auto &e : ctx->ev) cudaEventDestroy(e);
     for (auto &e : ctx->bev) cudaEventDestroy(e);
+    if (ctx->evBlock) cudaEventDestroy(ctx->evBlock);
     for (auto &st : ctx->bstream) cudaStreamDestroy(st);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -275,7 +285,7 @@ int cpecan_cuda_update_model(cpecan_ctx *ctx, int32_t model_id, const double *ma
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (model_id < 0 || model_id >= (int32_t) ctx->models.size()) { ctx->err = "update_model: bad model id"; return CPECAN_ERR_ARG; }
     CK(cudaSetDevice(ctx->device));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(waitStream(ctx, ctx->stream));
     const size_t tbl = (1 + 4096 * 5) * sizeof(double);
     Model &m = ctx->models[model_id];
     if (match) CK(cudaMemcpy(m.match, match, tbl, cudaMemcpyHostToDevice));
@@ -394,7 +404,7 @@ int cpecan_cuda_stage(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_param
     ctx->hOut.resize(n);
     CK(cudaMemcpyAsync(ctx->hOut.data(), ctx->dOut.p, n * sizeof(ItemOut), cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(ctx->ev[3], s));
-    CK(cudaStreamSynchronize(s));
+    CK(waitStream(ctx, s));
     {
         float ms = 0;
         cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->timing.h2d_ms = ms;
@@ -439,7 +449,7 @@ int cpecan_cuda_stage(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_param
     CK(ctx->dExpect.ensure(CPECAN_N_EXPECT * sizeof(double)));
     CK(cudaMemcpyAsync(ctx->dOrder.p, orderAll.data(), orderAll.size() * sizeof(int), cudaMemcpyHostToDevice, s));
     if (ctx->wantTotals) CK(ctx->dTotals.ensure(std::max<int64_t>(1, totTot) * sizeof(double)));
-    CK(cudaStreamSynchronize(s));
+    CK(waitStream(ctx, s));
     return CPECAN_OK;
 }
 
@@ -455,7 +465,7 @@ int cpecan_cuda_restage_model(cpecan_ctx *ctx, const cpecan_hmm *hmm) {
     if (ctx->machine != machineBefore) { ctx->err = "restage_model: the staged batch was prepared for the other state machine"; return CPECAN_ERR_ARG; }
     launchPrepX(ctx, ctx->stream);
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(waitStream(ctx, ctx->stream));
     return CPECAN_OK;
 }
 
@@ -511,7 +521,7 @@ int cpecan_cuda_wait(cpecan_ctx *ctx) {
     if (!ctx->running) return CPECAN_OK;
     CK(cudaSetDevice(ctx->device));
     ctx->running = false;
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(waitStream(ctx, ctx->stream));
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]);
     ctx->timing.align_ms = ms;
@@ -534,7 +544,7 @@ int cpecan_cuda_fetch_staged(cpecan_ctx *ctx, int32_t *pairs_out, cpecan_result 
     // the plan wrote band_cells / max_width into dOut, the align kernel the rest
     std::vector<ItemOut> out(n);
     CK(cudaMemcpyAsync(out.data(), ctx->dOut.p, n * sizeof(ItemOut), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    CK(waitStream(ctx, s));
     std::vector<long long> dst(n + 1, 0);
     for (int64_t i = 0; i < n; i++) {
         const int np = std::min(out[i].n_pairs, ctx->hItems[i].pair_cap);
@@ -562,7 +572,7 @@ int cpecan_cuda_fetch_staged(cpecan_ctx *ctx, int32_t *pairs_out, cpecan_result 
         ctx->timing.d2h_bytes += dst[n] * 12;
     }
     CK(cudaEventRecord(ctx->ev[7], s));
-    CK(cudaStreamSynchronize(s));
+    CK(waitStream(ctx, s));
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]);
     ctx->timing.d2h_ms = ms;
@@ -614,7 +624,7 @@ int cpecan_cuda_fetch_expectations(cpecan_ctx *ctx, double *expectations_out) {
     const int len = ctx->machine ? CPECAN_N_EXPECT_VANILLA : CPECAN_N_EXPECT;
     std::vector<double> tmp(len);
     CK(cudaMemcpyAsync(tmp.data(), ctx->dExpect.p, len * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(waitStream(ctx, ctx->stream));
     for (int i = 0; i < len; i++) expectations_out[i] += tmp[i];
     ctx->timing.d2h_bytes += len * 8;
     return CPECAN_OK;
