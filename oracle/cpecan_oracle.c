@@ -28,16 +28,22 @@
 #define MODEL_STRIDE 5
 #define SM_THREE_STATE 2
 #define SM_VANILLA 4
-enum { ST_M = 0, ST_X = 1, ST_Y = 2 };
+#define SM_FOUR_STATE 6       /* inc/stateMachine.h:20-29 */
+enum { ST_M = 0, ST_X = 1, ST_Y = 2, ST_LX = 3 };       /* match, shortGapX, shortGapY, longGapX (inc/stateMachine.h:31-33) */
+/* StateMachine4 transitions in the order this file keeps them (inc/stateMachine.h StateMachine4) */
+enum { T4_MATCH_CONTINUE = 0, T4_MATCH_FROM_SHORT_GAP_X, T4_MATCH_FROM_SHORT_GAP_Y, T4_MATCH_FROM_LONG_GAP_X,
+       T4_GAP_SHORT_OPEN_X, T4_GAP_SHORT_EXTEND_X, T4_GAP_SHORT_OPEN_Y, T4_GAP_SHORT_EXTEND_Y,
+       T4_GAP_LONG_OPEN_X, T4_GAP_LONG_EXTEND_X, T4_GAP_LONG_SWITCH_TO_X, T4_COUNT };
 
 typedef struct {
-    int32_t sm_type;          /* 2 = threeState (strawMan), 4 = vanilla */
+    int32_t sm_type;          /* 2 = threeState (strawMan), 4 = vanilla, 6 = fourState */
     int32_t strand;           /* unused by the DP; kept for the host mirror */
     const double *match;      /* EMISSION_MATCH_PROBS: 1 + 4096*5 (already scaled per read) */
     const double *gapy;       /* EMISSION_GAP_Y_PROBS: 1 + 4096*5 (never scaled, sm:631-651) */
     const double *gapx;       /* threeState: 4096 log-probs; vanilla: 60 skip-bin probabilities */
     double trans[9];          /* threeState, StateMachine3 field order (inc/stateMachine.h:179-187) */
     double vanilla[5];        /* M_TO_Y_NOT_X, E_TO_E, END_MATCH, END_FROM_X, END_FROM_Y */
+    double trans4[T4_COUNT];  /* fourState, T4_* order; gapx then holds 4096 zeros (emissions_signal_initEmissionsToZero) */
 } OracleModel;
 
 typedef struct {
@@ -218,7 +224,8 @@ typedef struct {
     const double *ev;         /* events of this (sub-)region: 3 doubles each */
     int64_t lX, lY;
     const int64_t *xmyL, *xmyR;
-    double **F, **B;          /* per-diagonal cell arrays (3 doubles per cell) or NULL when not alive */
+    int S;                    /* states per cell: 3, fourState 4 */
+    double **F, **B;          /* per-diagonal cell arrays (S doubles per cell) or NULL when not alive */
     /* expectation accumulators (mode 2) */
     double total;
     double *expT;             /* threeState: 9 transitions; vanilla: 60 bins */
@@ -228,11 +235,11 @@ typedef struct {
 static double *cell_at(Dp *dp, double **mat, int64_t xay, int64_t xmy) {
     if (xay < 0 || xay > dp->lX + dp->lY || mat[xay] == NULL) return NULL;
     if (xmy < dp->xmyL[xay] || xmy > dp->xmyR[xay]) return NULL;
-    return mat[xay] + ((xmy - dp->xmyL[xay]) / 2) * 3;
+    return mat[xay] + ((xmy - dp->xmyL[xay]) / 2) * dp->S;
 }
 static int64_t width_of(Dp *dp, int64_t xay) { return (dp->xmyR[xay] - dp->xmyL[xay]) / 2 + 1; }
 static double *new_diag(Dp *dp, double **mat, int64_t xay, double fill) {
-    int64_t n = width_of(dp, xay) * 3;
+    int64_t n = width_of(dp, xay) * dp->S;
     if (mat[xay] == NULL) mat[xay] = malloc(sizeof(double) * n);
     for (int64_t i = 0; i < n; i++) mat[xay][i] = fill;
     return mat[xay];
@@ -293,6 +300,31 @@ static void cell(Dp *dp, int mode, double *cur, double *lower, double *middle, d
             transition(dp, mode, upper, cur, ST_M, ST_Y, eP, t[4], k, 0);
             transition(dp, mode, upper, cur, ST_Y, ST_Y, eP, t[6], k, 0);
         }
+    } else if (m->sm_type == SM_FOUR_STATE) {
+        /* stateMachine4_cellCalculate (sm:867-897); emissions of getStateMachine4 (sm:1750-1759): gap X from the
+         * all-zero k-mer table, match and short gap Y the two-Gaussian model on the MATCH / GAP_Y tables */
+        int32_t k = ix >= 0 ? kmer_index(dp->ref + ix) : -1;
+        const double *t = m->trans4;
+        if (lower) {
+            double eP = k < 0 ? NEG_INF : m->gapx[k];
+            transition(dp, mode, lower, cur, ST_M, ST_X, eP, t[T4_GAP_SHORT_OPEN_X], k, 0);
+            transition(dp, mode, lower, cur, ST_X, ST_X, eP, t[T4_GAP_SHORT_EXTEND_X], k, 0);
+            transition(dp, mode, lower, cur, ST_M, ST_LX, eP, t[T4_GAP_LONG_OPEN_X], k, 0);
+            transition(dp, mode, lower, cur, ST_LX, ST_LX, eP, t[T4_GAP_LONG_EXTEND_X], k, 0);
+            transition(dp, mode, lower, cur, ST_Y, ST_LX, eP, t[T4_GAP_LONG_SWITCH_TO_X], k, 0);
+        }
+        if (middle) {
+            double eP = emit_two_gauss(m->match, k, ev);
+            transition(dp, mode, middle, cur, ST_M, ST_M, eP, t[T4_MATCH_CONTINUE], k, 0);
+            transition(dp, mode, middle, cur, ST_X, ST_M, eP, t[T4_MATCH_FROM_SHORT_GAP_X], k, 0);
+            transition(dp, mode, middle, cur, ST_Y, ST_M, eP, t[T4_MATCH_FROM_SHORT_GAP_Y], k, 0);
+            transition(dp, mode, middle, cur, ST_LX, ST_M, eP, t[T4_MATCH_FROM_LONG_GAP_X], k, 0);
+        }
+        if (upper) {
+            double eP = emit_two_gauss(m->gapy, k, ev);
+            transition(dp, mode, upper, cur, ST_M, ST_Y, eP, t[T4_GAP_SHORT_OPEN_Y], k, 0);
+            transition(dp, mode, upper, cur, ST_Y, ST_Y, eP, t[T4_GAP_SHORT_EXTEND_Y], k, 0);
+        }
     } else {
         /* sequence_getKmer2 (ref:320-325): pointer to the PREVIOUS k-mer, clamped at 0 */
         const char *p = dp->ref + (ix > 0 ? ix - 1 : 0);
@@ -339,10 +371,10 @@ static void sweep(Dp *dp, int mode, double **mc, int64_t xay, double **m1, doubl
 static double diag_dot(Dp *dp, double *a, double *b, int64_t xay) {
     double tot = NEG_INF;
     int64_t w = width_of(dp, xay);
+    const int S = dp->S;
     for (int64_t i = 0; i < w; i++) {
-        double c = a[3 * i] + b[3 * i];
-        c = LA(c, a[3 * i + 1] + b[3 * i + 1]);
-        c = LA(c, a[3 * i + 2] + b[3 * i + 2]);
+        double c = a[S * i] + b[S * i];
+        for (int st = 1; st < S; st++) c = LA(c, a[S * i + st] + b[S * i + st]);
         tot = LA(tot, c);
     }
     return tot;
@@ -372,7 +404,7 @@ typedef struct { int64_t *out; int64_t cap, n; int64_t offX, offY; } PairSink;
 static void posterior_diag(Dp *dp, int64_t xay, double total, double threshold, PairSink *sink) {
     if (xay == g_dbg_row && g_dbg_F) {
         int64_t w = (dp->xmyR[xay] - dp->xmyL[xay]) / 2 + 1;
-        for (int64_t i = 0; i < 3 * w; i++) { g_dbg_F[i] = dp->F[xay][i]; g_dbg_B[i] = dp->B[xay][i]; }
+        for (int64_t i = 0; i < dp->S * w; i++) { g_dbg_F[i] = dp->F[xay][i]; g_dbg_B[i] = dp->B[xay][i]; }
     }
     for (int64_t xmy = dp->xmyL[xay]; xmy <= dp->xmyR[xay]; xmy += 2) {
         int64_t x = (xay + xmy) / 2, y = (xay - xmy) / 2;
@@ -393,6 +425,15 @@ static void posterior_diag(Dp *dp, int64_t xay, double total, double threshold, 
 }
 
 static void state_vector(const OracleModel *m, int which /*0 start,1 raggedStart,2 end,3 raggedEnd*/, double *v) {
+    if (m->sm_type == SM_FOUR_STATE) {
+        const double *t = m->trans4;
+        if (which == 0) { v[0] = 0; v[1] = v[2] = v[3] = NEG_INF; }                          /* sm:775-779 (shared with 5) */
+        else if (which == 1) { v[0] = v[1] = NEG_INF; v[2] = 0; v[3] = 0; }                  /* sm:791-794 */
+        else if (which == 2) { v[0] = t[T4_MATCH_CONTINUE]; v[1] = t[T4_MATCH_FROM_SHORT_GAP_X];      /* sm:796-810 */
+                               v[2] = t[T4_MATCH_FROM_SHORT_GAP_Y]; v[3] = t[T4_MATCH_FROM_LONG_GAP_X]; }
+        else { v[0] = v[1] = v[2] = t[T4_GAP_LONG_OPEN_X]; v[3] = t[T4_GAP_LONG_EXTEND_X]; }  /* sm:812-826 */
+        return;
+    }
     if (which == 0) { v[0] = 0; v[1] = NEG_INF; v[2] = NEG_INF; return; }                 /* sm:1168-1172 */
     if (which == 1) { v[0] = NEG_INF; v[1] = 0; v[2] = 0; return; }                       /* sm:1174-1177 */
     if (m->sm_type == SM_THREE_STATE) {
@@ -407,7 +448,7 @@ static void state_vector(const OracleModel *m, int which /*0 start,1 raggedStart
 }
 static void fill_diag(Dp *dp, double **mat, int64_t xay, const double *v) {
     double *c = new_diag(dp, mat, xay, 0.0);
-    for (int64_t i = 0; i < width_of(dp, xay); i++) { c[3 * i] = v[0]; c[3 * i + 1] = v[1]; c[3 * i + 2] = v[2]; }
+    for (int64_t i = 0; i < width_of(dp, xay); i++) for (int st = 0; st < dp->S; st++) c[dp->S * i + st] = v[st];
 }
 
 /* ref:870-1006: one banded region with periodic traceback.
@@ -420,12 +461,12 @@ static void banded_region(const OracleModel *m, const char *ref, int64_t lX, con
     int64_t D = lX + lY;
     if (D == 0) return;
     Dp dp; memset(&dp, 0, sizeof(dp));
-    dp.m = m; dp.ref = ref; dp.ev = ev; dp.lX = lX; dp.lY = lY; dp.expT = expT; dp.expSkip = expSkip;
+    dp.m = m; dp.S = m->sm_type == SM_FOUR_STATE ? 4 : 3; dp.ref = ref; dp.ev = ev; dp.lX = lX; dp.lY = lY; dp.expT = expT; dp.expSkip = expSkip;
     int64_t *xl = malloc(sizeof(int64_t) * (D + 1)), *xr = malloc(sizeof(int64_t) * (D + 1));
     oracle_band(anchors, nA, lX, lY, p->diagonalExpansion, xl, xr);
     dp.xmyL = xl; dp.xmyR = xr;
     dp.F = calloc(D + 2, sizeof(double *)); dp.B = calloc(D + 2, sizeof(double *));
-    double v[3];
+    double v[4];
     state_vector(m, raggedLeft ? 1 : 0, v);
     fill_diag(&dp, dp.F, 0, v);
     int64_t tracedBackTo = 0;
@@ -523,13 +564,13 @@ int64_t oracle_align_unbanded(const OracleModel *m, const char *ref, int64_t lX,
                               double *totalOut) {
     int64_t D = lX + lY;
     Dp dp; memset(&dp, 0, sizeof(dp));
-    dp.m = m; dp.ref = ref; dp.ev = events; dp.lX = lX; dp.lY = lY;
+    dp.m = m; dp.S = m->sm_type == SM_FOUR_STATE ? 4 : 3; dp.ref = ref; dp.ev = events; dp.lX = lX; dp.lY = lY;
     int64_t *xl = malloc(sizeof(int64_t) * (D + 1)), *xr = malloc(sizeof(int64_t) * (D + 1));
     oracle_band(NULL, 0, lX, lY, 2, xl, xr);
     dp.xmyL = xl; dp.xmyR = xr;
     dp.F = calloc(D + 2, sizeof(double *)); dp.B = calloc(D + 2, sizeof(double *));
     for (int64_t i = 0; i <= D; i++) { new_diag(&dp, dp.F, i, NEG_INF); new_diag(&dp, dp.B, i, NEG_INF); }
-    double v[3];
+    double v[4];
     state_vector(m, raggedLeft ? 1 : 0, v); fill_diag(&dp, dp.F, 0, v);
     state_vector(m, raggedRight ? 3 : 2, v); fill_diag(&dp, dp.B, D, v);
     for (int64_t i = 0; i <= D; i++) sweep(&dp, MODE_FWD, dp.F, i, dp.F, dp.F, 1);

@@ -120,6 +120,27 @@ def main():
     np.savez_compressed(os.path.join(GOLDEN, "synthetic_golden.npz"), **syn)
 
 
+def four_state_goldens():
+    """The fourState machine (getStateMachine4) on the fixture read: the reference's own known answers are
+    988 aligned pairs banded and 988 without banding at ragged (1,1), e = 20 (tests/signalPairwiseTest.c:1199-1236).
+    Pins the oracle's four-state restatement ahead of the device path."""
+    os.chdir(os.path.join(HERE, "_ref"))
+    g = dict(np.load(os.path.join(GOLDEN, "zymo_golden.npz")))
+    ref = open(os.path.join(GOLDEN, "ZymoRef.txt")).readline().strip()
+    rd = R.load_npread(os.path.join(GOLDEN, "ZymoC_ch_1_file1.npRead"))
+    tp, tev, anch = rd["template_params"], rd["template_events"], g["anchors_template"]
+    out = {}
+    for tag, e, ragged in (("four_e20_r11", 20, (1, 1)), ("four_e20_r00", 20, (0, 0)), ("four_e50_r10", 50, (1, 0))):
+        pairs, totals = R.align_banded(R.FOUR_STATE, T_MODEL, ref, tev, anch, params=R.default_params(diagonalExpansion=e),
+                                       scale5=tp, ragged=ragged, want_totals=True)
+        out[tag + "_pairs"], out[tag + "_totals"] = pairs, totals
+        print(tag, len(pairs), int(pairs[:, 0].sum()))
+    pairs, total = R.align_unbanded(R.FOUR_STATE, T_MODEL, ref, tev, scale5=tp, ragged=(1, 1))
+    out["four_unbanded_r11_pairs"], out["four_unbanded_r11_total"] = pairs, np.float64(total)
+    print("four unbanded", len(pairs), total)
+    np.savez_compressed(os.path.join(GOLDEN, "zymo_four_state_golden.npz"), **out)
+
+
 def vanilla_align_goldens():
     """tests/golden/vanillaAlign/*: outputs of the UNMODIFIED reference CLI (oracle/_ref/vanillaAlign, `make -C oracle
     vanillaAlign lastz`) on the fixture 2D read.  The guide cigar comes from the reference's vendored lastz."""
@@ -152,4 +173,5 @@ def vanilla_align_goldens():
 
 if __name__ == "__main__":
     main()
+    four_state_goldens()
     vanilla_align_goldens()

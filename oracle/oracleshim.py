@@ -12,6 +12,7 @@ ORACLE_SO = os.path.join(HERE, "libcpecan_oracle.so")
 
 THREE_STATE = 2
 VANILLA = 4
+FOUR_STATE = 6
 N_KMERS = 4096
 
 # stateMachine3_setTransitionsToNanoporeDefaults (reference impl/stateMachine.c:1278-1289), StateMachine3 field order
@@ -33,9 +34,19 @@ VANILLA_STRAND = {None: (0.17, float(np.float32(0.55))),
                   1: (float(np.float32(0.14)), float(np.float32(0.49)))}
 
 
+# stateMachine4_construct's defaults (impl/stateMachine.c:993-1011) in the oracle's T4_* order: MATCH_CONTINUE,
+# MATCH_FROM_SHORT_GAP_X, MATCH_FROM_SHORT_GAP_Y, MATCH_FROM_LONG_GAP_X, GAP_SHORT_OPEN_X, GAP_SHORT_EXTEND_X,
+# GAP_SHORT_OPEN_Y, GAP_SHORT_EXTEND_Y, GAP_LONG_OPEN_X, GAP_LONG_EXTEND_X, GAP_LONG_SWITCH_TO_X
+FOUR_STATE_TRANSITIONS = np.array([
+    -0.23552123624314988, -0.21880828092192281, -0.013406326748077823, -5.6732801731704612,
+    -1.6269694202638481, -1.6269694202638481, -4.7241893208381773, -4.724189320832104,
+    -5.4173365013981227, -0.003442492794189331, -5.4173365013920494])
+
+
 class OracleModel(C.Structure):
     _fields_ = [("sm_type", C.c_int32), ("strand", C.c_int32), ("match", C.c_void_p), ("gapy", C.c_void_p),
-                ("gapx", C.c_void_p), ("trans", C.c_double * 9), ("vanilla", C.c_double * 5)]
+                ("gapx", C.c_void_p), ("trans", C.c_double * 9), ("vanilla", C.c_double * 5),
+                ("trans4", C.c_double * 11)]
 
 
 class OracleParams(C.Structure):
@@ -97,6 +108,10 @@ class Model:
         if sm_type == THREE_STATE:
             # stateMachine3_construct fills EMISSION_GAP_X_PROBS with log(0.1) (impl/stateMachine.c:1506-1508)
             self.gapx = np.full(N_KMERS, -2.3025850929940455) if gap_x is None else np.array(gap_x, dtype=np.float64)
+        elif sm_type == FOUR_STATE:
+            # getStateMachine4: emissions_signal_initEmissionsToZero, and the skip-bin line of the model file is not
+            # loaded for this type (impl/stateMachine.c:374-386, :282-294)
+            self.gapx = np.zeros(N_KMERS) if gap_x is None else np.array(gap_x, dtype=np.float64)
         else:
             # vanilla: 30 bins duplicated into [0..29] (beta) and [30..59] (alpha) (impl/stateMachine.c:282-294)
             self.gapx = np.concatenate([l2, l2]) if gap_x is None else np.array(gap_x, dtype=np.float64)
@@ -117,6 +132,8 @@ class Model:
             m.trans[i] = self.trans[i]
         for i in range(5):
             m.vanilla[i] = self.vanilla[i]
+        for i in range(11):
+            m.trans4[i] = FOUR_STATE_TRANSITIONS[i]
         return m
 
 

@@ -57,6 +57,8 @@ static StateMachine *makeStateMachine(int smType, const char *modelFile, const d
         sM = getStrawManStateMachine3(modelFile);
     } else if (smType == vanilla) {
         sM = getSignalStateMachine3Vanilla(modelFile);
+    } else if (smType == fourState) {
+        sM = getStateMachine4(modelFile);
     } else {
         fprintf(stderr, "ref_shim: unsupported state machine type %d\n", smType);
         return NULL;

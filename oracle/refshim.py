@@ -11,6 +11,7 @@ REF_SO = os.path.join(HERE, "_ref", "libcpecan_ref.so")
 
 THREE_STATE = 2
 VANILLA = 4
+FOUR_STATE = 6
 
 
 class RefParams(C.Structure):

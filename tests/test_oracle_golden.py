@@ -3,6 +3,8 @@
   * the known-answer vectors the reference's own CuTest suites hold for this path:
       tests/pairwiseAlignerTest.c:74-137 (band walk), :596-665 (split points), :139-149 (logAdd property),
       tests/signalPairwiseTest.c:580-685 (8 pairs), :795-897 (5 pairs), :1163,1173,1293,1303 (987/986/999/953)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -92,6 +94,27 @@ def test_fixture_banded_bit_exact(zymo, template_tables, tag, smt, e, ragged, co
         assert len(pairs) == count
     assert len({(int(x), int(y)) for _, x, y in pairs}) == len(pairs)
     assert pairs[:, 0].min() >= int(0.01 * 1e7) and pairs[:, 0].max() <= 10_000_000
+
+
+@pytest.mark.parametrize("tag,e,ragged,count", [("four_e20_r11", 20, (1, 1), 988), ("four_e20_r00", 20, (0, 0), 988),
+                                                  ("four_e50_r10", 50, (1, 0), None)])
+def test_fixture_four_state_bit_exact(zymo, template_tables, tag, e, ragged, count):
+    """The fourState machine (tests/signalPairwiseTest.c:1199-1236: 988 pairs with and without banding): the oracle's
+    four-state cell, start / end vectors and S-state dot products against goldens of the unmodified reference.  (The
+    device path does not build this machine yet -- DESIGN.md section 9; the oracle is pinned ahead of it.)"""
+    g = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "zymo_four_state_golden.npz")))
+    rd = zymo["read"]
+    m = O.Model(O.FOUR_STATE, tables=template_tables, scale5=rd["template_params"])
+    pairs, totals = O.align_banded(m, zymo["ref"], rd["template_events"], zymo["anchors_template"],
+                                   params=O.default_params(diagonalExpansion=e), ragged=ragged, want_totals=True)
+    assert np.array_equal(pairs, g[tag + "_pairs"])
+    assert np.array_equal(totals, g[tag + "_totals"], equal_nan=True)
+    if count is not None:
+        assert len(pairs) == count
+    if tag == "four_e20_r11":
+        up, ut = O.align_unbanded(m, zymo["ref"], rd["template_events"], ragged=(1, 1))
+        assert np.array_equal(up, g["four_unbanded_r11_pairs"]) and ut == float(g["four_unbanded_r11_total"])
+        assert len(up) == 988
 
 
 def test_fixture_band_size(zymo):
