@@ -11,8 +11,9 @@
  * bit-for-bit (identical (score,x,y) lists, identical per-diagonal totals)
  * against the unmodified reference sources compiled into oracle/_ref/ on the
  * reference's own fixture (987 / 986 / 999 / 953 aligned pairs,
- * tests/signalPairwiseTest.c:1163,1173,1293,1303) and on seeded synthetic reads;
- * the resulting golden vectors are committed under tests/golden/.
+ * tests/signalPairwiseTest.c:1163,1173,1293,1303; fourState 988 / 988, :1227,1236)
+ * and on seeded synthetic reads; the resulting golden vectors are committed
+ * under tests/golden/.  Machines: threeState (strawMan), vanilla, fourState.
  *
  * Each function cites the reference file:line whose behaviour it restates.
  * "ref" below = impl/pairwiseAligner.c, "sm" = impl/stateMachine.c.
