@@ -37,10 +37,10 @@ EXPANSIONS = (64, 128, 256)
 LX = 6700
 HBM_BYTES_PER_CELL = 25.0       # forward cell written + read once (24 B) + inputs/outputs (<1 B)
 # DRAM bytes per band cell of k_align2 from the ncu --set full capture committed under profiles/
-# (r1_ncu_k_align2_e64_v9_summary.txt: dram__bytes_read.sum 175.7 GB + dram__bytes_write.sum 98.5 GB for one launch over
-# 6.807e9 band cells): 14.5 B written + 25.8 B read per band cell (forward rows are float4 (M, X, Y, offset) written by
+# (r1_ncu_k_align2_e64_v11_summary.txt: dram__bytes_read.sum 174.0 GB + dram__bytes_write.sum 98.5 GB for one launch over
+# 6.807e9 band cells): 14.5 B written + 25.6 B read per band cell (forward rows are float4 (M, X, Y, offset) written by
 # the cells inside the band; the L2 prefetch of forward rows fetches whole 512-byte chunks)
-DRAM_BYTES_PER_CELL_NCU = 40.3
+DRAM_BYTES_PER_CELL_NCU = 40.0
 ISSUE_OPS_PER_CELL = 165.0
 METRIC = "banded_fwd_bwd_posterior_gcups"
 
