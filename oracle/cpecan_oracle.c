@@ -11,9 +11,10 @@
  * bit-for-bit (identical (score,x,y) lists, identical per-diagonal totals)
  * against the unmodified reference sources compiled into oracle/_ref/ on the
  * reference's own fixture (987 / 986 / 999 / 953 aligned pairs,
- * tests/signalPairwiseTest.c:1163,1173,1293,1303; fourState 988 / 988, :1227,1236)
- * and on seeded synthetic reads; the resulting golden vectors are committed
- * under tests/golden/.  Machines: threeState (strawMan), vanilla, fourState.
+ * tests/signalPairwiseTest.c:1163,1173,1293,1303; fourState 988 / 988, :1227,1236;
+ * echelon 857 / 1000, :1434,1445) and on seeded synthetic reads; the resulting
+ * golden vectors are committed under tests/golden/.  Machines: threeState
+ * (strawMan), vanilla, fourState, echelon.
  *
  * Each function cites the reference file:line whose behaviour it restates.
  * "ref" below = impl/pairwiseAligner.c, "sm" = impl/stateMachine.c.
@@ -30,6 +31,8 @@
 #define SM_THREE_STATE 2
 #define SM_VANILLA 4
 #define SM_FOUR_STATE 6       /* inc/stateMachine.h:20-29 */
+#define SM_ECHELON 5
+#define ECH_GAPX 6             /* match0 .. match5 = 0 .. 5, gapX = 6 (sm:1164-1166) */
 enum { ST_M = 0, ST_X = 1, ST_Y = 2, ST_LX = 3 };       /* match, shortGapX, shortGapY, longGapX (inc/stateMachine.h:31-33) */
 /* StateMachine4 transitions in the order this file keeps them (inc/stateMachine.h StateMachine4) */
 enum { T4_MATCH_CONTINUE = 0, T4_MATCH_FROM_SHORT_GAP_X, T4_MATCH_FROM_SHORT_GAP_Y, T4_MATCH_FROM_LONG_GAP_X,
@@ -37,11 +40,11 @@ enum { T4_MATCH_CONTINUE = 0, T4_MATCH_FROM_SHORT_GAP_X, T4_MATCH_FROM_SHORT_GAP
        T4_GAP_LONG_OPEN_X, T4_GAP_LONG_EXTEND_X, T4_GAP_LONG_SWITCH_TO_X, T4_COUNT };
 
 typedef struct {
-    int32_t sm_type;          /* 2 = threeState (strawMan), 4 = vanilla, 6 = fourState */
+    int32_t sm_type;          /* 2 = threeState (strawMan), 4 = vanilla, 6 = fourState, 5 = echelon */
     int32_t strand;           /* unused by the DP; kept for the host mirror */
     const double *match;      /* EMISSION_MATCH_PROBS: 1 + 4096*5 (already scaled per read) */
     const double *gapy;       /* EMISSION_GAP_Y_PROBS: 1 + 4096*5 (never scaled, sm:631-651) */
-    const double *gapx;       /* threeState: 4096 log-probs; vanilla: 60 skip-bin probabilities */
+    const double *gapx;       /* threeState: 4096 log-probs; vanilla, echelon: 60 skip-bin probabilities */
     double trans[9];          /* threeState, StateMachine3 field order (inc/stateMachine.h:179-187) */
     double vanilla[5];        /* M_TO_Y_NOT_X, E_TO_E, END_MATCH, END_FROM_X, END_FROM_Y */
     double trans4[T4_COUNT];  /* fourState, T4_* order; gapx then holds 4096 zeros (emissions_signal_initEmissionsToZero) */
@@ -225,7 +228,8 @@ typedef struct {
     const double *ev;         /* events of this (sub-)region: 3 doubles each */
     int64_t lX, lY;
     const int64_t *xmyL, *xmyR;
-    int S;                    /* states per cell: 3, fourState 4 */
+    int S;                    /* states per cell: 3, fourState 4, echelon 7 */
+    int64_t refLen;           /* characters from ref to the end of the sequence (echelon reads into the padding) */
     double **F, **B;          /* per-diagonal cell arrays (S doubles per cell) or NULL when not alive */
     /* expectation accumulators (mode 2) */
     double total;
@@ -274,6 +278,39 @@ static int skip_bin(const double *match, const char *p) {
     return b >= 30 ? 29 : (int) b;
 }
 
+/* ---- echelon (getStateMachineEchelon, sm:1773-1784): events may cover n = 1 .. 5 k-mers --------------------------
+ * The reference pads the nucleotide sequence with 30 'n' (ref:282-285; tests/signalPairwiseTest.c:1422) and reads up
+ * to 6 n + 6 characters past the getKmer2 pointer; rch() is that padded read. */
+static char rch(const Dp *dp, int64_t i) { return (i >= 0 && i < dp->refLen) ? dp->ref[i] : 'n'; }
+static int32_t kmer_index_at(const Dp *dp, int64_t i) {
+    char b[KMER_LEN];
+    for (int j = 0; j < KMER_LEN; j++) b[j] = rch(dp, i + j);
+    return kmer_index(b);
+}
+/* sm:388-419 on the padded sequence */
+static int skip_bin_at(const Dp *dp, int64_t i) {
+    double d = fabs(mdl(dp->m->match, kmer_index_at(dp, i + 1), 0) - mdl(dp->m->match, kmer_index_at(dp, i), 0));
+    int64_t b = (int64_t) (d / 0.5);
+    return b >= 30 ? 29 : (int) b;
+}
+/* emissions_signal_multipleKmerMatchProb (sm:530-549), quirks included: the fold starts from 0.0 (= log 1), and the
+ * run-off test looks at the single character 6 n past the pointer */
+static double multi_kmer_match(const Dp *dp, const double *tbl, int64_t i, const double *ev, int n) {
+    double p = 0.0;
+    for (int j = 0; j < n; j++) {
+        char last = rch(dp, i + KMER_LEN * n);
+        if (last >= 'A' && last <= 'Z') p = LA(p, emit_gauss_invgauss(tbl, kmer_index_at(dp, i + j + 1), ev));
+        else return NEG_INF;
+    }
+    return p - log((double) n);
+}
+/* emissions_signal_poissonPosteriorProb (sm:345-370) of the event's duration */
+static double duration_prob(const double *ev, int n) {
+    static const double lfact[6] = { 0.0, 0.0, 0.69314718056, 1.79175946923, 3.17805383035, 4.78749174278 };
+    double lambda = ev[2] / 0.00332005312085;
+    return (n + 1) * 0.1397619423751586 + n * log(lambda) - lfact[n] - 2 * lambda;
+}
+
 /* One cell: sm:1305-1334 (threeState) and sm:1368-1409 (vanilla).  ix / iy are SEQUENCE indices (matrix - 1);
  * the neighbour pointers may be NULL exactly as dpDiagonal_getCell returns NULL outside the band (ref:562-568). */
 static void cell(Dp *dp, int mode, double *cur, double *lower, double *middle, double *upper, int64_t ix, int64_t iy) {
@@ -300,6 +337,30 @@ static void cell(Dp *dp, int mode, double *cur, double *lower, double *middle, d
             double eP = emit_two_gauss(m->gapy, k, ev);
             transition(dp, mode, upper, cur, ST_M, ST_Y, eP, t[4], k, 0);
             transition(dp, mode, upper, cur, ST_Y, ST_Y, eP, t[6], k, 0);
+        }
+    } else if (m->sm_type == SM_ECHELON) {
+        /* stateMachineEchelon_cellCalculate (sm:1411-1460); getKmer2 pointer clamped at 0 (ref:320-325) */
+        const int64_t i = ix > 0 ? ix - 1 : 0;
+        const int bin = skip_bin_at(dp, i);
+        const double a_mx = m->gapx[bin], la_mx = log(a_mx), la_mh = log(1 - a_mx);
+        const double a_xx = m->gapx[bin + 30], la_xx = log(a_xx), la_xh = log(1 - a_xx);
+        if (lower) {
+            for (int n = 1; n < 6; n++) transition(dp, mode, lower, cur, n, ECH_GAPX, 0, la_mx, -1, 0);
+            transition(dp, mode, lower, cur, ECH_GAPX, ECH_GAPX, 0, la_xx, -1, 0);
+        }
+        if (middle) {
+            for (int n = 1; n < 6; n++)
+                for (int from = 0; from < 6; from++)
+                    transition(dp, mode, middle, cur, from, n, multi_kmer_match(dp, m->match, i, ev, n),
+                               la_mh + duration_prob(ev, n), -1, 0);
+            for (int n = 1; n < 6; n++)
+                transition(dp, mode, middle, cur, ECH_GAPX, n, multi_kmer_match(dp, m->match, i, ev, n),
+                           la_xh + duration_prob(ev, n), -1, 0);
+        }
+        if (upper) {
+            for (int n = 1; n < 6; n++)
+                transition(dp, mode, upper, cur, n, 0, emit_gauss_invgauss(m->gapy, kmer_index_at(dp, i + 1), ev),
+                           la_mh + duration_prob(ev, 0), -1, 0);
         }
     } else if (m->sm_type == SM_FOUR_STATE) {
         /* stateMachine4_cellCalculate (sm:867-897); emissions of getStateMachine4 (sm:1750-1759): gap X from the
@@ -409,7 +470,25 @@ static void posterior_diag(Dp *dp, int64_t xay, double total, double threshold, 
     }
     for (int64_t xmy = dp->xmyL[xay]; xmy <= dp->xmyR[xay]; xmy += 2) {
         int64_t x = (xay + xmy) / 2, y = (xay - xmy) / 2;
-        if (x > 0 && y > 0) {
+        if (x > 0 && y > 0 && dp->m->sm_type == SM_ECHELON) {
+            /* diagonalCalculationMultiPosteriorMatchProbs (ref:797-839): state s = 1 .. 5 pairs the event with s k-mers */
+            const double *f = cell_at(dp, dp->F, xay, xmy), *b = cell_at(dp, dp->B, xay, xmy);
+            for (int st = 1; st < 6; st++) {
+                double p = exp((f[st] + b[st]) - total);
+                if (p >= threshold) {
+                    if (p > 1.0) p = 1.0;
+                    p = floor(p * 10000000);
+                    for (int n = 0; n < st; n++) {
+                        if (sink->n < sink->cap) {
+                            sink->out[3 * sink->n] = (int64_t) p;
+                            sink->out[3 * sink->n + 1] = (x + n) - 1 + sink->offX;
+                            sink->out[3 * sink->n + 2] = y - 1 + sink->offY;
+                        }
+                        sink->n++;
+                    }
+                }
+            }
+        } else if (x > 0 && y > 0) {
             double lp = cell_at(dp, dp->F, xay, xmy)[ST_M] + cell_at(dp, dp->B, xay, xmy)[ST_M] - total;
             double p = exp(lp);
             if (p >= threshold) {
@@ -426,6 +505,14 @@ static void posterior_diag(Dp *dp, int64_t xay, double total, double threshold, 
 }
 
 static void state_vector(const OracleModel *m, int which /*0 start,1 raggedStart,2 end,3 raggedEnd*/, double *v) {
+    if (m->sm_type == SM_ECHELON) {
+        /* sm:1237-1262; the end "probabilities" are NOT logs in the reference (sm:1617-1619) and are used as they are */
+        for (int st = 0; st < 7; st++) v[st] = NEG_INF;
+        if (which == 0) v[1] = 0;
+        else if (which == 1) v[ECH_GAPX] = 0;
+        else { for (int st = 0; st < 6; st++) v[st] = 0.79015888282447311; v[ECH_GAPX] = 0.19652425498269727; }
+        return;
+    }
     if (m->sm_type == SM_FOUR_STATE) {
         const double *t = m->trans4;
         if (which == 0) { v[0] = 0; v[1] = v[2] = v[3] = NEG_INF; }                          /* sm:775-779 (shared with 5) */
@@ -462,12 +549,12 @@ static void banded_region(const OracleModel *m, const char *ref, int64_t lX, con
     int64_t D = lX + lY;
     if (D == 0) return;
     Dp dp; memset(&dp, 0, sizeof(dp));
-    dp.m = m; dp.S = m->sm_type == SM_FOUR_STATE ? 4 : 3; dp.ref = ref; dp.ev = ev; dp.lX = lX; dp.lY = lY; dp.expT = expT; dp.expSkip = expSkip;
+    dp.m = m; dp.S = m->sm_type == SM_FOUR_STATE ? 4 : (m->sm_type == SM_ECHELON ? 7 : 3); dp.refLen = (int64_t) strlen(ref); dp.ref = ref; dp.ev = ev; dp.lX = lX; dp.lY = lY; dp.expT = expT; dp.expSkip = expSkip;
     int64_t *xl = malloc(sizeof(int64_t) * (D + 1)), *xr = malloc(sizeof(int64_t) * (D + 1));
     oracle_band(anchors, nA, lX, lY, p->diagonalExpansion, xl, xr);
     dp.xmyL = xl; dp.xmyR = xr;
     dp.F = calloc(D + 2, sizeof(double *)); dp.B = calloc(D + 2, sizeof(double *));
-    double v[4];
+    double v[7];
     state_vector(m, raggedLeft ? 1 : 0, v);
     fill_diag(&dp, dp.F, 0, v);
     int64_t tracedBackTo = 0;
@@ -565,13 +652,13 @@ int64_t oracle_align_unbanded(const OracleModel *m, const char *ref, int64_t lX,
                               double *totalOut) {
     int64_t D = lX + lY;
     Dp dp; memset(&dp, 0, sizeof(dp));
-    dp.m = m; dp.S = m->sm_type == SM_FOUR_STATE ? 4 : 3; dp.ref = ref; dp.ev = events; dp.lX = lX; dp.lY = lY;
+    dp.m = m; dp.S = m->sm_type == SM_FOUR_STATE ? 4 : (m->sm_type == SM_ECHELON ? 7 : 3); dp.refLen = (int64_t) strlen(ref); dp.ref = ref; dp.ev = events; dp.lX = lX; dp.lY = lY;
     int64_t *xl = malloc(sizeof(int64_t) * (D + 1)), *xr = malloc(sizeof(int64_t) * (D + 1));
     oracle_band(NULL, 0, lX, lY, 2, xl, xr);
     dp.xmyL = xl; dp.xmyR = xr;
     dp.F = calloc(D + 2, sizeof(double *)); dp.B = calloc(D + 2, sizeof(double *));
     for (int64_t i = 0; i <= D; i++) { new_diag(&dp, dp.F, i, NEG_INF); new_diag(&dp, dp.B, i, NEG_INF); }
-    double v[4];
+    double v[7];
     state_vector(m, raggedLeft ? 1 : 0, v); fill_diag(&dp, dp.F, 0, v);
     state_vector(m, raggedRight ? 3 : 2, v); fill_diag(&dp, dp.B, D, v);
     for (int64_t i = 0; i <= D; i++) sweep(&dp, MODE_FWD, dp.F, i, dp.F, dp.F, 1);

@@ -140,6 +140,21 @@ def four_state_goldens():
     print("four unbanded", len(pairs), total)
     np.savez_compressed(os.path.join(GOLDEN, "zymo_four_state_golden.npz"), **out)
 
+    # The echelon machine (getStateMachineEchelon, 7 states, events covering 1 .. 5 k-mers, Poisson duration term,
+    # diagonalCalculationMultiPosteriorMatchProbs): the reference's known answers are 857 pairs banded and 1000 without
+    # banding at threshold 0.15, ragged (0,0) (tests/signalPairwiseTest.c:1388-1449).
+    out = {}
+    for tag, e, ragged, thr in (("echelon_e20_r00_t15", 20, (0, 0), 0.15), ("echelon_e50_r10_t15", 50, (1, 0), 0.15)):
+        pairs, totals = R.align_banded(R.ECHELON, T_MODEL, ref, tev, anch, scale5=tp, ragged=ragged, want_totals=True,
+                                       params=R.default_params(diagonalExpansion=e, threshold=thr))
+        out[tag + "_pairs"], out[tag + "_totals"] = pairs, totals
+        print(tag, len(pairs), int(pairs[:, 0].sum()))
+    pairs, total = R.align_unbanded(R.ECHELON, T_MODEL, ref, tev, scale5=tp, ragged=(0, 0),
+                                    params=R.default_params(threshold=0.15))
+    out["echelon_unbanded_r00_t15_pairs"], out["echelon_unbanded_r00_t15_total"] = pairs, np.float64(total)
+    print("echelon unbanded", len(pairs), total)
+    np.savez_compressed(os.path.join(GOLDEN, "zymo_echelon_golden.npz"), **out)
+
 
 def vanilla_align_goldens():
     """tests/golden/vanillaAlign/*: outputs of the UNMODIFIED reference CLI (oracle/_ref/vanillaAlign, `make -C oracle

@@ -13,6 +13,7 @@ ORACLE_SO = os.path.join(HERE, "libcpecan_oracle.so")
 THREE_STATE = 2
 VANILLA = 4
 FOUR_STATE = 6
+ECHELON = 5
 N_KMERS = 4096
 
 # stateMachine3_setTransitionsToNanoporeDefaults (reference impl/stateMachine.c:1278-1289), StateMachine3 field order

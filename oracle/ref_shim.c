@@ -59,6 +59,8 @@ static StateMachine *makeStateMachine(int smType, const char *modelFile, const d
         sM = getSignalStateMachine3Vanilla(modelFile);
     } else if (smType == fourState) {
         sM = getStateMachine4(modelFile);
+    } else if (smType == echelon) {
+        sM = getStateMachineEchelon(modelFile);
     } else {
         fprintf(stderr, "ref_shim: unsupported state machine type %d\n", smType);
         return NULL;
@@ -117,7 +119,8 @@ static int64_t g_xOffset = 0, g_yOffset = 0; /* unused for totals (region-local 
 static void recordingPosteriorFn(StateMachine *sM, int64_t xay, DpMatrix *f, DpMatrix *b, Sequence *sX, Sequence *sY,
                                  double totalProbability, PairwiseAlignmentParameters *p, void *extraArgs) {
     if (g_totals && xay >= 0 && xay < g_totalsLen) g_totals[xay] = totalProbability;
-    diagonalCalculationPosteriorMatchProbs(sM, xay, f, b, sX, sY, totalProbability, p, extraArgs);
+    if (sM->type == echelon) diagonalCalculationMultiPosteriorMatchProbs(sM, xay, f, b, sX, sY, totalProbability, p, extraArgs);
+    else diagonalCalculationPosteriorMatchProbs(sM, xay, f, b, sX, sY, totalProbability, p, extraArgs);
 }
 
 int64_t ref_align_banded(int smType, const char *modelFile, const double *scale5, int strand,
@@ -130,14 +133,17 @@ int64_t ref_align_banded(int smType, const char *modelFile, const double *scale5
     if (!sM) return -1;
     PairwiseAlignmentParameters *p = makeParams(rp);
     int64_t lX = sequence_correctSeqLength(strlen(refSeq), event);
-    Sequence *sX = sequence_construct2(lX, (void *) refSeq, smType == vanilla ? sequence_getKmer2 : sequence_getKmer,
+    Sequence *sX = sequence_construct2(lX, (void *) refSeq,
+                                       (smType == vanilla || smType == echelon) ? sequence_getKmer2 : sequence_getKmer,
                                        sequence_sliceNucleotideSequence2);
+    if (smType == echelon) sequence_padSequence(sX);     /* tests/signalPairwiseTest.c:1422-1423 */
     Sequence *sY = sequence_construct2(lY, (void *) events, sequence_getEvent, sequence_sliceEventSequence2);
     stList *anchorList = makeAnchors(anchors, nAnchors);
     g_totals = totalsOut; g_totalsLen = totalsLen; (void) g_xOffset; (void) g_yOffset;
     if (totalsOut) for (int64_t i = 0; i < totalsLen; i++) totalsOut[i] = NAN;
     stList *pairs = getAlignedPairsUsingAnchors(sM, sX, sY, anchorList, p,
-                                                totalsOut ? recordingPosteriorFn : diagonalCalculationPosteriorMatchProbs,
+                                                (totalsOut || smType == echelon) ? recordingPosteriorFn
+                                                                                 : diagonalCalculationPosteriorMatchProbs,
                                                 raggedLeft, raggedRight);
     g_totals = NULL; g_totalsLen = 0;
     int64_t n = drainPairs(pairs, out, cap);
@@ -160,7 +166,7 @@ int64_t ref_align_unbanded(int smType, const char *modelFile, const double *scal
     double tot = NAN;
     g_totals = &tot; g_totalsLen = 1; /* the same total is handed to every diagonal; record xay == 0 */
     stList *pairs = getAlignedPairsWithoutBanding(sM, (void *) refSeq, (void *) events, lX, lY, p,
-                                                  smType == vanilla ? sequence_getKmer2 : sequence_getKmer,
+                                                  (smType == vanilla || smType == echelon) ? sequence_getKmer2 : sequence_getKmer,
                                                   sequence_getEvent, recordingPosteriorFn, raggedLeft, raggedRight);
     g_totals = NULL; g_totalsLen = 0;
     if (totalOut) *totalOut = tot;

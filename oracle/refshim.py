@@ -12,6 +12,7 @@ REF_SO = os.path.join(HERE, "_ref", "libcpecan_ref.so")
 THREE_STATE = 2
 VANILLA = 4
 FOUR_STATE = 6
+ECHELON = 5
 
 
 class RefParams(C.Structure):

@@ -117,6 +117,26 @@ def test_fixture_four_state_bit_exact(zymo, template_tables, tag, e, ragged, cou
         assert len(up) == 988
 
 
+@pytest.mark.parametrize("tag,e,ragged,count", [("echelon_e20_r00_t15", 20, (0, 0), 857), ("echelon_e50_r10_t15", 50, (1, 0), None)])
+def test_fixture_echelon_bit_exact(zymo, template_tables, tag, e, ragged, count):
+    """The echelon machine (tests/signalPairwiseTest.c:1388-1449: 857 pairs banded, 1000 without banding at threshold
+    0.15): seven states, events covering 1 .. 5 k-mers read from the padded sequence, Poisson duration term, the
+    multi-state posterior.  Oracle pinned ahead of the device path, as for fourState."""
+    g = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "zymo_echelon_golden.npz")))
+    rd = zymo["read"]
+    m = O.Model(O.ECHELON, tables=template_tables, scale5=rd["template_params"])
+    prm = O.default_params(diagonalExpansion=e, threshold=0.15)
+    pairs, totals = O.align_banded(m, zymo["ref"], rd["template_events"], zymo["anchors_template"], params=prm,
+                                   ragged=ragged, want_totals=True)
+    assert np.array_equal(pairs, g[tag + "_pairs"])
+    assert np.array_equal(totals, g[tag + "_totals"], equal_nan=True)
+    if count is not None:
+        assert len(pairs) == count
+        up, ut = O.align_unbanded(m, zymo["ref"], rd["template_events"], params=prm, ragged=(0, 0))
+        assert np.array_equal(up, g["echelon_unbanded_r00_t15_pairs"]) and ut == float(g["echelon_unbanded_r00_t15_total"])
+        assert len(up) == 1000
+
+
 def test_fixture_band_size(zymo):
     """39 filtered anchors, 1692 diagonals, 140 469 band cells at e=20."""
     rd = zymo["read"]

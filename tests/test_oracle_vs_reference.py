@@ -34,13 +34,13 @@ def test_band_and_split_bit_exact():
             assert np.array_equal(O.split_points(pts, lX, lY, ms, rl, rr), R.split_points(pts, lX, lY, ms, rl, rr))
 
 
-@pytest.mark.parametrize("smt", [O.THREE_STATE, O.VANILLA, O.FOUR_STATE])
+@pytest.mark.parametrize("smt", [O.THREE_STATE, O.VANILLA, O.FOUR_STATE, O.ECHELON])
 @pytest.mark.parametrize("idx,lX,e,ragged,every,mind", [(40, 260, 20, (1, 1), 50, 1000), (41, 700, 64, (0, 1), 50, 300),
                                                          (42, 420, 10, (1, 0), 200, 1000)])
 def test_random_reads_bit_exact(template_tables, smt, idx, lX, e, ragged, every, mind):
     from cpecan_signal import synth
     r = synth.make_read(template_tables[0], idx, lX=lX, anchor_every=every,
-                        noise_dist="wald" if smt == O.VANILLA else "gauss")
+                        noise_dist="wald" if smt in (O.VANILLA, O.ECHELON) else "gauss")
     m = O.Model(smt, tables=template_tables, scale5=r.scale5, strand=0)
     po = O.default_params(diagonalExpansion=e, minDiagsBetweenTraceBack=mind)
     pr = R.default_params(diagonalExpansion=e, minDiagsBetweenTraceBack=mind)
@@ -49,7 +49,7 @@ def test_random_reads_bit_exact(template_tables, smt, idx, lX, e, ragged, every,
                               strand=0, ragged=ragged, want_totals=True)
     assert np.array_equal(got, want)
     assert np.array_equal(gt, wt, equal_nan=True)
-    if smt == O.FOUR_STATE:
+    if smt in (O.FOUR_STATE, O.ECHELON):
         return                     # the reference has no expectation container for this machine
     ge = O.expectations(m, r.ref, r.events, r.anchors, params=po, ragged=ragged)
     we = R.expectations(smt, synth.TEMPLATE_MODEL, r.ref, r.events, r.anchors, params=pr, scale5=r.scale5, strand=0,
