@@ -143,6 +143,41 @@ def test_edge_shapes_vs_oracle(engine, template_tables):
         print(i, stats)
 
 
+@pytest.mark.parametrize("machine", ["three", "vanilla"])
+def test_random_small_problems_vs_oracle(engine, template_tables, machine):
+    """Fuzz: batches of random small reads under parameter sets that force many tracebacks per read (traceback every
+    5 / 20 / 60 diagonals, 2 / 8 / 40 overlap diagonals), tiny expansions, sparse or no anchors and every ragged
+    combination, both machines -- each item against the oracle (pairs, scores, per-diagonal totals)."""
+    import oracleshim as O
+    from cpecan_signal import default_params, synth, vanilla_hmm
+    from cpecan_signal.engine import item_pairs
+    l1, l2, l3 = template_tables
+    rng = np.random.default_rng(77 if machine == "three" else 78)
+    smt = O.THREE_STATE if machine == "three" else O.VANILLA
+    for mind, tbd, e, thr in [(5, 2, 4, 0.01), (20, 8, 10, 0.2), (60, 40, 20, 0.01), (20, 2, 2, 0.01)]:
+        reads, anchors, ragged = [], [], []
+        for _ in range(14):
+            r = synth.make_read(l1, int(rng.integers(1, 1 << 30)), lX=int(rng.integers(8, 120)),
+                                anchor_every=int(rng.integers(5, 60)), noise_dist="gauss" if machine == "three" else "wald")
+            keep = rng.random(len(r.anchors)) < rng.choice([0.0, 0.3, 1.0])
+            reads.append(r); anchors.append(r.anchors[keep]); ragged.append((int(rng.integers(0, 2)), int(rng.integers(0, 2))))
+        mk = _three_state_batch if machine == "three" else _vanilla_batch
+        batch = mk(engine, template_tables, [r.ref for r in reads], [r.events for r in reads], anchors,
+                   [r.scale5 for r in reads], ragged)
+        kw = dict(diagonalExpansion=e, minDiagsBetweenTraceBack=mind, traceBackDiagonals=tbd, threshold=thr)
+        res, pairs, totals = engine.align_batch(batch, hmm=None if machine == "three" else vanilla_hmm("template"),
+                                                params=default_params(**kw), want_totals=True)
+        worst = 0
+        for i, r in enumerate(reads):
+            m = O.Model(smt, tables=(l1, l2, l3), scale5=r.scale5, strand=0)
+            want, wtot = O.align_banded(m, r.ref, r.events, anchors[i], params=O.default_params(**kw), ragged=ragged[i],
+                                        want_totals=True)
+            assert res[i]["status"] == 0, (i, kw)
+            worst = max(worst, parity.compare_pairs(item_pairs(res, pairs, i), want, threshold=thr)["worst_score_diff"])
+            parity.compare_totals(totals[i], wtot)
+        print(machine, kw, "worst score diff", worst)
+
+
 def test_c3_shape_batch_properties(engine, template_tables):
     """BASELINE config 3's shape (lX ~ 6700, ~8000 events, expansions 64 / 128 / 256, ~14 tracebacks per read) at a
     batch of several hundred reads, through properties that do not need the oracle -- plus the oracle on one read per
