@@ -175,6 +175,15 @@ def test_random_small_problems_vs_oracle(engine, template_tables, machine):
             assert res[i]["status"] == 0, (i, kw)
             worst = max(worst, parity.compare_pairs(item_pairs(res, pairs, i), want, threshold=thr)["worst_score_diff"])
             parity.compare_totals(totals[i], wtot)
+        # the E-step over the same batch: batch sums against the oracle's (transition / k-mer-skip / skip-bin counts)
+        got, eres = engine.expectations_batch(batch, hmm=None if machine == "three" else vanilla_hmm("template"),
+                                              params=default_params(**kw))
+        want = sum(O.expectations(O.Model(smt, tables=(l1, l2, l3), scale5=r.scale5, strand=0), r.ref, r.events, anchors[i],
+                                  params=O.default_params(**kw), ragged=ragged[i], pseudocount=0.0)
+                   for i, r in enumerate(reads))
+        assert (eres["status"] == 0).all()
+        np.testing.assert_allclose(got[:-1], want[:-1], rtol=EXP_RTOL, atol=2e-4)
+        assert abs(got[-1] - want[-1]) <= 1e-4 * abs(want[-1])
         print(machine, kw, "worst score diff", worst)
 
 
