@@ -225,6 +225,10 @@ class Engine:
         ptrs = [None if a is None else a.ctypes.data_as(C.c_void_p) for a in arrs]
         self._check(self.lib.cpecan_cuda_update_model(self.ctx, C.c_int32(model_id), *ptrs), "update_model")
 
+    def release_model(self, model_id):
+        """Frees the device tables of an uploaded model (its id may be handed out again)."""
+        self._check(self.lib.cpecan_cuda_release_model(self.ctx, C.c_int32(model_id)), "release_model")
+
     def set_resident_warps(self, warps_per_sm):
         """At most this many resident alignment warps per SM for the batches staged from now on (0 = all that fit)."""
         self._check(self.lib.cpecan_cuda_set_resident_warps(self.ctx, C.c_int32(int(warps_per_sm))), "set_resident_warps")
@@ -363,6 +367,13 @@ class Engine:
 
 
 def item_pairs(results, pairs, i, cap=None):
+    """The pairs of item i.  An item that overflowed its share of the pair buffer (status bit ITEM_PAIR_OVERFLOW) has
+    only the pairs that fitted in the buffer: its slice ends where the next item's begins."""
     r = results[i]
     n = int(r["n_pairs"])
+    if int(r["status"]) & ITEM_PAIR_OVERFLOW:
+        end = int(results[i + 1]["pair_off"]) if i + 1 < len(results) else None
+        if end is None:
+            raise EngineError("item %d overflowed its pair buffer (%d pairs): re-run with a larger pair_cap" % (i, n))
+        n = end - int(r["pair_off"])
     return pairs[int(r["pair_off"]): int(r["pair_off"]) + n]

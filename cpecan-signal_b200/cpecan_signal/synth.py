@@ -87,15 +87,19 @@ class SyntheticRead:
 
 
 def make_read(model_match, read_index, lX=6700, anchor_every=50, seed=SEED, skip_prob=0.10, stay_prob=0.25,
-              noise_dist="gauss"):
+              noise_dist="gauss", ref=None):
     """One synthetic read (counter-based seeding: the read is a function of (seed, read_index) only).
 
     reference = uniform ACGT of lX+5 nt; walking its k-mers, each is skipped w.p. 0.10, otherwise emits one event
     plus Geometric(0.25) extra 'stay' events; event mean ~ N(mu_k, sd_k), noise ~ N(nu_k, tau_k) truncated > 0,
     duration ~ Exp(0.01), all under per-read scaling (scale, shift, var, scale_sd, var_sd) drawn as SURVEY 8(d) says;
-    anchors = the true path sampled every `anchor_every` k-mers, run through filterToRemoveOverlap."""
+    anchors = the true path sampled every `anchor_every` k-mers, run through filterToRemoveOverlap.
+    ref: use this nucleotide string (ACGT only, lX = len - 5) instead of drawing one."""
     rng = np.random.default_rng([seed, read_index])
     codes = rng.integers(0, 4, size=lX + 5)
+    if ref is not None:                       # a given reference (e.g. the reverse complement of another read's)
+        lX = len(ref) - 5
+        codes = np.searchsorted(BASES, np.frombuffer(ref.encode(), dtype=np.uint8))
     kidx = np.zeros(lX, dtype=np.int64)
     for j in range(6):
         kidx = kidx * 4 + codes[j:j + lX]
@@ -130,3 +134,7 @@ def make_read(model_match, read_index, lX=6700, anchor_every=50, seed=SEED, skip
 def make_reads(n, lX=6700, first_index=0, model_path=TEMPLATE_MODEL, **kw):
     match = load_model_file(model_path)[0]
     return [make_read(match, first_index + i, lX=lX, **kw) for i in range(n)]
+
+
+def reverse_complement(seq):
+    return seq[::-1].translate(str.maketrans("ACGT", "TGCA"))

@@ -14,6 +14,7 @@
 #include "cpecan_cuda.h"
 #include "cpecan_kernels.cuh"
 #include "cpecan_align2.cuh"
+#include "cpecan_align3.cuh"
 
 using namespace cpecan;
 
@@ -40,11 +41,11 @@ struct DevBuf {
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
-struct Model { double *match = nullptr, *gapy = nullptr, *gapx = nullptr; int n_gapx = 0; };
+struct Model { double *match = nullptr, *gapy = nullptr, *gapx = nullptr; int n_gapx = 0; bool live = false; };
 
 struct Bucket {
     std::vector<int> order;      // item indices, largest first
-    int nCta = 0, ringRows = 0;
+    int nCta = 0, ringRows = 0, specRows = 0;
     long long stride = 0;        // float4 per CTA
     size_t scratchOff = 0;       // float4 into the scratch buffer
     size_t orderOff = 0;         // ints into the order buffer
@@ -76,12 +77,12 @@ struct cpecan_ctx {
     std::vector<Item> hItems;
     std::vector<ItemOut> hOut;
     DevBuf dItems, dOut, dRef, dRefOff, dEvSrc, dEvSrcOff, dAnchors, dScale, dCentre, dXp, dEv, dPairs, dOrder,
-           dQueue, dScratch, dTotals, dCompact, dCompactOff, dExpect;
+           dQueue, dScratch, dTotals, dCompact, dCompactOff, dExpect, dBits, dTbs, dFlags;
     int64_t pairCapTotal = 0, totalsLen = 0;
     Bucket buckets[NCFG2];
     int stagedMaxLX = 0;
     bool stagedScaled = false;
-    int occ2[NCFG2][2][2] = {};  // [bucket][machine][hasSX]
+    int occ2[NCFG2][2][2][2] = {};  // [bucket][machine][hasSX][expect]
     int occCap = 0;              // resident warps per SM this context may take (0 = all that fit)
     cudaEvent_t evBlock = nullptr;   // cudaEventBlockingSync: host threads sleep while they wait (several contexts per process)
     bool wantTotals = false;
@@ -109,30 +110,31 @@ static cudaError_t waitStream(cpecan_ctx *ctx, cudaStream_t s) {
 
 // k_align2<MACH, HAS_SX, EXPECT>: dispatch over the instantiations (the vanilla machine has no Y->X transition)
 template <typename F> auto dispatchK2(int mach, bool sx, bool ex, F f) {
-    if (mach) return ex ? f(k_align2<1, false, true>) : f(k_align2<1, false, false>);
-    if (sx) return ex ? f(k_align2<0, true, true>) : f(k_align2<0, true, false>);
-    return ex ? f(k_align2<0, false, true>) : f(k_align2<0, false, false>);
+    if (mach) return ex ? f(k_align3<1, false, true>) : f(k_align3<1, false, false>);
+    if (sx) return ex ? f(k_align3<0, true, true>) : f(k_align3<0, true, false>);
+    return ex ? f(k_align3<0, false, true>) : f(k_align3<0, false, false>);
 }
+inline size_t smemCfg2(int cfg, int mach, bool ex) { return align3_smem_bytes(cfg2N(cfg), ex && !mach); }
 cudaError_t prepCfg2(int cfg) {
-    const int bytes = (int) align2_smem_bytes(cfg2N(cfg));
     for (int mach = 0; mach < 2; mach++)
         for (int sx = 0; sx < 2; sx++)
             for (int ex = 0; ex < 2; ex++) {
+                const int bytes = (int) smemCfg2(cfg, mach, ex != 0);
                 cudaError_t e = dispatchK2(mach, sx != 0, ex != 0, [&](auto k) {
                     return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); });
                 if (e != cudaSuccess) return e;
             }
     return cudaSuccess;
 }
-int occCfg2(int cfg, int mach, bool sx) {
-    const size_t bytes = align2_smem_bytes(cfg2N(cfg));
-    return dispatchK2(mach, sx, false, [&](auto k) {
+int occCfg2(int cfg, int mach, bool sx, bool ex) {
+    const size_t bytes = smemCfg2(cfg, mach, ex);
+    return dispatchK2(mach, sx, ex, [&](auto k) {
         int nb = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, 32, bytes);
         return nb; });
 }
-void launchCfg2(int cfg, int mach, bool sx, bool expect, const KernelArgs2 &a, int nCta, cudaStream_t s) {
-    const size_t bytes = align2_smem_bytes(cfg2N(cfg));
+void launchCfg2(int cfg, int mach, bool sx, bool expect, const KernelArgs3 &a, int nCta, cudaStream_t s) {
+    const size_t bytes = smemCfg2(cfg, mach, expect);
     dispatchK2(mach, sx, expect, [&](auto k) { k<<<nCta, 32, bytes, s>>>(a); return 0; });
 }
 
@@ -203,11 +205,15 @@ int fillDevParams(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *p
     return CPECAN_OK;
 }
 
+// traceback points closer together than the zone of forward rows that keep all three states: keep them on every row
+bool allSpec(const cpecan_ctx *ctx) { return ctx->P.minDiags - ctx->P.tbDiags - 1 < ctx->P.tbDiags + 3; }
+
 void launchPrepX(cpecan_ctx *ctx, cudaStream_t s) {
     dim3 gx((unsigned) ctx->n, (unsigned) std::min(64, (ctx->stagedMaxLX + 256) / 256 + 1));
     k_prep_xparams<<<gx, 256, 0, s>>>(ctx->dItems.as<Item>(), ctx->dRefOff.as<long long>(), ctx->dRef.as<char>(),
                                      ctx->dModels.as<ModelTables>(), ctx->stagedScaled ? ctx->dScale.as<double>() : nullptr,
-                                     ctx->dCentre.as<double>(), ctx->dXp.as<float4>(), ctx->machine, ctx->mToYNotX);
+                                     ctx->dCentre.as<double>(), ctx->dXp.as<float4>(), ctx->machine, ctx->mToYNotX,
+                                     ctx->dFlags.as<int>());
     ctx->timing.kernel_launches += 1;
 }
 
@@ -234,7 +240,8 @@ int cpecan_cuda_init(int device, cpecan_ctx **ctx_out) {
     for (int c = 0; c < NCFG2; c++) {
         if (prepCfg2(c) != cudaSuccess) { cudaGetLastError(); break; }      // ring too large for this device's shared memory
         for (int mach = 0; mach < 2; mach++)
-            for (int sx = 0; sx < 2; sx++) ctx->occ2[c][mach][sx] = occCfg2(c, mach, sx != 0);
+            for (int sx = 0; sx < 2; sx++)
+                for (int ex = 0; ex < 2; ex++) ctx->occ2[c][mach][sx][ex] = occCfg2(c, mach, sx != 0, ex != 0);
     }
     *ctx_out = ctx;
     return CPECAN_OK;
@@ -244,10 +251,11 @@ void cpecan_cuda_destroy(cpecan_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (auto &m : ctx->models) { cudaFree(m.match); cudaFree(m.gapy); cudaFree(m.gapx); }
+    for (auto &m : ctx->models) if (m.live) { cudaFree(m.match); cudaFree(m.gapy); cudaFree(m.gapx); }
     DevBuf *bufs[] = { &ctx->dModels, &ctx->dItems, &ctx->dOut, &ctx->dRef, &ctx->dRefOff, &ctx->dEvSrc, &ctx->dEvSrcOff,
                        &ctx->dAnchors, &ctx->dScale, &ctx->dCentre, &ctx->dXp, &ctx->dEv, &ctx->dPairs, &ctx->dOrder,
-                       &ctx->dQueue, &ctx->dScratch, &ctx->dTotals, &ctx->dCompact, &ctx->dCompactOff, &ctx->dExpect };
+                       &ctx->dQueue, &ctx->dScratch, &ctx->dTotals, &ctx->dCompact, &ctx->dCompactOff, &ctx->dExpect,
+                       &ctx->dBits, &ctx->dTbs, &ctx->dFlags };
     for (auto *b : bufs) b->release();
     for (auto &e : ctx->ev) cudaEventDestroy(e);
     for (auto &e : ctx->bev) cudaEventDestroy(e);
@@ -273,9 +281,26 @@ int cpecan_cuda_upload_model(cpecan_ctx *ctx, const double *match, const double 
     CK(cudaMemcpy(m.match, match, tbl, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(m.gapy, gapy, tbl, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(m.gapx, gapx, n_gapx * sizeof(double), cudaMemcpyHostToDevice));
-    ctx->models.push_back(m);
+    m.live = true;
+    size_t slot = 0;
+    while (slot < ctx->models.size() && ctx->models[slot].live) slot++;      // reuse a released slot
+    if (slot == ctx->models.size()) ctx->models.push_back(m); else ctx->models[slot] = m;
     ctx->modelsDirty = true;
-    *model_id_out = (int32_t) ctx->models.size() - 1;
+    *model_id_out = (int32_t) slot;
+    return CPECAN_OK;
+}
+
+int cpecan_cuda_release_model(cpecan_ctx *ctx, int32_t model_id) {
+    if (!ctx) return CPECAN_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (model_id < 0 || model_id >= (int32_t) ctx->models.size() || !ctx->models[model_id].live) { ctx->err = "release_model: bad model id"; return CPECAN_ERR_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->running) { ctx->err = "release_model: a run is in flight"; return CPECAN_ERR_ARG; }
+    CK(waitStream(ctx, ctx->stream));
+    Model &m = ctx->models[model_id];
+    cudaFree(m.match); cudaFree(m.gapy); cudaFree(m.gapx);
+    m = Model();
+    ctx->modelsDirty = true;
     return CPECAN_OK;
 }
 
@@ -283,7 +308,7 @@ int cpecan_cuda_update_model(cpecan_ctx *ctx, int32_t model_id, const double *ma
                              const double *gapx) {
     if (!ctx) return CPECAN_ERR_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    if (model_id < 0 || model_id >= (int32_t) ctx->models.size()) { ctx->err = "update_model: bad model id"; return CPECAN_ERR_ARG; }
+    if (model_id < 0 || model_id >= (int32_t) ctx->models.size() || !ctx->models[model_id].live) { ctx->err = "update_model: bad model id"; return CPECAN_ERR_ARG; }
     CK(cudaSetDevice(ctx->device));
     CK(waitStream(ctx, ctx->stream));
     const size_t tbl = (1 + 4096 * 5) * sizeof(double);
@@ -294,19 +319,30 @@ int cpecan_cuda_update_model(cpecan_ctx *ctx, int32_t model_id, const double *ma
     return CPECAN_OK;
 }
 
-int cpecan_cuda_stage(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *params, int32_t mode,
-                      const cpecan_batch *B, int64_t pair_cap_total) {
-    if (!ctx || !hmm || !params || !B || B->n_items < 0) return CPECAN_ERR_ARG;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+}  // extern "C"
+
+namespace {
+
+// On every error exit of stage() the context holds NO staged batch (run_staged / fetch_staged then do nothing).
+struct StageGuard {
+    cpecan_ctx *c;
+    bool ok = false;
+    ~StageGuard() { if (!ok) { c->n = 0; for (auto &b : c->buckets) { b.order.clear(); b.nCta = 0; } } }
+};
+
+int stageL(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *params, int32_t mode, const cpecan_batch *B,
+           int64_t pair_cap_total, bool wantTotals) {
     CK(cudaSetDevice(ctx->device));
     if (ctx->running) { ctx->err = "stage: a run is in flight"; return CPECAN_ERR_ARG; }
+    StageGuard guard{ctx};
+    ctx->wantTotals = wantTotals;
     int rc = fillDevParams(ctx, hmm, params, mode);
     if (rc != CPECAN_OK) return rc;
     const int64_t n = B->n_items;
     ctx->n = n;
     ctx->mode = mode;
     ctx->timing = cpecan_timing{};
-    if (n == 0) return CPECAN_OK;
+    if (n == 0) { guard.ok = true; return CPECAN_OK; }
     cudaStream_t s = ctx->stream;
     const int needGapx = ctx->machine ? 60 : 4096;
 
@@ -321,7 +357,8 @@ int cpecan_cuda_stage(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_param
     // ---- host-side layout: prefix sums, per-item records -------------------------------------------------
     ctx->hItems.resize(n);
     std::vector<double> centre(n);
-    long long xpTot = 0, evTot = 0, totTot = 0;
+    long long xpTot = 0, evTot = 0, totTot = 0, bitsTot = 0, tbTot = 0;
+    const long long tbSpacing = std::max<long long>(1, ctx->P.minDiags - ctx->P.tbDiags - 1);
     int64_t sumLY = 0;
     for (int64_t i = 0; i < n; i++) sumLY += (B->ev_off[i + 1] - B->ev_off[i]) + 32;
     long long pairTot = 0;
@@ -331,7 +368,7 @@ int cpecan_cuda_stage(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_param
         Item &it = ctx->hItems[i];
         const int64_t refLen = B->ref_off[i + 1] - B->ref_off[i];
         const int64_t lX = refLen >= 5 ? refLen - 5 : 0, lY = B->ev_off[i + 1] - B->ev_off[i];
-        if (B->model_id[i] < 0 || B->model_id[i] >= (int) ctx->models.size()) { ctx->err = "bad model id"; return CPECAN_ERR_ARG; }
+        if (B->model_id[i] < 0 || B->model_id[i] >= (int) ctx->models.size() || !ctx->models[B->model_id[i]].live) { ctx->err = "bad model id"; return CPECAN_ERR_ARG; }
         if (ctx->models[B->model_id[i]].n_gapx < needGapx) {
             ctx->err = "model has too few gap-X entries for this state machine (threeState: 4096 log-probabilities, vanilla: 60 skip bins)";
             return CPECAN_ERR_ARG;
@@ -340,7 +377,10 @@ int cpecan_cuda_stage(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_param
         it.lX = (int) lX; it.lY = (int) lY; it.nA = (int) (B->anchor_off[i + 1] - B->anchor_off[i]);
         it.flags = B->ragged ? B->ragged[i] : 0;
         it.model_id = B->model_id[i];
-        it.pad0 = it.pad1 = 0;
+        // plan outputs: 2 bits per diagonal, and the traceback points (at least minDiags - tbDiags - 1 diagonals apart)
+        it.pad0 = (int) bitsTot; it.pad1 = (int) tbTot;
+        bitsTot += ((lX + lY) >> 4) + 1; tbTot += (lX + lY) / tbSpacing + 2;
+        if (bitsTot > 0x7fffffffLL || tbTot > 0x7fffffffLL) { ctx->err = "batch too large for the plan buffers"; return CPECAN_ERR_ARG; }
         // pair capacity: proportional share of the caller's buffer
         long long cap = (long long) ((long double) pair_cap_total * (long double) (lY + 32) / (long double) sumLY);
         it.pair_off = pairTot; it.pair_cap = (int) std::min<long long>(cap, 0x7fffffff);
@@ -371,6 +411,10 @@ int cpecan_cuda_stage(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_param
     CK(ctx->dXp.ensure(xpTot * (ctx->machine ? 4 : 3) * sizeof(float4)));
     CK(ctx->dEv.ensure(evTot * sizeof(float4)));
     CK(ctx->dPairs.ensure(std::max<long long>(1, pairTot) * 3 * sizeof(int)));
+    CK(ctx->dBits.ensure(std::max<long long>(1, bitsTot) * sizeof(unsigned)));
+    CK(ctx->dTbs.ensure(std::max<long long>(1, tbTot) * sizeof(int)));
+    CK(ctx->dFlags.ensure(n * sizeof(int)));
+    CK(cudaMemsetAsync(ctx->dFlags.p, 0, n * sizeof(int), s));
     CK(cudaMemcpyAsync(ctx->dItems.p, ctx->hItems.data(), n * sizeof(Item), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->dRef.p, B->ref, refBytes, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->dRefOff.p, B->ref_off, (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, s));
@@ -399,7 +443,8 @@ int cpecan_cuda_stage(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_param
     CK(cudaEventRecord(ctx->ev[2], s));
 
     // ---- plan: band cells, widest diagonal, longest run of live forward rows -------------------------------
-    k_plan<<<(unsigned) ((n + 127) / 128), 128, 0, s>>>(ctx->dItems.as<Item>(), (int) n, ctx->dAnchors.as<long long>(), ctx->P, ctx->dOut.as<ItemOut>());
+    k_plan3<<<(unsigned) ((n + 63) / 64), 64, 0, s>>>(ctx->dItems.as<Item>(), (int) n, ctx->dAnchors.as<long long>(), ctx->P, ctx->dOut.as<ItemOut>(),
+                                                    ctx->dBits.as<unsigned>(), ctx->dTbs.as<int>(), ctx->dFlags.as<int>());
     ctx->timing.kernel_launches += 1;
     ctx->hOut.resize(n);
     CK(cudaMemcpyAsync(ctx->hOut.data(), ctx->dOut.p, n * sizeof(ItemOut), cudaMemcpyDeviceToHost, s));
@@ -414,13 +459,13 @@ int cpecan_cuda_stage(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_param
 
     // ---- bucket by the ring size an alignment needs, order largest first ---------------------------------------
     for (auto &b : ctx->buckets) { b.order.clear(); b.nCta = 0; b.ringRows = 0; }
-    const int sx = ctx->hasSX ? 1 : 0;
+    const int sx = ctx->hasSX ? 1 : 0, ex = mode == CPECAN_MODE_EXPECTATION ? 1 : 0;
     int64_t cells = 0;
     for (int64_t i = 0; i < n; i++) {
         const ItemOut &o = ctx->hOut[i];
         cells += o.band_cells;
         int b = 0;
-        while (b < NCFG2 && (cfg2N(b) < o.max_width + CFG2_MARGIN || ctx->occ2[b][ctx->machine][sx] == 0)) b++;
+        while (b < NCFG2 && (cfg2N(b) < o.max_width + CFG2_MARGIN || ctx->occ2[b][ctx->machine][sx][ex] == 0)) b++;
         if (b == NCFG2) { ctx->err = "band wider than the widest ring this device's shared memory holds"; return CPECAN_ERR_BAND_TOO_WIDE; }
         ctx->buckets[b].order.push_back((int) i);
         ctx->buckets[b].ringRows = std::max(ctx->buckets[b].ringRows, o.max_rows);
@@ -433,10 +478,14 @@ int cpecan_cuda_stage(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_param
         Bucket &bk = ctx->buckets[b];
         if (bk.order.empty()) continue;
         std::stable_sort(bk.order.begin(), bk.order.end(), [&](int a, int c) { return ctx->hOut[a].band_cells > ctx->hOut[c].band_cells; });
-        int occ = std::max(1, ctx->occ2[b][ctx->machine][sx]);
+        int occ = std::max(1, ctx->occ2[b][ctx->machine][sx][ex]);
         if (ctx->occCap > 0) occ = std::min(occ, ctx->occCap);       // cpecan_cuda_set_resident_warps
         bk.nCta = (int) std::min<int64_t>((int64_t) bk.order.size(), (int64_t) ctx->prop.multiProcessorCount * occ);
-        bk.stride = (long long) bk.ringRows * cfg2N(b);           // float4 (M, X, Y, offset) per ring position and row
+        // forward rows: one float4 record per ring position and row; then the second plane (float2): posteriors keep
+        // the other two forward states of 2 * (tbDiags + 3) zone rows and 2 rows per 10 diagonals, the E-step the two
+        // emissions of every row
+        bk.specRows = (ex || allSpec(ctx)) ? bk.ringRows : 2 * (ctx->P.tbDiags + 3) + 2 * (bk.ringRows / 10 + 2);
+        bk.stride = (long long) bk.ringRows * cfg2N(b) + ((long long) bk.specRows * cfg2N(b) + 1) / 2;
         bk.scratchOff = scratch4; scratch4 += (size_t) bk.stride * bk.nCta;
         bk.orderOff = orderInts; orderInts += bk.order.size();
         orderAll.insert(orderAll.end(), bk.order.begin(), bk.order.end());
@@ -450,7 +499,19 @@ int cpecan_cuda_stage(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_param
     CK(cudaMemcpyAsync(ctx->dOrder.p, orderAll.data(), orderAll.size() * sizeof(int), cudaMemcpyHostToDevice, s));
     if (ctx->wantTotals) CK(ctx->dTotals.ensure(std::max<int64_t>(1, totTot) * sizeof(double)));
     CK(waitStream(ctx, s));
+    guard.ok = true;
     return CPECAN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cpecan_cuda_stage(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *params, int32_t mode,
+                      const cpecan_batch *B, int64_t pair_cap_total) {
+    if (!ctx || !hmm || !params || !B || B->n_items < 0) return CPECAN_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return stageL(ctx, hmm, params, mode, B, pair_cap_total, false);
 }
 
 int cpecan_cuda_restage_model(cpecan_ctx *ctx, const cpecan_hmm *hmm) {
@@ -469,9 +530,11 @@ int cpecan_cuda_restage_model(cpecan_ctx *ctx, const cpecan_hmm *hmm) {
     return CPECAN_OK;
 }
 
-int cpecan_cuda_run_staged_async(cpecan_ctx *ctx) {
-    if (!ctx) return CPECAN_ERR_ARG;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+}  // extern "C"
+
+namespace {
+
+int runAsyncL(cpecan_ctx *ctx) {
     CK(cudaSetDevice(ctx->device));
     if (ctx->n == 0) return CPECAN_OK;
     if (ctx->running) { ctx->err = "run_staged_async: the previous run was not waited for"; return CPECAN_ERR_ARG; }
@@ -484,17 +547,21 @@ int cpecan_cuda_run_staged_async(cpecan_ctx *ctx) {
     for (int b = 0; b < NCFG2; b++) {
         Bucket &bk = ctx->buckets[b];
         if (bk.order.empty()) continue;
-        KernelArgs2 a;
+        KernelArgs3 a;
         a.items = ctx->dItems.as<Item>();
         a.order = ctx->dOrder.as<int>() + bk.orderOff;
         a.n_items = (int) bk.order.size();
         a.queue = ctx->dQueue.as<int>() + b;
-        a.anchors = ctx->dAnchors.as<long long>();
         a.xparams = ctx->dXp.as<float4>();
         a.events = ctx->dEv.as<float4>();
+        a.bits = ctx->dBits.as<unsigned>();
+        a.tbs = ctx->dTbs.as<int>();
+        a.flags = ctx->dFlags.as<int>();
         a.scratch = ctx->dScratch.as<float4>() + bk.scratchOff;
         a.scratch_stride = bk.stride;
         a.ring_rows = bk.ringRows;
+        a.spec_rows = bk.specRows;
+        a.all_spec = allSpec(ctx) ? 1 : 0;
         a.ringN = cfg2N(b);
         a.zero = 0;
         a.pairs = ctx->dPairs.as<int>();
@@ -515,9 +582,7 @@ int cpecan_cuda_run_staged_async(cpecan_ctx *ctx) {
     return CPECAN_OK;
 }
 
-int cpecan_cuda_wait(cpecan_ctx *ctx) {
-    if (!ctx) return CPECAN_ERR_ARG;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+int waitL(cpecan_ctx *ctx) {
     if (!ctx->running) return CPECAN_OK;
     CK(cudaSetDevice(ctx->device));
     ctx->running = false;
@@ -528,14 +593,7 @@ int cpecan_cuda_wait(cpecan_ctx *ctx) {
     return CPECAN_OK;
 }
 
-int cpecan_cuda_run_staged(cpecan_ctx *ctx) {
-    int rc = cpecan_cuda_run_staged_async(ctx);
-    return rc == CPECAN_OK ? cpecan_cuda_wait(ctx) : rc;
-}
-
-int cpecan_cuda_fetch_staged(cpecan_ctx *ctx, int32_t *pairs_out, cpecan_result *results) {
-    if (!ctx || !results) return CPECAN_ERR_ARG;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+int fetchL(cpecan_ctx *ctx, int32_t *pairs_out, cpecan_result *results) {
     CK(cudaSetDevice(ctx->device));
     const int64_t n = ctx->n;
     if (n == 0) return CPECAN_OK;
@@ -580,17 +638,61 @@ int cpecan_cuda_fetch_staged(cpecan_ctx *ctx, int32_t *pairs_out, cpecan_result 
     return CPECAN_OK;
 }
 
+int fetchExpectL(cpecan_ctx *ctx, double *expectations_out) {
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->mode != CPECAN_MODE_EXPECTATION) { ctx->err = "fetch_expectations: the staged batch is not in expectation mode"; return CPECAN_ERR_ARG; }
+    const int len = ctx->machine ? CPECAN_N_EXPECT_VANILLA : CPECAN_N_EXPECT;
+    std::vector<double> tmp(len);
+    CK(cudaMemcpyAsync(tmp.data(), ctx->dExpect.p, len * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(waitStream(ctx, ctx->stream));
+    for (int i = 0; i < len; i++) expectations_out[i] += tmp[i];
+    ctx->timing.d2h_bytes += len * 8;
+    return CPECAN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cpecan_cuda_run_staged_async(cpecan_ctx *ctx) {
+    if (!ctx) return CPECAN_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return runAsyncL(ctx);
+}
+
+int cpecan_cuda_wait(cpecan_ctx *ctx) {
+    if (!ctx) return CPECAN_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return waitL(ctx);
+}
+
+int cpecan_cuda_run_staged(cpecan_ctx *ctx) {
+    if (!ctx) return CPECAN_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    int rc = runAsyncL(ctx);
+    return rc == CPECAN_OK ? waitL(ctx) : rc;
+}
+
+int cpecan_cuda_fetch_staged(cpecan_ctx *ctx, int32_t *pairs_out, cpecan_result *results) {
+    if (!ctx || !results) return CPECAN_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return fetchL(ctx, pairs_out, results);
+}
+
+// One lock for the whole call: two host threads sharing a context (the two strands of vanillaAlign.c:737-790) serialise
+// here instead of interleaving their stage / run / fetch steps.
 int cpecan_cuda_align_batch(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *params, int32_t mode,
                             const cpecan_batch *batch, int32_t *pairs_out, int64_t pair_cap_total,
                             cpecan_result *results, double *totals_out, const int64_t *tot_off) {
     if (!ctx) return CPECAN_ERR_CUDA;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!hmm || !params || !batch || batch->n_items < 0 || !results) { ctx->err = "align_batch: null argument"; return CPECAN_ERR_ARG; }
     if (mode != CPECAN_MODE_POSTERIOR && mode != CPECAN_MODE_UNBANDED) { ctx->err = "align_batch: mode must be POSTERIOR or UNBANDED"; return CPECAN_ERR_ARG; }
-    ctx->wantTotals = totals_out != nullptr;
-    int rc = cpecan_cuda_stage(ctx, hmm, params, mode, batch, pair_cap_total);
-    if (rc == CPECAN_OK) rc = cpecan_cuda_run_staged(ctx);
-    if (rc == CPECAN_OK) rc = cpecan_cuda_fetch_staged(ctx, pairs_out, results);
+    int rc = stageL(ctx, hmm, params, mode, batch, pair_cap_total, totals_out != nullptr);
+    if (rc == CPECAN_OK) rc = runAsyncL(ctx);
+    if (rc == CPECAN_OK) rc = waitL(ctx);
+    if (rc == CPECAN_OK) rc = fetchL(ctx, pairs_out, results);
     if (rc == CPECAN_OK && totals_out && ctx->n > 0) {
-        std::lock_guard<std::mutex> lk(ctx->mu);
         // debug totals: copy each item's slice to the caller's layout
         std::vector<double> tmp(ctx->totalsLen);
         CK(cudaMemcpy(tmp.data(), ctx->dTotals.p, ctx->totalsLen * sizeof(double), cudaMemcpyDeviceToHost));
@@ -607,27 +709,21 @@ int cpecan_cuda_align_batch(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan
 int cpecan_cuda_expectations_batch(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *params,
                                    const cpecan_batch *batch, double *expectations_out, cpecan_result *results) {
     if (!ctx) return CPECAN_ERR_CUDA;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!hmm || !params || !batch || batch->n_items < 0) { ctx->err = "expectations_batch: null argument"; return CPECAN_ERR_ARG; }
     if (!expectations_out || !results) { ctx->err = "expectations_batch: null output"; return CPECAN_ERR_ARG; }
-    ctx->wantTotals = false;
-    int rc = cpecan_cuda_stage(ctx, hmm, params, CPECAN_MODE_EXPECTATION, batch, 0);
-    if (rc == CPECAN_OK) rc = cpecan_cuda_run_staged(ctx);
-    if (rc == CPECAN_OK) rc = cpecan_cuda_fetch_staged(ctx, nullptr, results);
-    if (rc == CPECAN_OK && ctx->n > 0) rc = cpecan_cuda_fetch_expectations(ctx, expectations_out);
+    int rc = stageL(ctx, hmm, params, CPECAN_MODE_EXPECTATION, batch, 0, false);
+    if (rc == CPECAN_OK) rc = runAsyncL(ctx);
+    if (rc == CPECAN_OK) rc = waitL(ctx);
+    if (rc == CPECAN_OK) rc = fetchL(ctx, nullptr, results);
+    if (rc == CPECAN_OK && ctx->n > 0) rc = fetchExpectL(ctx, expectations_out);
     return rc;
 }
 
 int cpecan_cuda_fetch_expectations(cpecan_ctx *ctx, double *expectations_out) {
     if (!ctx || !expectations_out) return CPECAN_ERR_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    CK(cudaSetDevice(ctx->device));
-    if (ctx->mode != CPECAN_MODE_EXPECTATION) { ctx->err = "fetch_expectations: the staged batch is not in expectation mode"; return CPECAN_ERR_ARG; }
-    const int len = ctx->machine ? CPECAN_N_EXPECT_VANILLA : CPECAN_N_EXPECT;
-    std::vector<double> tmp(len);
-    CK(cudaMemcpyAsync(tmp.data(), ctx->dExpect.p, len * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(waitStream(ctx, ctx->stream));
-    for (int i = 0; i < len; i++) expectations_out[i] += tmp[i];
-    ctx->timing.d2h_bytes += len * 8;
-    return CPECAN_OK;
+    return fetchExpectL(ctx, expectations_out);
 }
 
 int cpecan_cuda_expectations_device_ptr(cpecan_ctx *ctx, double **dev_ptr_out) {

@@ -445,7 +445,14 @@ cpecan_ctx *gpuLocked() {
     return gCtx;
 }
 
-void modelDropLocked(StateMachine *sM) { gModels.erase(sM); }
+// the device tables of a state machine go with it (cpecan_cuda_release_model): a caller that builds one scaled state
+// machine per read and strand, as vanillaAlign.c does, would otherwise grow the device model list without bound
+void modelDropLocked(StateMachine *sM) {
+    auto it = gModels.find(sM);
+    if (it == gModels.end()) return;
+    if (gCtx) cpecan_cuda_release_model(gCtx, it->second);
+    gModels.erase(it);
+}
 
 int32_t modelIdLocked(cpecan_ctx *ctx, StateMachine *sM) {
     const int nGapX = sM->type == vanilla ? 60 : NUM_OF_KMERS;

@@ -132,6 +132,78 @@ __global__ void k_plan(const Item *items, int n, const long long *anchors, DevPa
     out[i] = o;
 }
 
+
+// ------------------------------------------------------------------------------------------------ plan kernel (k_align3)
+// One thread per item walks the band exactly as band_construct does (impl/pairwiseAligner.c:98-184: x-y limits with
+// parity fixing and C integer division, so odd expansions come out as in the reference) and leaves what k_align3 needs:
+//   * 2 bits per diagonal d = 0 .. D at word d / 16: bit 0 = lo(d) - lo(d-1), bit 1 = hi(d) - hi(d-1) (x limits);
+//   * the list of diagonals at which getPosteriorProbsWithBanding traces back (impl/pairwiseAligner.c:903-918);
+//   * band cells, widest diagonal, longest run of forward rows alive at a traceback;
+//   * flag bit 4 (CPECAN_ITEM_BAND_STEP) when a band edge moves backwards or by more than one cell (never for anchors
+//     that went through filterToRemoveOverlap): the alignment kernel skips such an item.
+__device__ __forceinline__ long long cp_clampz(long long z, long long l) { return z < 0 ? 0 : (z > l ? l : z); }
+__global__ void k_plan3(const Item *items, int n, const long long *anchors, DevParams P, ItemOut *out, unsigned *bits,
+                        int *tbs, int *flags) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Item it = items[i];
+    const long long *an = anchors + 2 * it.an_off;
+    const long long lX = it.lX, lY = it.lY, D = lX + lY, e = P.expansion;
+    unsigned *bw = bits + it.pad0;
+    int *tb = tbs + it.pad1;
+    long long ai = 0, pxay = 0, pxmy = 0, nxay = 0, nxmy = 0, xL = 0, yL = 0, xU = 0, yU = 0;
+    long long cells = 0;
+    int maxw = 0, maxrows = 1, ntb = 0, tracedBackTo = 0, flag = 0;
+    long long plo = 0, phi = 0;
+    unsigned word = 0;
+    for (long long xay = 0; xay <= D; xay++) {
+        long long l = xL - yL, r = xU - yU;
+        if ((xay + l) % 2 != 0) l++;
+        if ((xay + r) % 2 != 0) r++;
+        long long t;
+        t = (xay + l) / 2; if (t < xL) l += 2 * (xL - t);
+        t = (xay - l) / 2; if (yL < t) l += 2 * (t - yL);
+        t = (xay + r) / 2; if (xU < t) r -= 2 * (t - xU);
+        t = (xay - r) / 2; if (t < yU) r -= 2 * (yU - t);
+        const long long lo = (xay + l) / 2, hi = (xay + r) / 2;
+        if (xay > 0) {
+            const long long dl = lo - plo, dh = hi - phi;
+            if (dl < 0 || dl > 1 || dh < 0 || dh > 1) flag |= 4;
+            word |= (unsigned) ((dl & 1) | ((dh & 1) << 1)) << ((xay & 15) * 2);
+        } else if (lo != 0 || hi != 0) flag |= 4;
+        if ((xay & 15) == 15 || xay == D) { bw[xay >> 4] = word; word = 0; }
+        plo = lo; phi = hi;
+        const int w = (int) (hi - lo + 1);
+        if (w < 1) flag |= 4;
+        cells += w;
+        maxw = max(maxw, w);
+        if (xay > 0) {
+            const bool atEnd = xay == D;
+            const bool tbp = P.mode == 2 ? false : (xay >= tracedBackTo + P.minDiags && w <= 2 * e + 1);
+            if (atEnd || tbp) {
+                maxrows = max(maxrows, (int) xay - tracedBackTo + 1);
+                tracedBackTo = atEnd ? (int) xay : (int) xay - (P.tbDiags + 1);
+                tb[ntb++] = (int) xay;
+            }
+        }
+        if (nxay == xay) {
+            pxay = nxay; pxmy = nxmy;
+            long long x = lX, y = lY;
+            if (ai < it.nA) { x = an[2 * ai] + 1; y = an[2 * ai + 1] + 1; ai++; }
+            nxay = x + y; nxmy = x - y;
+            xL = cp_clampz((pxay + (pxmy - e)) / 2, lX);
+            yL = cp_clampz((nxay - (nxmy - e)) / 2, lY);
+            xU = cp_clampz((nxay + (nxmy + e)) / 2, lX);
+            yU = cp_clampz((pxay - (pxmy + e)) / 2, lY);
+        }
+    }
+    ItemOut o;
+    o.band_cells = cells; o.total_logprob = 0.0; o.n_pairs = 0; o.status = 0; o.n_tracebacks = ntb;
+    o.max_width = maxw; o.max_rows = maxrows + 2; o.pad = 0;
+    out[i] = o;
+    atomicOr(flags + i, flag);
+}
+
 // ------------------------------------------------------------------------------------------------ preparation
 // Events: reference layout (mean, noise, duration) doubles -> float4 (mean - centre, noise, 1 / noise,
 // -1.5 log(noise)); the last two serve the inverse-Gaussian noise term of the vanilla machine.  Entry 0 of each item
@@ -183,7 +255,7 @@ __device__ __forceinline__ int kmer_code(const char *s) {   // impl/stateMachine
 // k-mer pair starting at nucleotide 0.
 __global__ void k_prep_xparams(const Item *items, const long long *ref_off, const char *ref,
                                const ModelTables *models, const double *scale /*5 per item or null*/,
-                               const double *centre, float4 *out, int machine, double mToYNotX) {
+                               const double *centre, float4 *out, int machine, double mToYNotX, int *flags) {
     const int i = blockIdx.x;
     const Item it = items[i];
     const ModelTables mt = models[it.model_id];
@@ -203,6 +275,8 @@ __global__ void k_prep_xparams(const Item *items, const long long *ref_off, cons
             if (machine == 0) { if (x > 0) k = kmer_code(r + x - 1); }
             else { const int p = x >= 2 ? x - 2 : 0; kprev = kmer_code(r + p); k = kmer_code(r + p + 1); }
         }
+        // a reference k-mer that is not ACGT makes every path -inf: the E-step drops such a read (flag bit 8)
+        if (flags != nullptr && k < 0 && x >= (machine ? 0 : 1) && x <= it.lX) atomicOr(flags + i, 8);
         auto scaledMean = [&](int kk) { return kk < 0 ? 0.0 : (scaled ? mt.match[1 + 5 * kk] * sc + sh : mt.match[1 + 5 * kk]); };
         if (k >= 0) {
             const double *m = mt.match + 1 + 5 * k;

@@ -43,7 +43,10 @@ enum {
     CPECAN_ITEM_OK = 0,
     CPECAN_ITEM_PAIR_OVERFLOW = 1, /* more aligned pairs than pair_cap; n_pairs holds the true count */
     CPECAN_ITEM_NONFINITE = 2,     /* total probability was -inf / NaN (read skipped, reference would emit NaNs) */
-    CPECAN_ITEM_BAND_STEP = 4      /* band edge moved by more than one cell between diagonals (never for valid anchors) */
+    CPECAN_ITEM_BAND_STEP = 4,     /* band edge moved backwards or by more than one cell between diagonals (never for anchors that
+                                      went through filterToRemoveOverlap): the item is not aligned */
+    CPECAN_ITEM_BAD_KMER = 8       /* expectation mode: the reference holds a non-ACGT k-mer, every path is -inf; the read is
+                                      dropped from the sums as the reference drops it (status also carries NONFINITE) */
 };
 
 typedef struct cpecan_ctx cpecan_ctx;
@@ -126,6 +129,9 @@ int cpecan_cuda_upload_model(cpecan_ctx *ctx, const double *match, const double 
  * (continuousPairHmm_loadTransitionsAndKmerGapProbs rewrites EMISSION_GAP_X_PROBS, impl/continuousHmm.c:206-232). */
 int cpecan_cuda_update_model(cpecan_ctx *ctx, int32_t model_id, const double *match, const double *gapy,
                              const double *gapx);
+/* Free the device tables of an uploaded model; its id may be handed out again by a later upload.  What
+ * stateMachine_destruct (impl/stateMachine.c:1786-1788) is to the host tables. */
+int cpecan_cuda_release_model(cpecan_ctx *ctx, int32_t model_id);
 
 /* Posterior match probabilities for a batch.
  *   pairs_out   int32 triples (score, x, y), score = floor(p * 1e7) (PAIR_ALIGNMENT_PROB_1), x / y sequence

@@ -8,6 +8,13 @@ import numpy as np
 P_TOL = 1e-4
 SCORE_TOL = int(P_TOL * 1e7) + 2     # +2: floor() on both sides
 TOTAL_RTOL = 1e-4
+# The reference's logAdd (impl/pairwiseAligner.c:235-255) is DISCONTINUOUS: its cubic segments jump by 1.3e-4 at
+# |x - y| = 1, 1.7e-4 at 2.5, 4.2e-5 at 4.5, and by 4.5e-4 at the 7.5 cut-off (cubic(7.5) - 7.5 = 4.46e-4 against 0).
+# When a difference lies within rounding of such a bound, FP32 and the reference's doubles take different segments
+# (no finite precision short of the reference's own operation order can prevent that) and one cell's posterior moves
+# by up to the jump.  Measured: 1 aligned pair in 2.2 million on configuration 3.  Callers that pass
+# max_flips > 0 accept that many pairs per comparison whose score differs by at most FLIP_SCORE_TOL.
+FLIP_SCORE_TOL = int(4.5e-4 * 1e7) + SCORE_TOL
 
 
 def pair_dict(pairs):
@@ -20,21 +27,26 @@ def pair_dict(pairs):
     return d
 
 
-def compare_pairs(got, want, threshold=0.01):
+def compare_pairs(got, want, threshold=0.01, max_flips=0):
     """Returns a dict of statistics; raises AssertionError on a violation."""
     g, w = pair_dict(got), pair_dict(want)
     thr_hi = int((threshold + P_TOL) * 1e7) + 2
     worst = 0
+    flips = []
     for key, s in w.items():
         if key in g:
-            worst = max(worst, abs(g[key] - s))
-            assert abs(g[key] - s) <= SCORE_TOL, "pair %r: score %d vs reference %d" % (key, g[key], s)
+            df = abs(g[key] - s)
+            if df > SCORE_TOL and df <= FLIP_SCORE_TOL and len(flips) < max_flips:
+                flips.append((key, g[key], s))          # a logAdd segment flip (see FLIP_SCORE_TOL)
+                continue
+            worst = max(worst, df)
+            assert df <= SCORE_TOL, "pair %r: score %d vs reference %d" % (key, g[key], s)
         else:
             assert s <= thr_hi, "pair %r (score %d) missing and not within tolerance of the threshold" % (key, s)
     for key, s in g.items():
         if key not in w:
             assert s <= thr_hi, "extra pair %r (score %d) not within tolerance of the threshold" % (key, s)
-    return dict(n_got=len(g), n_want=len(w), common=len(set(g) & set(w)), worst_score_diff=worst)
+    return dict(n_got=len(g), n_want=len(w), common=len(set(g) & set(w)), worst_score_diff=worst, flips=flips)
 
 
 def compare_totals(got, want):
