@@ -2,5 +2,5 @@
 
 The compute path is the CUDA library only (libcpecan_cuda.so); importing this package never pulls in oracle/."""
 from . import em, engine, synth  # noqa: F401
-from .engine import (Engine, EngineError, HostBatch, default_params, three_state_hmm, vanilla_gapx,  # noqa: F401
-                     vanilla_hmm)
+from .engine import (Engine, EngineError, HostBatch, default_params, echelon_hmm, four_state_hmm,  # noqa: F401
+                     three_state_hmm, vanilla_gapx, vanilla_hmm)

@@ -11,6 +11,8 @@ LIB_PATH = os.environ.get("CPECAN_LIB") or os.path.join(PKG_ROOT, "libcpecan_cud
 
 SM_THREE_STATE = 2
 SM_VANILLA = 4
+SM_ECHELON = 5
+SM_FOUR_STATE = 6
 MODE_POSTERIOR = 0
 MODE_EXPECTATION = 1
 MODE_UNBANDED = 2
@@ -42,7 +44,30 @@ def default_params(**kw):
 
 class Hmm(C.Structure):
     _fields_ = [("sm_type", C.c_int32), ("reserved", C.c_int32), ("transitions", C.c_double * 9),
-                ("vanilla", C.c_double * 5)]
+                ("vanilla", C.c_double * 5), ("four_state", C.c_double * 11)]
+
+
+# stateMachine4_construct's defaults (reference impl/stateMachine.c:993-1011) in cpecan_hmm.four_state order
+FOUR_STATE_TRANSITIONS = (-0.23552123624314988, -0.21880828092192281, -0.013406326748077823, -5.6732801731704612,
+                          -1.6269694202638481, -1.6269694202638481, -4.7241893208381773, -4.724189320832104,
+                          -5.4173365013981227, -0.003442492794189331, -5.4173365013920494)
+
+
+def four_state_hmm(transitions=None):
+    """StateMachine4 (getStateMachine4): model with 4096 gap-X log-probabilities (zeros by default)."""
+    h = Hmm()
+    h.sm_type = SM_FOUR_STATE
+    t = FOUR_STATE_TRANSITIONS if transitions is None else transitions
+    for i in range(11):
+        h.four_state[i] = float(t[i])
+    return h
+
+
+def echelon_hmm():
+    """StateMachineEchelon (getStateMachineEchelon): model with the 60 skip bins of the vanilla machine."""
+    h = Hmm()
+    h.sm_type = SM_ECHELON
+    return h
 
 
 def three_state_hmm(transitions=None):

@@ -15,6 +15,7 @@
 #include "cpecan_kernels.cuh"
 #include "cpecan_align2.cuh"
 #include "cpecan_align3.cuh"
+#include "cpecan_generic.cuh"
 
 using namespace cpecan;
 
@@ -71,6 +72,8 @@ struct cpecan_ctx {
     int64_t n = 0;
     int mode = 0;
     int machine = 0;             // 0 three-state, 1 vanilla
+    int generic = 0;             // 0, or the StateMachineType run by k_align_generic: 6 fourState, 5 echelon
+    GenParams G{};
     double mToYNotX = 0.0;
     DevParams P{};
     bool hasSX = false;
@@ -138,6 +141,17 @@ void launchCfg2(int cfg, int mach, bool sx, bool expect, const KernelArgs3 &a, i
     dispatchK2(mach, sx, expect, [&](auto k) { k<<<nCta, 32, bytes, s>>>(a); return 0; });
 }
 
+// fourState / echelon: the FP64 kernel; ring size per bucket as for k_align3, occupancy from its shared-memory need
+template <typename F> auto dispatchGen(int sm, F f) { return sm == CPECAN_SM_ECHELON ? f(k_align_generic<5>, 7) : f(k_align_generic<6>, 4); }
+int occGen(int cfg, int sm) {
+    return dispatchGen(sm, [&](auto k, int S) {
+        const size_t bytes = generic_smem_bytes(cfg2N(cfg), S);
+        if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes) != cudaSuccess) { cudaGetLastError(); return 0; }
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, 32, bytes) != cudaSuccess) { cudaGetLastError(); return 0; }
+        return nb; });
+}
+
 __global__ void k_compact(const Item *items, const ItemOut *out, const long long *dstOff, int n, const int *src, int *dst) {
     const int i = blockIdx.x;
     if (i >= n) return;
@@ -176,10 +190,20 @@ int fillMachine(cpecan_ctx *ctx, const cpecan_hmm *hmm) {
         ctx->hasSX = false;
         ctx->machine = 1;
         ctx->mToYNotX = v[0];
+    } else if (hmm->sm_type == CPECAN_SM_FOUR_STATE || hmm->sm_type == CPECAN_SM_ECHELON) {
+        // the FP64 kernel of cpecan_generic.cuh: everything it needs is the type and, fourState, the 11 transitions
+        ctx->generic = hmm->sm_type;
+        ctx->G.sm = hmm->sm_type;
+        for (int i = 0; i < 11; i++) ctx->G.t4[i] = hmm->four_state[i];
+        P.tMC = P.tMX = P.tMY = P.tOX = P.tOY = P.tEX = P.tEY = 0.f; P.tSX = P.tSY = NI;
+        ctx->hasSX = false;
+        ctx->machine = 0;
+        P.vYM = P.vYY = 0.f;
     } else {
-        ctx->err = "state machine type not implemented on device (threeState = 2 and vanilla = 4 are)";
+        ctx->err = "state machine type not implemented on device (threeState = 2, vanilla = 4, echelon = 5, fourState = 6 are)";
         return CPECAN_ERR_ARG;
     }
+    if (hmm->sm_type == CPECAN_SM_THREE_STATE || hmm->sm_type == CPECAN_SM_VANILLA) ctx->generic = 0;
     P.machine = ctx->machine;
     P.hasSX = ctx->hasSX;
     return CPECAN_OK;
@@ -188,11 +212,17 @@ int fillMachine(cpecan_ctx *ctx, const cpecan_hmm *hmm) {
 int fillDevParams(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *p, int mode) {
     if (p->diagonalExpansion < 0 || p->diagonalExpansion % 2 != 0 || p->traceBackDiagonals < 1 ||
         p->minDiagsBetweenTraceBack < 2 || p->traceBackDiagonals + 1 >= p->minDiagsBetweenTraceBack) {
-        ctx->err = "invalid banding parameters (see impl/pairwiseAligner.c:880-884 of the reference)";
+        ctx->err = "invalid banding parameters (impl/pairwiseAligner.c:880-884 of the reference; and diagonalExpansion must be "
+                   "even here: with an odd one band_construct's band edges move backwards and by two cells, see INTEGRATION.md)";
         return CPECAN_ERR_ARG;
     }
     int rc = fillMachine(ctx, hmm);
     if (rc != CPECAN_OK) return rc;
+    if (ctx->generic && mode == CPECAN_MODE_EXPECTATION) {
+        ctx->err = "expectations are not defined for the fourState / echelon machines (the reference has no update function for them)";
+        return CPECAN_ERR_ARG;
+    }
+    ctx->G.threshold = p->threshold;
     DevParams &P = ctx->P;
     P.threshold = (float) p->threshold;
     P.minDiags = (int) p->minDiagsBetweenTraceBack;
@@ -344,7 +374,7 @@ int stageL(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *params, 
     ctx->timing = cpecan_timing{};
     if (n == 0) { guard.ok = true; return CPECAN_OK; }
     cudaStream_t s = ctx->stream;
-    const int needGapx = ctx->machine ? 60 : 4096;
+    const int needGapx = ctx->generic == CPECAN_SM_ECHELON ? 60 : (ctx->machine ? 60 : 4096);
 
     if (ctx->modelsDirty) {
         std::vector<ModelTables> mt(ctx->models.size());
@@ -408,8 +438,10 @@ int stageL(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *params, 
     CK(ctx->dEvSrcOff.ensure((n + 1) * sizeof(long long)));
     CK(ctx->dAnchors.ensure(std::max<int64_t>(1, nAn) * 2 * sizeof(long long)));
     CK(ctx->dCentre.ensure(n * sizeof(double)));
-    CK(ctx->dXp.ensure(xpTot * (ctx->machine ? 4 : 3) * sizeof(float4)));
-    CK(ctx->dEv.ensure(evTot * sizeof(float4)));
+    if (!ctx->generic) {
+        CK(ctx->dXp.ensure(xpTot * (ctx->machine ? 4 : 3) * sizeof(float4)));
+        CK(ctx->dEv.ensure(evTot * sizeof(float4)));
+    }
     CK(ctx->dPairs.ensure(std::max<long long>(1, pairTot) * 3 * sizeof(int)));
     CK(ctx->dBits.ensure(std::max<long long>(1, bitsTot) * sizeof(unsigned)));
     CK(ctx->dTbs.ensure(std::max<long long>(1, tbTot) * sizeof(int)));
@@ -433,7 +465,7 @@ int stageL(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *params, 
     CK(cudaEventRecord(ctx->ev[1], s));
 
     // ---- preparation kernels -----------------------------------------------------------------------------
-    {
+    if (!ctx->generic) {
         dim3 ge((unsigned) n, (unsigned) std::min(64, (maxLY + 256) / 256 + 1));
         k_prep_events<<<ge, 256, 0, s>>>(ctx->dItems.as<Item>(), ctx->dEvSrcOff.as<long long>(), ctx->dEvSrc.as<double>(),
                                         ctx->dCentre.as<double>(), ctx->dEv.as<float4>());
@@ -460,12 +492,16 @@ int stageL(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *params, 
     // ---- bucket by the ring size an alignment needs, order largest first ---------------------------------------
     for (auto &b : ctx->buckets) { b.order.clear(); b.nCta = 0; b.ringRows = 0; }
     const int sx = ctx->hasSX ? 1 : 0, ex = mode == CPECAN_MODE_EXPECTATION ? 1 : 0;
+    int occGenCache[NCFG2] = {};
+    if (ctx->generic) for (int b = 0; b < NCFG2; b++) occGenCache[b] = occGen(b, ctx->generic);
+    const int genS = ctx->generic == CPECAN_SM_ECHELON ? 7 : 4;
     int64_t cells = 0;
     for (int64_t i = 0; i < n; i++) {
         const ItemOut &o = ctx->hOut[i];
         cells += o.band_cells;
         int b = 0;
-        while (b < NCFG2 && (cfg2N(b) < o.max_width + CFG2_MARGIN || ctx->occ2[b][ctx->machine][sx][ex] == 0)) b++;
+        while (b < NCFG2 && (cfg2N(b) < o.max_width + CFG2_MARGIN ||
+                             (ctx->generic ? occGenCache[b] : ctx->occ2[b][ctx->machine][sx][ex]) == 0)) b++;
         if (b == NCFG2) { ctx->err = "band wider than the widest ring this device's shared memory holds"; return CPECAN_ERR_BAND_TOO_WIDE; }
         ctx->buckets[b].order.push_back((int) i);
         ctx->buckets[b].ringRows = std::max(ctx->buckets[b].ringRows, o.max_rows);
@@ -478,7 +514,7 @@ int stageL(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *params, 
         Bucket &bk = ctx->buckets[b];
         if (bk.order.empty()) continue;
         std::stable_sort(bk.order.begin(), bk.order.end(), [&](int a, int c) { return ctx->hOut[a].band_cells > ctx->hOut[c].band_cells; });
-        int occ = std::max(1, ctx->occ2[b][ctx->machine][sx][ex]);
+        int occ = std::max(1, ctx->generic ? occGenCache[b] : ctx->occ2[b][ctx->machine][sx][ex]);
         if (ctx->occCap > 0) occ = std::min(occ, ctx->occCap);       // cpecan_cuda_set_resident_warps
         bk.nCta = (int) std::min<int64_t>((int64_t) bk.order.size(), (int64_t) ctx->prop.multiProcessorCount * occ);
         // forward rows: one float4 record per ring position and row; then the second plane (float2): posteriors keep
@@ -486,6 +522,7 @@ int stageL(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *params, 
         // emissions of every row
         bk.specRows = (ex || allSpec(ctx)) ? bk.ringRows : 2 * (ctx->P.tbDiags + 3) + 2 * (bk.ringRows / 10 + 2);
         bk.stride = (long long) bk.ringRows * cfg2N(b) + ((long long) bk.specRows * cfg2N(b) + 1) / 2;
+        if (ctx->generic) bk.stride = ((long long) bk.ringRows * cfg2N(b) * genS + 1) / 2;     // S doubles per cell, in float4 units
         bk.scratchOff = scratch4; scratch4 += (size_t) bk.stride * bk.nCta;
         bk.orderOff = orderInts; orderInts += bk.order.size();
         orderAll.insert(orderAll.end(), bk.order.begin(), bk.order.end());
@@ -570,6 +607,19 @@ int runAsyncL(cpecan_ctx *ctx) {
         a.expect = ctx->dExpect.as<double>();
         a.P = ctx->P;
         CK(cudaStreamWaitEvent(ctx->bstream[b], ctx->ev[4], 0));
+        if (ctx->generic) {
+            KernelArgsG g;
+            g.items = a.items; g.order = a.order; g.n_items = a.n_items; g.queue = a.queue;
+            g.ref = ctx->dRef.as<char>(); g.ref_off = ctx->dRefOff.as<long long>();
+            g.events = ctx->dEvSrc.as<double>(); g.ev_src_off = ctx->dEvSrcOff.as<long long>();
+            g.models = ctx->dModels.as<ModelTables>(); g.scale = ctx->stagedScaled ? ctx->dScale.as<double>() : nullptr;
+            g.bits = a.bits; g.tbs = a.tbs; g.flags = a.flags;
+            g.scratch = reinterpret_cast<double *>(a.scratch); g.scratch_stride = bk.stride * 2;
+            g.ring_rows = bk.ringRows; g.ringN = cfg2N(b);
+            g.pairs = a.pairs; g.out = a.out; g.totals = a.totals; g.P = ctx->P; g.G = ctx->G;
+            dispatchGen(ctx->generic, [&](auto k, int S) {
+                k<<<bk.nCta, 32, generic_smem_bytes(cfg2N(b), S), ctx->bstream[b]>>>(g); return 0; });
+        } else
         launchCfg2(b, ctx->machine, ctx->hasSX, ctx->mode == CPECAN_MODE_EXPECTATION, a, bk.nCta, ctx->bstream[b]);
         CK(cudaEventRecord(ctx->bev[b], ctx->bstream[b]));
         CK(cudaStreamWaitEvent(s, ctx->bev[b], 0));
@@ -621,7 +671,7 @@ int fetchL(cpecan_ctx *ctx, int32_t *pairs_out, cpecan_result *results) {
         // prepared (24 B per event against ~13 B of aligned pairs), and a 100k-read batch has no 10 GB to spare
         const size_t packedBytes = (size_t) dst[n] * 3 * sizeof(int);
         int *packed = ctx->dEvSrc.as<int>();
-        if (packedBytes > ctx->dEvSrc.cap) { CK(ctx->dCompact.ensure(packedBytes)); packed = ctx->dCompact.as<int>(); }
+        if (packedBytes > ctx->dEvSrc.cap || ctx->generic) { CK(ctx->dCompact.ensure(packedBytes)); packed = ctx->dCompact.as<int>(); }
         CK(cudaMemcpyAsync(ctx->dCompactOff.p, dst.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, s));
         k_compact<<<(unsigned) n, 128, 0, s>>>(ctx->dItems.as<Item>(), ctx->dOut.as<ItemOut>(), ctx->dCompactOff.as<long long>(), (int) n,
                                               ctx->dPairs.as<int>(), packed);

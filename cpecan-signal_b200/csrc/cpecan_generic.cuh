@@ -1,0 +1,481 @@
+// cpecan_generic.cuh -- the reference's other two signal state machines on device: fourState (match, short gap X,
+// short gap Y, long gap X; impl/stateMachine.c:867-897, factory :1750-1759) and echelon (match0 .. match5, gap X: an
+// event may cover 1 .. 5 k-mers; :1411-1460, emissions :530-549, Poisson duration :345-370, factory :1773-1784), with
+// the banded schedule of getPosteriorProbsWithBanding (impl/pairwiseAligner.c:870-1006) and, for echelon,
+// diagonalCalculationMultiPosteriorMatchProbs (:797-839).
+//
+// These are the reference's experimental machines (its own test accepts 857 of 1000 pairs for echelon); here they run
+// in FP64 -- B200 issues FP64 at half the FP32 rate -- with the reference's arithmetic as it stands: absolute
+// log-probabilities, logAdd as lo + cubic(hi - lo), transitions pulled on the way forward and PUSHED on the way back
+// in the reference's order (a cell's backward value is folded from diagonal d+2 first, then from the cell above, then
+// from the cell to the right), so the results agree with the reference to the last digits and no offsets are needed.
+// One warp per alignment; the last diagonals live in shared memory as S planes of N doubles (3 buffers forward, 4 on
+// the way back: B of d+1 is kept for the second term of the total probability); forward cells spill to HBM as S doubles.
+// Band and traceback points come from k_plan3.  Expectations are not defined for these machines in the reference
+// (cellCalculateUpdateExpectations is NULL for echelon) and are refused.
+#pragma once
+#include <math_constants.h>
+#include "cpecan_kernels.cuh"
+
+namespace cpecan {
+
+#define CPG_NI (-CUDART_INF)
+
+struct GenParams {
+    int sm;                 // 6 = fourState, 5 = echelon (StateMachineType, inc/stateMachine.h:20-29)
+    double t4[11];          // fourState transitions: MATCH_CONTINUE, MATCH_FROM_SHORT_GAP_X, MATCH_FROM_SHORT_GAP_Y,
+                            // MATCH_FROM_LONG_GAP_X, GAP_SHORT_OPEN_X, GAP_SHORT_EXTEND_X, GAP_SHORT_OPEN_Y, GAP_SHORT_EXTEND_Y,
+                            // GAP_LONG_OPEN_X, GAP_LONG_EXTEND_X, GAP_LONG_SWITCH_TO_X
+    double threshold;
+};
+
+struct KernelArgsG {
+    const Item *items;
+    const int *order;
+    int n_items;
+    int *queue;
+    const char *ref;
+    const long long *ref_off;
+    const double *events;         // reference layout: (mean, noise, duration) per event
+    const long long *ev_src_off;
+    const ModelTables *models;
+    const double *scale;          // 5 per item or null
+    const unsigned *bits;
+    const int *tbs;
+    const int *flags;
+    double *scratch;              // per warp: ring_rows rows of N cells of S doubles
+    long long scratch_stride;     // doubles per warp
+    int ring_rows, ringN;
+    int *pairs;
+    ItemOut *out;
+    double *totals;
+    DevParams P;
+    GenParams G;
+};
+
+__host__ __device__ inline size_t generic_smem_bytes(int ringN, int S) { return (size_t) 4 * S * ringN * sizeof(double); }
+
+// impl/pairwiseAligner.c:235-255 with the reference's float-literal coefficients and branch structure
+__device__ __forceinline__ double g_poly(double x) {
+    if (x <= 1.00f) return ((-0.009350833524763f * x + 0.130659527668286f) * x + 0.498799810682272f) * x + 0.693203116424741f;
+    if (x <= 2.50f) return ((-0.014532321752540f * x + 0.139942324101744f) * x + 0.495635523139337f) * x + 0.692140569840976f;
+    if (x <= 4.50f) return ((-0.004605031767994f * x + 0.063427417320019f) * x + 0.695956496475118f) * x + 0.514272634594009f;
+    return ((-0.000458661602210f * x + 0.009695946122598f) * x + 0.930734667215156f) * x + 0.168037164329057f;
+}
+__device__ __forceinline__ double g_la(double x, double y) {
+    if (x < y) return (x == CPG_NI || y - x >= 7.5) ? y : g_poly(y - x) + x;
+    return (y == CPG_NI || x - y >= 7.5) ? x : g_poly(x - y) + y;
+}
+// impl/stateMachine.c:333-343 and :322-331
+__device__ __forceinline__ double g_log_gauss(double x, double mu, double sigma) {
+    if (sigma == 0.0) return CPG_NI;
+    const double a = (x - mu) / sigma;
+    return -0.91893853320467267 - log(sigma) + (-0.5 * a * a);
+}
+__device__ __forceinline__ double g_log_inv_gauss(double x, double mu, double lambda) {
+    const double a = (x - mu) / mu;
+    return (log(lambda) - 1.8378770664093453 - 3 * log(x) - lambda * a * a / x) / 2;
+}
+
+template <int SM> struct GenTraits;
+template <> struct GenTraits<6> { static constexpr int S = 4; };
+template <> struct GenTraits<5> { static constexpr int S = 7; };
+
+template <int SM>
+__global__ void __launch_bounds__(32) k_align_generic(const KernelArgsG A) {
+    constexpr int S = GenTraits<SM>::S;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    double *ring = reinterpret_cast<double *>(smraw);           // 4 buffers x S planes x N
+    const int N = A.ringN, NM = N - 1;
+    const int lane = threadIdx.x;
+    const DevParams &P = A.P;
+    const double NI = CPG_NI;
+    double *rows = A.scratch + (long long) blockIdx.x * A.scratch_stride;
+    const int R = A.ring_rows;
+    auto buf = [&](int b) -> double * { return ring + (size_t) b * S * N; };
+
+    for (;;) {
+        int qi = 0;
+        if (lane == 0) qi = atomicAdd(A.queue, 1);
+        qi = __shfl_sync(CP_FULL, qi, 0);
+        if (qi >= A.n_items) break;
+        const int itemIdx = A.order[qi];
+        const Item it = A.items[itemIdx];
+        const int lX = it.lX, lY = it.lY, D = lX + lY;
+        const int planFlags = A.flags[itemIdx];
+        if (D == 0 || (planFlags & 4) != 0) {
+            if (lane == 0) { ItemOut &o = A.out[itemIdx]; o.n_pairs = 0; o.status = D == 0 ? 0 : 6; o.total_logprob = 0.0; o.n_tracebacks = 0; }
+            continue;
+        }
+        const char *ref = A.ref + A.ref_off[itemIdx];
+        const int refLen = (int) (A.ref_off[itemIdx + 1] - A.ref_off[itemIdx]);
+        const double *evs = A.events + 3 * A.ev_src_off[itemIdx];
+        const ModelTables mt = A.models[it.model_id];
+        const unsigned *bitsp = A.bits + it.pad0;
+        const int *tbp = A.tbs + it.pad1;
+        int *pairs = A.pairs + 3 * it.pair_off;
+        double *dbgTot = (A.totals != nullptr && it.tot_off >= 0) ? A.totals + it.tot_off : nullptr;
+        const bool scaled = A.scale != nullptr;
+        double sc = 1, sh = 0, var = 1, scsd = 1, varsd = 1;
+        if (scaled) { const double *s5 = A.scale + 5 * itemIdx; sc = s5[0]; sh = s5[1]; var = s5[2]; scsd = s5[3]; varsd = s5[4]; }
+        int nPairs = 0, status = 0, nTb = 0;
+        double lastTotal = 0.0;
+
+        auto bandBits = [&](int d) -> unsigned { return (bitsp[d >> 4] >> ((d & 15) << 1)) & 3u; };
+        // the padded nucleotide sequence (sequence_padSequence, impl/pairwiseAligner.c:282-285) and its k-mer index
+        // (impl/stateMachine.c:104-139; -1 <=> index > 4096)
+        auto rch = [&](int i) -> char { return (i >= 0 && i < refLen) ? ref[i] : 'n'; };
+        auto kmerAt = [&](int i) -> int {
+            int v = 0;
+#pragma unroll
+            for (int j = 0; j < 6; j++) { const int b = base_code(rch(i + j)); if (b < 0) return -1; v = v * 4 + b; }
+            return v;
+        };
+        // model getters (impl/stateMachine.c:221-240; index > 4096 reads as 0.0) with emissions_signal_scaleModel folded
+        // in for the match table (:631-651); the gap-Y table is never scaled
+        auto matchParams = [&](int k, double &mu, double &sd, double &nu, double &tau, double &lam) {
+            if (k < 0) { mu = sd = nu = tau = lam = 0.0; return; }
+            const double *m = mt.match + 1 + 5 * k;
+            mu = m[0]; sd = m[1]; nu = m[2]; tau = m[3]; lam = m[4];
+            if (scaled) { mu = mu * sc + sh; sd = sd * var; nu = nu * scsd; lam = lam * varsd; tau = sqrt(pow(nu, 3.0) / lam); }
+        };
+        auto gapyParams = [&](int k, double &mu, double &sd, double &nu, double &tau, double &lam) {
+            if (k < 0) { mu = sd = nu = tau = lam = 0.0; return; }
+            const double *m = mt.gapy + 1 + 5 * k;
+            mu = m[0]; sd = m[1]; nu = m[2]; tau = m[3]; lam = m[4];
+        };
+        auto eventOf = [&](int y, double &m, double &n, double &dur) {      // y = matrix row; row 0 is the null event (:261-262)
+            if (y >= 1) { m = evs[3 * (y - 1)]; n = evs[3 * (y - 1) + 1]; dur = evs[3 * (y - 1) + 2]; }
+            else { m = NI; n = 0.0; dur = 0.0; }
+        };
+
+        // One cell in the reference's transition order.  FWD: cur[to] (+)= nb[from] + (eP + tP) (pull); BWD: the same
+        // statement with the roles swapped (push), impl/pairwiseAligner.c:365-383.  lo / mi / up: the neighbours
+        // (x-1, y), (x-1, y-1), (x, y-1), has*: whether they exist (inside the band of a live diagonal).
+        auto cellGen = [&](bool fwd, int x, int y, double *cur, double *lo_, bool hasLo, double *mi_, bool hasMi,
+                           double *up_, bool hasUp) {
+#define TRG(nb, from, to, eptp) do { if (fwd) cur[to] = g_la(cur[to], nb[from] + (eptp)); else nb[from] = g_la(nb[from], cur[to] + (eptp)); } while (0)
+            double em, en, edur;
+            eventOf(y, em, en, edur);
+            if (SM == 6) {
+                const int k = x >= 1 ? kmerAt(x - 1) : -1;
+                const double *t = A.G.t4;
+                if (hasLo) {
+                    const double eP = k < 0 ? NI : mt.gapx[k];
+                    TRG(lo_, 0, 1, eP + t[4]); TRG(lo_, 1, 1, eP + t[5]); TRG(lo_, 0, 3, eP + t[8]); TRG(lo_, 3, 3, eP + t[9]); TRG(lo_, 2, 3, eP + t[10]);
+                }
+                if (hasMi) {
+                    double mu, sd, nu, tau, lam;
+                    matchParams(k, mu, sd, nu, tau, lam);
+                    const double eP = g_log_gauss(em, mu, sd) + g_log_gauss(en, nu, tau);
+                    TRG(mi_, 0, 0, eP + t[0]); TRG(mi_, 1, 0, eP + t[1]); TRG(mi_, 2, 0, eP + t[2]); TRG(mi_, 3, 0, eP + t[3]);
+                }
+                if (hasUp) {
+                    double mu, sd, nu, tau, lam;
+                    gapyParams(k, mu, sd, nu, tau, lam);
+                    const double eP = g_log_gauss(em, mu, sd) + g_log_gauss(en, nu, tau);
+                    TRG(up_, 0, 2, eP + t[6]); TRG(up_, 2, 2, eP + t[7]);
+                }
+            } else {
+                // echelon: sequence_getKmer2 pointer i (clamped at 0), skip bin of (k-mer i, k-mer i+1) on the scaled match
+                // table, n = 1 .. 5 k-mers per event (impl/stateMachine.c:1411-1460)
+                const int i = x >= 2 ? x - 2 : 0;
+                double mu0, mu1, sd, nu, tau, lam;
+                matchParams(kmerAt(i), mu0, sd, nu, tau, lam);
+                matchParams(kmerAt(i + 1), mu1, sd, nu, tau, lam);
+                long long bin = (long long) (fabs(mu1 - mu0) / 0.5);
+                bin = bin >= 30 ? 29 : bin;
+                const double a_mx = mt.gapx[bin], a_xx = mt.gapx[bin + 30];
+                const double la_mx = log(a_mx), la_mh = log(1 - a_mx), la_xx = log(a_xx), la_xh = log(1 - a_xx);
+                if (hasLo) {
+#pragma unroll
+                    for (int n = 1; n < 6; n++) TRG(lo_, n, 6, 0 + la_mx);
+                    TRG(lo_, 6, 6, 0 + la_xx);
+                }
+                const double lfact[6] = { 0.0, 0.0, 0.69314718056, 1.79175946923, 3.17805383035, 4.78749174278 };
+                const double lambda = edur / 0.00332005312085;
+                const double llam = log(lambda);
+                if (hasMi) {
+                    // emissions_signal_multipleKmerMatchProb (:530-549): the fold starts from 0.0 and the run-off test
+                    // looks at the single character 6 n past the pointer
+                    double mk[6];
+                    double fold = 0.0;
+#pragma unroll
+                    for (int n = 1; n < 6; n++) {
+                        double mu, sdd, nuu, tt, ll;
+                        matchParams(kmerAt(i + n), mu, sdd, nuu, tt, ll);          // j = n - 1: k-mer i + j + 1
+                        fold = g_la(fold, g_log_gauss(em, mu, sdd) + g_log_inv_gauss(en, nuu, ll));
+                        const char last = rch(i + 6 * n);
+                        mk[n] = (last >= 'A' && last <= 'Z') ? fold - log((double) n) : NI;
+                    }
+#pragma unroll
+                    for (int n = 1; n < 6; n++) {
+                        const double dp = (n + 1) * 0.1397619423751586 + n * llam - lfact[n] - 2 * lambda;
+#pragma unroll
+                        for (int from = 0; from < 6; from++) TRG(mi_, from, n, mk[n] + (la_mh + dp));
+                    }
+#pragma unroll
+                    for (int n = 1; n < 6; n++) {
+                        const double dp = (n + 1) * 0.1397619423751586 + n * llam - lfact[n] - 2 * lambda;
+                        TRG(mi_, 6, n, mk[n] + (la_xh + dp));
+                    }
+                }
+                if (hasUp) {
+                    double mu, sdd, nuu, tt, ll;
+                    gapyParams(kmerAt(i + 1), mu, sdd, nuu, tt, ll);
+                    const double eP = g_log_gauss(em, mu, sdd) + g_log_inv_gauss(en, nuu, ll);
+                    const double dp0 = 1 * 0.1397619423751586 + 0 * llam - lfact[0] - 2 * lambda;
+#pragma unroll
+                    for (int n = 1; n < 6; n++) TRG(up_, n, 0, eP + (la_mh + dp0));
+                }
+            }
+#undef TRG
+        };
+        // note: multipleKmerMatchProb returns -inf from inside its loop as soon as the run-off test fails, and the test
+        // does not depend on the loop variable: for a given n the value is either the full fold or -inf (as above)
+
+        auto stateVector = [&](int which, double *v) {       // 0 start, 1 ragged start, 2 end, 3 ragged end
+            if (SM == 5) {
+                for (int st = 0; st < 7; st++) v[st] = NI;
+                if (which == 0) v[1] = 0; else if (which == 1) v[6] = 0;
+                else { for (int st = 0; st < 6; st++) v[st] = 0.79015888282447311; v[6] = 0.19652425498269727; }   // not logs (:1617-1619)
+            } else {
+                const double *t = A.G.t4;
+                if (which == 0) { v[0] = 0; v[1] = v[2] = v[3] = NI; }
+                else if (which == 1) { v[0] = v[1] = NI; v[2] = 0; v[3] = 0; }
+                else if (which == 2) { v[0] = t[0]; v[1] = t[1]; v[2] = t[2]; v[3] = t[3]; }
+                else { v[0] = v[1] = v[2] = t[8]; v[3] = t[9]; }
+            }
+        };
+        auto clearBuf = [&](int b, int l, int h) {           // -inf over positions l .. h of every plane
+            double *p = buf(b);
+            for (int x = l + lane; x <= h; x += 32)
+#pragma unroll
+                for (int st = 0; st < S; st++) p[st * N + (x & NM)] = NI;
+        };
+        auto rowPtr = [&](int d, int x) -> double * { return rows + ((long long) (d % R) * N + (x & NM)) * S; };
+
+        // ---- diagonal 0 -------------------------------------------------------------------------------------------
+        int f0 = 0, f1 = 1, f2 = 2;                            // ring buffers of diagonals d, d-1, d-2 (forward)
+        int lo = 0, hi = 0, lo1 = 0, hi1 = -1, lo2 = 0, hi2 = -1;   // band of d, d-1, d-2
+        if (lane == 0) {
+            double v[S];
+            stateVector((it.flags & 1) ? 1 : 0, v);
+            for (int st = 0; st < S; st++) { buf(f0)[st * N] = v[st]; rowPtr(0, 0)[st] = v[st]; }
+        }
+        __syncwarp();
+        int dcur = 0, tracedBackTo = 0;
+
+        while (tracedBackTo < D) {
+            const int Dt = tbp[nTb];
+            const bool atEnd = Dt == D;
+            const int tbf = Dt - (atEnd ? 0 : P.tbDiags + 1);
+            // =============================== forward ========================================================
+            for (int d = dcur + 1; d <= Dt; d++) {
+                { const int t = f2; f2 = f1; f1 = f0; f0 = t; }
+                lo2 = lo1; hi2 = hi1; lo1 = lo; hi1 = hi;
+                const unsigned b = bandBits(d);
+                lo += b & 1; hi += b >> 1;
+                double *F0 = buf(f0), *F1 = buf(f1), *F2 = buf(f2);
+                for (int xb = lo; xb <= hi; xb += 32) {
+                    const int x = xb + lane;
+                    if (x <= hi) {
+                        double cur[S], nl[S], nm[S], nu_[S];
+                        const bool hasLo = x - 1 >= lo1 && x - 1 <= hi1, hasMi = x - 1 >= lo2 && x - 1 <= hi2, hasUp = x >= lo1 && x <= hi1;
+#pragma unroll
+                        for (int st = 0; st < S; st++) {
+                            cur[st] = NI;
+                            nl[st] = hasLo ? F1[st * N + ((x - 1) & NM)] : NI;
+                            nm[st] = hasMi ? F2[st * N + ((x - 1) & NM)] : NI;
+                            nu_[st] = hasUp ? F1[st * N + (x & NM)] : NI;
+                        }
+                        cellGen(true, x, d - x, cur, nl, hasLo, nm, hasMi, nu_, hasUp);
+                        double *rp = rowPtr(d, x);
+#pragma unroll
+                        for (int st = 0; st < S; st++) { F0[st * N + (x & NM)] = cur[st]; rp[st] = cur[st]; }
+                    }
+                }
+                __syncwarp();
+            }
+            dcur = Dt;
+
+            // =============================== traceback ======================================================
+            nTb++;
+            {
+                int b0 = 0, b1 = 1, b2 = 2, bp = 3;            // ring buffers of B of d, d-1, d-2 and d+1
+                int blo = lo, bhi = hi;                        // band of d
+                double endv[S];
+                stateVector((atEnd && (it.flags & 2)) ? 3 : 2, endv);
+                for (int x = blo + lane; x <= bhi; x += 32)
+#pragma unroll
+                    for (int st = 0; st < S; st++) buf(b0)[st * N + (x & NM)] = endv[st];
+                int l1 = 0, h1 = -1, l2 = 0, h2 = -1, lp = 0, hp = -1;   // band of d-1, d-2, d+1
+                { const unsigned b = bandBits(Dt); l1 = blo - (int) (b & 1); h1 = bhi - (int) (b >> 1); }
+                if (Dt > tracedBackTo + 1) clearBuf(b1, l1 - 1, h1 + 1);
+                __syncwarp();
+                double total = NI;
+                long long count = 0;
+                for (int d = Dt; d > tracedBackTo; d--) {
+                    if (d >= 2) { const unsigned b = bandBits(d - 1); l2 = l1 - (int) (b & 1); h2 = h1 - (int) (b >> 1); } else { l2 = 0; h2 = -1; }
+                    const bool liveMi = d > tracedBackTo + 2, sweepB = d > tracedBackTo + 1;
+                    if (liveMi) clearBuf(b2, l2 - 1, h2 + 1);
+                    __syncwarp();
+                    double *B0 = buf(b0), *B1 = buf(b1), *B2 = buf(b2), *Bp = buf(bp);
+                    if (sweepB) {
+                        for (int xb = blo; xb <= bhi; xb += 32) {
+                            const int x = xb + lane;
+                            const bool act = x <= bhi;
+                            double cur[S], nb[S];
+                            if (act)
+#pragma unroll
+                                for (int st = 0; st < S; st++) cur[st] = B0[st * N + (x & NM)];
+                            const bool hasLo = act && x - 1 >= l1 && x - 1 <= h1, hasMi = act && liveMi && x - 1 >= l2 && x - 1 <= h2,
+                                       hasUp = act && x >= l1 && x <= h1;
+                            // the reference's order inside a cell is lower, middle, upper; the three go to different cells, so
+                            // only the order in which ONE cell receives matters: from d+2 (earlier), then as "upper" of the
+                            // cell above it, then as "lower" of the cell to its right (ascending x - y)
+                            if (hasMi) {
+#pragma unroll
+                                for (int st = 0; st < S; st++) nb[st] = B2[st * N + ((x - 1) & NM)];
+                                cellGen(false, x, d - x, cur, nullptr, false, nb, true, nullptr, false);
+#pragma unroll
+                                for (int st = 0; st < S; st++) B2[st * N + ((x - 1) & NM)] = nb[st];
+                            }
+                            if (hasUp) {
+#pragma unroll
+                                for (int st = 0; st < S; st++) nb[st] = B1[st * N + (x & NM)];
+                                cellGen(false, x, d - x, cur, nullptr, false, nullptr, false, nb, true);
+#pragma unroll
+                                for (int st = 0; st < S; st++) B1[st * N + (x & NM)] = nb[st];
+                            }
+                            __syncwarp();
+                            if (hasLo) {
+#pragma unroll
+                                for (int st = 0; st < S; st++) nb[st] = B1[st * N + ((x - 1) & NM)];
+                                cellGen(false, x, d - x, cur, nb, true, nullptr, false, nullptr, false);
+#pragma unroll
+                                for (int st = 0; st < S; st++) B1[st * N + ((x - 1) & NM)] = nb[st];
+                            }
+                            __syncwarp();
+                        }
+                    }
+                    if (d <= tbf) {
+                        const bool doTotal = P.mode == 2 ? (d == Dt) : (count % P.totalEvery == 0);
+                        count++;
+                        if (doTotal) {
+                            // diagonalCalculationTotalProbability (impl/pairwiseAligner.c:736-754): serial left folds
+                            auto diagDot = [&](auto getA, const double *Bb, int l, int h) -> double {
+                                double tot = NI;
+                                for (int xb = l; xb <= h; xb += 32) {
+                                    const int x = xb + lane;
+                                    double c = NI;
+                                    if (x <= h) {
+                                        double a[S];
+                                        getA(x, a);
+                                        c = a[0] + Bb[(x & NM)];
+#pragma unroll
+                                        for (int st = 1; st < S; st++) c = g_la(c, a[st] + Bb[st * N + (x & NM)]);
+                                    }
+                                    const int cnt = min(32, h - xb + 1);
+                                    for (int j = 0; j < cnt; j++) tot = g_la(tot, __shfl_sync(CP_FULL, c, j));
+                                }
+                                return tot;
+                            };
+                            double tot = diagDot([&](int x, double *a) { const double *rp = rowPtr(d, x);
+#pragma unroll
+                                                     for (int st = 0; st < S; st++) a[st] = rp[st]; }, B0, blo, bhi);
+                            double t2 = CUDART_NAN;
+                            if (d < Dt && d - 1 >= 0) {
+                                // match-only forward step from F[d-1] into a -inf clone shaped like B[d+1], dotted with B[d+1]
+                                int lm, hm;
+                                { const unsigned b = bandBits(d); lm = blo - (int) (b & 1); hm = bhi - (int) (b >> 1); }
+                                t2 = diagDot([&](int x, double *a) {
+                                    double nm[S];
+                                    const bool hasMi = x - 1 >= lm && x - 1 <= hm;
+#pragma unroll
+                                    for (int st = 0; st < S; st++) { a[st] = NI; nm[st] = NI; }
+                                    if (hasMi) {
+                                        const double *rp = rowPtr(d - 1, x - 1);
+#pragma unroll
+                                        for (int st = 0; st < S; st++) nm[st] = rp[st];
+                                    }
+                                    cellGen(true, x, d + 1 - x, a, nullptr, false, nm, hasMi, nullptr, false);
+                                }, Bp, lp, hp);
+                                tot = g_la(tot, t2);
+                            }
+                            total = tot;
+                            if (!(tot > -1e300)) status |= 2;
+                            if (dbgTot != nullptr && lane == 0) { dbgTot[(D + 1) + d] = tot; dbgTot[2 * (D + 1) + d] = t2; }
+                        }
+                        if (d == D) lastTotal = total;
+                        if (dbgTot != nullptr && lane == 0) dbgTot[d] = total;
+                        // posteriors: impl/pairwiseAligner.c:756-795 (match state) and :797-839 (echelon: states 1 .. 5,
+                        // an event matched to st k-mers gives st pairs)
+                        for (int xb = blo; xb <= bhi; xb += 32) {
+                            const int x = xb + lane, y = d - x;
+                            int cnt = 0;
+                            int sc_[6] = { 0, 0, 0, 0, 0, 0 };
+                            if (x <= bhi && x > 0 && y > 0) {
+                                const double *rp = rowPtr(d, x);
+                                if (SM == 5) {
+#pragma unroll
+                                    for (int st = 1; st < 6; st++) {
+                                        double p = exp((rp[st] + B0[st * N + (x & NM)]) - total);
+                                        if (p >= A.G.threshold) { if (p > 1.0) p = 1.0; sc_[st] = (int) floor(p * 10000000); cnt += st; } else sc_[st] = -1;
+                                    }
+                                } else {
+                                    double p = exp(rp[0] + B0[(x & NM)] - total);
+                                    if (p >= A.G.threshold) { if (p > 1.0) p = 1.0; sc_[1] = (int) floor(p * 10000000); cnt = 1; } else sc_[1] = -1;
+                                }
+                            }
+                            int incl = cnt;                     // inclusive prefix sum over the lanes
+#pragma unroll
+                            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(CP_FULL, incl, o); if (lane >= o) incl += t; }
+                            int pos = nPairs + incl - cnt;
+                            if (cnt > 0) {
+                                if (SM == 5) {
+                                    for (int st = 1; st < 6; st++)
+                                        if (sc_[st] >= 0)
+                                            for (int n = 0; n < st; n++) {
+                                                if (pos < it.pair_cap) { pairs[3 * pos] = sc_[st]; pairs[3 * pos + 1] = (x + n) - 1; pairs[3 * pos + 2] = y - 1; }
+                                                pos++;
+                                            }
+                                } else if (pos < it.pair_cap) { pairs[3 * pos] = sc_[1]; pairs[3 * pos + 1] = x - 1; pairs[3 * pos + 2] = y - 1; }
+                            }
+                            nPairs += __shfl_sync(CP_FULL, incl, 31);
+                        }
+                    }
+                    // next diagonal: B(d) becomes "d+1", d-1 -> d, d-2 -> d-1, the old d+1 buffer is the new d-2
+                    { const int t = bp; bp = b0; b0 = b1; b1 = b2; b2 = t; }
+                    lp = blo; hp = bhi; blo = l1; bhi = h1; l1 = l2; h1 = h2;
+                    __syncwarp();
+                }
+            }
+            tracedBackTo = tbf;
+
+            // =============================== restore the forward state at Dt ==============================
+            if (tracedBackTo < D) {
+                f0 = 0; f1 = 1; f2 = 2;
+                const unsigned b = bandBits(Dt);
+                lo1 = lo - (int) (b & 1); hi1 = hi - (int) (b >> 1);
+                lo2 = 0; hi2 = -1;                                // re-derived when the sweep advances
+                for (int x = lo + lane; x <= hi; x += 32) { const double *rp = rowPtr(Dt, x);
+#pragma unroll
+                    for (int st = 0; st < S; st++) buf(f0)[st * N + (x & NM)] = rp[st]; }
+                for (int x = lo1 + lane; x <= hi1; x += 32) { const double *rp = rowPtr(Dt - 1, x);
+#pragma unroll
+                    for (int st = 0; st < S; st++) buf(f1)[st * N + (x & NM)] = rp[st]; }
+                __syncwarp();
+            }
+        }
+        if (lane == 0) {
+            ItemOut &o = A.out[itemIdx];
+            o.n_pairs = nPairs;
+            o.status = status | (nPairs > it.pair_cap ? 1 : 0);
+            o.total_logprob = lastTotal;
+            o.n_tracebacks = nTb;
+        }
+    }
+}
+
+}  // namespace cpecan

@@ -29,7 +29,7 @@ enum {
 };
 
 /* State-machine types, numbered as the reference's StateMachineType (inc/stateMachine.h:20-29). */
-enum { CPECAN_SM_THREE_STATE = 2, CPECAN_SM_VANILLA = 4 };
+enum { CPECAN_SM_THREE_STATE = 2, CPECAN_SM_VANILLA = 4, CPECAN_SM_ECHELON = 5, CPECAN_SM_FOUR_STATE = 6 };
 
 /* Work modes. */
 enum {
@@ -70,6 +70,11 @@ typedef struct {
                                GAP_SWITCH_TO_X, GAP_SWITCH_TO_Y (log space, -inf allowed) */
     double vanilla[5];      /* vanilla: TRANSITION_M_TO_Y_NOT_X, TRANSITION_E_TO_E, DEFAULT_END_MATCH_PROB,
                                DEFAULT_END_FROM_X_PROB, DEFAULT_END_FROM_Y_PROB */
+    double four_state[11];  /* fourState (StateMachine4, inc/stateMachine.h:130-152; defaults impl/stateMachine.c:993-1011):
+                               MATCH_CONTINUE, MATCH_FROM_SHORT_GAP_X, MATCH_FROM_SHORT_GAP_Y, MATCH_FROM_LONG_GAP_X,
+                               GAP_SHORT_OPEN_X, GAP_SHORT_EXTEND_X, GAP_SHORT_OPEN_Y, GAP_SHORT_EXTEND_Y, GAP_LONG_OPEN_X,
+                               GAP_LONG_EXTEND_X, GAP_LONG_SWITCH_TO_X (log space).  echelon carries no parameters of its
+                               own: its skip bins are the model's 60 gap-X entries, its end vector the reference's constants. */
 } cpecan_hmm;
 
 /* A batch of work items in flat (structure-of-arrays) host buffers.  All *_off arrays have n_items+1 entries.

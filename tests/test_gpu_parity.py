@@ -33,7 +33,7 @@ def test_fixture_banded_three_state(engine, zymo, template_tables, tag, e, ragge
     stats = parity.compare_pairs(got, want)
     worst_total = parity.compare_totals(totals[0], zymo[tag + "_totals"])
     print(tag, stats, "worst |total diff|", worst_total, "cells", res[0]["band_cells"])
-    assert abs(stats["n_got"] - 987) <= 2
+    assert stats["n_got"] == stats["n_want"] == 987
     # emission order: the device list reversed is the reference's list
     if stats["n_got"] == stats["n_want"]:
         assert np.array_equal(parity.reverse_regions(got)[:, 1:], want[:, 1:])
@@ -53,7 +53,7 @@ def test_fixture_unbanded_three_state(engine, zymo, template_tables):
     stats = parity.compare_pairs(got, zymo["three_unbanded_pairs"])
     print(stats, res[0]["total_logprob"], float(zymo["three_unbanded_total"]))
     assert abs(res[0]["total_logprob"] - float(zymo["three_unbanded_total"])) <= 1e-4 * abs(float(zymo["three_unbanded_total"]))
-    assert abs(stats["n_got"] - 986) <= 2
+    assert stats["n_got"] == stats["n_want"] == 986
 
 
 def test_tiny_known_answer(engine, zymo, template_tables):
@@ -354,7 +354,7 @@ def test_fixture_banded_vanilla(engine, zymo, template_tables, tag, e, ragged, c
     worst_total = parity.compare_totals(totals[0], zymo[tag + "_totals"])
     print(tag, stats, worst_total)
     if count is not None:
-        assert abs(stats["n_got"] - count) <= 2
+        assert stats["n_got"] == stats["n_want"] == count
 
 
 def test_fixture_unbanded_vanilla(engine, zymo, template_tables):
@@ -368,7 +368,7 @@ def test_fixture_unbanded_vanilla(engine, zymo, template_tables):
     assert res[0]["status"] == 0
     stats = parity.compare_pairs(item_pairs(res, pairs, 0), zymo["vanilla_unbanded_pairs"])
     assert abs(res[0]["total_logprob"] - float(zymo["vanilla_unbanded_total"])) <= 1e-4 * abs(float(zymo["vanilla_unbanded_total"]))
-    assert abs(stats["n_got"] - 953) <= 2
+    assert stats["n_got"] == stats["n_want"] == 953
 
 
 def test_tiny_known_answer_vanilla(engine, zymo, template_tables):
@@ -494,8 +494,9 @@ def test_split_regions_as_items(engine, syn_golden, template_tables):
 
 
 def test_argument_errors_are_reported(engine, template_tables):
-    """Integer status + message, never an abort: odd expansion (not representable by the device band walker), a model
-    with too few gap-X entries for the machine, an unknown state-machine type."""
+    """Integer status + message, never an abort: banding parameters the reference rejects (traceBackDiagonals + 1 >=
+    minDiagsBetweenTraceBack, impl/pairwiseAligner.c:880-884), an odd expansion (the one documented restriction:
+    INTEGRATION.md), a model with too few gap-X entries for the machine, an unknown state-machine type."""
     from cpecan_signal import EngineError, HostBatch, default_params, synth, vanilla_hmm
     from cpecan_signal.engine import Hmm
     l1, l2, l3 = template_tables
@@ -503,6 +504,8 @@ def test_argument_errors_are_reported(engine, template_tables):
     mid = engine.upload_model(l1, l3, np.full(4096, -2.3025850929940455))
     hb = HostBatch([r.ref], [r.events], [r.anchors], model_ids=[mid], scales=[r.scale5], ragged=[(1, 1)])
     with pytest.raises(EngineError, match="banding parameters"):
+        engine.align_batch(hb, params=default_params(traceBackDiagonals=40, minDiagsBetweenTraceBack=41))
+    with pytest.raises(EngineError, match="must be even"):
         engine.align_batch(hb, params=default_params(diagonalExpansion=21))
     mid60 = engine.upload_model(l1, l3, np.full(60, 0.1))
     hb60 = HostBatch([r.ref], [r.events], [r.anchors], model_ids=[mid60], scales=[r.scale5], ragged=[(1, 1)])
@@ -510,7 +513,7 @@ def test_argument_errors_are_reported(engine, template_tables):
         engine.align_batch(hb60)                                   # three-state needs 4096 entries
     engine.align_batch(hb60, hmm=vanilla_hmm("template"))          # vanilla is fine with 60
     bad = Hmm()
-    bad.sm_type = 6                                                # fourState: not implemented on device
+    bad.sm_type = 3                                                # threeState_hdp: not implemented on device
     with pytest.raises(EngineError, match="not implemented"):
         engine.align_batch(hb, hmm=bad)
     # a band wider than the widest shared-memory ring (a long read without anchors): refused, not mis-computed
