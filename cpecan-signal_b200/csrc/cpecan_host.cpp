@@ -62,8 +62,13 @@ void *stList_pop(stList *list) {
     list->v.pop_back();
     return p;
 }
+// sonLib sorts the pointer array with qsort through a file-scope comparator; the same here (thread-local, so the two
+// OpenMP sections of vanillaAlign.c may sort at once)
+static thread_local int (*tlsCmp)(const void *, const void *) = nullptr;
+static int sortTrampoline(const void *a, const void *b) { return tlsCmp(*(void *const *) a, *(void *const *) b); }
 void stList_sort(stList *list, int (*cmpFn)(const void *a, const void *b)) {
-    std::stable_sort(list->v.begin(), list->v.end(), [cmpFn](void *a, void *b) { return cmpFn(a, b) < 0; });
+    tlsCmp = cmpFn;
+    if (!list->v.empty()) qsort(list->v.data(), list->v.size(), sizeof(void *), sortTrampoline);
 }
 void stList_setDestructor(stList *list, void (*destructElement)(void *)) { list->destruct = destructElement; }
 
@@ -113,6 +118,18 @@ Sequence *sequence_sliceEventSequence2(Sequence *in, int64_t start, int64_t slic
 void sequence_sequenceDestroy(Sequence *seq) { free(seq); }
 void *sequence_getKmer(void *elements, int64_t index) { return index >= 0 ? (void *) ((char *) elements + index) : (void *) NCHAR_; }
 void *sequence_getKmer2(void *elements, int64_t index) { return (char *) elements + (index > 0 ? index - 1 : 0); }
+void *sequence_getKmer3(void *elements, int64_t index) { return (char *) elements + (index >= 0 ? index : 0); }   // :327-331
+// impl/pairwiseAligner.c:282-285: 30 'n' behind the nucleotides (the echelon machine reads k-mers past the end); as in
+// the reference the old buffer is not freed -- the caller still owns it
+void sequence_padSequence(Sequence *sequence) {
+    const char *e = (const char *) sequence->elements;
+    const size_t n = strlen(e);
+    char *padded = (char *) malloc(n + 31);
+    memcpy(padded, e, n);
+    memset(padded + n, 'n', 30);
+    padded[n + 30] = 0;
+    sequence->elements = padded;
+}
 void *sequence_getEvent(void *elements, int64_t index) {
     return index >= 0 ? (void *) ((double *) elements + index * NB_EVENT_PARAMS) : (void *) NULLEVENT_;
 }
@@ -360,7 +377,8 @@ static void loadPoreModel(StateMachine *sM, const char *modelFile) {
     fclose(fh);
     memcpy(sM->EMISSION_MATCH_PROBS, l1.data(), sizeof(double) * TABLE_LEN);
     memcpy(sM->EMISSION_GAP_Y_PROBS, l3.data(), sizeof(double) * TABLE_LEN);
-    if (sM->type == vanilla) for (int i = 0; i < 30; i++) { sM->EMISSION_GAP_X_PROBS[i] = l2[i]; sM->EMISSION_GAP_X_PROBS[i + 30] = l2[i]; }
+    if (sM->type == vanilla || sM->type == echelon)             // :282-294
+        for (int i = 0; i < 30; i++) { sM->EMISSION_GAP_X_PROBS[i] = l2[i]; sM->EMISSION_GAP_X_PROBS[i + 30] = l2[i]; }
 }
 
 static void initBase(StateMachine *sM, StateMachineType type, int64_t nGapX) {
@@ -414,6 +432,67 @@ StateMachine *getSignalStateMachine3Vanilla(const char *modelFile) {            
     return &m->model;
 }
 
+// getStateMachine4 (impl/stateMachine.c:1750-1759, constructor :960-1011): gap-X emissions all zero, the model's
+// skip-bin line is not loaded for this type
+static double sm4_start(StateMachine *, int64_t st) { return st == match ? 0 : LOG_ZERO; }                     // :775-779
+static double sm4_raggedStart(StateMachine *, int64_t st) { return (st == shortGapY || st == longGapX) ? 0 : LOG_ZERO; }   // :791-794
+static double sm4_end(StateMachine *sM, int64_t st) {                                                       // :796-810
+    StateMachine4 *m = (StateMachine4 *) sM;
+    switch (st) {
+        case match: return m->TRANSITION_MATCH_CONTINUE;
+        case shortGapX: return m->TRANSITION_MATCH_FROM_SHORT_GAP_X;
+        case shortGapY: return m->TRANSITION_MATCH_FROM_SHORT_GAP_Y;
+        case longGapX: return m->TRANSITION_MATCH_FROM_LONG_GAP_X;
+    }
+    return 0.0;
+}
+static double sm4_raggedEnd(StateMachine *sM, int64_t st) {                                                 // :812-826
+    StateMachine4 *m = (StateMachine4 *) sM;
+    return st == longGapX ? m->TRANSITION_GAP_LONG_EXTEND_X : m->TRANSITION_GAP_LONG_OPEN_X;
+}
+StateMachine *getStateMachine4(const char *modelFile) {
+    StateMachine4 *m = (StateMachine4 *) calloc(1, sizeof(StateMachine4));
+    initBase(&m->model, fourState, NUM_OF_KMERS);
+    m->model.stateNumber = 4;
+    m->model.startStateProb = sm4_start; m->model.raggedStartStateProb = sm4_raggedStart;
+    m->model.endStateProb = sm4_end; m->model.raggedEndStateProb = sm4_raggedEnd;
+    m->TRANSITION_MATCH_CONTINUE = -0.23552123624314988;
+    m->TRANSITION_GAP_SHORT_OPEN_X = -1.6269694202638481;
+    m->TRANSITION_GAP_SHORT_OPEN_Y = -4.7241893208381773;
+    m->TRANSITION_GAP_LONG_OPEN_X = -5.4173365013981227;
+    m->TRANSITION_GAP_SHORT_EXTEND_X = -1.6269694202638481;
+    m->TRANSITION_MATCH_FROM_SHORT_GAP_X = -0.21880828092192281;
+    m->TRANSITION_GAP_LONG_EXTEND_X = -0.003442492794189331;
+    m->TRANSITION_MATCH_FROM_LONG_GAP_X = -5.6732801731704612;
+    m->TRANSITION_MATCH_FROM_SHORT_GAP_Y = -0.013406326748077823;
+    m->TRANSITION_GAP_SHORT_EXTEND_Y = -4.724189320832104;
+    m->TRANSITION_GAP_LONG_SWITCH_TO_X = -5.4173365013920494;
+    loadPoreModel(&m->model, modelFile);
+    return &m->model;
+}
+
+// getStateMachineEchelon (impl/stateMachine.c:1773-1784, constructor :1602-1640): seven states, the model's 30 skip bins
+// twice (as the vanilla machine), end "probabilities" that are not logs (:1617-1619, kept as they are)
+static double sme_start(StateMachine *, int64_t st) { return st == 1 ? 0 : LOG_ZERO; }                        // :1237-1245
+static double sme_raggedStart(StateMachine *, int64_t st) { return st == 6 ? 0 : LOG_ZERO; }                  // :1247-1253
+static double sme_end(StateMachine *sM, int64_t st) {                                                       // :1255-1262
+    StateMachineEchelon *m = (StateMachineEchelon *) sM;
+    return st == 6 ? m->DEFAULT_END_FROM_X_PROB : m->DEFAULT_END_MATCH_PROB;
+}
+StateMachine *getStateMachineEchelon(const char *modelFile) {
+    StateMachineEchelon *m = (StateMachineEchelon *) calloc(1, sizeof(StateMachineEchelon));
+    initBase(&m->model, echelon, 60);
+    m->model.stateNumber = 7;
+    m->model.matchState = 1;
+    m->model.startStateProb = sme_start; m->model.raggedStartStateProb = sme_raggedStart;
+    m->model.endStateProb = sme_end; m->model.raggedEndStateProb = sme_end;
+    m->DEFAULT_END_MATCH_PROB = 0.79015888282447311;
+    m->DEFAULT_END_FROM_X_PROB = 0.19652425498269727;
+    m->BACKGROUND_EVENT_PROB = -3.0;
+    loadPoreModel(&m->model, modelFile);
+    return &m->model;
+}
+
 // impl/stateMachine.c:631-651: the MATCH table only; the table's own noise_sd column is replaced
 void emissions_signal_scaleModel(StateMachine *sM, double scale, double shift, double var, double scale_sd, double var_sd) {
     double *t = sM->EMISSION_MATCH_PROBS;
@@ -455,7 +534,7 @@ void modelDropLocked(StateMachine *sM) {
 }
 
 int32_t modelIdLocked(cpecan_ctx *ctx, StateMachine *sM) {
-    const int nGapX = sM->type == vanilla ? 60 : NUM_OF_KMERS;
+    const int nGapX = (sM->type == vanilla || sM->type == echelon) ? 60 : NUM_OF_KMERS;
     auto it = gModels.find(sM);
     if (it != gModels.end()) {
         if (cpecan_cuda_update_model(ctx, it->second, sM->EMISSION_MATCH_PROBS, sM->EMISSION_GAP_Y_PROBS, sM->EMISSION_GAP_X_PROBS) != CPECAN_OK)
@@ -485,8 +564,18 @@ cpecan_hmm hmmOf(StateMachine *sM) {
         const double v[5] = { m->TRANSITION_M_TO_Y_NOT_X, m->TRANSITION_E_TO_E, m->DEFAULT_END_MATCH_PROB,
                               m->DEFAULT_END_FROM_X_PROB, m->DEFAULT_END_FROM_Y_PROB };
         memcpy(h.vanilla, v, sizeof(v));
+    } else if (sM->type == fourState) {
+        StateMachine4 *m = (StateMachine4 *) sM;
+        h.sm_type = CPECAN_SM_FOUR_STATE;
+        const double t[11] = { m->TRANSITION_MATCH_CONTINUE, m->TRANSITION_MATCH_FROM_SHORT_GAP_X, m->TRANSITION_MATCH_FROM_SHORT_GAP_Y,
+                               m->TRANSITION_MATCH_FROM_LONG_GAP_X, m->TRANSITION_GAP_SHORT_OPEN_X, m->TRANSITION_GAP_SHORT_EXTEND_X,
+                               m->TRANSITION_GAP_SHORT_OPEN_Y, m->TRANSITION_GAP_SHORT_EXTEND_Y, m->TRANSITION_GAP_LONG_OPEN_X,
+                               m->TRANSITION_GAP_LONG_EXTEND_X, m->TRANSITION_GAP_LONG_SWITCH_TO_X };
+        memcpy(h.four_state, t, sizeof(t));
+    } else if (sM->type == echelon) {
+        h.sm_type = CPECAN_SM_ECHELON;
     } else {
-        st_errAbort("cpecan: state machine type %d is not implemented on the GPU (threeState and vanilla are)", (int) sM->type);
+        st_errAbort("cpecan: state machine type %d is not implemented on the GPU (threeState, vanilla, echelon, fourState are)", (int) sM->type);
     }
     return h;
 }
@@ -495,6 +584,7 @@ bool sameHmm(const cpecan_hmm &a, const cpecan_hmm &b) {
     if (a.sm_type != b.sm_type) return false;
     for (int i = 0; i < 9; i++) if (!(a.transitions[i] == b.transitions[i] || (std::isinf(a.transitions[i]) && std::isinf(b.transitions[i])))) return false;
     for (int i = 0; i < 5; i++) if (a.vanilla[i] != b.vanilla[i]) return false;
+    for (int i = 0; i < 11; i++) if (a.four_state[i] != b.four_state[i]) return false;
     return true;
 }
 
@@ -518,8 +608,9 @@ struct Flat {
 void checkSequences(StateMachine *sM, Sequence *sX, Sequence *sY) {
     // the type-erased sequences are recognised by their accessors (SURVEY 7 "Function-pointer API"): anything else
     // cannot be read by the device path
-    void *(*wantX)(void *, int64_t) = sM->type == vanilla ? sequence_getKmer2 : sequence_getKmer;
-    if (sX->get != wantX) st_errAbort("cpecan: the reference sequence must use %s for this state machine", sM->type == vanilla ? "sequence_getKmer2" : "sequence_getKmer");
+    const bool k2 = sM->type == vanilla || sM->type == echelon;          // vanillaAlign.c:224-249
+    void *(*wantX)(void *, int64_t) = k2 ? sequence_getKmer2 : sequence_getKmer;
+    if (sX->get != wantX) st_errAbort("cpecan: the reference sequence must use %s for this state machine", k2 ? "sequence_getKmer2" : "sequence_getKmer");
     if (sY->get != sequence_getEvent) st_errAbort("cpecan: the read sequence must be an event sequence (sequence_getEvent)");
 }
 
@@ -592,6 +683,20 @@ void runPosterior(cpecan_ctx *ctx, const cpecan_hmm &hmm, const cpecan_params &p
         if (res[(size_t) i].status & CPECAN_ITEM_BAND_STEP) st_errAbort("cpecan: anchors are not strictly increasing (run filterToRemoveOverlap)");
         stList *out = results[f.owner[(size_t) i]];
         const int32_t *t = triples.data() + 3 * res[(size_t) i].pair_off;
+        if (mode == CPECAN_MODE_UNBANDED) {
+            // the reference lists ascending diagonals, x ascending inside a diagonal (impl/pairwiseAligner.c:1560-1562); the
+            // device emits descending diagonals, x ascending: reverse the order of the diagonals, keep each one's run
+            int64_t k = res[(size_t) i].n_pairs;
+            while (k > 0) {
+                int64_t k0 = k - 1;
+                const int32_t dgl = t[3 * k0 + 1] + t[3 * k0 + 2];
+                while (k0 > 0 && t[3 * (k0 - 1) + 1] + t[3 * (k0 - 1) + 2] == dgl) k0--;
+                for (int64_t j = k0; j < k; j++)
+                    stList_append(out, stIntTuple_construct3(t[3 * j], t[3 * j + 1] + f.offX[(size_t) i], t[3 * j + 2] + f.offY[(size_t) i]));
+                k = k0;
+            }
+            continue;
+        }
         for (int64_t k = res[(size_t) i].n_pairs - 1; k >= 0; k--)
             stList_append(out, stIntTuple_construct3(t[3 * k], t[3 * k + 1] + f.offX[(size_t) i], t[3 * k + 2] + f.offY[(size_t) i]));
     }
@@ -622,6 +727,17 @@ void diagonalCalculation_Expectations(StateMachine *, int64_t, DpMatrix *, DpMat
                                       PairwiseAlignmentParameters *, void *) {
     noCpuPath("diagonalCalculation_Expectations");
 }
+void diagonalCalculationMultiPosteriorMatchProbs(StateMachine *, int64_t, DpMatrix *, DpMatrix *, Sequence *, Sequence *, double,
+                                                 PairwiseAlignmentParameters *, void *) {
+    noCpuPath("diagonalCalculationMultiPosteriorMatchProbs");
+}
+// the posterior callback must be the one the machine's cells are made for (vanillaAlign.c:232-249)
+static void checkPosteriorFn(StateMachine *sM, void (*fn)(StateMachine *, int64_t, DpMatrix *, DpMatrix *, Sequence *, Sequence *,
+                                                          double, PairwiseAlignmentParameters *, void *), const char *who) {
+    if (sM->type == echelon ? fn != diagonalCalculationMultiPosteriorMatchProbs : fn != diagonalCalculationPosteriorMatchProbs)
+        st_errAbort("%s: the GPU path implements diagonalCalculationPosteriorMatchProbs (threeState, vanilla, fourState) and "
+                    "diagonalCalculationMultiPosteriorMatchProbs (echelon)", who);
+}
 
 void getAlignedPairsUsingAnchorsBatch(int64_t n, StateMachine **sMs, Sequence **sXs, Sequence **sYs, stList **anchorPairs,
                                       PairwiseAlignmentParameters *p, bool raggedLeft, bool raggedRight, stList **results) {
@@ -629,20 +745,29 @@ void getAlignedPairsUsingAnchorsBatch(int64_t n, StateMachine **sMs, Sequence **
     cpecan_ctx *ctx = gpuLocked();
     const cpecan_params prm = paramsOf(p);
     for (int64_t i = 0; i < n; i++) results[i] = stList_construct3(0, (void (*)(void *)) stIntTuple_destruct);
-    int64_t i = 0;
-    while (i < n) {                                 // one GPU batch per run of reads sharing the machine's transitions
-        const cpecan_hmm hmm = hmmOf(sMs[i]);
+    // one GPU batch per DISTINCT machine (type + transitions), whatever the order of the reads: a caller that submits
+    // template, complement, template, complement, ... of the vanilla machine (whose strands differ in two transitions)
+    // gets two batches, not one per strand of every read
+    std::vector<cpecan_hmm> hmms;
+    std::vector<std::vector<int64_t>> groups;
+    for (int64_t i = 0; i < n; i++) {
+        const cpecan_hmm h = hmmOf(sMs[i]);
+        size_t g = 0;
+        while (g < hmms.size() && !sameHmm(hmms[g], h)) g++;
+        if (g == hmms.size()) { hmms.push_back(h); groups.emplace_back(); }
+        groups[g].push_back(i);
+    }
+    for (size_t g = 0; g < hmms.size(); g++) {
         Flat f;
-        int64_t j = i;
-        for (; j < n && sameHmm(hmm, hmmOf(sMs[j])); j++) {
+        for (int64_t j : groups[g]) {
             checkSequences(sMs[j], sXs[j], sYs[j]);
             // A negative length happens in the reference's own pipeline (vanillaAlign.c:645-651 slices the complement
-            // events with a DECREASING event map); the reference then walks a degenerate band and reports no pair.
+            // events with a DECREASING event map); the reference then walks a degenerate band along y = 0 and reports no
+            // pair (a posterior needs y > 0).
             if (sXs[j]->length < 0 || sYs[j]->length < 0) continue;
             addRead(f, j, modelIdLocked(ctx, sMs[j]), sXs[j], sYs[j], anchorPairs[j], p, raggedLeft, raggedRight);
         }
-        runPosterior(ctx, hmm, prm, CPECAN_MODE_POSTERIOR, f, results);
-        i = j;
+        runPosterior(ctx, hmms[g], prm, CPECAN_MODE_POSTERIOR, f, results);
     }
 }
 
@@ -651,22 +776,20 @@ stList *getAlignedPairsUsingAnchors(StateMachine *sM, Sequence *SsX, Sequence *S
                                     void (*diagonalPosteriorProbFn)(StateMachine *, int64_t, DpMatrix *, DpMatrix *, Sequence *,
                                                                     Sequence *, double, PairwiseAlignmentParameters *, void *),
                                     bool alignmentHasRaggedLeftEnd, bool alignmentHasRaggedRightEnd) {
-    if (diagonalPosteriorProbFn != diagonalCalculationPosteriorMatchProbs)
-        st_errAbort("getAlignedPairsUsingAnchors: only diagonalCalculationPosteriorMatchProbs is implemented on the GPU");
+    checkPosteriorFn(sM, diagonalPosteriorProbFn, "getAlignedPairsUsingAnchors");
     stList *result = nullptr;
     getAlignedPairsUsingAnchorsBatch(1, &sM, &SsX, &SsY, &anchorPairs, p, alignmentHasRaggedLeftEnd, alignmentHasRaggedRightEnd, &result);
     return result;
 }
 
 // impl/pairwiseAligner.c:1512-1569: full matrix, ONE totalProbability at the last diagonal.  The reference hands the
-// pairs back in ascending-diagonal order; the device emits descending diagonals, so the list is reversed here.
+// pairs back in ascending-diagonal order, x ascending inside a diagonal; runPosterior re-orders the device's list so.
 stList *getAlignedPairsWithoutBanding(StateMachine *sM, void *cX, void *cY, int64_t lX, int64_t lY, PairwiseAlignmentParameters *p,
                                       void *(*getXFcn)(void *, int64_t), void *(*getYFcn)(void *, int64_t),
                                       void (*diagonalPosteriorProbFn)(StateMachine *, int64_t, DpMatrix *, DpMatrix *, Sequence *,
                                                                       Sequence *, double, PairwiseAlignmentParameters *, void *),
                                       bool alignmentHasRaggedLeftEnd, bool alignmentHasRaggedRightEnd) {
-    if (diagonalPosteriorProbFn != diagonalCalculationPosteriorMatchProbs)
-        st_errAbort("getAlignedPairsWithoutBanding: only diagonalCalculationPosteriorMatchProbs is implemented on the GPU");
+    checkPosteriorFn(sM, diagonalPosteriorProbFn, "getAlignedPairsWithoutBanding");
     std::lock_guard<std::mutex> lk(gMu);
     cpecan_ctx *ctx = gpuLocked();
     Sequence sX = { lX, cX, getXFcn, nullptr }, sY = { lY, cY, getYFcn, nullptr };
@@ -696,8 +819,21 @@ void getExpectationsUsingAnchors(StateMachine *sM, Hmm *hmmExpectations, Sequenc
     std::lock_guard<std::mutex> lk(gMu);
     cpecan_ctx *ctx = gpuLocked();
     checkSequences(sM, SsX, SsY);
-    if (SsX->length < 0 || SsY->length < 0) return;   // degenerate input (see getAlignedPairsUsingAnchorsBatch): nothing is added
+    if (SsX->length < 0) return;
     Flat f;
+    if (SsY->length < 0) {
+        // vanillaAlign.c:645-651 slices the complement events with a DECREASING event map: a negative length.  The
+        // reference's band code then walks lX + lY diagonals of one cell each along y = 0 -- the first lX + lY k-mers
+        // against no event at all (on the fixture: 244 gap-X steps, likelihood -234346.938040 in its expectation file).
+        // The same item is submitted here: lX + lY k-mers, zero events, no anchors.
+        const int64_t lXd = SsX->length + SsY->length;
+        if (lXd <= 0) return;
+        Sequence sX = *SsX, sY = *SsY;
+        sX.length = lXd; sY.length = 0;
+        stList *none = stList_construct();
+        addRead(f, 0, modelIdLocked(ctx, sM), &sX, &sY, none, p, alignmentHasRaggedLeftEnd, alignmentHasRaggedRightEnd);
+        stList_destruct(none);
+    } else
     addRead(f, 0, modelIdLocked(ctx, sM), SsX, SsY, anchorPairs, p, alignmentHasRaggedLeftEnd, alignmentHasRaggedRightEnd);
     if (f.n() == 0) return;
     cpecan_batch b = batchOf(f);
@@ -912,6 +1048,259 @@ void nanopore_nanoporeReadDestruct(NanoporeRead *np) {
     if (!np) return;
     free(np->twoDread); free(np->templateEventMap); free(np->templateEvents); free(np->complementEventMap); free(np->complementEvents);
     free(np);
+}
+
+}  // extern "C"
+
+// ===================================================================== the rest of the caller-side surface
+// What the reference's own callers of this path (vanillaAlign.c, tests/signalPairwiseTest.c) reach besides the entry
+// points above: the per-field HMM accessors of inc/continuousHmm.h:39-100, the anchor conversion of a guide cigar,
+// read descaling, and the few sonLib string / cigar helpers they call directly (sonLib is un-vendored, include.mk:2).
+extern "C" {
+
+void continuousPairHmm_addToTransitionsExpectation(Hmm *hmm, int64_t from, int64_t to, double p) { ph_addT(hmm, from, to, p); }
+void continuousPairHmm_setTransitionExpectation(Hmm *hmm, int64_t from, int64_t to, double p) { ph_setT(hmm, from, to, p); }
+double continuousPairHmm_getTransitionExpectation(Hmm *hmm, int64_t from, int64_t to) { return ph_getT(hmm, from, to); }
+void continuousPairHmm_addToKmerGapExpectation(Hmm *hmm, int64_t state, int64_t k, int64_t ignore, double p) { ph_addE(hmm, state, k, ignore, p); }
+void continuousPairHmm_setKmerGapExpectation(Hmm *hmm, int64_t state, int64_t k, int64_t ignore, double p) { ph_setE(hmm, state, k, ignore, p); }
+double continuousPairHmm_getKmerGapExpectation(Hmm *hmm, int64_t state, int64_t k, int64_t ignore) { return ph_getE(hmm, state, k, ignore); }
+void continuousPairHmm_normalize(Hmm *hmm) { hmmContinuous_normalize(hmm, threeState); }                    // :173-190
+void continuousPairHmm_destruct(Hmm *hmm) { hmmContinuous_destruct(hmm, threeState); }
+// impl/continuousHmm.c:206-232: the trained transitions and k-mer skip probabilities into a live state machine
+void continuousPairHmm_loadTransitionsAndKmerGapProbs(StateMachine *sM, Hmm *hmm) {
+    StateMachine3 *m = (StateMachine3 *) sM;
+    m->TRANSITION_MATCH_CONTINUE = log(ph_getT(hmm, match, match));
+    m->TRANSITION_GAP_OPEN_X = log(ph_getT(hmm, match, shortGapX));
+    m->TRANSITION_GAP_OPEN_Y = log(ph_getT(hmm, match, shortGapY));
+    m->TRANSITION_MATCH_FROM_GAP_X = log(ph_getT(hmm, shortGapX, match));
+    m->TRANSITION_GAP_EXTEND_X = log(1 - ph_getT(hmm, shortGapX, match));
+    m->TRANSITION_GAP_SWITCH_TO_Y = -INFINITY;
+    m->TRANSITION_MATCH_FROM_GAP_Y = log(ph_getT(hmm, shortGapY, match));
+    m->TRANSITION_GAP_EXTEND_Y = log(ph_getT(hmm, shortGapY, shortGapY));
+    m->TRANSITION_GAP_SWITCH_TO_X = log(ph_getT(hmm, shortGapY, shortGapX));
+    for (int64_t i = 0; i < NUM_OF_KMERS; i++) sM->EMISSION_GAP_X_PROBS[i] = log(ph_getE(hmm, 0, i, 0));
+}
+void continuousPairHmm_writeToFile(Hmm *hmm, FILE *fh) {                                                    // :234-271 (no header line)
+    PairHmm *h = (PairHmm *) hmm;
+    if (anyNaN(h->transitions, 9)) return;
+    for (double t : h->transitions) fprintf(fh, "%f\t", t);
+    fprintf(fh, "%f\n", hmm->likelihood);
+    for (double k : h->kmerGap) fprintf(fh, "%f\t", k);
+    fprintf(fh, "\n");
+}
+Hmm *continuousPairHmm_loadFromFile(const char *fileName) {                                                 // :273-340
+    FILE *fh = fopen(fileName, "r");
+    if (!fh) st_errAbort("continuousPairHmm_loadFromFile: cannot open %s", fileName);
+    std::vector<double> head = readDoublesLine(fh, fileName);
+    if (head.size() < 3) st_errAbort("Failed to parse the header of %s", fileName);
+    Hmm *hmm = hmmContinuous_getEmptyHmm(threeState, 0.0, 0.0);
+    std::vector<double> l1 = readDoublesLine(fh, fileName), l2 = readDoublesLine(fh, fileName);
+    if (l1.size() != 10) st_errAbort("Incorrect number of transitions in the input HMM file %s, got %lld instead of 10\n", fileName, (long long) l1.size());
+    if (l2.size() != NUM_OF_KMERS) st_errAbort("Incorrect number of emissions in the input HMM file %s, got %lld instead of %d\n", fileName, (long long) l2.size(), NUM_OF_KMERS);
+    for (int i = 0; i < 9; i++) ((PairHmm *) hmm)->transitions[i] = l1[(size_t) i];
+    hmm->likelihood = l1[9];
+    for (int64_t i = 0; i < NUM_OF_KMERS; i++) ((PairHmm *) hmm)->kmerGap[i] = l2[(size_t) i];
+    fclose(fh);
+    return hmm;
+}
+void vanillaHmm_addToKmerSkipBinExpectation(Hmm *hmm, int64_t bin, int64_t ignore, double p) { vh_addT(hmm, bin, ignore, p); }
+void vanillaHmm_setKmerSkipBinExpectation(Hmm *hmm, int64_t bin, int64_t ignore, double p) { vh_setT(hmm, bin, ignore, p); }
+double vanillaHmm_getKmerSkipBinExpectation(Hmm *hmm, int64_t bin, int64_t ignore) { return vh_getT(hmm, bin, ignore); }
+void vanillaHmm_normalizeKmerSkipBins(Hmm *hmm) { hmmContinuous_normalize(hmm, vanilla); }                  // :424-433
+void vanillaHmm_loadKmerSkipBinExpectations(StateMachine *sM, Hmm *hmm) {                                   // :457-466
+    for (int i = 0; i < 60; i++) sM->EMISSION_GAP_X_PROBS[i] = vh_getT(hmm, i, 0);
+}
+void vanillaHmm_destruct(Hmm *hmm) { hmmContinuous_destruct(hmm, vanilla); }
+int64_t hmmContinuous_howManyAssignments(Hmm *hmm) {                                                        // :944-950: HDP containers only
+    st_errAbort("hmmContinuous: this type of Hmm doesn't have assignments got type: %lld", (long long) hmm->type);
+    return 0;
+}
+
+// impl/stateMachine.c:141-153
+int64_t emissions_discrete_getKmerIndexFromKmer(void *kmer) {
+    char k[KMER_LENGTH + 1];
+    memcpy(k, kmer, KMER_LENGTH);
+    k[KMER_LENGTH] = 0;
+    return emissions_discrete_getKmerIndex(k);
+}
+
+// impl/nanopore.c:34-38, 228-236 -- the loop steps by NB_EVENT_PARAMS over nb_events INDICES, as the reference's does
+// (only the first third of the events is descaled there; kept: this is what a caller of the reference gets)
+void nanopore_descaleNanoporeRead(NanoporeRead *np) {
+    for (int64_t i = 0; i < np->nbTemplateEvents; i += NB_EVENT_PARAMS) np->templateEvents[i] = (np->templateEvents[i] - np->templateParams.shift) / np->templateParams.scale;
+    for (int64_t i = 0; i < np->nbComplementEvents; i += NB_EVENT_PARAMS) np->complementEvents[i] = (np->complementEvents[i] - np->complementParams.shift) / np->complementParams.scale;
+    np->scaled = false;
+}
+
+// ---- sonLib helpers the callers use directly
+void *st_malloc(size_t size) { void *p = malloc(size ? size : 1); if (!p) st_errAbort("st_malloc: out of memory"); return p; }
+void *st_calloc(int64_t n, size_t size) { void *p = calloc((size_t) (n > 0 ? n : 1), size ? size : 1); if (!p) st_errAbort("st_calloc: out of memory"); return p; }
+void st_uglyf(const char *format, ...) { va_list ap; va_start(ap, format); vfprintf(stderr, format, ap); va_end(ap); }
+void st_logDebug(const char *, ...) {}
+char *stString_copy(const char *s) { return s ? strdup(s) : nullptr; }
+char *stString_print(const char *format, ...) {
+    va_list ap, ap2;
+    va_start(ap, format);
+    va_copy(ap2, ap);
+    const int n = vsnprintf(nullptr, 0, format, ap);
+    va_end(ap);
+    char *out = (char *) st_malloc((size_t) n + 1);
+    vsnprintf(out, (size_t) n + 1, format, ap2);
+    va_end(ap2);
+    return out;
+}
+char *stString_getSubString(const char *s, int64_t start, int64_t length) {
+    char *out = (char *) st_malloc((size_t) length + 1);
+    memcpy(out, s + start, (size_t) length);
+    out[length] = 0;
+    return out;
+}
+char *stString_replace(const char *s, const char *what, const char *with) {
+    std::string out;
+    const size_t nw = strlen(what);
+    while (*s) {
+        if (nw && strncmp(s, what, nw) == 0) { out += with; s += nw; }
+        else out.push_back(*s++);
+    }
+    return strdup(out.c_str());
+}
+char *stString_reverseComplementString(const char *s) {
+    const size_t n = strlen(s);
+    char *r = (char *) st_malloc(n + 1);
+    for (size_t i = 0; i < n; i++) {
+        const char c = s[n - 1 - i];
+        char o = c;
+        switch (c) {
+            case 'A': o = 'T'; break; case 'C': o = 'G'; break; case 'G': o = 'C'; break; case 'T': o = 'A'; break;
+            case 'a': o = 't'; break; case 'c': o = 'g'; break; case 'g': o = 'c'; break; case 't': o = 'a'; break;
+        }
+        r[i] = o;
+    }
+    r[n] = 0;
+    return r;
+}
+char *stFile_getLineFromFile(FILE *fh) {                       // the next line without its newline; NULL at end of file
+    std::string line;
+    int c = fgetc(fh);
+    if (c == EOF) return nullptr;
+    for (; c != EOF && c != '\n'; c = fgetc(fh)) line.push_back((char) c);
+    return strdup(line.c_str());
+}
+
+// ---- the guide alignment (exonerate cigar: "cigar: query qStart qEnd qStrand target tStart tEnd tStrand score (op len)*";
+// sonLib's cigarRead puts the QUERY into contig2 / start2 / end2 and the target into contig1, M -> MATCH, D -> INDEL_X,
+// I -> INDEL_Y, '+' -> strand 1)
+static void destroyOp(void *op) { free(op); }
+struct PairwiseAlignment *cigarRead(FILE *fh) {
+    char *line = stFile_getLineFromFile(fh);
+    if (!line) return nullptr;
+    std::vector<std::string> tok;
+    for (char *t = strtok(line, " \t\r"); t; t = strtok(nullptr, " \t\r")) tok.push_back(t);
+    free(line);
+    if (tok.size() < 10 || tok[0] != "cigar:") return nullptr;
+    struct PairwiseAlignment *pA = (struct PairwiseAlignment *) st_malloc(sizeof(struct PairwiseAlignment));
+    pA->contig2 = strdup(tok[1].c_str()); pA->start2 = atoll(tok[2].c_str()); pA->end2 = atoll(tok[3].c_str()); pA->strand2 = tok[4] == "+";
+    pA->contig1 = strdup(tok[5].c_str()); pA->start1 = atoll(tok[6].c_str()); pA->end1 = atoll(tok[7].c_str()); pA->strand1 = tok[8] == "+";
+    pA->score = (float) atof(tok[9].c_str());
+    struct List *ops = (struct List *) st_malloc(sizeof(struct List));
+    const size_t nOps = (tok.size() - 10) / 2;
+    ops->list = (void **) st_malloc(sizeof(void *) * (nOps ? nOps : 1));
+    ops->length = 0; ops->maxLength = (int64_t) nOps; ops->destroyElement = destroyOp;
+    for (size_t i = 10; i + 1 < tok.size(); i += 2) {
+        struct AlignmentOperation *op = (struct AlignmentOperation *) st_malloc(sizeof(struct AlignmentOperation));
+        op->opType = tok[i] == "M" ? PAIRWISE_MATCH : (tok[i] == "D" ? PAIRWISE_INDEL_X : PAIRWISE_INDEL_Y);
+        op->length = atoll(tok[i + 1].c_str());
+        op->score = 0.f;
+        ops->list[ops->length++] = op;
+    }
+    pA->operationList = ops;
+    return pA;
+}
+void destructPairwiseAlignment(struct PairwiseAlignment *pA) {
+    if (!pA) return;
+    for (int64_t i = 0; i < pA->operationList->length; i++) free(pA->operationList->list[i]);
+    free(pA->operationList->list); free(pA->operationList);
+    free(pA->contig1); free(pA->contig2); free(pA);
+}
+void checkPairwiseAlignment(struct PairwiseAlignment *pA) {    // the operations must add up to the two intervals
+    int64_t lx = 0, ly = 0;
+    for (int64_t i = 0; i < pA->operationList->length; i++) {
+        struct AlignmentOperation *op = (struct AlignmentOperation *) pA->operationList->list[i];
+        if (op->opType != PAIRWISE_INDEL_Y) lx += op->length;
+        if (op->opType != PAIRWISE_INDEL_X) ly += op->length;
+    }
+    if (llabs(pA->end1 - pA->start1) != lx || llabs(pA->end2 - pA->start2) != ly)
+        st_errAbort("checkPairwiseAlignment: cigar operations do not match the intervals");
+}
+// impl/pairwiseAligner.c:1039-1063: the match columns of the guide alignment, `trim` dropped at both ends of every match
+stList *convertPairwiseForwardStrandAlignmentToAnchorPairs(struct PairwiseAlignment *pA, int64_t trim) {
+    stList *pairs = stList_construct3(0, (void (*)(void *)) stIntTuple_destruct);
+    int64_t j = pA->start1, k = pA->start2;
+    for (int64_t i = 0; i < pA->operationList->length; i++) {
+        struct AlignmentOperation *op = (struct AlignmentOperation *) pA->operationList->list[i];
+        if (op->opType == PAIRWISE_MATCH) for (int64_t l = trim; l < op->length - trim; l++) stList_append(pairs, stIntTuple_construct2(j + l, k + l));
+        if (op->opType != PAIRWISE_INDEL_Y) j += op->length;
+        if (op->opType != PAIRWISE_INDEL_X) k += op->length;
+    }
+    return pairs;
+}
+
+// ---- "methods tested and possibly useful elsewhere" (inc/pairwiseAligner.h:193-277): the per-cell / per-diagonal
+// pieces of the CPU DP.  Here the diagonals live on the GPU and are never materialised on the host; the symbols exist
+// so that code written against the header links, and abort (no CPU path) if anything calls them.
+#define CPECAN_NO_HOST_DP(name, ret, args) ret name args { noCpuPath(#name); abort(); }
+typedef struct _dpDiagonal DpDiagonal;
+CPECAN_NO_HOST_DP(cell_calculateForward, void, (StateMachine *, double *, double *, double *, double *, void *, void *, void *))
+CPECAN_NO_HOST_DP(cell_calculateBackward, void, (StateMachine *, double *, double *, double *, double *, void *, void *, void *))
+CPECAN_NO_HOST_DP(dpDiagonal_construct, DpDiagonal *, (Diagonal, int64_t))
+CPECAN_NO_HOST_DP(dpDiagonal_clone, DpDiagonal *, (DpDiagonal *))
+CPECAN_NO_HOST_DP(dpDiagonal_equals, bool, (DpDiagonal *, DpDiagonal *))
+CPECAN_NO_HOST_DP(dpDiagonal_destruct, void, (DpDiagonal *))
+CPECAN_NO_HOST_DP(dpDiagonal_getCell, double *, (DpDiagonal *, int64_t))
+CPECAN_NO_HOST_DP(dpDiagonal_dotProduct, double, (DpDiagonal *, DpDiagonal *))
+CPECAN_NO_HOST_DP(dpDiagonal_zeroValues, void, (DpDiagonal *))
+CPECAN_NO_HOST_DP(dpDiagonal_initialiseValues, void, (DpDiagonal *, StateMachine *, double (*)(StateMachine *, int64_t)))
+CPECAN_NO_HOST_DP(dpMatrix_construct, DpMatrix *, (int64_t, int64_t))
+CPECAN_NO_HOST_DP(dpMatrix_destruct, void, (DpMatrix *))
+CPECAN_NO_HOST_DP(dpMatrix_getDiagonal, DpDiagonal *, (DpMatrix *, int64_t))
+CPECAN_NO_HOST_DP(dpMatrix_getActiveDiagonalNumber, int64_t, (DpMatrix *))
+CPECAN_NO_HOST_DP(dpMatrix_createDiagonal, DpDiagonal *, (DpMatrix *, Diagonal))
+CPECAN_NO_HOST_DP(dpMatrix_deleteDiagonal, void, (DpMatrix *, int64_t))
+CPECAN_NO_HOST_DP(diagonalCalculationForward, void, (StateMachine *, int64_t, DpMatrix *, Sequence *, Sequence *))
+CPECAN_NO_HOST_DP(diagonalCalculationBackward, void, (StateMachine *, int64_t, DpMatrix *, Sequence *, Sequence *))
+CPECAN_NO_HOST_DP(diagonalCalculationTotalProbability, double, (StateMachine *, int64_t, DpMatrix *, DpMatrix *, Sequence *, Sequence *))
+// impl/pairwiseAligner.c:385-397: these two are plain arithmetic and are provided
+double cell_dotProduct(double *cell1, double *cell2, int64_t stateNumber) {
+    double total = cell1[0] + cell2[0];
+    for (int64_t i = 1; i < stateNumber; i++) total = logAdd(total, cell1[i] + cell2[i]);
+    return total;
+}
+double cell_dotProduct2(double *cell, StateMachine *sM, double (*getStateValue)(StateMachine *, int64_t)) {
+    double total = cell[0] + getStateValue(sM, 0);
+    for (int64_t i = 1; i < sM->stateNumber; i++) total = logAdd(total, cell[i] + getStateValue(sM, i));
+    return total;
+}
+
+// getPosteriorProbsWithBanding (impl/pairwiseAligner.c:870-1006) hands every diagonal to a CALLBACK on the host; here the
+// two callbacks the reference ships select the device mode, and the results come back as lists.  A caller that used the
+// callback form directly gets the aligned pairs through extraArgs exactly as diagonalCalculationPosteriorMatchProbs would
+// have appended them (extraArgs = the stList of aligned pairs, :756-795).
+void getPosteriorProbsWithBanding(StateMachine *sM, stList *anchorPairs, Sequence *sX, Sequence *sY, PairwiseAlignmentParameters *p,
+                                  bool alignmentHasRaggedLeftEnd, bool alignmentHasRaggedRightEnd,
+                                  void (*diagonalPosteriorProbFn)(StateMachine *, int64_t, DpMatrix *, DpMatrix *, Sequence *, Sequence *,
+                                                                  double, PairwiseAlignmentParameters *, void *),
+                                  void *extraArgs) {
+    checkPosteriorFn(sM, diagonalPosteriorProbFn, "getPosteriorProbsWithBanding");
+    // one region, no splitting: splitMatrixBiggerThanThis is lifted for this call
+    PairwiseAlignmentParameters q = *p;
+    q.splitMatrixBiggerThanThis = INT64_MAX;
+    stList *res = getAlignedPairsUsingAnchors(sM, sX, sY, anchorPairs, &q, diagonalPosteriorProbFn, alignmentHasRaggedLeftEnd, alignmentHasRaggedRightEnd);
+    // getAlignedPairsUsingAnchors reversed the region's list (the coordinate-correction callback pops); undo it: the
+    // callback form appends in traceback order
+    stList *out = (stList *) extraArgs;
+    for (int64_t i = stList_length(res) - 1; i >= 0; i--) { stList_append(out, stList_get(res, i)); stList_set(res, i, nullptr); }
+    stList_setDestructor(res, nullptr);
+    stList_destruct(res);
 }
 
 }  // extern "C"

@@ -2,8 +2,9 @@
  * cpecan_host.h -- the reference's C API for the signal hot path, re-declared for libcpecan_host.so.
  *
  * This is the drop-in boundary on the CALLER's side: same names, argument meaning, struct layouts
- * and error behaviour as the reference's cPecanLib.a for this path, so that vanillaAlign.c and the CuTest suites link
- * against it unchanged.  Every entry point cites the reference declaration it replaces.  The DP itself runs in
+ * and error behaviour as the reference's cPecanLib.a for this path: the reference's UNMODIFIED vanillaAlign.c, compiled
+ * against the reference's own headers, links against libcpecan_host.so (plus stubs for the out-of-scope HDP symbols) and
+ * reproduces the reference binary's output -- tests/test_vanilla_align_drop_in.py does exactly that.  Every entry point cites the reference declaration it replaces.  The DP itself runs in
  * libcpecan_cuda.so (include/cpecan_cuda.h); there is NO CPU fallback: getAlignedPairsUsingAnchors and friends abort
  * (st_errAbort semantics: message + abort) when no CUDA device is usable.
  *
@@ -43,6 +44,32 @@ int64_t stIntTuple_length(stIntTuple *t);
 int stIntTuple_cmpFn(const void *a, const void *b);
 int stIntTuple_equalsFn(const void *a, const void *b);
 void st_errAbort(const char *format, ...);                   /* message on stderr + abort() */
+void *st_malloc(size_t size);
+void *st_calloc(int64_t n, size_t size);
+void st_uglyf(const char *format, ...);                      /* printf to stderr */
+void st_logDebug(const char *format, ...);
+char *stString_copy(const char *s);
+char *stString_print(const char *format, ...);
+char *stString_getSubString(const char *s, int64_t start, int64_t length);
+char *stString_replace(const char *s, const char *what, const char *with);
+char *stString_reverseComplementString(const char *s);
+char *stFile_getLineFromFile(FILE *fileHandle);              /* the next line without its newline, NULL at end of file */
+
+/* sonLib's pairwiseAlignment.h: the guide alignment vanillaAlign.c reads from stdin (exonerate cigar) */
+#define PAIRWISE_INDEL_X 0
+#define PAIRWISE_INDEL_Y 1
+#define PAIRWISE_MATCH 2
+struct List { void **list; int64_t length; int64_t maxLength; void (*destroyElement)(void *); };
+struct AlignmentOperation { int64_t opType; int64_t length; float score; };
+struct PairwiseAlignment {
+    char *contig1; int64_t start1; int64_t end1; int64_t strand1;
+    char *contig2; int64_t start2; int64_t end2; int64_t strand2;
+    float score;
+    struct List *operationList;
+};
+struct PairwiseAlignment *cigarRead(FILE *fileHandle);
+void destructPairwiseAlignment(struct PairwiseAlignment *pA);
+void checkPairwiseAlignment(struct PairwiseAlignment *pA);
 
 /* ---------------------------------------------------------------- inc/pairwiseAligner.h */
 #define PAIR_ALIGNMENT_PROB_1 10000000                       /* inc/pairwiseAligner.h:26 */
@@ -65,6 +92,8 @@ Sequence *sequence_sliceEventSequence2(Sequence *inputSequence, int64_t start, i
 void sequence_sequenceDestroy(Sequence *seq);                                                               /* :63 */
 void *sequence_getKmer(void *elements, int64_t index);                                                      /* :67 */
 void *sequence_getKmer2(void *elements, int64_t index);                                                     /* :70 */
+void *sequence_getKmer3(void *elements, int64_t index);                                                     /* :72 */
+void sequence_padSequence(Sequence *sequence);                                                              /* :56 */
 void *sequence_getEvent(void *elements, int64_t index);                                                     /* :75 */
 int64_t sequence_correctSeqLength(int64_t length, SequenceType type);                                       /* :77 */
 
@@ -137,6 +166,46 @@ void getExpectationsUsingAnchors(StateMachine *sM, Hmm *hmmExpectations, Sequenc
                                                                     Sequence *, Sequence *, double,
                                                                     PairwiseAlignmentParameters *, void *),
                                  bool alignmentHasRaggedLeftEnd, bool alignmentHasRaggedRightEnd);
+
+void diagonalCalculationMultiPosteriorMatchProbs(StateMachine *sM, int64_t xay, DpMatrix *forwardDpMatrix,  /* :251-254 */
+                                                 DpMatrix *backwardDpMatrix, Sequence *sX, Sequence *sY,
+                                                 double totalProbability, PairwiseAlignmentParameters *p, void *extraArgs);
+/* The callback form (:266-277): the two callbacks above select the device mode; the aligned pairs are appended to
+ * extraArgs (an stList) in traceback order, as diagonalCalculationPosteriorMatchProbs would have done. */
+void getPosteriorProbsWithBanding(StateMachine *sM, stList *anchorPairs, Sequence *sX, Sequence *sY,
+                                  PairwiseAlignmentParameters *p, bool alignmentHasRaggedLeftEnd, bool alignmentHasRaggedRightEnd,
+                                  void (*diagonalPosteriorProbFn)(StateMachine *, int64_t, DpMatrix *, DpMatrix *,
+                                                                  Sequence *, Sequence *, double,
+                                                                  PairwiseAlignmentParameters *, void *),
+                                  void *extraArgs);
+stList *convertPairwiseForwardStrandAlignmentToAnchorPairs(struct PairwiseAlignment *pA, int64_t trim);     /* :109 */
+
+/* "Methods tested and possibly useful elsewhere" (:193-245): the per-cell / per-diagonal pieces of the CPU DP.  The
+ * diagonals live on the GPU here; the symbols exist so that code written against the reference header links, and all
+ * but the two dot products (plain arithmetic) abort when called -- there is no CPU path. */
+typedef struct _dpDiagonal DpDiagonal;
+void cell_calculateForward(StateMachine *sM, double *current, double *lower, double *middle, double *upper, void *cX, void *cY, void *extraArgs);
+void cell_calculateBackward(StateMachine *sM, double *current, double *lower, double *middle, double *upper, void *cX, void *cY, void *extraArgs);
+double cell_dotProduct(double *cell1, double *cell2, int64_t stateNumber);
+double cell_dotProduct2(double *cell1, StateMachine *sM, double (*getStateValue)(StateMachine *, int64_t));
+DpDiagonal *dpDiagonal_construct(Diagonal diagonal, int64_t stateNumber);
+DpDiagonal *dpDiagonal_clone(DpDiagonal *diagonal);
+bool dpDiagonal_equals(DpDiagonal *diagonal1, DpDiagonal *diagonal2);
+void dpDiagonal_destruct(DpDiagonal *dpDiagonal);
+double *dpDiagonal_getCell(DpDiagonal *dpDiagonal, int64_t xmy);
+double dpDiagonal_dotProduct(DpDiagonal *diagonal1, DpDiagonal *diagonal2);
+void dpDiagonal_zeroValues(DpDiagonal *diagonal);
+void dpDiagonal_initialiseValues(DpDiagonal *diagonal, StateMachine *sM, double (*getStateValue)(StateMachine *, int64_t));
+DpMatrix *dpMatrix_construct(int64_t diagonalNumber, int64_t stateNumber);
+void dpMatrix_destruct(DpMatrix *dpMatrix);
+DpDiagonal *dpMatrix_getDiagonal(DpMatrix *dpMatrix, int64_t xay);
+int64_t dpMatrix_getActiveDiagonalNumber(DpMatrix *dpMatrix);
+DpDiagonal *dpMatrix_createDiagonal(DpMatrix *dpMatrix, Diagonal diagonal);
+void dpMatrix_deleteDiagonal(DpMatrix *dpMatrix, int64_t xay);
+void diagonalCalculationForward(StateMachine *sM, int64_t xay, DpMatrix *dpMatrix, Sequence *sX, Sequence *sY);
+void diagonalCalculationBackward(StateMachine *sM, int64_t xay, DpMatrix *dpMatrix, Sequence *sX, Sequence *sY);
+double diagonalCalculationTotalProbability(StateMachine *sM, int64_t xay, DpMatrix *forwardDpMatrix, DpMatrix *backwardDpMatrix,
+                                           Sequence *sX, Sequence *sY);
 
 int sortByXPlusYCoordinate(const void *i, const void *j);                                                   /* :316 */
 int sortByXPlusYCoordinate2(const void *i, const void *j);                                                  /* :318 */
@@ -220,13 +289,45 @@ typedef struct _StateMachine3vanilla {                                          
     double (*getMatchProbFcn)(const double *eventModel, void *kmer, void *event);
 } StateMachine3Vanilla;
 
-StateMachine *getStrawManStateMachine3(const char *modelFile);                                              /* :368 */
-StateMachine *getSignalStateMachine3Vanilla(const char *modelFile);                                         /* :374 */
+typedef struct _StateMachine4 {                                                                             /* :132-170 */
+    StateMachine model;
+    double TRANSITION_MATCH_CONTINUE;
+    double TRANSITION_MATCH_FROM_SHORT_GAP_X;
+    double TRANSITION_MATCH_FROM_LONG_GAP_X;
+    double TRANSITION_MATCH_FROM_SHORT_GAP_Y;
+    double TRANSITION_GAP_SHORT_OPEN_X;
+    double TRANSITION_GAP_SHORT_EXTEND_X;
+    double TRANSITION_GAP_SHORT_OPEN_Y;
+    double TRANSITION_GAP_SHORT_EXTEND_Y;
+    double TRANSITION_GAP_LONG_OPEN_X;
+    double TRANSITION_GAP_LONG_EXTEND_X;
+    double TRANSITION_GAP_LONG_SWITCH_TO_X;
+    double (*getXGapProbFcn)(const double *emissionXGapProbs, void *kmer);
+    double (*getYGapProbFcn)(const double *scaledMatchModel, void *kmer, void *event);
+    double (*getMatchProbFcn)(const double *matchModel, void *kmer, void *event);
+} StateMachine4;
+
+typedef struct _StateMachineEchelon {                                                                       /* :233-245 */
+    StateMachine model;
+    double BACKGROUND_EVENT_PROB;
+    double DEFAULT_END_MATCH_PROB;
+    double DEFAULT_END_FROM_X_PROB;
+    double (*getKmerSkipProb)(StateMachine *sM, void *kmerList, bool getAlpha);
+    double (*getDurationProb)(void *event, int64_t n);
+    double (*getMatchProbFcn)(const double *eventModel, void *kmers, void *event, int64_t n);
+    double (*getScaledMatchProbFcn)(const double *scaledEventModel, void *kmer, void *event);
+} StateMachineEchelon;
+
+StateMachine *getStrawManStateMachine3(const char *modelFile);                                              /* :372 */
+StateMachine *getSignalStateMachine3Vanilla(const char *modelFile);                                         /* :380 */
+StateMachine *getStateMachine4(const char *modelFile);                                                      /* :378 */
+StateMachine *getStateMachineEchelon(const char *modelFile);                                                /* :382 */
 void emissions_signal_scaleModel(StateMachine *sM, double scale, double shift, double var, double scale_sd,
                                  double var_sd);                                                            /* :341-342 */
 void stateMachine3_setTransitionsToNanoporeDefaults(StateMachine *sM);
 void stateMachine3Vanilla_setStrandTransitionsToDefaults(StateMachine *sM, Strand strand);                  /* :383 */
 int64_t emissions_discrete_getKmerIndex(void *kmer);                                                        /* :305 */
+int64_t emissions_discrete_getKmerIndexFromKmer(void *kmer);
 void stateMachine_destruct(StateMachine *stateMachine);                                                     /* :387 */
 
 /* ---------------------------------------------------------------- inc/continuousHmm.h */
@@ -236,6 +337,25 @@ void hmmContinuous_writeToFile(const char *outFile, Hmm *hmm, StateMachineType t
 void hmmContinuous_loadSignalHmm(const char *hmmFile, StateMachine *sM, StateMachineType type);             /* :104 */
 void hmmContinuous_destruct(Hmm *hmm, StateMachineType type);                                               /* :119 */
 void vanillaHmm_implantMatchModelsintoHmm(StateMachine *sM, Hmm *hmm);                                      /* :87 */
+int64_t hmmContinuous_howManyAssignments(Hmm *hmm);                                                         /* :128: HDP containers only, aborts */
+/* the per-field accessors (:39-100) over the containers hmmContinuous_getEmptyHmm returns */
+void continuousPairHmm_addToTransitionsExpectation(Hmm *hmm, int64_t from, int64_t to, double p);
+void continuousPairHmm_setTransitionExpectation(Hmm *hmm, int64_t from, int64_t to, double p);
+double continuousPairHmm_getTransitionExpectation(Hmm *hmm, int64_t from, int64_t to);
+void continuousPairHmm_addToKmerGapExpectation(Hmm *hmm, int64_t state, int64_t kmerIndex, int64_t ignore, double p);
+void continuousPairHmm_setKmerGapExpectation(Hmm *hmm, int64_t state, int64_t kmerIndex, int64_t ignore, double p);
+double continuousPairHmm_getKmerGapExpectation(Hmm *hmm, int64_t state, int64_t kmerIndex, int64_t ignore);
+void continuousPairHmm_loadTransitionsAndKmerGapProbs(StateMachine *sM, Hmm *hmm);
+void continuousPairHmm_normalize(Hmm *hmm);
+void continuousPairHmm_destruct(Hmm *hmm);
+void continuousPairHmm_writeToFile(Hmm *hmm, FILE *fileHandle);
+Hmm *continuousPairHmm_loadFromFile(const char *fileName);
+void vanillaHmm_addToKmerSkipBinExpectation(Hmm *hmm, int64_t bin, int64_t ignore, double p);
+void vanillaHmm_setKmerSkipBinExpectation(Hmm *hmm, int64_t bin, int64_t ignore, double p);
+double vanillaHmm_getKmerSkipBinExpectation(Hmm *hmm, int64_t bin, int64_t ignore);
+void vanillaHmm_normalizeKmerSkipBins(Hmm *hmm);
+void vanillaHmm_loadKmerSkipBinExpectations(StateMachine *sM, Hmm *hmm);
+void vanillaHmm_destruct(Hmm *hmm);
 
 /* ---------------------------------------------------------------- inc/nanopore.h */
 #define NB_EVENT_PARAMS 3
@@ -256,6 +376,7 @@ typedef struct _nanoporeRead {                                                  
 NanoporeRead *nanopore_loadNanoporeReadFromFile(const char *nanoporeReadFile);                              /* :31 */
 stList *nanopore_remapAnchorPairs(stList *anchorPairs, int64_t *eventMap);                                  /* :33 */
 stList *nanopore_remapAnchorPairsWithOffset(stList *unmappedPairs, int64_t *eventMap, int64_t mapOffset);   /* :35 */
+void nanopore_descaleNanoporeRead(NanoporeRead *npRead);                                                    /* :37 */
 void nanopore_nanoporeReadDestruct(NanoporeRead *npRead);                                                   /* :39 */
 
 /* ---------------------------------------------------------------- additive: batching and device selection */

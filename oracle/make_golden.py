@@ -175,7 +175,7 @@ def vanilla_align_goldens():
         open(os.path.join(out_dir, "guide.cigar"), "w").write(cigar)
         base = ["-T", T_MODEL, "-C", C_MODEL, "-L", "readA", "-q", os.path.join(GOLDEN, "ZymoC_ch_1_file1.npRead"),
                 "-r", os.path.join(GOLDEN, "ZymoRef.txt")]
-        for tag, flag in (("s", ["-s"]), ("v", [])):
+        for tag, flag in (("s", ["-s"]), ("v", []), ("f", ["-f"]), ("e", ["-e"])):
             tsv = os.path.join(td, "out_%s.tsv" % tag)
             r = subprocess.run([os.path.join(ref_dir, "vanillaAlign")] + flag + base + ["-u", tsv], input=cigar,
                                capture_output=True, text=True, check=True)

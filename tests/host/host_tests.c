@@ -224,13 +224,22 @@ static void test_fixture(const char *golden, const char *models) {
         Sequence *sY = sequence_construct2(lY, np->templateEvents, sequence_getEvent, sequence_sliceEventSequence2);
         stList *pairs = getAlignedPairsUsingAnchors(sM, sX, sY, anchors, p, diagonalCalculationPosteriorMatchProbs, 0, 0);
         printf("strawMan banded pairs %lld (reference 987)\n", (long long) stList_length(pairs));
-        CHECK(llabs(stList_length(pairs) - 987) <= 2);
+        CHECK(stList_length(pairs) == 987);
         checkAlignedPairs(pairs, lX, lY);
         stList_destruct(pairs);
         pairs = getAlignedPairsWithoutBanding(sM, ref, np->templateEvents, lX, lY, p, sequence_getKmer, sequence_getEvent,
                                               diagonalCalculationPosteriorMatchProbs, 0, 0);
         printf("strawMan un-banded pairs %lld (reference 986)\n", (long long) stList_length(pairs));
-        CHECK(llabs(stList_length(pairs) - 986) <= 2);
+        CHECK(stList_length(pairs) == 986);
+        {   /* the reference's order: ascending diagonals, x ascending inside a diagonal (impl/pairwiseAligner.c:1560-1562) */
+            int ordered = 1;
+            for (int64_t i = 1; i < stList_length(pairs); i++) {
+                stIntTuple *a = stList_get(pairs, i - 1), *b = stList_get(pairs, i);
+                const int64_t da = stIntTuple_get(a, 1) + stIntTuple_get(a, 2), db = stIntTuple_get(b, 1) + stIntTuple_get(b, 2);
+                if (db < da || (db == da && stIntTuple_get(b, 1) <= stIntTuple_get(a, 1))) ordered = 0;
+            }
+            CHECK(ordered);
+        }
         stList_destruct(pairs);
         /* EM, tests/signalPairwiseTest.c:1604-1714: start from an uninformed HMM (the reference randomises it), then
          * expectations -> normalise -> load into the state machine; the likelihood must not get worse (5 % slack) */
@@ -266,7 +275,7 @@ static void test_fixture(const char *golden, const char *models) {
         Sequence *sY = sequence_construct2(lY, np->templateEvents, sequence_getEvent, sequence_sliceEventSequence2);
         stList *pairs = getAlignedPairsUsingAnchors(sM, sX, sY, anchors, p, diagonalCalculationPosteriorMatchProbs, 0, 0);
         printf("vanilla banded pairs %lld (reference 999)\n", (long long) stList_length(pairs));
-        CHECK(llabs(stList_length(pairs) - 999) <= 2);
+        CHECK(stList_length(pairs) == 999);
         checkAlignedPairs(pairs, lX, lY);
         stList_destruct(pairs);
         Hmm *hmm = hmmContinuous_getEmptyHmm(vanilla, 0.0001, 0.0);
@@ -275,6 +284,38 @@ static void test_fixture(const char *golden, const char *models) {
         CHECK(isfinite(hmm->likelihood) && hmm->getTransitionsExpFcn(hmm, 0, 0) > 0.0001);
         hmmContinuous_destruct(hmm, vanilla);
         sequence_sequenceDestroy(sX); sequence_sequenceDestroy(sY); stateMachine_destruct(sM);
+    }
+    {   /* fourState: 988 banded and 988 un-banded, ragged (1,1) (tests/signalPairwiseTest.c:1199-1236) */
+        StateMachine *sM = getStateMachine4(model);
+        emissions_signal_scaleModel(sM, np->templateParams.scale, np->templateParams.shift, np->templateParams.var,
+                                    np->templateParams.scale_sd, np->templateParams.var_sd);
+        Sequence *sX = sequence_construct2(lX, ref, sequence_getKmer, sequence_sliceNucleotideSequence2);
+        Sequence *sY = sequence_construct2(lY, np->templateEvents, sequence_getEvent, sequence_sliceEventSequence2);
+        stList *pairs = getAlignedPairsUsingAnchors(sM, sX, sY, anchors, p, diagonalCalculationPosteriorMatchProbs, 1, 1);
+        printf("fourState banded pairs %lld (reference 988)\n", (long long) stList_length(pairs));
+        CHECK(stList_length(pairs) == 988);
+        checkAlignedPairs(pairs, lX, lY);
+        stList_destruct(pairs);
+        pairs = getAlignedPairsWithoutBanding(sM, ref, np->templateEvents, lX, lY, p, sequence_getKmer, sequence_getEvent,
+                                              diagonalCalculationPosteriorMatchProbs, 1, 1);
+        CHECK(stList_length(pairs) == 988);
+        stList_destruct(pairs);
+        sequence_sequenceDestroy(sX); sequence_sequenceDestroy(sY); stateMachine_destruct(sM);
+    }
+    {   /* echelon: 857 banded at threshold 0.15 with the padded sequence and the multi-state posterior (:1388-1449) */
+        StateMachine *sM = getStateMachineEchelon(model);
+        emissions_signal_scaleModel(sM, np->templateParams.scale, np->templateParams.shift, np->templateParams.var,
+                                    np->templateParams.scale_sd, np->templateParams.var_sd);
+        Sequence *sX = sequence_construct2(lX, ref, sequence_getKmer2, sequence_sliceNucleotideSequence2);
+        sequence_padSequence(sX);
+        Sequence *sY = sequence_construct2(lY, np->templateEvents, sequence_getEvent, sequence_sliceEventSequence2);
+        p->threshold = 0.15;
+        stList *pairs = getAlignedPairsUsingAnchors(sM, sX, sY, anchors, p, diagonalCalculationMultiPosteriorMatchProbs, 0, 0);
+        printf("echelon banded pairs %lld (reference 857)\n", (long long) stList_length(pairs));
+        CHECK(stList_length(pairs) == 857);
+        stList_destruct(pairs);
+        p->threshold = 0.01;
+        free(sX->elements); sequence_sequenceDestroy(sX); sequence_sequenceDestroy(sY); stateMachine_destruct(sM);
     }
     /* two reads in one GPU batch == two calls */
     {
@@ -285,7 +326,7 @@ static void test_fixture(const char *golden, const char *models) {
         Sequence *sY = sequence_construct2(lY, np->templateEvents, sequence_getEvent, sequence_sliceEventSequence2);
         StateMachine *sMs[2] = { sM, sM }; Sequence *xs[2] = { sX, sX }, *ys[2] = { sY, sY }; stList *as[2] = { anchors, anchors }, *res[2];
         getAlignedPairsUsingAnchorsBatch(2, sMs, xs, ys, as, p, 0, 0, res);
-        CHECK(stList_length(res[0]) == stList_length(res[1]) && llabs(stList_length(res[0]) - 987) <= 2);
+        CHECK(stList_length(res[0]) == stList_length(res[1]) && stList_length(res[0]) == 987);
         stList_destruct(res[0]); stList_destruct(res[1]);
         sequence_sequenceDestroy(sX); sequence_sequenceDestroy(sY); stateMachine_destruct(sM);
     }

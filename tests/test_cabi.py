@@ -28,7 +28,7 @@ def test_struct_sizes_match_header():
     """ctypes mirrors vs the C layouts (sizes computed from the header's field lists)."""
     from cpecan_signal import engine
     assert C.sizeof(engine.Params) == 8 + 5 * 8
-    assert C.sizeof(engine.Hmm) == 8 + 9 * 8 + 5 * 8
+    assert C.sizeof(engine.Hmm) == 8 + 9 * 8 + 5 * 8 + 11 * 8
     assert C.sizeof(engine.Batch) == 8 + 9 * 8
     assert C.sizeof(engine.Result) == 4 * 8 + 2 * 4 and engine.RESULT_DTYPE.itemsize == C.sizeof(engine.Result)
     assert C.sizeof(engine.Timing) == 6 * 8 + 4 * 8 + 2 * 4
