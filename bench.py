@@ -205,9 +205,11 @@ def em_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from cpecan_signal import Engine, HostBatch, default_params, em, synth, three_state_hmm
-    B = min(args.reads_per_gpu, 8192)
+    B = min(args.reads_per_gpu, 125000)             # config 5: 1M reads over 8 GPUs = 125k per GPU (81 GB resident at e = 64)
     e = 64
-    reads = generate_reads(B, 50_000_000 + rank * 1_000_000, procs=max(1, min(32, (os.cpu_count() or 1) // max(1, world))))
+    n_unique = min(B, args.unique_reads)
+    reads = generate_reads(n_unique, 50_000_000 + rank * 1_000_000, procs=max(1, min(32, (os.cpu_count() or 1) // max(1, world))))
+    reads = [reads[i % n_unique] for i in range(B)]
     l1, _, l3 = synth.load_model_file(synth.TEMPLATE_MODEL)
     eng = Engine(local)
     mid = eng.upload_model(l1, l3, np.full(4096, -2.3025850929940455))
@@ -217,7 +219,8 @@ def em_arm(args):
     hmm = three_state_hmm()
     eng.stage(hb, hmm=hmm, params=params, mode=1, pair_cap=1)
     cells_rank = eng.timing()["band_cells"]
-    view = torch.as_tensor(em._DevView(eng.expectations_device_ptr(), em.N_EXPECT), device="cuda")
+    if world > 1:
+        em.join_engine_communicator(eng)          # the C-ABI's own NCCL communicator; torch carries only the id
     model = em.ContinuousPairHmm()
     td = tempfile.mkdtemp()
     path = [os.path.join(td, "template_trained.hmm")]
@@ -230,12 +233,16 @@ def em_arm(args):
         if world > 1:
             dist.barrier()
 
+    estep_ms, allreduce_ms = [], []
+
     def step():
         nonlocal hmm
         eng.run_staged()
+        estep_ms.append(eng.timing()["align_ms"])
         if world > 1:
-            dist.all_reduce(view, op=dist.ReduceOp.SUM)
-            torch.cuda.synchronize()
+            t_ar = time.perf_counter()
+            eng.allreduce_expectations()              # ncclAllReduce(sum, fp64) of the 4106 doubles, in place, blocking
+            allreduce_ms.append((time.perf_counter() - t_ar) * 1e3)
         vec = np.zeros(em.N_EXPECT)
         eng.fetch_expectations(vec)
         loaded = em.em_iteration(model, vec, B * world, hmm_path, rank=rank, barrier=barrier if world > 1 else None)
@@ -247,6 +254,7 @@ def em_arm(args):
     for _ in range(args.warmup):
         step()
     barrier()
+    estep_ms.clear(); allreduce_ms.clear()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
@@ -267,8 +275,12 @@ def em_arm(args):
             "reads_per_s": B * world * args.steps / wall,
             "config": {"workload": "C5: Baum-Welch iteration (E-step kernels + all-reduce of 4106 doubles + M-step), "
                                    "synthetic reads lX~6700 x lY~8000, e=64, three-state", "reads_per_gpu": B,
-                       "allreduce_bytes": em.N_EXPECT * 8, "collective": "nccl all_reduce in place on the device accumulator"
-                       if world > 1 else "none (1 rank)"},
+                       "distinct_reads_per_gpu": n_unique, "reads_total": B * world,
+                       "allreduce_bytes": em.N_EXPECT * 8,
+                       "collective": "ncclAllReduce(sum, fp64) in place on the device accumulator through the C-ABI "
+                                     "(cpecan_cuda_allreduce_expectations)" if world > 1 else "none (1 rank)"},
+            "estep_kernel_ms_rank0": float(np.mean(estep_ms)), "estep_gcups_rank0": 2.0 * cells_rank / float(np.mean(estep_ms)) / 1e6,
+            "allreduce_ms_rank0": float(np.mean(allreduce_ms)) if allreduce_ms else None,
             "likelihoods": [float(v) for v in model.running_likelihoods[-3:]]}), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -270,15 +270,28 @@ class _DevView:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
 
 
+def join_engine_communicator(engine):
+    """One NCCL communicator over the engines of all torch.distributed ranks, owned by the C-ABI
+    (cpecan_cuda_nccl_init): rank 0 draws the unique id, torch.distributed only carries its 128 bytes."""
+    import torch.distributed as dist
+    ids = [engine.nccl_unique_id() if dist.get_rank() == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    engine.nccl_init(dist.get_world_size(), dist.get_rank(), ids[0])
+
+
 def gpu_estep(engine, batch, hmm, params, distributed):
     """E-step of this rank's shard on its GPU; the batch sums are all-reduced IN PLACE in the device accumulator
     (the kernel's atomics and the NCCL collective share one buffer), then fetched once.  The vector has 4106 entries
-    for the three-state machine and 61 for the vanilla one (hmm.sm_type)."""
+    for the three-state machine and 61 for the vanilla one (hmm.sm_type).  distributed: True = all-reduce through
+    torch.distributed on a view of the device buffer; "cabi" = through the engine's own communicator
+    (join_engine_communicator), the path a C driver takes."""
     import torch
     n = N_EXPECT_VANILLA if hmm is not None and int(hmm.sm_type) == VANILLA else N_EXPECT
     engine.stage(batch, hmm=hmm, params=params, mode=1, pair_cap=1)
     engine.run_staged()
-    if distributed:
+    if distributed == "cabi":
+        engine.allreduce_expectations()
+    elif distributed:
         view = torch.as_tensor(_DevView(engine.expectations_device_ptr(), n), device="cuda")
         allreduce_sum(view, True)
         torch.cuda.synchronize()
@@ -295,7 +308,11 @@ def em_iteration(model, estep_sum, n_reads_total, hmm_path, rank=0, pseudocount=
     model.likelihood = 0.0
     vec = np.array(estep_sum, dtype=np.float64, copy=True)
     vec[:-1] += pseudocount * n_reads_total
-    model.add_expectations(vec)
+    if not model.add_expectations(vec):
+        # The device drops a read whose totals are non-finite from the batch sums (status CPECAN_ITEM_NONFINITE), so a
+        # NaN here means the sums themselves are broken: normalising "the previous model plus pseudocounts" silently would
+        # be a wrong M-step.  The reference skips such expectation files one by one (nanoporeLib.py:1006-1011).
+        raise ValueError("E-step sums are not finite: no M-step was done")
     model.normalize()
     if rank == 0:
         tmp = hmm_path + ".tmp"

@@ -356,6 +356,22 @@ class Engine:
         self._check(self.lib.cpecan_cuda_expectations_device_ptr(self.ctx, C.byref(p)), "expectations_device_ptr")
         return p.value
 
+    # multi-GPU training through the C-ABI's own NCCL communicator (include/cpecan_cuda.h)
+    NCCL_ID_BYTES = 128
+
+    def nccl_unique_id(self):
+        buf = C.create_string_buffer(self.NCCL_ID_BYTES)
+        self._check(self.lib.cpecan_cuda_nccl_unique_id(buf), "nccl_unique_id")
+        return bytes(buf.raw)
+
+    def nccl_init(self, n_ranks, rank, unique_id):
+        assert len(unique_id) == self.NCCL_ID_BYTES
+        self._check(self.lib.cpecan_cuda_nccl_init(self.ctx, C.c_int32(n_ranks), C.c_int32(rank), C.c_char_p(unique_id)), "nccl_init")
+
+    def allreduce_expectations(self):
+        """In-place ncclAllReduce(sum, fp64) of the device accumulator over the communicator of nccl_init()."""
+        self._check(self.lib.cpecan_cuda_allreduce_expectations(self.ctx), "allreduce_expectations")
+
     def fetch_expectations(self, out):
         self._check(self.lib.cpecan_cuda_fetch_expectations(self.ctx, out.ctypes.data_as(C.c_void_p)), "fetch_expectations")
         return out

@@ -1,6 +1,7 @@
 // cpecan_cuda.cu -- host side of the C-ABI declared in include/cpecan_cuda.h: context, staging, kernel launches.
 // All device work runs on the context's own streams; timings come from CUDA events on those streams.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -54,6 +55,37 @@ struct Bucket {
 
 }  // namespace
 
+// ---- NCCL through dlopen: the library is needed only by multi-GPU training
+namespace {
+struct Nccl {
+    void *h = nullptr;
+    int (*getUniqueId)(void *) = nullptr;
+    int (*commInitRank)(void **, int, char[128], int) = nullptr;      // ncclUniqueId is passed by value: 128 bytes
+    int (*allReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*commDestroy)(void *) = nullptr;
+    const char *(*getErrorString)(int) = nullptr;
+};
+struct NcclId { char b[CPECAN_NCCL_UNIQUE_ID_BYTES]; };
+Nccl *ncclLib(std::string &err) {
+    static Nccl L;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    if (L.h) return &L;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { err = std::string("libnccl.so.2 not found: ") + dlerror(); return nullptr; }
+    L.getUniqueId = (int (*)(void *)) dlsym(h, "ncclGetUniqueId");
+    L.commInitRank = (int (*)(void **, int, char[128], int)) dlsym(h, "ncclCommInitRank");
+    L.allReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t)) dlsym(h, "ncclAllReduce");
+    L.commDestroy = (int (*)(void *)) dlsym(h, "ncclCommDestroy");
+    L.getErrorString = (const char *(*)(int)) dlsym(h, "ncclGetErrorString");
+    if (!L.getUniqueId || !L.commInitRank || !L.allReduce) { err = "libnccl.so.2 lacks ncclGetUniqueId / ncclCommInitRank / ncclAllReduce"; return nullptr; }
+    L.h = h;
+    return &L;
+}
+}  // namespace
+
+
 struct cpecan_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -91,6 +123,8 @@ struct cpecan_ctx {
     bool wantTotals = false;
     std::vector<int64_t> hTotOff;
     cpecan_timing timing{};
+    void *ncclComm = nullptr;    // ncclComm_t (cpecan_cuda_nccl_init)
+    int ncclRanks = 0;
 };
 
 namespace {
@@ -290,6 +324,7 @@ void cpecan_cuda_destroy(cpecan_ctx *ctx) {
     for (auto &e : ctx->ev) cudaEventDestroy(e);
     for (auto &e : ctx->bev) cudaEventDestroy(e);
     if (ctx->evBlock) cudaEventDestroy(ctx->evBlock);
+    if (ctx->ncclComm) { std::string e; Nccl *L = ncclLib(e); if (L && L->commDestroy) L->commDestroy(ctx->ncclComm); }
     for (auto &st : ctx->bstream) cudaStreamDestroy(st);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -774,6 +809,47 @@ int cpecan_cuda_fetch_expectations(cpecan_ctx *ctx, double *expectations_out) {
     if (!ctx || !expectations_out) return CPECAN_ERR_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
     return fetchExpectL(ctx, expectations_out);
+}
+
+int cpecan_cuda_nccl_unique_id(void *id_out) {
+    if (!id_out) return CPECAN_ERR_ARG;
+    std::string err;
+    Nccl *L = ncclLib(err);
+    if (!L) return CPECAN_ERR_CUDA;
+    return L->getUniqueId(id_out) == 0 ? CPECAN_OK : CPECAN_ERR_CUDA;
+}
+
+int cpecan_cuda_nccl_init(cpecan_ctx *ctx, int32_t n_ranks, int32_t rank, const void *id) {
+    if (!ctx || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return CPECAN_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    Nccl *L = ncclLib(ctx->err);
+    if (!L) return CPECAN_ERR_CUDA;
+    if (ctx->ncclComm) { if (L->commDestroy) L->commDestroy(ctx->ncclComm); ctx->ncclComm = nullptr; }
+    // ncclResult_t ncclCommInitRank(ncclComm_t *comm, int nranks, ncclUniqueId commId, int rank): the id goes by value
+    typedef int (*InitFn)(void **, int, NcclId, int);
+    NcclId nid;
+    memcpy(nid.b, id, sizeof(nid.b));
+    const int rc = ((InitFn) L->commInitRank)(&ctx->ncclComm, n_ranks, nid, rank);
+    if (rc != 0) { ctx->err = std::string("ncclCommInitRank: ") + (L->getErrorString ? L->getErrorString(rc) : "error"); ctx->ncclComm = nullptr; return CPECAN_ERR_CUDA; }
+    ctx->ncclRanks = n_ranks;
+    return CPECAN_OK;
+}
+
+int cpecan_cuda_allreduce_expectations(cpecan_ctx *ctx) {
+    if (!ctx) return CPECAN_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->ncclComm) { ctx->err = "allreduce_expectations: call cpecan_cuda_nccl_init first"; return CPECAN_ERR_ARG; }
+    if (ctx->running) { ctx->err = "allreduce_expectations: a run is in flight (wait for it)"; return CPECAN_ERR_ARG; }
+    Nccl *L = ncclLib(ctx->err);
+    if (!L) return CPECAN_ERR_CUDA;
+    CK(ctx->dExpect.ensure(CPECAN_N_EXPECT * sizeof(double)));
+    const size_t len = ctx->machine ? CPECAN_N_EXPECT_VANILLA : CPECAN_N_EXPECT;
+    const int rc = L->allReduce(ctx->dExpect.p, ctx->dExpect.p, len, /* ncclDouble */ 8, /* ncclSum */ 0, ctx->ncclComm, ctx->stream);
+    if (rc != 0) { ctx->err = std::string("ncclAllReduce: ") + (L->getErrorString ? L->getErrorString(rc) : "error"); return CPECAN_ERR_CUDA; }
+    CK(waitStream(ctx, ctx->stream));
+    return CPECAN_OK;
 }
 
 int cpecan_cuda_expectations_device_ptr(cpecan_ctx *ctx, double **dev_ptr_out) {

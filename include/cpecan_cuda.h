@@ -166,6 +166,17 @@ int cpecan_cuda_expectations_batch(cpecan_ctx *ctx, const cpecan_hmm *hmm, const
  * in place across GPUs (NCCL over NVLink) before fetch_expectations() ADDS it to a host vector. */
 int cpecan_cuda_fetch_expectations(cpecan_ctx *ctx, double *expectations_out);
 int cpecan_cuda_expectations_device_ptr(cpecan_ctx *ctx, double **dev_ptr_out);
+/* Multi-GPU training without Python: one context per GPU (one process or host thread each),
+ * joined in ONE NCCL communicator.  Rank 0 calls nccl_unique_id() and hands the 128 bytes to the others by whatever
+ * means the driver has (a file, a pipe, MPI); every rank then calls nccl_init().  allreduce_expectations() sums the
+ * device accumulators of all ranks in place -- ncclAllReduce(ncclSum, ncclDouble) over NVLink / NVSwitch, 4106 doubles
+ * (vanilla: 61), on the context's stream -- so that the following fetch_expectations() returns the whole job's sums on
+ * every rank: what scripts/trainModels.py:244-330 gets by adding up one expectation file per read.  libnccl.so.2 is
+ * opened at run time (dlopen); CPECAN_ERR_CUDA with a message if it is missing. */
+#define CPECAN_NCCL_UNIQUE_ID_BYTES 128
+int cpecan_cuda_nccl_unique_id(void *id_out);
+int cpecan_cuda_nccl_init(cpecan_ctx *ctx, int32_t n_ranks, int32_t rank, const void *id);
+int cpecan_cuda_allreduce_expectations(cpecan_ctx *ctx);
 
 /* Device-resident variant used to measure kernel-only throughput: stage() copies and prepares a batch in HBM once,
  * run_staged() re-runs plan + align kernels on it (results stay on device), fetch_staged() copies results back. */
