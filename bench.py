@@ -13,8 +13,9 @@ across ranks with no data-path collective (weak scaling: B reads per GPU).
   e2e        the same metric through the C-ABI call with HOST buffers: H2D of the batch, preparation, plan, kernels
              and D2H of the aligned pairs all inside the timed region; the batch is streamed in sub-batches through
              two contexts per expansion so that one context's copies run under the others' kernels
-  roofline   HBM bytes (25 B per band cell) / kernel time against MEASURED_PEAKS.json, plus the FP32
-             issue-rate roofline SURVEY.md 8(d) defines (165 issue-ops per band cell)
+  roofline   the binding bound: the FP32 issue-rate roofline SURVEY.md 8(d) defines (165 issue-ops per band cell against
+             SMs x 128 lanes x clock); roofline_hbm: 25 algorithmic bytes per band cell / kernel time against
+             MEASURED_PEAKS.json, with the DRAM traffic ncu measured per expansion (profiles/r2_dram_bytes_per_cell.json)
   cpu_baseline / --impl reference
              the reference's own C code (oracle/_ref, unmodified sources; else the oracle port) on all host cores,
              one process per read as the reference's drivers do, on a bounded sample of the same reads.
@@ -36,11 +37,6 @@ sys.path.insert(0, os.path.join(ROOT, "cpecan-signal_b200"))
 EXPANSIONS = (64, 128, 256)
 LX = 6700
 HBM_BYTES_PER_CELL = 25.0       # forward cell written + read once (24 B) + inputs/outputs (<1 B)
-# DRAM bytes per band cell of k_align2 from the ncu --set full capture committed under profiles/
-# (r1_ncu_k_align2_e64_v11_summary.txt: dram__bytes_read.sum 174.0 GB + dram__bytes_write.sum 98.5 GB for one launch over
-# 6.807e9 band cells): 14.5 B written + 25.6 B read per band cell (forward rows are float4 (M, X, Y, offset) written by
-# the cells inside the band; the L2 prefetch of forward rows fetches whole 512-byte chunks)
-DRAM_BYTES_PER_CELL_NCU = 40.0
 ISSUE_OPS_PER_CELL = 165.0
 METRIC = "banded_fwd_bwd_posterior_gcups"
 
@@ -116,6 +112,19 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- CPU reference arm
+def _mapped_cpu_library(kind):
+    """The library that ran the timed call, as this worker process has it mapped (/proc/self/maps): makes "kind" provable
+    from the output.  (libcpecan_oracle.so may be mapped as well: the parent counted the band cells with it before the
+    fork; the timed call of kind "reference" goes through oracle/refshim.py into libcpecan_ref.so only.)"""
+    want = "libcpecan_ref" if kind == "reference" else "libcpecan_oracle"
+    try:
+        with open("/proc/self/maps") as fh:
+            libs = sorted({line.split()[-1] for line in fh if want in line})
+        return [os.path.relpath(p, ROOT) for p in libs]
+    except OSError:
+        return []
+
+
 def _cpu_one(args):
     """One read through the reference's getAlignedPairsUsingAnchors (process-per-read, as scripts/signalAlign.py)."""
     kind, read, e = args
@@ -133,7 +142,7 @@ def _cpu_one(args):
         pairs, _ = O.align_banded(m, read.ref, read.events, read.anchors,
                                   params=O.default_params(diagonalExpansion=e), ragged=(1, 1))
         sec, n = time.perf_counter() - t0, len(pairs)
-    return sec, n
+    return sec, n, _mapped_cpu_library(kind)
 
 
 def cpu_kind():
@@ -156,7 +165,8 @@ def run_cpu_sample(reads, exps, cores):
     with mp.get_context("fork").Pool(cores) as pool:
         res = pool.map(_cpu_one, jobs, chunksize=1)
     wall = time.perf_counter() - t0
-    return wall, cells, sum(s for s, _ in res)
+    run_cpu_sample.libraries = sorted({lib for r in res for lib in r[2]})       # what the worker processes had mapped
+    return wall, cells, sum(r[0] for r in res)
 
 
 def reference_arm(args):
@@ -184,6 +194,7 @@ def reference_arm(args):
             "config": {"workload": "C3 synthetic reads lX~6700 lY~8000, expansions 64/128/256 evenly, three-state, "
                                    "bounded sample of %d reads per step" % len(reads), "reads_per_step": len(reads)},
             "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": cores, "kind": cpu_kind(),
+                             "library_timed": getattr(run_cpu_sample, "libraries", []),
                              "sample": "%d reads per step, one process per read on %d cores" % (len(reads), cores)},
             "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -303,6 +314,12 @@ def main():
                          "contexts, so that one's copies run under the other's kernels")
     ap.add_argument("--pairs-per-event", type=float, default=2.0, help="capacity of the aligned-pair buffers (the batch yields ~1.1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, the driver's contract): --reads-per-gpu reads on EVERY GPU; strong: ONE batch of "
+                         "--reads-per-gpu reads (BASELINE config 4: 'the same batch sharded across 2/4/8') dealt to the ranks "
+                         "by band cells, longest first (em.shard_by_cells)")
+    ap.add_argument("--machine", default="three", choices=["three", "vanilla"],
+                    help="state machine of the posterior workload (the headline is the three-state machine)")
     ap.add_argument("--workload", default="posterior", choices=["posterior", "em"],
                     help="posterior = BASELINE config 3/4 (default, the headline); em = config 5, one Baum-Welch "
                          "iteration per step (E-step kernels + NCCL all-reduce + M-step)")
@@ -327,23 +344,39 @@ def main():
     from cpecan_signal import Engine, HostBatch, default_params
     from cpecan_signal.engine import RESULT_DTYPE
 
+    from cpecan_signal import em as _em
     B = args.reads_per_gpu - args.reads_per_gpu % 3
     n_unique = min(B, max(3, args.unique_reads - args.unique_reads % 3))
-    reads = generate_reads(n_unique, rank * 1_000_000, procs=max(1, min(32, (os.cpu_count() or 1) // max(1, world))))
-    reads = [reads[i % n_unique] for i in range(B)]          # n_unique is a multiple of 3: a read keeps its expansion
+    if args.scaling == "strong" and world > 1:
+        # ONE batch for the whole job: every rank generates the same distinct reads (seed 0), read i of the batch is
+        # distinct read i % n_unique with expansion EXPANSIONS[i % 3]; the ranks take the shards of a longest-first
+        # deal by band cells ((lX + lY) * (e + 40) is proportional to them for these reads)
+        reads = generate_reads(n_unique, 0, procs=max(1, min(32, (os.cpu_count() or 1) // max(1, world))))
+        weight = np.array([(reads[i % n_unique].lX + reads[i % n_unique].lY) * (EXPANSIONS[i % 3] + 40) for i in range(B)])
+        mine = _em.shard_by_cells(weight, world)[rank]
+        by_exp = [[reads[i % n_unique] for i in mine if i % 3 == j] for j in range(3)]
+        B = len(mine)
+    else:
+        reads = generate_reads(n_unique, rank * 1_000_000, procs=max(1, min(32, (os.cpu_count() or 1) // max(1, world))))
+        reads = [reads[i % n_unique] for i in range(B)]          # n_unique is a multiple of 3: a read keeps its expansion
+        by_exp = [reads[j::3] for j in range(3)]
     engines, batches, outs = [], [], []
     l1 = l3 = None
     from cpecan_signal import synth
-    l1, _, l3 = synth.load_model_file(synth.TEMPLATE_MODEL)
+    l1, l2, l3 = synth.load_model_file(synth.TEMPLATE_MODEL)
     tbl_match, tbl_gapy = l1, l3
+    from cpecan_signal import vanilla_gapx, vanilla_hmm
+    vanilla = args.machine == "vanilla"
+    gapx_tbl = vanilla_gapx(l2) if vanilla else np.full(4096, -2.3025850929940455)
+    bench_hmm = vanilla_hmm("template") if vanilla else None
     order = sorted(range(3), key=lambda j: -EXPANSIONS[j])      # widest band first: its tail is filled by the others
     SUB = max(1, args.e2e_subbatches)
     host = Engine(local)                    # owns the page-locked host memory of both legs (stages nothing itself)
     for j in order:
         e = EXPANSIONS[j]
-        sub = reads[j::3]
+        sub = by_exp[j]
         eng = Engine(local)
-        mid = eng.upload_model(l1, l3, np.full(4096, -2.3025850929940455))
+        mid = eng.upload_model(l1, l3, gapx_tbl)
         hb = HostBatch([r.ref for r in sub], [r.events for r in sub], [r.anchors for r in sub],
                        model_ids=[mid] * len(sub), scales=[r.scale5 for r in sub], ragged=[(1, 1)] * len(sub))
         host.pin_batch(hb)
@@ -357,7 +390,8 @@ def main():
     # host memory: at 8 ranks per box keep only the pinned batches and the small sample the CPU baseline needs
     n_keep = max(3, min(3 * (os.cpu_count() or 1), 192, B))
     n_keep -= n_keep % 3
-    reads = reads[:n_keep]
+    reads = [by_exp[i % 3][i // 3] for i in range(min(n_keep, 3 * min(len(b) for b in by_exp)))]
+    del by_exp
     import gc
     gc.collect()
 
@@ -383,8 +417,9 @@ def main():
 
     # ---- resident (kernel-only) measurement -----------------------------------------------------------------
     for eng, hb, p, o in zip(engines, batches, params, outs):
-        eng.stage(hb, params=p, pair_cap=len(o[1]))
-    cells_rank = sum(eng.timing()["band_cells"] for eng in engines)
+        eng.stage(hb, hmm=bench_hmm, params=p, pair_cap=len(o[1]))
+    cells_by_engine = [eng.timing()["band_cells"] for eng in engines]
+    cells_rank = sum(cells_by_engine)
     _free, _tot = torch.cuda.mem_get_info()
     print("rank %d: batch staged; device memory: %.1f of %.1f GB free" % (rank, _free / 1e9, _tot / 1e9), file=sys.stderr, flush=True)
     def resident_step():
@@ -444,7 +479,7 @@ def main():
         for _ in range(min(2, SUB)):
             eng = Engine(local)
             eng.set_resident_warps(8)
-            eng.upload_model(tbl_match, tbl_gapy, np.full(4096, -2.3025850929940455))
+            eng.upload_model(tbl_match, tbl_gapy, gapx_tbl)
             pair.append((eng, []))
         off = 0
         for k in range(SUB):
@@ -460,7 +495,7 @@ def main():
     def run_lane(i):
         eng, tasks = lanes[i]
         for sb, p, o in tasks:
-            eng.align_batch(sb, None, p, 0, None, False, o)
+            eng.align_batch(sb, bench_hmm, p, 0, None, False, o)
             tm = eng.timing()
             counters[i][0] += tm["h2d_bytes"]; counters[i][1] += tm["d2h_bytes"]; counters[i][2] += tm["kernel_launches"]
 
@@ -506,15 +541,27 @@ def main():
     sm_clock_hz = (clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)) * 1e6 if clocks else 1965e6
     issue_peak = info["sm_count"] * 128 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6
     issue_ach = ISSUE_OPS_PER_CELL * cells_steps / kern_s
+    # DRAM bytes per band cell of k_align3, measured with ncu per expansion (tools: profiles/r2_dram_bytes_per_cell.json)
+    dram_traffic_per_launch = None
+    try:
+        per_cell = json.load(open(os.path.join(ROOT, "profiles", "r2_dram_bytes_per_cell.json")))
+        dram_traffic_per_launch = sum(float(per_cell[str(EXPANSIONS[j])]) * cells_by_engine[k] for k, j in enumerate(order)) / len(engines)
+    except Exception:
+        pass
     line = {
         "metric": METRIC, "value": gcups, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "reads_per_s": reads_total * args.steps / wall, "band_cells_per_s": cells_total * args.steps / wall,
         "config": {"workload": "C3: batched synthetic reads lX~6700 x lY~8000 events, 6-mer template model, anchors "
-                               "every 50 k-mers, expansions 64/128/256 evenly, three-state, threshold 0.01, ragged (1,1)",
+                               "every 50 k-mers, expansions 64/128/256 evenly, %s, threshold 0.01, ragged (1,1)" % (
+                                   "vanilla machine" if vanilla else "three-state"),
+                   "distinct_reads": "the batch tiles %d distinct reads; every copy has its own host and device buffers, so a "
+                                     "copy shares no cache line with another" % n_unique,
                    "reads_per_gpu": B, "distinct_reads_per_gpu": n_unique, "reads_total": int(reads_total), "band_cells_per_step": int(cells_total),
-                   "aligned_pairs_rank0": n_pairs, "sharding": "reads partitioned over ranks, no collective",
+                   "aligned_pairs_rank0": n_pairs,
+                   "sharding": ("ONE batch of %d reads dealt to the ranks by band cells, longest first; no collective" % int(reads_total))
+                   if (args.scaling == "strong" and world > 1) else "reads partitioned over ranks (the same number on every GPU), no collective",
                    "l2": "inputs + forward spill per step >> 126 MB L2 (no flush needed)"},
         "e2e": {"value": e2e_gcups, "unit": "GCUPS", "h2d_bytes_per_step": int(h2d / args.steps),
                 "d2h_bytes_per_step": int(d2h / args.steps), "ms_per_step": e2e_wall / args.steps * 1e3,
@@ -523,17 +570,21 @@ def main():
         "gpu_launches": int(launches),
         "gpu_launches_e2e": int(e2e_launches),
         "kernel_ms_per_step": kern_ms_max / args.steps,
-        "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved_gbs / hbm_peak,
-                     "traffic": DRAM_BYTES_PER_CELL_NCU * cells_rank / len(engines),   # bytes per launch (ncu, see above)
-                     "algorithmic_bytes_per_launch": HBM_BYTES_PER_CELL * cells_rank / len(engines),
-                     "peak_source": peak_src,
-                     "algorithmic_bytes_per_band_cell": HBM_BYTES_PER_CELL},
-        "roofline_issue": {"bound": "fp32_issue", "achieved": issue_ach / 1e12, "peak": issue_peak / 1e12,
-                           "unit": "Tissue-op/s", "frac": issue_ach / issue_peak,
-                           "ops_per_band_cell": ISSUE_OPS_PER_CELL, "sm_count": info["sm_count"],
-                           "clock_mhz_for_peak": float(peaks.get("sm_max_mhz", 1965.0)),
-                           "frac_at_observed_clock": issue_ach / (info["sm_count"] * 128 * sm_clock_hz)},
+        # the bound that binds this kernel (north_star: FP32 / SFU issue rate against the per-cell op count of SURVEY.md
+        # 8(d)); the HBM roofline of the forward-row spill is reported beside it
+        "roofline": {"bound": "fp32_issue", "achieved": issue_ach / 1e12, "peak": issue_peak / 1e12,
+                     "unit": "Tissue-op/s", "frac": issue_ach / issue_peak,
+                     "ops_per_band_cell": ISSUE_OPS_PER_CELL, "sm_count": info["sm_count"],
+                     "clock_mhz_for_peak": float(peaks.get("sm_max_mhz", 1965.0)),
+                     "frac_at_observed_clock": issue_ach / (info["sm_count"] * 128 * sm_clock_hz),
+                     "traffic": dram_traffic_per_launch, "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + "
+                     "dram__bytes_write.sum per band cell and expansion, profiles/r2_dram_bytes_per_cell.json, x this run's cells)",
+                     "peak_source": "148 SMs x 128 FP32 lanes x sm_max_mhz of MEASURED_PEAKS.json" if "sm_max_mhz" in peaks else "fallback 1965 MHz"},
+        "roofline_hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved_gbs / hbm_peak, "traffic": dram_traffic_per_launch,
+                         "measured_dram_gbs": dram_traffic_per_launch * len(engines) * args.steps / kern_s / 1e9 if dram_traffic_per_launch else None,
+                         "algorithmic_bytes_per_launch": HBM_BYTES_PER_CELL * cells_rank / len(engines),
+                         "peak_source": peak_src, "algorithmic_bytes_per_band_cell": HBM_BYTES_PER_CELL},
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:
@@ -544,6 +595,7 @@ def main():
         wall_c, cells_c, core_s = run_cpu_sample(sample, exps, cores)
         line["cpu_baseline"] = {"value": 2.0 * cells_c / wall_c / 1e9, "unit": "GCUPS", "cores": cores,
                                 "kind": cpu_kind(),
+                                "library_timed": getattr(run_cpu_sample, "libraries", []),
                                 "sample": "%d reads of the same batch, one process per read on %d cores, %.1f s wall, "
                                           "%.1f core-s" % (n_s, cores, wall_c, core_s),
                                 "band_cells_per_core_s": cells_c / core_s}

@@ -410,18 +410,26 @@ __global__ void __launch_bounds__(32, CP_MINB3) k_align3(const KernelArgs3 A) {
                         if (HAS_SX) bY = LA(bY, gx1 + tSX);
                     };
                     // posterior of one cell + G = B + emission, re-based, back into the ring
+                    // E-step: the forward cells of the three predecessors of cell x (lower, middle, upper), requested at the top
+                    // of a chunk so that the ~100 instructions of cellB hide their latency (they were the kernel's hottest
+                    // stall, 14 % of all samples, when loaded at their first use)
+                    struct Pred { float4 L, M, U; };
+                    auto loadPred = [&](int x, bool inb) -> Pred {
+                        Pred P3 = { NIENT, NIENT, NIENT };
+                        if (EXPECT && post && inb) {
+                            if (x - 1 >= el1 && x - 1 <= eh1) P3.L = frow1[(x - 1) & NM];
+                            if (x - 1 >= el2 && x - 1 <= eh2) P3.M = frow2[(x - 1) & NM];
+                            if (x >= el1 && x <= eh1) P3.U = frow1[x & NM];
+                        }
+                        return P3;
+                    };
                     auto cellPost = [&](int x, int s, bool inb, float bM, float bX, float bY, float U, float eM, float eY,
-                                        float eX, float Fx, float Fw, float myLog, int kw) {
+                                        float eX, float Fx, float Fw, float myLog, int kw, const Pred &P3) {
                         if (EXPECT) {
                             if (post) {
                                 // diagonalCalculation_Expectations (impl/pairwiseAligner.c:841-863): for every transition
                                 // into this cell p = exp(F_pred[from] + B[to] + eP + tP - total) (:426-443)
-                                float4 FL = NIENT, FM = NIENT, FU = NIENT;
-                                if (inb) {
-                                    if (x - 1 >= el1 && x - 1 <= eh1) FL = frow1[(x - 1) & NM];
-                                    if (x - 1 >= el2 && x - 1 <= eh2) FM = frow2[(x - 1) & NM];
-                                    if (x >= el1 && x <= eh1) FU = frow1[s];
-                                }
+                                const float4 FL = P3.L, FM = P3.M, FU = P3.U;
                                 float4 pdo = NIENT;
                                 if (MACH) pdo = xpD[min(x, lX + 1)];
                                 const float tOX = MACH ? pdo.x : gOX, tEX = MACH ? pdo.y : gEX, tMC = MACH ? pdo.z : gMC,
@@ -478,10 +486,11 @@ __global__ void __launch_bounds__(32, CP_MINB3) k_align3(const KernelArgs3 A) {
                             const bool inb = x >= blo && x <= bhi;
                             const auto cur = G;
                             loadB(min(c + 1, nch - 1));                // the next chunk (after the last one: again this one)
+                            const Pred P3 = loadPred(x, inb);
                             float bM, bX, bY, U;
                             cellB(x, s, make_float4(cur.tOX, cur.tEX, cur.tMC, cur.tMX), cur.myLog, bM, bX, bY, U);
                             __syncwarp();
-                            cellPost(x, s, inb, bM, bX, bY, U, cur.eM, cur.eY, cur.eX, cur.Fx, cur.Fw, cur.myLog, cur.kw);
+                            cellPost(x, s, inb, bM, bX, bY, U, cur.eM, cur.eY, cur.eX, cur.Fx, cur.Fw, cur.myLog, cur.kw, P3);
                             __syncwarp();
                             reduceB();
                         }
@@ -562,8 +571,9 @@ __global__ void __launch_bounds__(32, CP_MINB3) k_align3(const KernelArgs3 A) {
                             const float4 b = A2[s];
                             const auto cur = G;
                             loadB(min(c + 1, nch - 1));
+                            const Pred P3 = loadPred(x, inb);
                             __syncwarp();
-                            cellPost(x, s, inb, b.x, b.y, b.z, b.w, cur.eM, cur.eY, cur.eX, cur.Fx, cur.Fw, cur.myLog, cur.kw);
+                            cellPost(x, s, inb, b.x, b.y, b.z, b.w, cur.eM, cur.eY, cur.eX, cur.Fx, cur.Fw, cur.myLog, cur.kw, P3);
                             __syncwarp();
                             reduceB();
                         }

@@ -19,6 +19,9 @@ def test_reference_arm_prints_the_contract_line():
     assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["cpu_baseline"]["value"] == d["value"]
+    # provenance: the library the worker processes had mapped says which code was timed
+    libs = d["cpu_baseline"]["library_timed"]
+    assert libs and all(("libcpecan_ref" in p) == (d["cpu_baseline"]["kind"] == "reference") for p in libs), libs
     assert d["e2e"] == {"value": d["value"], "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
 

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--lx", type=int, default=6700)
     ap.add_argument("--unique", type=int, default=0, help="generate only this many distinct reads and tile them")
     ap.add_argument("--machine", default="three", choices=["three", "vanilla"])
+    ap.add_argument("--mode", default="posterior", choices=["posterior", "em"])
     a = ap.parse_args()
     nu = a.unique or a.n
     reads = generate_reads(nu, 5_000_000, lX=a.lx)
@@ -32,7 +33,10 @@ def main():
     mid = eng.upload_model(l1, l3, vanilla_gapx(l2) if a.machine == "vanilla" else np.full(4096, -2.3025850929940455))
     hb = HostBatch([r.ref for r in reads], [r.events for r in reads], [r.anchors for r in reads],
                    model_ids=[mid] * len(reads), scales=[r.scale5 for r in reads], ragged=[(1, 1)] * len(reads))
-    eng.stage(hb, hmm=hmm, params=default_params(diagonalExpansion=a.e), pair_cap=eng.default_pair_capacity(hb, 3))
+    if a.mode == "em":
+        eng.stage(hb, hmm=hmm, params=default_params(diagonalExpansion=a.e), mode=1, pair_cap=1)
+    else:
+        eng.stage(hb, hmm=hmm, params=default_params(diagonalExpansion=a.e), pair_cap=eng.default_pair_capacity(hb, 3))
     cells = eng.timing()["band_cells"]
     for i in range(a.reps):
         eng.run_staged()
@@ -40,6 +44,11 @@ def main():
         print("e=%d n=%d cells=%.3e align_ms=%.2f  %.2f Gcells/s  %.2f GCUPS  G=%d ctas=%d" % (
             a.e, a.n, cells, t["align_ms"], cells / t["align_ms"] / 1e6, 2 * cells / t["align_ms"] / 1e6,
             t["warps_per_item"], t["ctas"]), flush=True)
+    if a.mode == "em":
+        vec = np.zeros(eng.N_EXPECT_VANILLA if a.machine == "vanilla" else eng.N_EXPECT)
+        eng.fetch_expectations(vec)
+        print("expectations:", vec[:9], vec[-1])
+        return
     res, _ = eng.fetch_staged()
     print("status!=0:", int((res["status"] != 0).sum()), "pairs:", int(res["n_pairs"].sum()))
 
