@@ -73,9 +73,32 @@ struct KernelArgs3 {
     DevParams P;
 };
 
+// CP_TMA_ROWS (an A/B build, off by default -- profiles/r2_tma_rows_ab.txt): the traceback fetches the forward row of the
+// NEXT diagonal with cp.async.bulk (TMA, one instruction from one lane, completion on an mbarrier) into a shared-memory
+// stage instead of one LDG.128 per cell; costs 2 N float4 of shared memory per warp.
+#ifdef CP_TMA_ROWS
+#define CP_TMA_STAGE_BYTES(ringN) ((size_t) (ringN) * 32 + 16)
+#else
+#define CP_TMA_STAGE_BYTES(ringN) ((size_t) 0)
+#endif
 __host__ __device__ inline size_t align3_smem_bytes(int ringN, bool colAcc) {
-    return (size_t) ringN * (2 * 16) + CP_LAT_BYTES + (colAcc ? (size_t) ringN * 4 : 0);
+    return (size_t) ringN * (2 * 16) + CP_LAT_BYTES + (colAcc ? (size_t) ringN * 4 : 0) + CP_TMA_STAGE_BYTES(ringN);
 }
+
+#ifdef CP_TMA_ROWS
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned phase) {
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra WAIT_%=;\n\t}"
+                 :: "r"(bar), "r"(phase) : "memory");
+}
+#endif
 
 // forward rows are written once and read once, ~1000 diagonals later: keep them out of L1 (evict-first), which the
 // column records and events re-read on every diagonal need
@@ -102,6 +125,15 @@ __global__ void __launch_bounds__(32, CP_MINB3) k_align3(const KernelArgs3 A) {
     const int N = A.ringN, NM = N - 1;
     float4 *ring = reinterpret_cast<float4 *>(smraw);             // 2 * N entries
     float *colAcc = reinterpret_cast<float *>(smraw + (size_t) N * 32 + CP_LAT_BYTES);   // EXPECT, three-state: N floats
+#ifdef CP_TMA_ROWS
+    float4 *stage = reinterpret_cast<float4 *>(smraw + (size_t) N * 32 + CP_LAT_BYTES + ((EXPECT && !MACH) ? (size_t) N * 4 : 0));   // 2 x N
+    const unsigned stageAddr = (unsigned) __cvta_generic_to_shared(stage);
+    const unsigned barAddr = stageAddr + (unsigned) N * 32;
+    if (threadIdx.x == 0) { mbar_init(barAddr, 1); mbar_init(barAddr + 8, 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    unsigned tmaPhase0 = 0, tmaPhase1 = 0;
+#endif
 
     const int lane = threadIdx.x;
     const DevParams &P = A.P;
@@ -325,6 +357,28 @@ __global__ void __launch_bounds__(32, CP_MINB3) k_align3(const KernelArgs3 A) {
                     if ((dd >> 4) != bwIdx) { bwIdx = dd >> 4; bwWord = bitsp[bwIdx]; }
                     return (bwWord >> ((dd & 15) << 1)) & 3u;
                 };
+#ifdef CP_TMA_ROWS
+                // one lane asks the TMA unit for the band cells of a forward row: positions (x & NM), x = l .. h, of the row in
+                // HBM into the same positions of stage buffer `sb` (two pieces when the ring wraps)
+                auto tmaFetchRow = [&](int row, int l, int h, int sb) {
+                    if (lane == 0 && !EXPECT) {
+                        const float4 *src = rows + (long long) row * N;
+                        const int p0 = l & NM, p1 = h & NM;
+                        const unsigned bar = barAddr + 8u * sb, dst = stageAddr + (unsigned) sb * N * 16u;
+                        if (p0 <= p1) {
+                            const unsigned bytes = (unsigned) (p1 - p0 + 1) * 16u;
+                            mbar_expect_tx(bar, bytes);
+                            bulk_g2s(dst + p0 * 16u, src + p0, bytes, bar);
+                        } else {
+                            const unsigned b0 = (unsigned) (N - p0) * 16u, b1 = (unsigned) (p1 + 1) * 16u;
+                            mbar_expect_tx(bar, b0 + b1);
+                            bulk_g2s(dst + p0 * 16u, src + p0, b0, bar);
+                            bulk_g2s(dst, src, b1, bar);
+                        }
+                    }
+                };
+                if (!EXPECT) tmaFetchRow(rowB, blo, bhi, 0);
+#endif
                 for (int d = Dt; d > tracedBackTo; d--) {
                     if (d < Dt) {
                         const unsigned b = bandBitsC(d + 1);
@@ -334,6 +388,20 @@ __global__ void __launch_bounds__(32, CP_MINB3) k_align3(const KernelArgs3 A) {
                     const float4 *frow = rows + (long long) rowB * N;
                     const float2 *erow = plane2 + (long long) rowB * N;          // EXPECT
                     const bool post = d <= tbf;
+#ifdef CP_TMA_ROWS
+                    const int sb = (Dt - d) & 1;
+                    if (!EXPECT) {
+                        // the row of the next diagonal goes into the other stage buffer (every lane is done with it: the warp
+                        // barriers at the end of the previous diagonal), then wait for this diagonal's row
+                        if (d - 1 > tracedBackTo) {
+                            const unsigned bn = bandBitsC(d);
+                            tmaFetchRow(rowB == 0 ? R - 1 : rowB - 1, blo - (int) (bn & 1), bhi - (int) (bn >> 1), sb ^ 1);
+                        }
+                        mbar_wait(barAddr + 8u * sb, sb ? tmaPhase1 : tmaPhase0);
+                        if (sb) tmaPhase1 ^= 1; else tmaPhase0 ^= 1;
+                    }
+                    const float4 *srow_stage = stage + (size_t) sb * N;
+#endif
                     const int wlo = max(blo - 1, 0), nch = ((min(bhi + 1, lX) - wlo) >> 5) + 1;
                     const int plo = max(blo, 1), phi = min(bhi, d - 1);   // cells with x > 0 and y > 0 report posteriors
                     bool doTotal = false;
@@ -354,7 +422,11 @@ __global__ void __launch_bounds__(32, CP_MINB3) k_align3(const KernelArgs3 A) {
                         if (MACH) q.dR = xpD[min(x + 1, lX + 1)];
                         q.F = make_float4(NI, NI, NI, NI);
                         if (EXPECT) { float2 e2 = make_float2(NI, NI); if (in) e2 = ROWLD2(erow + (x & NM)); q.F.z = e2.x; q.F.w = e2.y; }
+#ifdef CP_TMA_ROWS
+                        else if (in) q.F = srow_stage[x & NM];
+#else
                         else if (in) q.F = ROWLD4(frow + (x & NM));
+#endif
                     };
                     auto reduceB = [&]() {
                         // POSTERIOR record: (F_match, offset, eM, eY); EXPECT: (-, -, eM, eY)
