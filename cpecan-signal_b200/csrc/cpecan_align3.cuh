@@ -572,14 +572,22 @@ __global__ void __launch_bounds__(32, CP_MINB3) k_align3(const KernelArgs3 A) {
                         OrderedFold fold1;
                         fold1.reset();
                         const float2 *srow = specRowOf(d);
-                        for (int c = 0; c < nch; c++) {
-                            const int x = wlo + (c << 5) + lane, s = x & NM;
-                            const bool inb = x >= blo && x <= bhi;
-                            float4 F = NIENT;                          // (M, X, Y, offset) of the forward cell
-                            if (inb) {
+                        // the forward cell (M, X, Y, offset) of a chunk is requested a chunk ahead of its use
+                        auto loadF = [&](int cc) -> float4 {
+                            const int x = wlo + (cc << 5) + lane, s = x & NM;
+                            float4 F = NIENT;
+                            if (cc < nch && x >= blo && x <= bhi) {
                                 if (EXPECT) F = frow[s];
                                 else { const float4 f = frow[s]; const float2 xy = srow[s]; F = make_float4(f.x, xy.x, xy.y, f.y); }
                             }
+                            return F;
+                        };
+                        float4 Fn = loadF(0);
+                        for (int c = 0; c < nch; c++) {
+                            const int x = wlo + (c << 5) + lane, s = x & NM;
+                            const bool inb = x >= blo && x <= bhi;
+                            const float4 F = Fn;
+                            Fn = loadF(c + 1);
                             float bM, bX, bY, U;
                             float4 pdR = NIENT;
                             float myLog = 0.f;
@@ -609,13 +617,22 @@ __global__ void __launch_bounds__(32, CP_MINB3) k_align3(const KernelArgs3 A) {
                             const float2 *sprev = specRowOf(d - 1);
                             OrderedFold fold2;
                             fold2.reset();
+                            auto loadFp = [&](int xb) -> float4 {        // forward cell of x - 1 on diagonal d - 1, a round ahead
+                                const int x = xb + lane;
+                                float4 F = NIENT;
+                                if (x <= h1 && x - 1 >= lm1 && x - 1 <= hm1) {
+                                    if (EXPECT) F = fprev[(x - 1) & NM];
+                                    else { const float4 f = fprev[(x - 1) & NM]; const float2 xy = sprev[(x - 1) & NM]; F = make_float4(f.x, xy.x, xy.y, f.y); }
+                                }
+                                return F;
+                            };
+                            float4 Fpn = loadFp(l1);
                             for (int xb = l1; xb <= h1; xb += 32) {
                                 const int x = xb + lane;
                                 float val = NI;
+                                const float4 F = Fpn;
+                                Fpn = loadFp(xb + 32);
                                 if (x <= h1 && x - 1 >= lm1 && x - 1 <= hm1) {
-                                    float4 F;
-                                    if (EXPECT) F = fprev[(x - 1) & NM];
-                                    else { const float4 f = fprev[(x - 1) & NM]; const float2 xy = sprev[(x - 1) & NM]; F = make_float4(f.x, xy.x, xy.y, f.y); }
                                     const float4 Gn = A1[x & NM];
                                     float4 pdx = NIENT;
                                     if (MACH) pdx = xpD[min(x, lX + 1)];

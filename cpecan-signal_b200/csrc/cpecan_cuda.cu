@@ -24,7 +24,7 @@ namespace {
 
 // one warp per alignment; ring of N = 128 << bucket positions (power of two) in shared memory
 constexpr int NCFG2 = 6;
-constexpr int CFG2_MARGIN = 40;                   // ring positions beyond the widest diagonal (window + look-ahead)
+constexpr int CFG2_MARGIN = 40;                   // ring positions beyond the widest diagonal (window + the rest of its last chunk)
 inline int cfg2N(int b) { return 128 << b; }
 
 struct DevBuf {
