@@ -155,6 +155,13 @@ __global__ void __launch_bounds__(32, CP_MINB3) k_align3(const KernelArgs3 A) {
 #endif
     const float gMC = P.tMC, gMX = P.tMX, gOX = P.tOX, gOY = P.tOY, gEX = P.tEX, tSX = P.tSX;
     const float tMY = MACH ? P.vYM : P.tMY, tEY = MACH ? P.vYY : P.tEY;
+#ifndef CP_NJ
+#define CP_NJ 1
+#endif
+    // chunks per task of the posterior sweeps.  2 gives every lane two independent dependency chains (165 registers, 12
+    // resident warps): measured equal at e = 128 / 256 and 11 % slower at e = 64, where a diagonal has 3 - 4 chunks and the odd
+    // one wastes half a task (profiles/r2_tma_rows_ab.txt) -- so 1 it is; the E-step's body is too wide for two anyway
+    constexpr int NJ = EXPECT ? 1 : CP_NJ;
     const int ZONE = P.tbDiags + 3;           // forward diagonals tbf-1 .. Dt keep all three states
     const bool allSpec = EXPECT || A.all_spec != 0;
     const bool unbanded = P.mode == 2;
@@ -247,36 +254,39 @@ __global__ void __launch_bounds__(32, CP_MINB3) k_align3(const KernelArgs3 A) {
                 bool spec = allSpec || k <= 1 || k10 <= 1;
                 float2 *srow = allSpec ? plane2 + (long long) rowF * N
                                       : plane2 + (long long) (k <= 1 ? zonePar * ZONE + (1 - k) : 2 * ZONE + 2 * (kq - 1) + k10) * N;
-                // Software pipeline over the (diagonal, chunk) tasks: the column records and the event of task i+1 are
-                // requested at the top of task i (before the warp barrier, which ptxas does not move loads across) and
-                // reduced at its END to the emissions (vanilla: + transitions) task i+1 needs.
-                struct { float4 a, b, c, d, ev; } r;
-                bool inb = false, ninb = false;
-                auto load = [&](int dd, int x, bool in) {
+                // Software pipeline over the tasks: a task is NJ (= 1, see above) neighbouring chunks of one diagonal; the
+                // column records and the events of task i+1 are requested at
+                // the top of task i (before the warp barrier, which ptxas does not move loads across) and reduced at its END
+                // to the emissions (vanilla: + transitions) task i+1 needs.  c is the TOP chunk of the task: it covers chunks
+                // c, c-1, .. c-NJ+1 as far as they exist.
+                struct { float4 a, b, c, d, ev; } r[NJ];
+                bool inb[NJ], ninb[NJ];
+                auto load = [&](int j, int dd, int x, bool in) {
                     const int xx = in ? x : lX + 1;                   // outside the band: the all -inf dummy record
-                    r.a = xpA[xx]; r.b = xpB[xx]; r.c = xpC[xx];
-                    if (MACH) r.d = xpD[xx];
-                    r.ev = evp[in ? dd - x : 0];
+                    r[j].a = xpA[xx]; r[j].b = xpB[xx]; r[j].c = xpC[xx];
+                    if (MACH) r[j].d = xpD[xx];
+                    r[j].ev = evp[in ? dd - x : 0];
                 };
-                struct { float eM, eY, eX, tOX, tEX, tMC, tMX, tOY; } E;
-                auto reduce = [&]() {
-                    E.eM = emit(r.a, r.b, r.c, r.ev, false); E.eY = emit(r.a, r.b, r.c, r.ev, true);
-                    const float cz = __int_as_float(__float_as_int(r.c.z) | (__float_as_int(r.c.w) & A.zero));
-                    E.eX = MACH ? 0.f : cz;           // vanilla: the dummy record's transitions are -inf
+                struct { float eM, eY, eX, tOX, tEX, tMC, tMX, tOY; } E[NJ];
+                auto reduce = [&](int j) {
+                    E[j].eM = emit(r[j].a, r[j].b, r[j].c, r[j].ev, false); E[j].eY = emit(r[j].a, r[j].b, r[j].c, r[j].ev, true);
+                    const float cz = __int_as_float(__float_as_int(r[j].c.z) | (__float_as_int(r[j].c.w) & A.zero));
+                    E[j].eX = MACH ? 0.f : cz;           // vanilla: the dummy record's transitions are -inf
                     // impl/stateMachine.c:1368-1409: the vanilla transitions are those of THIS column
-                    E.tOX = MACH ? r.d.x : gOX; E.tEX = MACH ? r.d.y : gEX; E.tMC = MACH ? r.d.z : gMC;
-                    E.tMX = MACH ? r.d.w : gMX; E.tOY = MACH ? cz : gOY;
+                    E[j].tOX = MACH ? r[j].d.x : gOX; E[j].tEX = MACH ? r[j].d.y : gEX; E[j].tMC = MACH ? r[j].d.z : gMC;
+                    E[j].tMX = MACH ? r[j].d.w : gMX; E[j].tOY = MACH ? cz : gOY;
                 };
-                {
-                    const int x0 = wlo + (c << 5) + lane;
-                    ninb = x0 >= lo && x0 <= hi;
-                    load(d, x0, ninb);
-                    inb = ninb;
-                    reduce();
+#pragma unroll
+                for (int j = 0; j < NJ; j++) {
+                    const int x0 = wlo + ((c - j) << 5) + lane;
+                    ninb[j] = c - j >= 0 && x0 >= lo && x0 <= hi;
+                    load(j, d, x0, ninb[j]);
+                    inb[j] = ninb[j];
+                    reduce(j);
                 }
                 for (;;) {
-                    const bool last = c == 0;
-                    int nd = d, nc = c - 1, nlo = lo, nhi = hi, nwlo = wlo;
+                    const bool last = c < NJ;                        // the task reaches chunk 0
+                    int nd = d, nc = c - NJ, nlo = lo, nhi = hi, nwlo = wlo;
                     const bool stop = last && d >= Dt;
                     if (last && !stop) {
                         nd = d + 1;
@@ -287,31 +297,51 @@ __global__ void __launch_bounds__(32, CP_MINB3) k_align3(const KernelArgs3 A) {
                         nc = (min(nhi + 1, lX) - nwlo) >> 5;
                     }
                     {
-                        const int x = wlo + (c << 5) + lane;
-                        const int s = x & NM, sl = (x - 1) & NM;
-                        const int nx = nwlo + (max(nc, 0) << 5) + lane;
-                        ninb = nx >= nlo && nx <= nhi && !stop;
-                        load(nd, nx, ninb);                          // next task (the dummy record at the stop)
-                        const float4 own = A1[s], L = A1[sl], Mi = A2[sl];
-                        __syncwarp();
-                        const float U = fmaxf(own.w, fmaxf(L.w, Mi.w));
-                        // impl/stateMachine.c:1314-1333: transitions folded in code order, emission added once
-                        float tX = LA(L.x + E.tOX, L.y + E.tEX);
-                        if (HAS_SX) tX = LA(tX, L.z + tSX);
-                        float tM = LAP(LAP(Mi.x + E.tMC, Mi.y + E.tMX), Mi.z + tMY);
-                        float tY = LA(own.x + E.tOY, own.z + tEY);
-                        float cM = tM + (E.eM + (Mi.w - U)), cX = tX + (E.eX + (L.w - U)), cY = tY + (E.eY + (own.w - U));
-                        float co = U;
-                        rebase(cM, cX, cY, co);
-                        if (!inb) co = -CP_BIG;                      // the emissions of the dummy record made the cell -inf
-                        A2[s] = make_float4(cM, cX, cY, co);         // descending x: in place over the d-2 entry
-                        if (inb) {
-                            if (EXPECT) { ROWST4(frow + s, make_float4(cM, cX, cY, co)); ROWST2(srow + s, make_float2(E.eM, E.eY)); }
-                            else { ROWST4(frow + s, make_float4(cM, co, E.eM, E.eY)); if (spec) ROWST2(srow + s, make_float2(cX, cY)); }
+                        float4 own[NJ], L[NJ], Mi[NJ];
+                        int sj[NJ];
+#pragma unroll
+                        for (int j = 0; j < NJ; j++) {
+                            const int nx = nwlo + ((nc - j) << 5) + lane;
+                            ninb[j] = nc - j >= 0 && nx >= nlo && nx <= nhi && !stop;
+                            load(j, nd, nx, ninb[j]);                // next task (the dummy record at the stop)
+                        }
+#pragma unroll
+                        for (int j = 0; j < NJ; j++) {
+                            const int x = wlo + ((c - j) << 5) + lane;
+                            const int s = x & NM, sl = (x - 1) & NM;
+                            sj[j] = s;
+                            own[j] = A1[s]; L[j] = A1[sl]; Mi[j] = A2[sl];
                         }
                         __syncwarp();
-                        inb = ninb;
-                        reduce();
+                        float4 e4[NJ];
+#pragma unroll
+                        for (int j = 0; j < NJ; j++) {
+                            const float U = fmaxf(own[j].w, fmaxf(L[j].w, Mi[j].w));
+                            // impl/stateMachine.c:1314-1333: transitions folded in code order, emission added once
+                            float tX = LA(L[j].x + E[j].tOX, L[j].y + E[j].tEX);
+                            if (HAS_SX) tX = LA(tX, L[j].z + tSX);
+                            float tM = LAP(LAP(Mi[j].x + E[j].tMC, Mi[j].y + E[j].tMX), Mi[j].z + tMY);
+                            float tY = LA(own[j].x + E[j].tOY, own[j].z + tEY);
+                            float cM = tM + (E[j].eM + (Mi[j].w - U)), cX = tX + (E[j].eX + (L[j].w - U)), cY = tY + (E[j].eY + (own[j].w - U));
+                            float co = U;
+                            rebase(cM, cX, cY, co);
+                            if (!inb[j]) co = -CP_BIG;               // the emissions of the dummy record made the cell -inf
+                            e4[j] = make_float4(cM, cX, cY, co);
+                        }
+#pragma unroll
+                        for (int j = 0; j < NJ; j++) {
+                            if (c - j >= 0) {                        // (a chunk that does not exist stores nothing)
+                                const int s = sj[j];
+                                A2[s] = e4[j];                       // descending x: in place over the d-2 entry
+                                if (inb[j]) {
+                                    if (EXPECT) { ROWST4(frow + s, e4[j]); ROWST2(srow + s, make_float2(E[j].eM, E[j].eY)); }
+                                    else { ROWST4(frow + s, make_float4(e4[j].x, e4[j].w, E[j].eM, E[j].eY)); if (spec) ROWST2(srow + s, make_float2(e4[j].y, e4[j].z)); }
+                                }
+                            }
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < NJ; j++) { inb[j] = ninb[j]; reduce(j); }
                     }
                     if (last) {
                         { float4 *t = A1; A1 = A2; A2 = t; }
@@ -409,11 +439,14 @@ __global__ void __launch_bounds__(32, CP_MINB3) k_align3(const KernelArgs3 A) {
                     // What one cell of the backward sweep needs besides the ring: the forward sweep's record (match value,
                     // offset, the two emissions), the gap emission of the column (three-state) or the transitions of the
                     // successors' columns (vanilla), the k-mer index / skip bin for the E-step.  Requested a chunk ahead.
-                    struct { float4 F; float4 dR; float cz, ex; int kw; } q;
-                    struct { float eM, eY, eX, Fx, Fw, tOX, tEX, tMC, tMX, myLog; int kw; } G;
-                    auto loadB = [&](int cc) {
+                    struct QRec { float4 F; float4 dR; float cz, ex; int kw; };
+                    struct GRec { float eM, eY, eX, Fx, Fw, tOX, tEX, tMC, tMX, myLog; int kw; };
+                    QRec qq[NJ];
+                    GRec GG[NJ];
+                    auto loadBj = [&](int j, int cc) {                 // chunk cc (one that does not exist reads as outside the band)
+                        QRec &q = qq[j];
                         const int x = wlo + (cc << 5) + lane;
-                        const bool in = x >= blo && x <= bhi;
+                        const bool in = cc < nch && x >= blo && x <= bhi;
                         const int xx = in ? x : lX + 1;
                         const float4 *cp = xpC + xx;
                         q.cz = reinterpret_cast<const float *>(cp)[2];
@@ -428,13 +461,21 @@ __global__ void __launch_bounds__(32, CP_MINB3) k_align3(const KernelArgs3 A) {
                         else if (in) q.F = ROWLD4(frow + (x & NM));
 #endif
                     };
-                    auto reduceB = [&]() {
+                    auto reduceBj = [&](int j) {
+                        const QRec &q = qq[j];
+                        GRec &G = GG[j];
                         // POSTERIOR record: (F_match, offset, eM, eY); EXPECT: (-, -, eM, eY)
                         G.eM = q.F.z; G.eY = q.F.w; G.Fx = q.F.x; G.Fw = EXPECT ? 0.f : q.F.y;
                         G.eX = q.ex; G.myLog = q.cz; G.kw = q.kw;
                         G.tOX = MACH ? q.dR.x : 0.f; G.tEX = MACH ? q.dR.y : 0.f; G.tMC = MACH ? q.dR.z : 0.f; G.tMX = MACH ? q.dR.w : 0.f;
                     };
-                    if (!doTotal) loadB(0);
+                    auto loadB = [&](int cc) { loadBj(0, cc); };
+                    auto reduceB = [&]() { reduceBj(0); };
+                    GRec &G = GG[0];
+                    if (!doTotal) {
+#pragma unroll
+                        for (int j = 0; j < NJ; j++) loadBj(j, j);
+                    }
                     if (d - 2 > tracedBackTo) {
                         // the forward records of diagonal d-2 were written >= 1000 diagonals ago: DRAM -> L2 now
                         const int rowP = rowB >= 2 ? rowB - 2 : rowB - 2 + R;
@@ -552,19 +593,34 @@ __global__ void __launch_bounds__(32, CP_MINB3) k_align3(const KernelArgs3 A) {
                     };
 
                     if (!doTotal) {
-                        reduceB();
-                        for (int c = 0; c < nch; c++) {                // ascending x: in-place update of the d+2 entries
-                            const int x = wlo + (c << 5) + lane, s = x & NM;
-                            const bool inb = x >= blo && x <= bhi;
-                            const auto cur = G;
-                            loadB(min(c + 1, nch - 1));                // the next chunk (after the last one: again this one)
-                            const Pred P3 = loadPred(x, inb);
-                            float bM, bX, bY, U;
-                            cellB(x, s, make_float4(cur.tOX, cur.tEX, cur.tMC, cur.tMX), cur.myLog, bM, bX, bY, U);
+#pragma unroll
+                        for (int j = 0; j < NJ; j++) reduceBj(j);
+                        for (int c = 0; c < nch; c += NJ) {            // ascending x: in-place update of the d+2 entries; NJ chunks per task
+                            GRec cur[NJ];
+                            Pred P3[NJ];
+                            float bM[NJ], bX[NJ], bY[NJ], U[NJ];
+#pragma unroll
+                            for (int j = 0; j < NJ; j++) cur[j] = GG[j];
+#pragma unroll
+                            for (int j = 0; j < NJ; j++) loadBj(j, c + NJ + j);      // the next task's chunks
+#pragma unroll
+                            for (int j = 0; j < NJ; j++) {
+                                const int x = wlo + ((c + j) << 5) + lane;
+                                P3[j] = loadPred(x, c + j < nch && x >= blo && x <= bhi);
+                                cellB(x, x & NM, make_float4(cur[j].tOX, cur[j].tEX, cur[j].tMC, cur[j].tMX), cur[j].myLog, bM[j], bX[j], bY[j], U[j]);
+                            }
                             __syncwarp();
-                            cellPost(x, s, inb, bM, bX, bY, U, cur.eM, cur.eY, cur.eX, cur.Fx, cur.Fw, cur.myLog, cur.kw, P3);
+#pragma unroll
+                            for (int j = 0; j < NJ; j++) {
+                                if (c + j < nch) {                     // (a chunk that does not exist stores nothing and reports nothing)
+                                    const int x = wlo + ((c + j) << 5) + lane;
+                                    cellPost(x, x & NM, x >= blo && x <= bhi, bM[j], bX[j], bY[j], U[j], cur[j].eM, cur[j].eY, cur[j].eX,
+                                             cur[j].Fx, cur[j].Fw, cur[j].myLog, cur[j].kw, P3[j]);
+                                }
+                            }
                             __syncwarp();
-                            reduceB();
+#pragma unroll
+                            for (int j = 0; j < NJ; j++) reduceBj(j);
                         }
                     } else {
                         // ---- totalProbability (impl/pairwiseAligner.c:736-754), recomputed every 10th posterior diagonal

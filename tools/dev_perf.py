@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--unique", type=int, default=0, help="generate only this many distinct reads and tile them")
     ap.add_argument("--machine", default="three", choices=["three", "vanilla"])
     ap.add_argument("--mode", default="posterior", choices=["posterior", "em"])
+    ap.add_argument("--thr", type=float, default=0.01, help="posterior threshold (1.1: no pair is ever reported)")
     a = ap.parse_args()
     nu = a.unique or a.n
     reads = generate_reads(nu, 5_000_000, lX=a.lx)
@@ -36,7 +37,7 @@ def main():
     if a.mode == "em":
         eng.stage(hb, hmm=hmm, params=default_params(diagonalExpansion=a.e), mode=1, pair_cap=1)
     else:
-        eng.stage(hb, hmm=hmm, params=default_params(diagonalExpansion=a.e), pair_cap=eng.default_pair_capacity(hb, 3))
+        eng.stage(hb, hmm=hmm, params=default_params(diagonalExpansion=a.e, threshold=a.thr), pair_cap=eng.default_pair_capacity(hb, 3))
     cells = eng.timing()["band_cells"]
     for i in range(a.reps):
         eng.run_staged()
