@@ -333,11 +333,62 @@ static void test_fixture(const char *golden, const char *models) {
     pairwiseAlignmentBandingParameters_destruct(p); stList_destruct(anchors); nanopore_nanoporeReadDestruct(np); free(ref);
 }
 
+/* the caller-side helpers vanillaAlign.c uses around the alignment call (cigar -> anchors, padding, strings, HMM fields) */
+static void test_caller_side(void) {
+    FILE *f = fopen("/tmp/cpecan_host_test.cigar", "w");
+    fprintf(f, "cigar: read 3 14 + ref 10 22 + 77 M 4 D 2 M 3 I 1 M 3\n");
+    fclose(f);
+    f = fopen("/tmp/cpecan_host_test.cigar", "r");
+    struct PairwiseAlignment *pA = cigarRead(f);
+    fclose(f);
+    CHECK(pA != NULL && pA->start1 == 10 && pA->end1 == 22 && pA->strand1 == 1 && pA->start2 == 3 && pA->end2 == 14 && pA->strand2 == 1);
+    CHECK(strcmp(pA->contig1, "ref") == 0 && strcmp(pA->contig2, "read") == 0 && pA->operationList->length == 5);
+    checkPairwiseAlignment(pA);
+    stList *an = convertPairwiseForwardStrandAlignmentToAnchorPairs(pA, 1);       /* trim 1 at both ends of every match */
+    /* M4 at (10,3): (11,4),(12,5); D2: x += 2; M3 at (16,7): (17,8); I1: y += 1; M3 at (19,11): (20,12) */
+    const int64_t want[4][2] = { {11,4},{12,5},{17,8},{20,12} };
+    CHECK(stList_length(an) == 4);
+    for (int i = 0; i < 4 && i < stList_length(an); i++) { stIntTuple *t = stList_get(an, i); CHECK(stIntTuple_get(t, 0) == want[i][0] && stIntTuple_get(t, 1) == want[i][1]); }
+    stList_destruct(an); destructPairwiseAlignment(pA);
+    char *rc = stString_reverseComplementString("AACGTn");
+    CHECK(strcmp(rc, "nACGTT") == 0); free(rc);
+    char *rp = stString_replace("ACCGC", "C", "E"); CHECK(strcmp(rp, "AEEGE") == 0); free(rp);
+    char *sub = stString_getSubString("ABCDEFG", 2, 3); CHECK(strcmp(sub, "CDE") == 0); free(sub);
+    char *pr = stString_print("%s-%d", "x", 7); CHECK(strcmp(pr, "x-7") == 0); free(pr);
+    char seq[] = "ACGTACGTAC";
+    Sequence *sX = sequence_construct2(5, seq, sequence_getKmer2, sequence_sliceNucleotideSequence2);
+    sequence_padSequence(sX);
+    CHECK(strlen((char *) sX->elements) == 40 && ((char *) sX->elements)[10] == 'n' && strncmp((char *) sX->elements, seq, 10) == 0);
+    CHECK(sequence_getKmer3(sX->elements, -1) == sX->elements && (char *) sequence_getKmer3(sX->elements, 2) == (char *) sX->elements + 2);
+    free(sX->elements); sequence_sequenceDestroy(sX);
+    CHECK(emissions_discrete_getKmerIndexFromKmer("ACGTACGGGG") == emissions_discrete_getKmerIndex("ACGTAC"));
+    Hmm *h = hmmContinuous_getEmptyHmm(threeState, 0.5, 0.0);
+    continuousPairHmm_addToTransitionsExpectation(h, 0, 1, 2.0);
+    CHECK(continuousPairHmm_getTransitionExpectation(h, 0, 1) == 2.5);
+    continuousPairHmm_setKmerGapExpectation(h, 0, 17, 0, 3.0);
+    CHECK(continuousPairHmm_getKmerGapExpectation(h, 0, 17, 0) == 3.0);
+    continuousPairHmm_normalize(h);
+    CHECK(fabs(continuousPairHmm_getTransitionExpectation(h, 0, 0) + continuousPairHmm_getTransitionExpectation(h, 0, 1) + continuousPairHmm_getTransitionExpectation(h, 0, 2) - 1.0) < 1e-12);
+    continuousPairHmm_destruct(h);
+    Hmm *v = hmmContinuous_getEmptyHmm(vanilla, 0.0, 0.0);
+    vanillaHmm_addToKmerSkipBinExpectation(v, 3, 0, 1.5);
+    CHECK(vanillaHmm_getKmerSkipBinExpectation(v, 3, 0) == 1.5);
+    vanillaHmm_destruct(v);
+    double c1[3] = { -1.0, -2.0, -INFINITY }, c2[3] = { -0.5, -0.25, -3.0 };
+    CHECK(fabs(cell_dotProduct(c1, c2, 3) - logAdd(logAdd(-1.5, -2.25), -INFINITY)) < 1e-12);
+    /* stList_sort: qsort over the tuples */
+    stList *l = stList_construct3(0, (void (*)(void *)) stIntTuple_destruct);
+    stList_append(l, stIntTuple_construct3(5, 4, 4)); stList_append(l, stIntTuple_construct3(9, 1, 1)); stList_append(l, stIntTuple_construct3(7, 2, 3));
+    stList_sort(l, sortByXPlusYCoordinate2);
+    CHECK(stIntTuple_get(stList_get(l, 0), 1) == 1 && stIntTuple_get(stList_get(l, 2), 1) == 4);
+    stList_destruct(l);
+}
+
 int main(int argc, char **argv) {
     if (argc < 4) { fprintf(stderr, "usage: %s cpu|gpu <golden dir> <models dir>\n", argv[0]); return 2; }
     if (!strcmp(argv[1], "cpu")) {
         test_diagonal(); test_bands(); test_logAdd(); test_getSplitPoints(); test_filterToRemoveOverlap();
-        test_scaleModel(argv[3]); test_hmm_container(argv[2]);
+        test_scaleModel(argv[3]); test_hmm_container(argv[2]); test_caller_side();
     } else {
         test_tiny(argv[3]); test_fixture(argv[2], argv[3]);
     }
