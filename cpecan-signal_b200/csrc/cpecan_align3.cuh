@@ -23,7 +23,7 @@
 //     the band (was: one FP64 global atomic per band cell).
 #pragma once
 #include "cpecan_kernels.cuh"
-#include "cpecan_align2.cuh"
+#include "cpecan_logadd.cuh"
 
 namespace cpecan {
 

@@ -14,7 +14,7 @@
 
 #include "cpecan_cuda.h"
 #include "cpecan_kernels.cuh"
-#include "cpecan_align2.cuh"
+#include "cpecan_logadd.cuh"
 #include "cpecan_align3.cuh"
 #include "cpecan_generic.cuh"
 
@@ -145,7 +145,7 @@ static cudaError_t waitStream(cpecan_ctx *ctx, cudaStream_t s) {
     return e != cudaSuccess ? e : cudaEventSynchronize(ctx->evBlock);
 }
 
-// k_align2<MACH, HAS_SX, EXPECT>: dispatch over the instantiations (the vanilla machine has no Y->X transition)
+// k_align3<MACH, HAS_SX, EXPECT>: dispatch over the instantiations (the vanilla machine has no Y->X transition)
 template <typename F> auto dispatchK2(int mach, bool sx, bool ex, F f) {
     if (mach) return ex ? f(k_align3<1, false, true>) : f(k_align3<1, false, false>);
     if (sx) return ex ? f(k_align3<0, true, true>) : f(k_align3<0, true, false>);

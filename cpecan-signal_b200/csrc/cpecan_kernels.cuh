@@ -1,6 +1,6 @@
 // cpecan_kernels.cuh -- shared device code of the banded signal pair-HMM engine (sm_100a): parameter / item records,
-// the band geometry in closed form, the plan kernel and the staging kernels that turn the reference's FP64 inputs into
-// the FP32 records the alignment kernel (cpecan_align2.cuh) streams.
+// the plan kernel (the band of band_construct and the traceback schedule, walked once per item) and the staging kernels
+// that turn the reference's FP64 inputs into the FP32 records the alignment kernel (cpecan_align3.cuh) streams.
 //
 // Reference semantics restated here (nothing is translated from the C sources):
 //   band_construct                    impl/pairwiseAligner.c:98-184
@@ -65,73 +65,6 @@ __device__ __forceinline__ float logadd(float x, float y) {
     const float r = lo + la_poly(d);
     return (d < 7.5f) ? r : hi;           // NaN / inf / >= 7.5 all fall through to hi
 }
-
-// ------------------------------------------------------------------------------------------------ band geometry
-// impl/pairwiseAligner.c:98-184 in closed form: between the previous anchor p and the next anchor n (matrix
-// coordinates = sequence + 1) the band is the rectangle [p.x - e/2, n.x + e/2] x [p.y - e/2, n.y + e/2] clamped to
-// the matrix; diagonal d (p.x+p.y < d <= n.x+n.y) keeps the cells x in [max(xL, d - yL), min(xU, d - yU)].
-struct BandWalker {
-    const long long *anchors;  // pairs
-    int nA, lX, lY, h;
-    int ai;                    // index of the "next" anchor of the current box
-    int pd, nd;                // x+y of previous / next point
-    int xL, yL, xU, yU;
-
-    __device__ __forceinline__ void setBox() {
-        int px = 0, py = 0, nx = lX, ny = lY;
-        if (ai > 0) { px = (int) anchors[2 * (ai - 1)] + 1; py = (int) anchors[2 * (ai - 1) + 1] + 1; }
-        if (ai < nA) { nx = (int) anchors[2 * ai] + 1; ny = (int) anchors[2 * ai + 1] + 1; }
-        pd = px + py; nd = nx + ny;
-        xL = min(max(px - h, 0), lX);
-        yL = min(max(ny + h, 0), lY);
-        xU = min(max(nx + h, 0), lX);
-        yU = min(max(py - h, 0), lY);
-    }
-    __device__ __forceinline__ void init(const long long *a, int nA_, int lX_, int lY_, int expansion) {
-        anchors = a; nA = nA_; lX = lX_; lY = lY_; h = expansion / 2; ai = 0; setBox();
-    }
-    // x range of diagonal d; moves the box forwards or backwards as needed
-    __device__ __forceinline__ void range(int d, int &lo, int &hi) {
-        while (d > nd && ai < nA) { ai++; setBox(); }
-        while (d <= pd && ai > 0) { ai--; setBox(); }
-        lo = max(xL, d - yL);
-        hi = min(xU, d - yU);
-    }
-};
-
-// ------------------------------------------------------------------------------------------------ plan kernel
-// One thread per item: walks the band once and reports the work (band cells), the widest diagonal and the longest
-// run of forward rows that must be alive at a traceback (sizes the per-CTA forward spill ring).
-__global__ void k_plan(const Item *items, int n, const long long *anchors, DevParams P, ItemOut *out) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    Item it = items[i];
-    BandWalker bw;
-    bw.init(anchors + 2 * it.an_off, it.nA, it.lX, it.lY, P.expansion);
-    const int D = it.lX + it.lY;
-    long long cells = 0;
-    int maxw = 0, maxrows = 1, ntb = 0, tracedBackTo = 0;
-    for (int d = 0; d <= D; d++) {
-        int lo, hi;
-        bw.range(d, lo, hi);
-        int w = hi - lo + 1;
-        cells += w;
-        maxw = max(maxw, w);
-        if (d == 0) continue;
-        bool atEnd = d == D;
-        bool tb = P.mode == 2 ? false : (d >= tracedBackTo + P.minDiags && w <= 2 * P.expansion + 1);
-        if (atEnd || tb) {
-            maxrows = max(maxrows, d - tracedBackTo + 1);
-            tracedBackTo = atEnd ? d : d - (P.tbDiags + 1);
-            ntb++;
-        }
-    }
-    ItemOut o;
-    o.band_cells = cells; o.total_logprob = 0.0; o.n_pairs = 0; o.status = 0; o.n_tracebacks = ntb;
-    o.max_width = maxw; o.max_rows = maxrows + 2; o.pad = 0;
-    out[i] = o;
-}
-
 
 // ------------------------------------------------------------------------------------------------ plan kernel (k_align3)
 // One thread per item walks the band exactly as band_construct does (impl/pairwiseAligner.c:98-184: x-y limits with
