@@ -258,6 +258,11 @@ class Engine:
         """At most this many resident alignment warps per SM for the batches staged from now on (0 = all that fit)."""
         self._check(self.lib.cpecan_cuda_set_resident_warps(self.ctx, C.c_int32(int(warps_per_sm))), "set_resident_warps")
 
+    def set_exact_arithmetic(self, on=True):
+        """threeState / vanilla posterior batches staged from now on run on the FP64 kernel in the reference's own operation
+        order (scores equal to the last digit) instead of the FP32 one."""
+        self._check(self.lib.cpecan_cuda_set_exact_arithmetic(self.ctx, C.c_int32(1 if on else 0)), "set_exact_arithmetic")
+
     def device_info(self):
         sm, clk, mem = C.c_int32(), C.c_int32(), C.c_int64()
         self._check(self.lib.cpecan_cuda_device_info(self.ctx, C.byref(sm), C.byref(clk), C.byref(mem)), "device_info")

@@ -43,7 +43,12 @@ struct DevBuf {
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
-struct Model { double *match = nullptr, *gapy = nullptr, *gapx = nullptr; int n_gapx = 0; bool live = false; };
+struct Model {
+    double *match = nullptr, *gapy = nullptr, *gapx = nullptr; int n_gapx = 0; bool live = false;
+    // cpecan_cuda_upload_hdp
+    bool hdp = false; double *hdpY = nullptr, *hdpSlope = nullptr; int *hdpKmer = nullptr; int hdpLen = 0;
+    double x0 = 0, x1 = 0, xn = 0, step = 0;
+};
 
 struct Bucket {
     std::vector<int> order;      // item indices, largest first
@@ -104,15 +109,17 @@ struct cpecan_ctx {
     int64_t n = 0;
     int mode = 0;
     int machine = 0;             // 0 three-state, 1 vanilla
-    int generic = 0;             // 0, or the StateMachineType run by k_align_generic: 6 fourState, 5 echelon
+    int generic = 0;             // 0, or the StateMachineType run by k_align_generic: 6 fourState, 5 echelon; and 2 threeState /
+                                 // 4 vanilla when the band is one k_align3 does not take (odd diagonalExpansion)
     GenParams G{};
+    bool exact = false;          // cpecan_cuda_set_exact_arithmetic: threeState / vanilla posteriors on the FP64 kernel
     double mToYNotX = 0.0;
     DevParams P{};
     bool hasSX = false;
     std::vector<Item> hItems;
     std::vector<ItemOut> hOut;
     DevBuf dItems, dOut, dRef, dRefOff, dEvSrc, dEvSrcOff, dAnchors, dScale, dCentre, dXp, dEv, dPairs, dOrder,
-           dQueue, dScratch, dTotals, dCompact, dCompactOff, dExpect, dBits, dTbs, dFlags;
+           dQueue, dScratch, dTotals, dCompact, dCompactOff, dExpect, dBits, dTbs, dFlags, dBands, dBandOff;
     int64_t pairCapTotal = 0, totalsLen = 0;
     Bucket buckets[NCFG2];
     int stagedMaxLX = 0;
@@ -176,7 +183,16 @@ void launchCfg2(int cfg, int mach, bool sx, bool expect, const KernelArgs3 &a, i
 }
 
 // fourState / echelon: the FP64 kernel; ring size per bucket as for k_align3, occupancy from its shared-memory need
-template <typename F> auto dispatchGen(int sm, F f) { return sm == CPECAN_SM_ECHELON ? f(k_align_generic<5>, 7) : f(k_align_generic<6>, 4); }
+template <typename F> auto dispatchGen(int sm, F f) {
+    switch (sm) {
+        case CPECAN_SM_ECHELON: return f(k_align_generic<5>, 7);
+        case CPECAN_SM_THREE_STATE: return f(k_align_generic<2>, 3);
+        case CPECAN_SM_THREE_STATE_HDP: return f(k_align_generic<3>, 3);
+        case CPECAN_SM_VANILLA: return f(k_align_generic<4>, 3);
+        default: return f(k_align_generic<6>, 4);
+    }
+}
+int genStates(int sm) { return sm == CPECAN_SM_ECHELON ? 7 : (sm == CPECAN_SM_FOUR_STATE ? 4 : 3); }
 int occGen(int cfg, int sm) {
     return dispatchGen(sm, [&](auto k, int S) {
         const size_t bytes = generic_smem_bytes(cfg2N(cfg), S);
@@ -224,6 +240,15 @@ int fillMachine(cpecan_ctx *ctx, const cpecan_hmm *hmm) {
         ctx->hasSX = false;
         ctx->machine = 1;
         ctx->mToYNotX = v[0];
+    } else if (hmm->sm_type == CPECAN_SM_THREE_STATE_HDP) {
+        // the FP64 kernel with the three-state transitions; emissions from the item's HDP model
+        ctx->generic = hmm->sm_type;
+        ctx->G.sm = hmm->sm_type;
+        for (int i = 0; i < 9; i++) ctx->G.t3[i] = hmm->transitions[i];
+        P.tMC = P.tMX = P.tMY = P.tOX = P.tOY = P.tEX = P.tEY = 0.f; P.tSX = P.tSY = NI;
+        ctx->hasSX = false;
+        ctx->machine = 0;
+        P.vYM = P.vYY = 0.f;
     } else if (hmm->sm_type == CPECAN_SM_FOUR_STATE || hmm->sm_type == CPECAN_SM_ECHELON) {
         // the FP64 kernel of cpecan_generic.cuh: everything it needs is the type and, fourState, the 11 transitions
         ctx->generic = hmm->sm_type;
@@ -234,7 +259,7 @@ int fillMachine(cpecan_ctx *ctx, const cpecan_hmm *hmm) {
         ctx->machine = 0;
         P.vYM = P.vYY = 0.f;
     } else {
-        ctx->err = "state machine type not implemented on device (threeState = 2, vanilla = 4, echelon = 5, fourState = 6 are)";
+        ctx->err = "state machine type not implemented on device (threeState = 2, threeStateHdp = 3, vanilla = 4, echelon = 5, fourState = 6 are)";
         return CPECAN_ERR_ARG;
     }
     if (hmm->sm_type == CPECAN_SM_THREE_STATE || hmm->sm_type == CPECAN_SM_VANILLA) ctx->generic = 0;
@@ -244,17 +269,32 @@ int fillMachine(cpecan_ctx *ctx, const cpecan_hmm *hmm) {
 }
 
 int fillDevParams(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *p, int mode) {
-    if (p->diagonalExpansion < 0 || p->diagonalExpansion % 2 != 0 || p->traceBackDiagonals < 1 ||
+    if (p->diagonalExpansion < 0 || p->traceBackDiagonals < 1 ||
         p->minDiagsBetweenTraceBack < 2 || p->traceBackDiagonals + 1 >= p->minDiagsBetweenTraceBack) {
-        ctx->err = "invalid banding parameters (impl/pairwiseAligner.c:880-884 of the reference; and diagonalExpansion must be "
-                   "even here: with an odd one band_construct's band edges move backwards and by two cells, see INTEGRATION.md)";
+        ctx->err = "invalid banding parameters (impl/pairwiseAligner.c:880-884 of the reference)";
         return CPECAN_ERR_ARG;
     }
     int rc = fillMachine(ctx, hmm);
     if (rc != CPECAN_OK) return rc;
     if (ctx->generic && mode == CPECAN_MODE_EXPECTATION) {
-        ctx->err = "expectations are not defined for the fourState / echelon machines (the reference has no update function for them)";
+        ctx->err = hmm->sm_type == CPECAN_SM_THREE_STATE_HDP
+            ? "expectations of the threeStateHdp machine (event-to-k-mer assignment lists) are not implemented on device"
+            : "expectations are not defined for the fourState / echelon machines (the reference has no update function for them)";
         return CPECAN_ERR_ARG;
+    }
+    if (!ctx->generic && (p->diagonalExpansion % 2 != 0 || (ctx->exact && mode != CPECAN_MODE_EXPECTATION))) {
+        // with an odd expansion band_construct's band edges move backwards and by two cells from one diagonal to the next
+        // (impl/pairwiseAligner.c:98-170): k_align3's one-step band walk does not take that; the FP64 kernel, which reads
+        // explicit band edges, does
+        // (and it is the one cpecan_cuda_set_exact_arithmetic asks for)
+        if (mode == CPECAN_MODE_EXPECTATION) {
+            ctx->err = "expectations need an even diagonalExpansion (posteriors take odd ones too, on the FP64 kernel; see INTEGRATION.md)";
+            return CPECAN_ERR_ARG;
+        }
+        ctx->generic = hmm->sm_type;
+        ctx->G.sm = hmm->sm_type;
+        for (int i = 0; i < 9; i++) ctx->G.t3[i] = hmm->transitions[i];
+        for (int i = 0; i < 5; i++) ctx->G.van[i] = hmm->vanilla[i];
     }
     ctx->G.threshold = p->threshold;
     DevParams &P = ctx->P;
@@ -315,11 +355,11 @@ void cpecan_cuda_destroy(cpecan_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (auto &m : ctx->models) if (m.live) { cudaFree(m.match); cudaFree(m.gapy); cudaFree(m.gapx); }
+    for (auto &m : ctx->models) if (m.live) { cudaFree(m.match); cudaFree(m.gapy); cudaFree(m.gapx); cudaFree(m.hdpY); cudaFree(m.hdpSlope); cudaFree(m.hdpKmer); }
     DevBuf *bufs[] = { &ctx->dModels, &ctx->dItems, &ctx->dOut, &ctx->dRef, &ctx->dRefOff, &ctx->dEvSrc, &ctx->dEvSrcOff,
                        &ctx->dAnchors, &ctx->dScale, &ctx->dCentre, &ctx->dXp, &ctx->dEv, &ctx->dPairs, &ctx->dOrder,
                        &ctx->dQueue, &ctx->dScratch, &ctx->dTotals, &ctx->dCompact, &ctx->dCompactOff, &ctx->dExpect,
-                       &ctx->dBits, &ctx->dTbs, &ctx->dFlags };
+                       &ctx->dBits, &ctx->dTbs, &ctx->dFlags, &ctx->dBands, &ctx->dBandOff };
     for (auto *b : bufs) b->release();
     for (auto &e : ctx->ev) cudaEventDestroy(e);
     for (auto &e : ctx->bev) cudaEventDestroy(e);
@@ -355,6 +395,37 @@ int cpecan_cuda_upload_model(cpecan_ctx *ctx, const double *match, const double 
     return CPECAN_OK;
 }
 
+int cpecan_cuda_upload_hdp(cpecan_ctx *ctx, double grid_start, double grid_stop, int64_t grid_length, int32_t n_distr,
+                           const double *density, const double *slopes, const int32_t *kmer_distr, int32_t *model_id_out) {
+    if (!ctx || !density || !slopes || !kmer_distr || !model_id_out) return CPECAN_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (grid_length < 2 || grid_length > 0x7fffffff || n_distr < 1 || !(grid_start < grid_stop)) { ctx->err = "upload_hdp: bad grid or no distribution"; return CPECAN_ERR_ARG; }
+    for (int k = 0; k < 4096; k++) if (kmer_distr[k] < -1 || kmer_distr[k] >= n_distr) { ctx->err = "upload_hdp: k-mer points outside the distributions"; return CPECAN_ERR_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    Model m;
+    m.hdp = true;
+    m.hdpLen = (int) grid_length;
+    // linspace (impl/hdp_math_utils.c:497-510): grid[i] = start + i * dx, the last point is `stop` itself
+    m.step = (grid_stop - grid_start) / (double) (grid_length - 1);
+    m.x0 = grid_start + 0 * m.step;
+    m.x1 = grid_length == 2 ? grid_stop : grid_start + 1 * m.step;
+    m.xn = grid_stop;
+    const size_t bytes = (size_t) n_distr * (size_t) grid_length * sizeof(double);
+    CK(cudaMalloc(&m.hdpY, bytes));
+    CK(cudaMalloc(&m.hdpSlope, bytes));
+    CK(cudaMalloc(&m.hdpKmer, 4096 * sizeof(int)));
+    CK(cudaMemcpy(m.hdpY, density, bytes, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(m.hdpSlope, slopes, bytes, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(m.hdpKmer, kmer_distr, 4096 * sizeof(int), cudaMemcpyHostToDevice));
+    m.live = true;
+    size_t slot = 0;
+    while (slot < ctx->models.size() && ctx->models[slot].live) slot++;
+    if (slot == ctx->models.size()) ctx->models.push_back(m); else ctx->models[slot] = m;
+    ctx->modelsDirty = true;
+    *model_id_out = (int32_t) slot;
+    return CPECAN_OK;
+}
+
 int cpecan_cuda_release_model(cpecan_ctx *ctx, int32_t model_id) {
     if (!ctx) return CPECAN_ERR_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -363,7 +434,7 @@ int cpecan_cuda_release_model(cpecan_ctx *ctx, int32_t model_id) {
     if (ctx->running) { ctx->err = "release_model: a run is in flight"; return CPECAN_ERR_ARG; }
     CK(waitStream(ctx, ctx->stream));
     Model &m = ctx->models[model_id];
-    cudaFree(m.match); cudaFree(m.gapy); cudaFree(m.gapx);
+    cudaFree(m.match); cudaFree(m.gapy); cudaFree(m.gapx); cudaFree(m.hdpY); cudaFree(m.hdpSlope); cudaFree(m.hdpKmer);
     m = Model();
     ctx->modelsDirty = true;
     return CPECAN_OK;
@@ -378,6 +449,7 @@ int cpecan_cuda_update_model(cpecan_ctx *ctx, int32_t model_id, const double *ma
     CK(waitStream(ctx, ctx->stream));
     const size_t tbl = (1 + 4096 * 5) * sizeof(double);
     Model &m = ctx->models[model_id];
+    if (m.hdp) { ctx->err = "update_model: an HDP model has no pore-model tables"; return CPECAN_ERR_ARG; }
     if (match) CK(cudaMemcpy(m.match, match, tbl, cudaMemcpyHostToDevice));
     if (gapy) CK(cudaMemcpy(m.gapy, gapy, tbl, cudaMemcpyHostToDevice));
     if (gapx) CK(cudaMemcpy(m.gapx, gapx, m.n_gapx * sizeof(double), cudaMemcpyHostToDevice));
@@ -409,11 +481,17 @@ int stageL(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *params, 
     ctx->timing = cpecan_timing{};
     if (n == 0) { guard.ok = true; return CPECAN_OK; }
     cudaStream_t s = ctx->stream;
-    const int needGapx = ctx->generic == CPECAN_SM_ECHELON ? 60 : (ctx->machine ? 60 : 4096);
+    const bool wantHdp = ctx->generic == CPECAN_SM_THREE_STATE_HDP;
+    const int needGapx = wantHdp ? 0 : (ctx->generic == CPECAN_SM_ECHELON ? 60 : (ctx->machine ? 60 : 4096));
 
     if (ctx->modelsDirty) {
         std::vector<ModelTables> mt(ctx->models.size());
-        for (size_t i = 0; i < mt.size(); i++) { mt[i].match = ctx->models[i].match; mt[i].gapy = ctx->models[i].gapy; mt[i].gapx = ctx->models[i].gapx; mt[i].n_gapx = ctx->models[i].n_gapx; }
+        for (size_t i = 0; i < mt.size(); i++) {
+            const Model &m = ctx->models[i];
+            mt[i].match = m.match; mt[i].gapy = m.gapy; mt[i].gapx = m.gapx; mt[i].n_gapx = m.n_gapx;
+            mt[i].hdp_y = m.hdpY; mt[i].hdp_slope = m.hdpSlope; mt[i].hdp_kmer = m.hdpKmer; mt[i].hdp_len = m.hdpLen;
+            mt[i].hdp_x0 = m.x0; mt[i].hdp_x1 = m.x1; mt[i].hdp_xn = m.xn; mt[i].hdp_step = m.step;
+        }
         CK(ctx->dModels.ensure(std::max<size_t>(1, mt.size()) * sizeof(ModelTables)));
         if (!mt.empty()) CK(cudaMemcpy(ctx->dModels.p, mt.data(), mt.size() * sizeof(ModelTables), cudaMemcpyHostToDevice));
         ctx->modelsDirty = false;
@@ -422,7 +500,8 @@ int stageL(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *params, 
     // ---- host-side layout: prefix sums, per-item records -------------------------------------------------
     ctx->hItems.resize(n);
     std::vector<double> centre(n);
-    long long xpTot = 0, evTot = 0, totTot = 0, bitsTot = 0, tbTot = 0;
+    long long xpTot = 0, evTot = 0, totTot = 0, bitsTot = 0, tbTot = 0, bandTot = 0;
+    std::vector<long long> bandOff(ctx->generic ? n : 0);
     const long long tbSpacing = std::max<long long>(1, ctx->P.minDiags - ctx->P.tbDiags - 1);
     int64_t sumLY = 0;
     for (int64_t i = 0; i < n; i++) sumLY += (B->ev_off[i + 1] - B->ev_off[i]) + 32;
@@ -434,6 +513,10 @@ int stageL(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *params, 
         const int64_t refLen = B->ref_off[i + 1] - B->ref_off[i];
         const int64_t lX = refLen >= 5 ? refLen - 5 : 0, lY = B->ev_off[i + 1] - B->ev_off[i];
         if (B->model_id[i] < 0 || B->model_id[i] >= (int) ctx->models.size() || !ctx->models[B->model_id[i]].live) { ctx->err = "bad model id"; return CPECAN_ERR_ARG; }
+        if (ctx->models[B->model_id[i]].hdp != wantHdp) {
+            ctx->err = "the threeStateHdp machine takes models from cpecan_cuda_upload_hdp, the other machines from cpecan_cuda_upload_model";
+            return CPECAN_ERR_ARG;
+        }
         if (ctx->models[B->model_id[i]].n_gapx < needGapx) {
             ctx->err = "model has too few gap-X entries for this state machine (threeState: 4096 log-probabilities, vanilla: 60 skip bins)";
             return CPECAN_ERR_ARG;
@@ -445,6 +528,7 @@ int stageL(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *params, 
         // plan outputs: 2 bits per diagonal, and the traceback points (at least minDiags - tbDiags - 1 diagonals apart)
         it.pad0 = (int) bitsTot; it.pad1 = (int) tbTot;
         bitsTot += ((lX + lY) >> 4) + 1; tbTot += (lX + lY) / tbSpacing + 2;
+        if (ctx->generic) { bandOff[i] = bandTot; bandTot += lX + lY + 1; }
         if (bitsTot > 0x7fffffffLL || tbTot > 0x7fffffffLL) { ctx->err = "batch too large for the plan buffers"; return CPECAN_ERR_ARG; }
         // pair capacity: proportional share of the caller's buffer
         long long cap = (long long) ((long double) pair_cap_total * (long double) (lY + 32) / (long double) sumLY);
@@ -482,6 +566,11 @@ int stageL(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *params, 
     CK(ctx->dTbs.ensure(std::max<long long>(1, tbTot) * sizeof(int)));
     CK(ctx->dFlags.ensure(n * sizeof(int)));
     CK(cudaMemsetAsync(ctx->dFlags.p, 0, n * sizeof(int), s));
+    if (ctx->generic) {
+        CK(ctx->dBands.ensure(std::max<long long>(1, bandTot) * sizeof(int2)));
+        CK(ctx->dBandOff.ensure(n * sizeof(long long)));
+        CK(cudaMemcpyAsync(ctx->dBandOff.p, bandOff.data(), n * sizeof(long long), cudaMemcpyHostToDevice, s));
+    }
     CK(cudaMemcpyAsync(ctx->dItems.p, ctx->hItems.data(), n * sizeof(Item), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->dRef.p, B->ref, refBytes, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->dRefOff.p, B->ref_off, (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, s));
@@ -511,7 +600,8 @@ int stageL(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *params, 
 
     // ---- plan: band cells, widest diagonal, longest run of live forward rows -------------------------------
     k_plan3<<<(unsigned) ((n + 63) / 64), 64, 0, s>>>(ctx->dItems.as<Item>(), (int) n, ctx->dAnchors.as<long long>(), ctx->P, ctx->dOut.as<ItemOut>(),
-                                                    ctx->dBits.as<unsigned>(), ctx->dTbs.as<int>(), ctx->dFlags.as<int>());
+                                                    ctx->dBits.as<unsigned>(), ctx->dTbs.as<int>(), ctx->dFlags.as<int>(),
+                                                    ctx->generic ? ctx->dBands.as<int2>() : nullptr, ctx->dBandOff.as<long long>());
     ctx->timing.kernel_launches += 1;
     ctx->hOut.resize(n);
     CK(cudaMemcpyAsync(ctx->hOut.data(), ctx->dOut.p, n * sizeof(ItemOut), cudaMemcpyDeviceToHost, s));
@@ -529,7 +619,7 @@ int stageL(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *params, 
     const int sx = ctx->hasSX ? 1 : 0, ex = mode == CPECAN_MODE_EXPECTATION ? 1 : 0;
     int occGenCache[NCFG2] = {};
     if (ctx->generic) for (int b = 0; b < NCFG2; b++) occGenCache[b] = occGen(b, ctx->generic);
-    const int genS = ctx->generic == CPECAN_SM_ECHELON ? 7 : 4;
+    const int genS = genStates(ctx->generic);
     int64_t cells = 0;
     for (int64_t i = 0; i < n; i++) {
         const ItemOut &o = ctx->hOut[i];
@@ -648,7 +738,7 @@ int runAsyncL(cpecan_ctx *ctx) {
             g.ref = ctx->dRef.as<char>(); g.ref_off = ctx->dRefOff.as<long long>();
             g.events = ctx->dEvSrc.as<double>(); g.ev_src_off = ctx->dEvSrcOff.as<long long>();
             g.models = ctx->dModels.as<ModelTables>(); g.scale = ctx->stagedScaled ? ctx->dScale.as<double>() : nullptr;
-            g.bits = a.bits; g.tbs = a.tbs; g.flags = a.flags;
+            g.bands = ctx->dBands.as<int2>(); g.band_off = ctx->dBandOff.as<long long>(); g.tbs = a.tbs; g.flags = a.flags;
             g.scratch = reinterpret_cast<double *>(a.scratch); g.scratch_stride = bk.stride * 2;
             g.ring_rows = bk.ringRows; g.ringN = cfg2N(b);
             g.pairs = a.pairs; g.out = a.out; g.totals = a.totals; g.P = ctx->P; g.G = ctx->G;
@@ -878,6 +968,13 @@ int cpecan_cuda_set_resident_warps(cpecan_ctx *ctx, int32_t warps_per_sm) {
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (warps_per_sm < 0) { ctx->err = "set_resident_warps: negative"; return CPECAN_ERR_ARG; }
     ctx->occCap = warps_per_sm;
+    return CPECAN_OK;
+}
+
+int cpecan_cuda_set_exact_arithmetic(cpecan_ctx *ctx, int32_t on) {
+    if (!ctx) return CPECAN_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->exact = on != 0;
     return CPECAN_OK;
 }
 

@@ -4,6 +4,12 @@
 // the banded schedule of getPosteriorProbsWithBanding (impl/pairwiseAligner.c:870-1006) and, for echelon,
 // diagonalCalculationMultiPosteriorMatchProbs (:797-839).
 //
+// Also here: threeStateHdp (impl/stateMachine.c:1336-1366, factory :1738-1749) -- the three-state
+// topology with the match and gap-Y emissions read from a NanoporeHDP: the spline-interpolated posterior predictive
+// density of the k-mer's Dirichlet process at the event mean (impl/nanopore_hdp.c:390-392, impl/hdp.c:2577-2599,
+// impl/hdp_math_utils.c:471-495).  The reference adds that DENSITY (not its logarithm) to the log-transition; so does
+// this kernel.
+//
 // These are the reference's experimental machines (its own test accepts 857 of 1000 pairs for echelon); here they run
 // in FP64 -- B200 issues FP64 at half the FP32 rate -- with the reference's arithmetic as it stands: absolute
 // log-probabilities, logAdd as lo + cubic(hi - lo), transitions pulled on the way forward and PUSHED on the way back
@@ -22,7 +28,10 @@ namespace cpecan {
 #define CPG_NI (-CUDART_INF)
 
 struct GenParams {
-    int sm;                 // 6 = fourState, 5 = echelon (StateMachineType, inc/stateMachine.h:20-29)
+    int sm;                 // 6 = fourState, 5 = echelon, 3 = threeStateHdp, and -- for band shapes k_align3 does not take (odd expansions) --
+                            // 2 = threeState, 4 = vanilla (StateMachineType, inc/stateMachine.h:20-29)
+    double t3[9];           // threeState transitions, StateMachine3 field order
+    double van[5];          // vanilla: M_TO_Y_NOT_X, E_TO_E, END_MATCH, END_FROM_X, END_FROM_Y
     double t4[11];          // fourState transitions: MATCH_CONTINUE, MATCH_FROM_SHORT_GAP_X, MATCH_FROM_SHORT_GAP_Y,
                             // MATCH_FROM_LONG_GAP_X, GAP_SHORT_OPEN_X, GAP_SHORT_EXTEND_X, GAP_SHORT_OPEN_Y, GAP_SHORT_EXTEND_Y,
                             // GAP_LONG_OPEN_X, GAP_LONG_EXTEND_X, GAP_LONG_SWITCH_TO_X
@@ -40,7 +49,8 @@ struct KernelArgsG {
     const long long *ev_src_off;
     const ModelTables *models;
     const double *scale;          // 5 per item or null
-    const unsigned *bits;
+    const int2 *bands;            // plan: (lo, hi) of every diagonal, item i at band_off[i]
+    const long long *band_off;
     const int *tbs;
     const int *flags;
     double *scratch;              // per warp: ring_rows rows of N cells of S doubles
@@ -80,6 +90,9 @@ __device__ __forceinline__ double g_log_inv_gauss(double x, double mu, double la
 template <int SM> struct GenTraits;
 template <> struct GenTraits<6> { static constexpr int S = 4; };
 template <> struct GenTraits<5> { static constexpr int S = 7; };
+template <> struct GenTraits<2> { static constexpr int S = 3; };
+template <> struct GenTraits<3> { static constexpr int S = 3; };
+template <> struct GenTraits<4> { static constexpr int S = 3; };
 
 template <int SM>
 __global__ void __launch_bounds__(32) k_align_generic(const KernelArgsG A) {
@@ -103,7 +116,7 @@ __global__ void __launch_bounds__(32) k_align_generic(const KernelArgsG A) {
         const Item it = A.items[itemIdx];
         const int lX = it.lX, lY = it.lY, D = lX + lY;
         const int planFlags = A.flags[itemIdx];
-        if (D == 0 || (planFlags & 4) != 0) {
+        if (D == 0 || (planFlags & 16) != 0) {                  // nothing to align, or a diagonal of the band is empty
             if (lane == 0) { ItemOut &o = A.out[itemIdx]; o.n_pairs = 0; o.status = D == 0 ? 0 : 6; o.total_logprob = 0.0; o.n_tracebacks = 0; }
             continue;
         }
@@ -111,7 +124,7 @@ __global__ void __launch_bounds__(32) k_align_generic(const KernelArgsG A) {
         const int refLen = (int) (A.ref_off[itemIdx + 1] - A.ref_off[itemIdx]);
         const double *evs = A.events + 3 * A.ev_src_off[itemIdx];
         const ModelTables mt = A.models[it.model_id];
-        const unsigned *bitsp = A.bits + it.pad0;
+        const int2 *bandp = A.bands + A.band_off[itemIdx];
         const int *tbp = A.tbs + it.pad1;
         int *pairs = A.pairs + 3 * it.pair_off;
         double *dbgTot = (A.totals != nullptr && it.tot_off >= 0) ? A.totals + it.tot_off : nullptr;
@@ -121,7 +134,7 @@ __global__ void __launch_bounds__(32) k_align_generic(const KernelArgsG A) {
         int nPairs = 0, status = 0, nTb = 0;
         double lastTotal = 0.0;
 
-        auto bandBits = [&](int d) -> unsigned { return (bitsp[d >> 4] >> ((d & 15) << 1)) & 3u; };
+        auto bandOf = [&](int d, int &l, int &h) { if (d >= 0 && d <= D) { const int2 b = bandp[d]; l = b.x; h = b.y; } else { l = 0; h = -1; } };
         // the padded nucleotide sequence (sequence_padSequence, impl/pairwiseAligner.c:282-285) and its k-mer index
         // (impl/stateMachine.c:104-139; -1 <=> index > 4096)
         auto rch = [&](int i) -> char { return (i >= 0 && i < refLen) ? ref[i] : 'n'; };
@@ -144,6 +157,28 @@ __global__ void __launch_bounds__(32) k_align_generic(const KernelArgsG A) {
             const double *m = mt.gapy + 1 + 5 * k;
             mu = m[0]; sd = m[1]; nu = m[2]; tau = m[3]; lam = m[4];
         };
+        // dir_proc_density of the k-mer's distribution (impl/hdp.c:2577-2599) through grid_spline_interp
+        // (impl/hdp_math_utils.c:471-495); the grid is linspace(start, stop, n) (:497-510)
+        auto hdpDensity = [&](int k, double q) -> double {
+            const int t = k >= 0 ? mt.hdp_kmer[k] : -1;
+            if (t < 0) { status |= 8; return 0.0; }
+            const double *yv = mt.hdp_y + (long long) t * mt.hdp_len, *sl = mt.hdp_slope + (long long) t * mt.hdp_len;
+            const int n = mt.hdp_len - 1;
+            double r;
+            if (q <= mt.hdp_x0) r = yv[0] - sl[0] * (mt.hdp_x0 - q);
+            else if (q >= mt.hdp_xn) r = yv[n] + sl[n] * (q - mt.hdp_xn);
+            else {
+                const double dx = mt.hdp_x1 - mt.hdp_x0;
+                int il = (int) ((q - mt.hdp_x0) / dx);
+                il = il > n - 1 ? n - 1 : il;
+                const double xl = __dadd_rn(mt.hdp_x0, __dmul_rn((double) il, mt.hdp_step));     // linspace's own rounding, no FMA
+                const double dy = yv[il + 1] - yv[il];
+                const double a = sl[il] * dx - dy, b = dy - sl[il + 1] * dx;
+                const double tl = (q - xl) / dx, tr = 1.0 - tl;
+                r = tr * yv[il] + tl * yv[il + 1] + tl * tr * (a * tr + b * tl);
+            }
+            return r > 0.0 ? r : 0.0;
+        };
         auto eventOf = [&](int y, double &m, double &n, double &dur) {      // y = matrix row; row 0 is the null event (:261-262)
             if (y >= 1) { m = evs[3 * (y - 1)]; n = evs[3 * (y - 1) + 1]; dur = evs[3 * (y - 1) + 2]; }
             else { m = NI; n = 0.0; dur = 0.0; }
@@ -157,7 +192,71 @@ __global__ void __launch_bounds__(32) k_align_generic(const KernelArgsG A) {
 #define TRG(nb, from, to, eptp) do { if (fwd) cur[to] = g_la(cur[to], nb[from] + (eptp)); else nb[from] = g_la(nb[from], cur[to] + (eptp)); } while (0)
             double em, en, edur;
             eventOf(y, em, en, edur);
-            if (SM == 6) {
+            if (SM == 2) {
+                // stateMachine3_cellCalculate (impl/stateMachine.c:1305-1334); sequence_getKmer: index < 0 reads "n"
+                const int k = x >= 1 ? kmerAt(x - 1) : -1;
+                const double *t = A.G.t3;
+                if (hasLo) {
+                    const double eP = k < 0 ? NI : mt.gapx[k];
+                    TRG(lo_, 0, 1, eP + t[3]); TRG(lo_, 1, 1, eP + t[5]); TRG(lo_, 2, 1, eP + t[7]);
+                }
+                if (hasMi) {
+                    double mu, sd, nu, tau, lam;
+                    matchParams(k, mu, sd, nu, tau, lam);
+                    const double eP = g_log_gauss(em, mu, sd) + g_log_gauss(en, nu, tau);
+                    TRG(mi_, 0, 0, eP + t[0]); TRG(mi_, 1, 0, eP + t[1]); TRG(mi_, 2, 0, eP + t[2]);
+                }
+                if (hasUp) {
+                    double mu, sd, nu, tau, lam;
+                    gapyParams(k, mu, sd, nu, tau, lam);
+                    const double eP = g_log_gauss(em, mu, sd) + g_log_gauss(en, nu, tau);
+                    TRG(up_, 0, 2, eP + t[4]); TRG(up_, 2, 2, eP + t[6]);
+                }
+            } else if (SM == 3) {
+                // stateMachine3HDP_cellCalculate (impl/stateMachine.c:1336-1366); sequence_getKmer3: index < 0 reads k-mer 0
+                const int k = kmerAt(x >= 1 ? x - 1 : 0);
+                const double *t = A.G.t3;
+                if (hasLo) {
+                    const double eP = -2.3025850929940455;
+                    TRG(lo_, 0, 1, eP + t[3]); TRG(lo_, 1, 1, eP + t[5]); TRG(lo_, 2, 1, eP + t[7]);
+                }
+                if (hasMi) {
+                    const double eP = hdpDensity(k, em);
+                    TRG(mi_, 0, 0, eP + t[0]); TRG(mi_, 1, 0, eP + t[1]); TRG(mi_, 2, 0, eP + t[2]);
+                }
+                if (hasUp) {
+                    const double eP = hdpDensity(k, em);
+                    TRG(up_, 0, 2, eP + t[4]); TRG(up_, 2, 2, eP + t[6]);
+                }
+            } else if (SM == 4) {
+                // stateMachine3Vanilla_cellCalculate (impl/stateMachine.c:1368-1409); sequence_getKmer2: the pointer to the
+                // PREVIOUS k-mer, clamped at 0; the skip bin of (k-mer i, k-mer i+1) on the scaled match table
+                const int i = x >= 2 ? x - 2 : 0;
+                double mu0, mu1, sd, nu, tau, lam;
+                matchParams(kmerAt(i), mu0, sd, nu, tau, lam);
+                const int k = kmerAt(i + 1);
+                matchParams(k, mu1, sd, nu, tau, lam);
+                long long bin = (long long) (fabs(mu1 - mu0) / 0.5);
+                bin = bin >= 30 ? 29 : bin;
+                const double a_mx = mt.gapx[bin];
+                const double a_my = (1 - a_mx) * A.G.van[0];
+                const double a_mm = 1.0f - a_my - a_mx;
+                const double a_yy = A.G.van[1];
+                const double a_ym = 1.0f - a_yy;
+                const double a_xx = mt.gapx[bin + 30];
+                const double a_xm = 1.0f - a_xx;
+                if (hasLo) { TRG(lo_, 0, 1, 0 + log(a_mx)); TRG(lo_, 1, 1, 0 + log(a_xx)); }
+                if (hasMi) {
+                    const double eP = g_log_gauss(em, mu1, sd) + g_log_inv_gauss(en, nu, lam);
+                    TRG(mi_, 0, 0, eP + log(a_mm)); TRG(mi_, 1, 0, eP + log(a_xm)); TRG(mi_, 2, 0, eP + log(a_ym));
+                }
+                if (hasUp) {
+                    double mu, sdd, nuu, tt, ll;
+                    gapyParams(k, mu, sdd, nuu, tt, ll);
+                    const double eP = g_log_gauss(em, mu, sdd) + g_log_inv_gauss(en, nuu, ll);
+                    TRG(up_, 0, 2, eP + log(a_my)); TRG(up_, 2, 2, eP + log(a_yy));
+                }
+            } else if (SM == 6) {
                 const int k = x >= 1 ? kmerAt(x - 1) : -1;
                 const double *t = A.G.t4;
                 if (hasLo) {
@@ -239,6 +338,17 @@ __global__ void __launch_bounds__(32) k_align_generic(const KernelArgsG A) {
                 for (int st = 0; st < 7; st++) v[st] = NI;
                 if (which == 0) v[1] = 0; else if (which == 1) v[6] = 0;
                 else { for (int st = 0; st < 6; st++) v[st] = 0.79015888282447311; v[6] = 0.19652425498269727; }   // not logs (:1617-1619)
+            } else if (SM == 2 || SM == 3 || SM == 4) {
+                // impl/stateMachine.c:1168-1235
+                if (which == 0) { v[0] = 0; v[1] = v[2] = NI; }
+                else if (which == 1) { v[0] = NI; v[1] = 0; v[2] = 0; }
+                else if (SM != 4) {
+                    const double *t = A.G.t3;
+                    if (which == 2) { v[0] = t[0]; v[1] = t[1]; v[2] = t[2]; } else { v[0] = (t[3] + t[4]) / 2.0; v[1] = t[5]; v[2] = t[6]; }
+                } else {
+                    const double *e = A.G.van;
+                    if (which == 2) { v[0] = e[2]; v[1] = e[3]; v[2] = e[4]; } else { v[0] = (e[3] + e[4]) / 2.0; v[1] = e[3]; v[2] = e[4]; }
+                }
             } else {
                 const double *t = A.G.t4;
                 if (which == 0) { v[0] = 0; v[1] = v[2] = v[3] = NI; }
@@ -274,8 +384,7 @@ __global__ void __launch_bounds__(32) k_align_generic(const KernelArgsG A) {
             for (int d = dcur + 1; d <= Dt; d++) {
                 { const int t = f2; f2 = f1; f1 = f0; f0 = t; }
                 lo2 = lo1; hi2 = hi1; lo1 = lo; hi1 = hi;
-                const unsigned b = bandBits(d);
-                lo += b & 1; hi += b >> 1;
+                bandOf(d, lo, hi);
                 double *F0 = buf(f0), *F1 = buf(f1), *F2 = buf(f2);
                 for (int xb = lo; xb <= hi; xb += 32) {
                     const int x = xb + lane;
@@ -310,13 +419,13 @@ __global__ void __launch_bounds__(32) k_align_generic(const KernelArgsG A) {
 #pragma unroll
                     for (int st = 0; st < S; st++) buf(b0)[st * N + (x & NM)] = endv[st];
                 int l1 = 0, h1 = -1, l2 = 0, h2 = -1, lp = 0, hp = -1;   // band of d-1, d-2, d+1
-                { const unsigned b = bandBits(Dt); l1 = blo - (int) (b & 1); h1 = bhi - (int) (b >> 1); }
+                bandOf(Dt - 1, l1, h1);
                 if (Dt > tracedBackTo + 1) clearBuf(b1, l1 - 1, h1 + 1);
                 __syncwarp();
                 double total = NI;
                 long long count = 0;
                 for (int d = Dt; d > tracedBackTo; d--) {
-                    if (d >= 2) { const unsigned b = bandBits(d - 1); l2 = l1 - (int) (b & 1); h2 = h1 - (int) (b >> 1); } else { l2 = 0; h2 = -1; }
+                    bandOf(d - 2, l2, h2);
                     const bool liveMi = d > tracedBackTo + 2, sweepB = d > tracedBackTo + 1;
                     if (liveMi) clearBuf(b2, l2 - 1, h2 + 1);
                     __syncwarp();
@@ -388,7 +497,7 @@ __global__ void __launch_bounds__(32) k_align_generic(const KernelArgsG A) {
                             if (d < Dt && d - 1 >= 0) {
                                 // match-only forward step from F[d-1] into a -inf clone shaped like B[d+1], dotted with B[d+1]
                                 int lm, hm;
-                                { const unsigned b = bandBits(d); lm = blo - (int) (b & 1); hm = bhi - (int) (b >> 1); }
+                                bandOf(d - 1, lm, hm);
                                 t2 = diagDot([&](int x, double *a) {
                                     double nm[S];
                                     const bool hasMi = x - 1 >= lm && x - 1 <= hm;
@@ -456,8 +565,7 @@ __global__ void __launch_bounds__(32) k_align_generic(const KernelArgsG A) {
             // =============================== restore the forward state at Dt ==============================
             if (tracedBackTo < D) {
                 f0 = 0; f1 = 1; f2 = 2;
-                const unsigned b = bandBits(Dt);
-                lo1 = lo - (int) (b & 1); hi1 = hi - (int) (b >> 1);
+                bandOf(Dt - 1, lo1, hi1);
                 lo2 = 0; hi2 = -1;                                // re-derived when the sweep advances
                 for (int x = lo + lane; x <= hi; x += 32) { const double *rp = rowPtr(Dt, x);
 #pragma unroll
@@ -468,6 +576,7 @@ __global__ void __launch_bounds__(32) k_align_generic(const KernelArgsG A) {
                 __syncwarp();
             }
         }
+        status = __reduce_or_sync(CP_FULL, status);          // bit 8 is raised by single lanes
         if (lane == 0) {
             ItemOut &o = A.out[itemIdx];
             o.n_pairs = nPairs;

@@ -513,6 +513,7 @@ namespace {
 std::mutex gMu;
 cpecan_ctx *gCtx = nullptr;
 int gDevice = -1;
+int gExact = -1;                                // cpecan_host_set_exact_arithmetic / $CPECAN_EXACT
 std::map<StateMachine *, int32_t> gModels;      // device copies of the tables, refreshed at every submit (the public
                                                 // EMISSION_* / TRANSITION_* fields are mutable)
 cpecan_ctx *gpuLocked() {
@@ -520,6 +521,8 @@ cpecan_ctx *gpuLocked() {
         int dev = gDevice >= 0 ? gDevice : (getenv("CPECAN_DEVICE") ? atoi(getenv("CPECAN_DEVICE")) : 0);
         if (cpecan_cuda_init(dev, &gCtx) != CPECAN_OK)
             st_errAbort("cpecan: no usable CUDA device %d; the banded DP has no CPU fallback in this build", dev);
+        if (gExact < 0) gExact = getenv("CPECAN_EXACT") ? atoi(getenv("CPECAN_EXACT")) : 0;
+        cpecan_cuda_set_exact_arithmetic(gCtx, gExact);
     }
     return gCtx;
 }
@@ -710,6 +713,12 @@ void cpecan_host_set_device(int device) {
     std::lock_guard<std::mutex> lk(gMu);
     if (gCtx && device != gDevice) st_errAbort("cpecan_host_set_device: the GPU context already exists");
     gDevice = device;
+}
+
+void cpecan_host_set_exact_arithmetic(int on) {
+    std::lock_guard<std::mutex> lk(gMu);
+    gExact = on ? 1 : 0;
+    if (gCtx) cpecan_cuda_set_exact_arithmetic(gCtx, gExact);
 }
 
 void stateMachine_destruct(StateMachine *sM) {                 // impl/stateMachine.c:1786-1788 leaks the tables; freed here

@@ -48,24 +48,6 @@ struct __align__(8) ItemOut {
     int n_pairs, status, n_tracebacks, max_width, max_rows, pad;
 };
 
-// ------------------------------------------------------------------------------------------------ logAdd
-// impl/pairwiseAligner.c:238-255.  Coefficients are the reference's float literals (exact in FP32).
-__device__ __forceinline__ float la_poly(float x) {
-    const bool s1 = x <= 1.0f, s2 = x <= 2.5f, s3 = x <= 4.5f;
-    const float a = s1 ? -0.009350833524763f : (s2 ? -0.014532321752540f : (s3 ? -0.004605031767994f : -0.000458661602210f));
-    const float b = s1 ? 0.130659527668286f : (s2 ? 0.139942324101744f : (s3 ? 0.063427417320019f : 0.009695946122598f));
-    const float c = s1 ? 0.498799810682272f : (s2 ? 0.495635523139337f : (s3 ? 0.695956496475118f : 0.930734667215156f));
-    const float d = s1 ? 0.693203116424741f : (s2 ? 0.692140569840976f : (s3 ? 0.514272634594009f : 0.168037164329057f));
-    return fmaf(fmaf(fmaf(a, x, b), x, c), x, d);
-}
-
-__device__ __forceinline__ float logadd(float x, float y) {
-    const float hi = fmaxf(x, y), lo = fminf(x, y);
-    const float d = hi - lo;              // NaN when both are -inf, +inf when only lo is
-    const float r = lo + la_poly(d);
-    return (d < 7.5f) ? r : hi;           // NaN / inf / >= 7.5 all fall through to hi
-}
-
 // ------------------------------------------------------------------------------------------------ plan kernel (k_align3)
 // One thread per item walks the band exactly as band_construct does (impl/pairwiseAligner.c:98-184: x-y limits with
 // parity fixing and C integer division, so odd expansions come out as in the reference) and leaves what k_align3 needs:
@@ -73,10 +55,11 @@ __device__ __forceinline__ float logadd(float x, float y) {
 //   * the list of diagonals at which getPosteriorProbsWithBanding traces back (impl/pairwiseAligner.c:903-918);
 //   * band cells, widest diagonal, longest run of forward rows alive at a traceback;
 //   * flag bit 4 (CPECAN_ITEM_BAND_STEP) when a band edge moves backwards or by more than one cell (never for anchors
-//     that went through filterToRemoveOverlap): the alignment kernel skips such an item.
+//     that went through filterToRemoveOverlap and an even expansion): k_align3 skips such an item; flag bit 16 when a
+//     diagonal is empty (no kernel aligns that);
 __device__ __forceinline__ long long cp_clampz(long long z, long long l) { return z < 0 ? 0 : (z > l ? l : z); }
 __global__ void k_plan3(const Item *items, int n, const long long *anchors, DevParams P, ItemOut *out, unsigned *bits,
-                        int *tbs, int *flags) {
+                        int *tbs, int *flags, int2 *bands /* or null */, const long long *band_off) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const Item it = items[i];
@@ -84,6 +67,9 @@ __global__ void k_plan3(const Item *items, int n, const long long *anchors, DevP
     const long long lX = it.lX, lY = it.lY, D = lX + lY, e = P.expansion;
     unsigned *bw = bits + it.pad0;
     int *tb = tbs + it.pad1;
+    // the FP64 kernel (cpecan_generic.cuh) takes the band as explicit (lo, hi) per diagonal: it also serves the bands of odd
+    // expansions, whose edges move backwards and by two cells
+    int2 *bandOut = bands != nullptr ? bands + band_off[i] : nullptr;
     long long ai = 0, pxay = 0, pxmy = 0, nxay = 0, nxmy = 0, xL = 0, yL = 0, xU = 0, yU = 0;
     long long cells = 0;
     int maxw = 0, maxrows = 1, ntb = 0, tracedBackTo = 0, flag = 0;
@@ -99,6 +85,7 @@ __global__ void k_plan3(const Item *items, int n, const long long *anchors, DevP
         t = (xay + r) / 2; if (xU < t) r -= 2 * (t - xU);
         t = (xay - r) / 2; if (t < yU) r -= 2 * (yU - t);
         const long long lo = (xay + l) / 2, hi = (xay + r) / 2;
+        if (bandOut != nullptr) bandOut[xay] = make_int2((int) lo, (int) hi);
         if (xay > 0) {
             const long long dl = lo - plo, dh = hi - phi;
             if (dl < 0 || dl > 1 || dh < 0 || dh > 1) flag |= 4;
@@ -107,7 +94,7 @@ __global__ void k_plan3(const Item *items, int n, const long long *anchors, DevP
         if ((xay & 15) == 15 || xay == D) { bw[xay >> 4] = word; word = 0; }
         plo = lo; phi = hi;
         const int w = (int) (hi - lo + 1);
-        if (w < 1) flag |= 4;
+        if (w < 1) flag |= 4 | 16;
         cells += w;
         maxw = max(maxw, w);
         if (xay > 0) {
@@ -161,6 +148,12 @@ __global__ void k_prep_events(const Item *items, const long long *ev_src_off, co
 struct ModelTables {      // device pointers of one uploaded pore model
     const double *match, *gapy, *gapx;
     int n_gapx;
+    // an HDP model (cpecan_cuda_upload_hdp) instead: per distinct distribution the posterior predictive density on the
+    // sampling grid and its spline slopes, and for every ACGT 6-mer the distribution it reads (-1: none)
+    const double *hdp_y, *hdp_slope;
+    const int *hdp_kmer;
+    double hdp_x0, hdp_x1, hdp_xn, hdp_step;   // grid[0], grid[1], grid[n-1], (stop - start) / (n - 1)
+    int hdp_len;
 };
 
 __device__ __forceinline__ int base_code(char b) {

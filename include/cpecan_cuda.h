@@ -29,7 +29,7 @@ enum {
 };
 
 /* State-machine types, numbered as the reference's StateMachineType (inc/stateMachine.h:20-29). */
-enum { CPECAN_SM_THREE_STATE = 2, CPECAN_SM_VANILLA = 4, CPECAN_SM_ECHELON = 5, CPECAN_SM_FOUR_STATE = 6 };
+enum { CPECAN_SM_THREE_STATE = 2, CPECAN_SM_THREE_STATE_HDP = 3, CPECAN_SM_VANILLA = 4, CPECAN_SM_ECHELON = 5, CPECAN_SM_FOUR_STATE = 6 };
 
 /* Work modes. */
 enum {
@@ -130,6 +130,16 @@ const char *cpecan_cuda_last_error(cpecan_ctx *ctx);
 int cpecan_cuda_upload_model(cpecan_ctx *ctx, const double *match, const double *gapy, const double *gapx,
                              int32_t n_gapx, int32_t *model_id_out);
 
+/* Upload one NanoporeHDP for the threeStateHdp machine (getHdpStateMachine3, impl/stateMachine.c:1738-1749): what
+ * get_nanopore_kmer_density (impl/nanopore_hdp.c:390-392) reads.  The sampling grid is linspace(grid_start, grid_stop,
+ * grid_length) (impl/hdp_math_utils.c:497-510); `density` and `slopes` hold n_distr rows of grid_length doubles (the
+ * posterior predictive of an observed Dirichlet process and its spline slopes, impl/hdp.c:2540-2575); kmer_distr[k]
+ * is the row the k-th ACGT 6-mer reads (its own process, or the nearest observed ancestor: impl/hdp.c:2588-2591), or
+ * -1 when the HDP's alphabet cannot spell it.  The id returned lives in the same space as pore-model ids and is
+ * released the same way; items of a threeStateHdp batch must carry such an id, items of the other machines must not. */
+int cpecan_cuda_upload_hdp(cpecan_ctx *ctx, double grid_start, double grid_stop, int64_t grid_length, int32_t n_distr,
+                           const double *density, const double *slopes, const int32_t *kmer_distr, int32_t *model_id_out);
+
 /* Overwrite tables of an uploaded model in place (NULL = keep): what the M-step loaders do to a live StateMachine
  * (continuousPairHmm_loadTransitionsAndKmerGapProbs rewrites EMISSION_GAP_X_PROBS, impl/continuousHmm.c:206-232). */
 int cpecan_cuda_update_model(cpecan_ctx *ctx, int32_t model_id, const double *match, const double *gapy,
@@ -200,6 +210,13 @@ void cpecan_cuda_host_free(cpecan_ctx *ctx, void *p);
  * afterwards (0 = as many as fit, the default).  Callers that stream sub-batches through several contexts at once give
  * each a share, so that the forward-row rings (sized by the resident warps) of all of them fit in HBM. */
 int cpecan_cuda_set_resident_warps(cpecan_ctx *ctx, int32_t warps_per_sm);
+
+/* Arithmetic of the threeState / vanilla posterior batches staged afterwards.  0 (default): the FP32 kernel (k_align3),
+ * whose posteriors agree with the reference's FP64 ones to ~1e-4 apart from rare logAdd segment flips.
+ * 1: the FP64 kernel in the reference's own operation order -- the same pair lists, scores equal to the last digit of
+ * floor(p * 1e7) -- at a fraction of the FP32 rate (profiles/).  Batches with an odd diagonalExpansion always run that
+ * way (their band is one the FP32 kernel does not walk); expectations are FP32 only. */
+int cpecan_cuda_set_exact_arithmetic(cpecan_ctx *ctx, int32_t on);
 
 int cpecan_cuda_get_timing(cpecan_ctx *ctx, cpecan_timing *out);
 int cpecan_cuda_device_info(cpecan_ctx *ctx, int32_t *sm_count, int32_t *clock_khz, int64_t *hbm_bytes);

@@ -386,6 +386,9 @@ void getAlignedPairsUsingAnchorsBatch(int64_t n, StateMachine **sMs, Sequence **
                                       PairwiseAlignmentParameters *p, bool raggedLeft, bool raggedRight, stList **results);
 /* Device for this process (default: $CPECAN_DEVICE or 0); must be called before the first alignment. */
 void cpecan_host_set_device(int device);
+/* Posteriors of the threeState / vanilla machines in FP64 and the reference's own operation order (scores equal to the
+ * last digit; slower) instead of FP32 (default: $CPECAN_EXACT or 0); see cpecan_cuda_set_exact_arithmetic. */
+void cpecan_host_set_exact_arithmetic(int on);
 
 #ifdef __cplusplus
 }

@@ -3,10 +3,12 @@
  *
  * Minimal stand-in for benedictpaten/sonLib, which the reference depends on
  * (include.mk:2 of the reference: sonLibRootPath=${rootPath}../sonLib) but does
- * not vendor and does not pin.  Only the ~45 symbols the hot-path sources
+ * not vendor and does not pin.  Only the symbols the hot-path sources
  * (impl/pairwiseAligner.c, impl/stateMachine.c, impl/nanopore.c,
- * impl/continuousHmm.c, impl/discreteHmm.c) reference are provided; they are
- * containers and string/file helpers, none of the DP arithmetic lives here.
+ * impl/continuousHmm.c, impl/discreteHmm.c) and, for the threeStateHdp goldens,
+ * the HDP sources (impl/hdp.c, impl/nanopore_hdp.c, impl/hdp_math_utils.c)
+ * reference are provided; they are containers and string/file helpers, none of
+ * the DP arithmetic lives here.
  * Used exclusively to compile the UNMODIFIED reference sources into
  * oracle/_ref/ so the oracle restatement can be pinned against them.
  */
@@ -50,6 +52,23 @@ void *stList_pop(stList *l);
 void stList_sort(stList *l, int (*cmp)(const void *, const void *));
 void stList_setDestructor(stList *l, void (*destructElement)(void *));
 double *stList_toDoublePtr(stList *l, int64_t *lengthOut);
+int64_t *stList_toIntPtr(stList *l, int64_t *lengthOut);
+void stList_removeItem(stList *l, void *item);
+stListIterator *stList_getIterator(stList *l);
+void *stList_getNext(stListIterator *it);
+void stList_destructIterator(stListIterator *it);
+
+/* stSet: hash set of pointers (identity), iteration in table order */
+stSet *stSet_construct(void);
+stSet *stSet_construct2(void (*destructElement)(void *));
+void stSet_destruct(stSet *s);
+void stSet_insert(stSet *s, void *item);
+void *stSet_search(stSet *s, void *item);
+void *stSet_remove(stSet *s, void *item);
+int64_t stSet_size(stSet *s);
+stSetIterator *stSet_getIterator(stSet *s);
+void *stSet_getNext(stSetIterator *it);
+void stSet_destructIterator(stSetIterator *it);
 
 /* stIntTuple: fixed small tuple of int64 */
 stIntTuple *stIntTuple_construct2(int64_t a, int64_t b);
@@ -70,6 +89,7 @@ char *stString_print(const char *fmt, ...);
 char *stString_copy(const char *s);
 char *stString_getSubString(const char *s, int64_t start, int64_t length);
 stList *stString_split(const char *s);
+stList *stString_splitByString(const char *s, const char *delim);
 char *stFile_getLineFromFile(FILE *f);
 /* used by the reference's vanillaAlign.c only (oracle/vanilla_align_stubs.c) */
 char *stString_reverseComplementString(const char *s);

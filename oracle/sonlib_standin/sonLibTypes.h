@@ -7,5 +7,7 @@ typedef struct _stList stList;
 typedef struct _stIntTuple stIntTuple;
 typedef struct _stSortedSet stSortedSet;
 typedef struct _stSet stSet;
+typedef struct _stSetIterator stSetIterator;
+typedef struct _stListIterator stListIterator;
 typedef struct _stHash stHash;
 #endif

@@ -77,11 +77,13 @@ static int sortShim(const void *a, const void *b, void *cmp) {
 void stList_sort(stList *l, int (*cmp)(const void *, const void *)) {
     qsort_r(l->items, l->n, sizeof(void *), sortShim, (void *) cmp);
 }
+#ifndef STANDIN_REAL_HDP   /* impl/hdp_math_utils.c defines this one itself */
 double *stList_toDoublePtr(stList *l, int64_t *lengthOut) {
     double *d = st_malloc(sizeof(double) * (l->n ? l->n : 1));
     for (int64_t i = 0; i < l->n; i++) d[i] = *(double *) l->items[i];
     *lengthOut = l->n; return d;
 }
+#endif
 
 /* ------------------------------------------------------------ stIntTuple */
 struct _stIntTuple { int64_t n; int64_t v[4]; };
@@ -223,9 +225,101 @@ void destructPairwiseAlignment(struct PairwiseAlignment *pA) {
     free(pA->contig1); free(pA->contig2); free(pA);
 }
 
-/* ----------------------------------------------- HDP symbols (out of scope)
+/* ------------------------------------------ containers the HDP sources use */
+#ifndef STANDIN_REAL_HDP
+int64_t *stList_toIntPtr(stList *l, int64_t *lengthOut) {
+    int64_t *v = st_malloc(sizeof(int64_t) * (l->n ? l->n : 1));
+    for (int64_t i = 0; i < l->n; i++) if (sscanf(l->items[i], "%" SCNd64, &v[i]) != 1) st_errAbort("stList_toIntPtr: not an integer");
+    *lengthOut = l->n;
+    return v;
+}
+#endif
+void stList_removeItem(stList *l, void *item) {
+    for (int64_t i = 0; i < l->n; i++)
+        if (l->items[i] == item) { memmove(l->items + i, l->items + i + 1, sizeof(void *) * (l->n - i - 1)); l->n--; return; }
+}
+struct _stListIterator { stList *l; int64_t i; };
+stListIterator *stList_getIterator(stList *l) { stListIterator *it = st_malloc(sizeof(*it)); it->l = l; it->i = 0; return it; }
+void *stList_getNext(stListIterator *it) { return it->i < it->l->n ? it->l->items[it->i++] : NULL; }
+void stList_destructIterator(stListIterator *it) { free(it); }
+
+#define SET_TOMB ((void *) 1)
+struct _stSet { void **slot; int64_t cap, n, used; void (*destructElement)(void *); };
+struct _stSetIterator { stSet *s; int64_t i; };
+static uint64_t ptrHash(void *p) { uint64_t x = (uint64_t) (uintptr_t) p; x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; return x; }
+stSet *stSet_construct2(void (*d)(void *)) {
+    stSet *s = st_calloc(1, sizeof(*s));
+    s->cap = 8; s->slot = st_calloc(s->cap, sizeof(void *)); s->destructElement = d;
+    return s;
+}
+stSet *stSet_construct(void) { return stSet_construct2(NULL); }
+void stSet_destruct(stSet *s) {
+    if (s->destructElement) for (int64_t i = 0; i < s->cap; i++) if (s->slot[i] && s->slot[i] != SET_TOMB) s->destructElement(s->slot[i]);
+    free(s->slot); free(s);
+}
+static void setPut(stSet *s, void *item) {
+    int64_t i = (int64_t) (ptrHash(item) & (uint64_t) (s->cap - 1)), tomb = -1;
+    while (s->slot[i]) {
+        if (s->slot[i] == item) return;
+        if (s->slot[i] == SET_TOMB && tomb < 0) tomb = i;
+        i = (i + 1) & (s->cap - 1);
+    }
+    if (tomb >= 0) i = tomb; else s->used++;
+    s->slot[i] = item; s->n++;
+}
+void stSet_insert(stSet *s, void *item) {
+    if (item == NULL || item == SET_TOMB) st_errAbort("stSet_insert: reserved pointer");
+    if (2 * (s->used + 1) > s->cap) {
+        void **old = s->slot; int64_t oc = s->cap;
+        s->cap = 2 * s->n + 2 > s->cap ? 2 * s->cap : s->cap;      /* grow, or only clear the tombstones */
+        s->slot = st_calloc(s->cap, sizeof(void *)); s->n = 0; s->used = 0;
+        for (int64_t i = 0; i < oc; i++) if (old[i] && old[i] != SET_TOMB) setPut(s, old[i]);
+        free(old);
+    }
+    setPut(s, item);
+}
+static int64_t setFind(stSet *s, void *item) {
+    int64_t i = (int64_t) (ptrHash(item) & (uint64_t) (s->cap - 1));
+    while (s->slot[i]) { if (s->slot[i] == item) return i; i = (i + 1) & (s->cap - 1); }
+    return -1;
+}
+void *stSet_search(stSet *s, void *item) { return setFind(s, item) >= 0 ? item : NULL; }
+void *stSet_remove(stSet *s, void *item) {
+    int64_t i = setFind(s, item);
+    if (i < 0) return NULL;
+    s->slot[i] = SET_TOMB; s->n--;
+    return item;
+}
+int64_t stSet_size(stSet *s) { return s->n; }
+stSetIterator *stSet_getIterator(stSet *s) { stSetIterator *it = st_malloc(sizeof(*it)); it->s = s; it->i = 0; return it; }
+void *stSet_getNext(stSetIterator *it) {
+    while (it->i < it->s->cap) { void *p = it->s->slot[it->i++]; if (p && p != SET_TOMB) return p; }
+    return NULL;
+}
+void stSet_destructIterator(stSetIterator *it) { free(it); }
+
+stList *stString_splitByString(const char *s, const char *delim) {
+    stList *l = stList_construct3(0, free);
+    size_t nd = strlen(delim);
+    const char *p = s;
+    for (;;) {
+        const char *q = nd ? strstr(p, delim) : NULL;
+        size_t n = q ? (size_t) (q - p) : strlen(p);
+        char *tok = st_malloc(n + 1); memcpy(tok, p, n); tok[n] = 0;
+        stList_append(l, tok);
+        if (!q) break;
+        p = q + nd;
+    }
+    return l;
+}
+
+#ifndef STANDIN_REAL_HDP
+/* ----------------------------------------------- HDP symbols (stubs)
  * stateMachine.c / continuousHmm.c reference four HDP entry points for the
- * threeStateHdp variant, which this project does not cover. */
+ * threeStateHdp variant; builds without the reference's HDP sources
+ * (libcpecan_ref.so, oracle/_ref/vanillaAlign) get aborting stubs, the
+ * HDP golden generator (oracle/_ref/vanillaAlign_hdp, -DSTANDIN_REAL_HDP)
+ * links the real ones. */
 typedef struct _nanoporeHDP NanoporeHDP;
 double get_nanopore_kmer_density(NanoporeHDP *nhdp, void *kmer, void *event) {
     (void) nhdp; (void) kmer; (void) event; st_errAbort("HDP emissions are out of scope"); return 0.0;
@@ -237,3 +331,4 @@ void pass_data_to_hdp(void *hdp, double *data, int64_t *dp_ids, int64_t length) 
     (void) hdp; (void) data; (void) dp_ids; (void) length; st_errAbort("HDP is out of scope");
 }
 void reset_hdp_data(void *hdp) { (void) hdp; st_errAbort("HDP is out of scope"); }
+#endif

@@ -45,6 +45,7 @@ void checkPairwiseAlignment(struct PairwiseAlignment *pA) {
     int64_t ex = pA->end1 - pA->start1, ey = pA->end2 - pA->start2;
     if (llabs(ex) != lx || llabs(ey) != ly) st_errAbort("checkPairwiseAlignment: cigar operations do not match the intervals");
 }
+#ifndef STANDIN_REAL_HDP
 #define HDP_STUB(sig) sig { st_errAbort("HDP is out of scope for the oracle build"); return 0; }
 HDP_STUB(void *deserialize_nhdp(const char *f))
 HDP_STUB(int serialize_nhdp(void *h, const char *f))
@@ -52,3 +53,4 @@ HDP_STUB(int destroy_nanopore_hdp(void *h))
 HDP_STUB(int execute_nhdp_gibbs_sampling(void *h, int64_t a, int64_t b, int64_t c, int d))
 HDP_STUB(int finalize_nhdp_distributions(void *h))
 HDP_STUB(int nanoporeHdp_buildNanoporeHdpFromAlignment(int t, const char *a, const char *b, const char *c, const char *d, const char *e))
+#endif

@@ -495,8 +495,8 @@ def test_split_regions_as_items(engine, syn_golden, template_tables):
 
 def test_argument_errors_are_reported(engine, template_tables):
     """Integer status + message, never an abort: banding parameters the reference rejects (traceBackDiagonals + 1 >=
-    minDiagsBetweenTraceBack, impl/pairwiseAligner.c:880-884), an odd expansion (the one documented restriction:
-    INTEGRATION.md), a model with too few gap-X entries for the machine, an unknown state-machine type."""
+    minDiagsBetweenTraceBack, impl/pairwiseAligner.c:880-884), expectations with an odd expansion (posteriors take one, on
+    the FP64 kernel: INTEGRATION.md), a model with too few gap-X entries for the machine, an unknown state-machine type."""
     from cpecan_signal import EngineError, HostBatch, default_params, synth, vanilla_hmm
     from cpecan_signal.engine import Hmm
     l1, l2, l3 = template_tables
@@ -505,8 +505,8 @@ def test_argument_errors_are_reported(engine, template_tables):
     hb = HostBatch([r.ref], [r.events], [r.anchors], model_ids=[mid], scales=[r.scale5], ragged=[(1, 1)])
     with pytest.raises(EngineError, match="banding parameters"):
         engine.align_batch(hb, params=default_params(traceBackDiagonals=40, minDiagsBetweenTraceBack=41))
-    with pytest.raises(EngineError, match="must be even"):
-        engine.align_batch(hb, params=default_params(diagonalExpansion=21))
+    with pytest.raises(EngineError, match="even diagonalExpansion"):
+        engine.expectations_batch(hb, params=default_params(diagonalExpansion=21))
     mid60 = engine.upload_model(l1, l3, np.full(60, 0.1))
     hb60 = HostBatch([r.ref], [r.events], [r.anchors], model_ids=[mid60], scales=[r.scale5], ragged=[(1, 1)])
     with pytest.raises(EngineError, match="gap-X"):
@@ -527,3 +527,52 @@ def test_argument_errors_are_reported(engine, template_tables):
     hb0 = HostBatch([r.ref], [np.zeros((0, 3))], [np.zeros((0, 2))], model_ids=[mid], scales=[r.scale5], ragged=[(1, 1)])
     res, pairs, _ = engine.align_batch(hb0)
     assert res[0]["status"] == 0 and res[0]["n_pairs"] == 0
+
+
+@pytest.mark.parametrize("machine", ["three", "vanilla"])
+def test_odd_expansions_vs_oracle(engine, template_tables, machine):
+    """The reference takes odd diagonalExpansion values (its band edges then move backwards and by two cells between
+    diagonals, impl/pairwiseAligner.c:98-170).  Such batches run on the FP64 kernel with explicit band edges: random
+    reads, odd expansions, several traceback parameter sets, every ragged combination -- same pair lists as the oracle,
+    scores to the last digit, totals to 1e-9, band cells exact."""
+    import oracleshim as O
+    from cpecan_signal import HostBatch, default_params, synth, three_state_hmm, vanilla_gapx, vanilla_hmm
+    from cpecan_signal.engine import item_pairs
+    l1, l2, l3 = template_tables
+    rng = np.random.default_rng(131 if machine == "three" else 132)
+    van = machine == "vanilla"
+    hmm = vanilla_hmm("template") if van else three_state_hmm()
+    mid = engine.upload_model(l1, l3, vanilla_gapx(l2) if van else np.full(4096, -2.3025850929940455))
+    for mind, tbd, e, thr, lxs in [(5, 2, 3, 0.01, (8, 150)), (20, 8, 11, 0.2, (8, 150)), (60, 40, 21, 0.05, (20, 300)),
+                                   (1000, 40, 51, 0.01, (700, 1500)), (1000, 40, 1, 0.01, (8, 300))]:
+        reads, anchors, ragged = [], [], []
+        for _ in range(8):
+            r = synth.make_read(l1, int(rng.integers(1, 1 << 30)), lX=int(rng.integers(*lxs)),
+                                anchor_every=int(rng.integers(5, 60)), noise_dist="wald" if van else "gauss")
+            keep = rng.random(len(r.anchors)) < rng.choice([0.3, 1.0])
+            reads.append(r); anchors.append(r.anchors[keep]); ragged.append((int(rng.integers(0, 2)), int(rng.integers(0, 2))))
+        batch = HostBatch([r.ref for r in reads], [r.events for r in reads], anchors, model_ids=[mid] * len(reads),
+                          scales=[r.scale5 for r in reads], ragged=ragged)
+        kw = dict(diagonalExpansion=e, minDiagsBetweenTraceBack=mind, traceBackDiagonals=tbd, threshold=thr)
+        res, pairs, totals = engine.align_batch(batch, hmm=hmm, params=default_params(**kw), want_totals=True, pair_cap=400000)
+        worst = 0
+        for i, r in enumerate(reads):
+            m = (O.Model(O.VANILLA, tables=(l1, l2, l3), scale5=r.scale5, strand=0) if van
+                 else O.Model(O.THREE_STATE, tables=(l1, l2, l3), scale5=r.scale5))
+            want, wtot = O.align_banded(m, r.ref, r.events, anchors[i], params=O.default_params(**kw), ragged=ragged[i],
+                                        want_totals=True)
+            assert res[i]["status"] == 0, (i, kw, res[i]["status"])
+            lX, lY = len(r.ref) - 5, len(r.events)
+            assert res[i]["band_cells"] == O.band_cells(anchors[i], lX, lY, O.default_params(**kw))
+            got = np.asarray(parity.reverse_regions(item_pairs(res, pairs, i)), dtype=np.int64).reshape(-1, 3)
+            want = np.asarray(want, dtype=np.int64).reshape(-1, 3)
+            assert got.shape == want.shape and np.array_equal(got[:, 1:], want[:, 1:]), (i, kw)
+            if len(got):
+                worst = max(worst, int(np.abs(got[:, 0] - want[:, 0]).max()))
+            mask = ~np.isnan(wtot)
+            assert np.array_equal(mask, ~np.isnan(totals[i]))
+            if mask.any():
+                assert float(np.abs(totals[i][mask] - wtot[mask]).max()) <= 1e-9 * max(1.0, float(np.abs(wtot[mask]).max()))
+        print(machine, kw, "worst score diff", worst)
+        assert worst <= 2
+    engine.release_model(mid)

@@ -53,13 +53,13 @@ def _rows(path, multi=False):
     return rows
 
 
-def _run(flags, extra, tmp_path):
+def _run(flags, extra, tmp_path, env=None):
     args = flags + ["-T", os.path.join(PKG, "models", "template_median68pA.model"),
                     "-C", os.path.join(PKG, "models", "complement_median68pA_pop2.model"), "-L", "readA",
                     "-q", os.path.join(GOLD, "ZymoC_ch_1_file1.npRead"), "-r", os.path.join(GOLD, "ZymoRef.txt")] + extra
     with open(os.path.join(VA, "guide.cigar")) as fin:
         r = subprocess.run([EXE] + args, stdin=fin, capture_output=True, text=True, timeout=600,
-                           env=dict(os.environ, OMP_NUM_THREADS="2"))
+                           env=dict(os.environ, OMP_NUM_THREADS="2", **(env or {})))
     assert r.returncode == 0, r.stderr[-3000:]
     return r.stdout
 
@@ -95,6 +95,27 @@ def test_unmodified_vanilla_align_posteriors(tmp_path, flag, tag):
         assert int(g.split("(")[0]) == int(w.split("(")[0])
         gs, ws = g.split("(")[1].rstrip(")"), w.split("(")[1].rstrip(")")
         assert ("nan" in gs) if "nan" in ws else abs(float(gs) - float(ws)) < 0.01
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flag,tag", [("-s", "s"), ("", "v")])
+def test_unmodified_vanilla_align_exact_arithmetic(tmp_path, flag, tag):
+    """CPECAN_EXACT=1 (cpecan_host_set_exact_arithmetic): the threeState / vanilla posteriors in FP64 and the reference's
+    operation order -- the posterior file row for row what the reference binary writes, no row missing or extra, the
+    printed posteriors (%f: six decimals) equal to 1e-6."""
+    if not os.path.exists(EXE):
+        pytest.skip("oracle/_ref/vanillaAlign_dropin is built only where /root/reference exists")
+    out = str(tmp_path / "post.tsv")
+    _run([flag] if flag else [], ["-u", out], tmp_path, env={"CPECAN_EXACT": "1"})
+    got, want = _rows(out), _rows(os.path.join(VA, "out_%s.tsv" % tag))
+    assert got.keys() == want.keys()
+    worst = 0.0
+    for key, ws in want.items():
+        g, w = got[key][0], ws[0]
+        assert g[:12] == w[:12] and g[13:] == w[13:], (g, w)
+        worst = max(worst, abs(float(g[12]) - float(w[12])))
+    print(tag, len(got), "rows, worst posterior difference", worst)
+    assert worst <= 1.000001e-6
 
 
 @pytest.mark.gpu

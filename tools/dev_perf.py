@@ -23,12 +23,15 @@ def main():
     ap.add_argument("--machine", default="three", choices=["three", "vanilla"])
     ap.add_argument("--mode", default="posterior", choices=["posterior", "em"])
     ap.add_argument("--thr", type=float, default=0.01, help="posterior threshold (1.1: no pair is ever reported)")
+    ap.add_argument("--exact", action="store_true", help="cpecan_cuda_set_exact_arithmetic: the FP64 kernel")
     a = ap.parse_args()
     nu = a.unique or a.n
     reads = generate_reads(nu, 5_000_000, lX=a.lx)
     reads = [reads[i % nu] for i in range(a.n)]
     l1, l2, l3 = synth.load_model_file(synth.TEMPLATE_MODEL)
     eng = Engine(0)
+    if a.exact:
+        eng.set_exact_arithmetic(True)
     from cpecan_signal import vanilla_gapx, vanilla_hmm
     hmm = vanilla_hmm("template") if a.machine == "vanilla" else None
     mid = eng.upload_model(l1, l3, vanilla_gapx(l2) if a.machine == "vanilla" else np.full(4096, -2.3025850929940455))
