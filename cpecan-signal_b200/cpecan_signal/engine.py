@@ -13,6 +13,7 @@ SM_THREE_STATE = 2
 SM_VANILLA = 4
 SM_ECHELON = 5
 SM_FOUR_STATE = 6
+SM_THREE_STATE_HDP = 7
 MODE_POSTERIOR = 0
 MODE_EXPECTATION = 1
 MODE_UNBANDED = 2
@@ -76,6 +77,13 @@ def three_state_hmm(transitions=None):
     t = NANOPORE_TRANSITIONS if transitions is None else transitions
     for i in range(9):
         h.transitions[i] = float(t[i])
+    return h
+
+
+def hdp_hmm(transitions=None):
+    """StateMachine3_HDP (getHdpStateMachine3): the three-state transitions; the items' models come from upload_hdp."""
+    h = three_state_hmm(transitions)
+    h.sm_type = SM_THREE_STATE_HDP
     return h
 
 
@@ -243,6 +251,21 @@ class Engine:
         self._check(self.lib.cpecan_cuda_upload_model(self.ctx, match.ctypes.data_as(C.c_void_p),
                                                       gapy.ctypes.data_as(C.c_void_p), gapx.ctypes.data_as(C.c_void_p),
                                                       C.c_int32(gapx.size), C.byref(mid)), "upload_model")
+        return mid.value
+
+    def upload_hdp(self, hdp):
+        """A NanoporeHdp (cpecan_signal.hdp.load_nhdp) for the threeStateHdp machine; the id is released with release_model."""
+        dens = np.ascontiguousarray(hdp.density, dtype=np.float64)
+        slopes = np.ascontiguousarray(hdp.slopes, dtype=np.float64)
+        kd = np.ascontiguousarray(hdp.kmer_distr, dtype=np.int32)
+        assert dens.shape == slopes.shape == (dens.shape[0], hdp.grid_length) and kd.size == N_KMERS
+        if hdp.kmer_length != 6:
+            raise EngineError("the HDP is over %d-mers, the alignment over 6-mers" % hdp.kmer_length)
+        mid = C.c_int32(-1)
+        self._check(self.lib.cpecan_cuda_upload_hdp(self.ctx, C.c_double(hdp.grid_start), C.c_double(hdp.grid_stop),
+                                                    C.c_int64(hdp.grid_length), C.c_int32(dens.shape[0]),
+                                                    dens.ctypes.data_as(C.c_void_p), slopes.ctypes.data_as(C.c_void_p),
+                                                    kd.ctypes.data_as(C.c_void_p), C.byref(mid)), "upload_hdp")
         return mid.value
 
     def update_model(self, model_id, match=None, gapy=None, gapx=None):

@@ -187,7 +187,7 @@ template <typename F> auto dispatchGen(int sm, F f) {
     switch (sm) {
         case CPECAN_SM_ECHELON: return f(k_align_generic<5>, 7);
         case CPECAN_SM_THREE_STATE: return f(k_align_generic<2>, 3);
-        case CPECAN_SM_THREE_STATE_HDP: return f(k_align_generic<3>, 3);
+        case CPECAN_SM_THREE_STATE_HDP: return f(k_align_generic<7>, 3);
         case CPECAN_SM_VANILLA: return f(k_align_generic<4>, 3);
         default: return f(k_align_generic<6>, 4);
     }
@@ -259,7 +259,7 @@ int fillMachine(cpecan_ctx *ctx, const cpecan_hmm *hmm) {
         ctx->machine = 0;
         P.vYM = P.vYY = 0.f;
     } else {
-        ctx->err = "state machine type not implemented on device (threeState = 2, threeStateHdp = 3, vanilla = 4, echelon = 5, fourState = 6 are)";
+        ctx->err = "state machine type not implemented on device (threeState = 2, vanilla = 4, echelon = 5, fourState = 6, threeStateHdp = 7 are)";
         return CPECAN_ERR_ARG;
     }
     if (hmm->sm_type == CPECAN_SM_THREE_STATE || hmm->sm_type == CPECAN_SM_VANILLA) ctx->generic = 0;

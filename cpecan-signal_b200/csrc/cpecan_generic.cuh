@@ -28,7 +28,7 @@ namespace cpecan {
 #define CPG_NI (-CUDART_INF)
 
 struct GenParams {
-    int sm;                 // 6 = fourState, 5 = echelon, 3 = threeStateHdp, and -- for band shapes k_align3 does not take (odd expansions) --
+    int sm;                 // 6 = fourState, 5 = echelon, 7 = threeStateHdp, and -- for band shapes k_align3 does not take (odd expansions) --
                             // 2 = threeState, 4 = vanilla (StateMachineType, inc/stateMachine.h:20-29)
     double t3[9];           // threeState transitions, StateMachine3 field order
     double van[5];          // vanilla: M_TO_Y_NOT_X, E_TO_E, END_MATCH, END_FROM_X, END_FROM_Y
@@ -91,7 +91,7 @@ template <int SM> struct GenTraits;
 template <> struct GenTraits<6> { static constexpr int S = 4; };
 template <> struct GenTraits<5> { static constexpr int S = 7; };
 template <> struct GenTraits<2> { static constexpr int S = 3; };
-template <> struct GenTraits<3> { static constexpr int S = 3; };
+template <> struct GenTraits<7> { static constexpr int S = 3; };
 template <> struct GenTraits<4> { static constexpr int S = 3; };
 
 template <int SM>
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(32) k_align_generic(const KernelArgsG A) {
                     const double eP = g_log_gauss(em, mu, sd) + g_log_gauss(en, nu, tau);
                     TRG(up_, 0, 2, eP + t[4]); TRG(up_, 2, 2, eP + t[6]);
                 }
-            } else if (SM == 3) {
+            } else if (SM == 7) {
                 // stateMachine3HDP_cellCalculate (impl/stateMachine.c:1336-1366); sequence_getKmer3: index < 0 reads k-mer 0
                 const int k = kmerAt(x >= 1 ? x - 1 : 0);
                 const double *t = A.G.t3;
@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(32) k_align_generic(const KernelArgsG A) {
                 for (int st = 0; st < 7; st++) v[st] = NI;
                 if (which == 0) v[1] = 0; else if (which == 1) v[6] = 0;
                 else { for (int st = 0; st < 6; st++) v[st] = 0.79015888282447311; v[6] = 0.19652425498269727; }   // not logs (:1617-1619)
-            } else if (SM == 2 || SM == 3 || SM == 4) {
+            } else if (SM == 2 || SM == 7 || SM == 4) {
                 // impl/stateMachine.c:1168-1235
                 if (which == 0) { v[0] = 0; v[1] = v[2] = NI; }
                 else if (which == 1) { v[0] = NI; v[1] = 0; v[2] = 0; }

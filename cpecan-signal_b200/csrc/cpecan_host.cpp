@@ -9,7 +9,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <fstream>
 #include <map>
+#include <sstream>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -507,6 +509,207 @@ void emissions_signal_scaleModel(StateMachine *sM, double scale, double shift, d
 
 }  // extern "C"
 
+// ============================================================================== NanoporeHDP (threeStateHdp)
+// What get_nanopore_kmer_density needs of the reference's HierarchicalDirichletProcess: the sampling grid and, per
+// OBSERVED Dirichlet process, the posterior predictive density on it with its spline slopes.  Everything else in a
+// serialised HDP (data, Gibbs state, factor tree) is read past.
+namespace {
+
+struct HdpTables {
+    double gridStart = 0, gridStop = 0;
+    int64_t gridLength = 0, numDps = 0;
+    std::vector<double> grid;               // linspace (impl/hdp_math_utils.c:497-510)
+    std::vector<int64_t> parent;            // -1: the base process
+    std::vector<int32_t> row;               // per process: its row in density / slopes, or -1 (not observed)
+    std::vector<double> density, slopes;
+    bool splinesFinalized = false;
+    int32_t deviceModel = -1;               // cpecan_cuda_upload_hdp id, once an alignment has used it
+};
+
+std::vector<double> splitDoubles(const std::string &line) {
+    std::vector<double> v;
+    const char *p = line.c_str();
+    char *end = nullptr;
+    for (;;) {
+        const double d = strtod(p, &end);
+        if (end == p) break;
+        v.push_back(d); p = end;
+    }
+    return v;
+}
+
+bool nextLine(std::ifstream &in, std::string &line, const char *what, const char *path) {
+    if (!std::getline(in, line)) st_errAbort("deserialize_nhdp: %s ends before %s", path, what);
+    return true;
+}
+
+// kmer_id (impl/nanopore_hdp.c:348-380): big-endian word over the HDP's sorted alphabet; the reference exits on a
+// character outside it
+int64_t hdpKmerId(const NanoporeHDP *nhdp, const char *kmer, bool fatal) {
+    int64_t id = 0;
+    for (int64_t i = 0; i < nhdp->kmer_length; i++) {
+        const char *q = (const char *) memchr(nhdp->alphabet, kmer[i], (size_t) nhdp->alphabet_size);
+        if (q == nullptr || kmer[i] == 0) {
+            if (!fatal) return -1;
+            fprintf(stderr, "vanillaAlign - ERROR: K-mer contains character outside alphabet. Got offending kmer is: %.*s. alphabet is %s\n",
+                    (int) nhdp->kmer_length, kmer, nhdp->alphabet);
+            exit(EXIT_FAILURE);
+        }
+        id = id * nhdp->alphabet_size + (q - nhdp->alphabet);
+    }
+    return id;
+}
+
+int32_t hdpRowOf(const HdpTables *t, int64_t dp) {           // impl/hdp.c:2588-2591: the nearest observed ancestor
+    while (dp >= 0 && t->row[(size_t) dp] < 0) dp = t->parent[(size_t) dp];
+    return dp < 0 ? -1 : t->row[(size_t) dp];
+}
+
+}  // namespace
+
+extern "C" {
+
+NanoporeHDP *deserialize_nhdp(const char *filepath) {
+    std::ifstream in(filepath);
+    if (!in) st_errAbort("deserialize_nhdp: cannot open %s", filepath);
+    std::string line;
+    NanoporeHDP *nhdp = (NanoporeHDP *) calloc(1, sizeof(NanoporeHDP));
+    HdpTables *t = new HdpTables();
+    nhdp->hdp = t;
+    nextLine(in, line, "the alphabet size", filepath); nhdp->alphabet_size = atoll(line.c_str());
+    nextLine(in, line, "the alphabet", filepath);
+    { std::istringstream is(line); std::string a; is >> a;
+      if ((int64_t) a.size() != nhdp->alphabet_size || a.empty()) st_errAbort("deserialize_nhdp: alphabet '%s' does not have %lld characters", a.c_str(), (long long) nhdp->alphabet_size);
+      std::sort(a.begin(), a.end());                       // package_nanopore_hdp keeps it sorted (impl/nanopore_hdp.c:38-55)
+      nhdp->alphabet = strdup(a.c_str()); }
+    nextLine(in, line, "the k-mer length", filepath); nhdp->kmer_length = atoll(line.c_str());
+    // ---- deserialize_hdp (impl/hdp.c:3009-3270)
+    nextLine(in, line, "splines_finalized", filepath); t->splinesFinalized = atoll(line.c_str()) != 0;
+    nextLine(in, line, "has_data", filepath); const bool hasData = atoll(line.c_str()) != 0;
+    nextLine(in, line, "sample_gamma", filepath); const bool sampleGamma = atoll(line.c_str()) != 0;
+    nextLine(in, line, "num_dps", filepath); t->numDps = atoll(line.c_str());
+    if (t->numDps <= 0) st_errAbort("deserialize_nhdp: %s has no Dirichlet processes", filepath);
+    std::vector<int64_t> dataDp;
+    if (hasData) {
+        nextLine(in, line, "the data", filepath);
+        nextLine(in, line, "the data assignments", filepath);
+        const char *p = line.c_str(); char *end = nullptr;
+        for (;;) { const long long v = strtoll(p, &end, 10); if (end == p) break; dataDp.push_back(v); p = end; }
+    }
+    nextLine(in, line, "the base parameters", filepath);
+    nextLine(in, line, "the sampling grid", filepath);
+    { std::vector<double> g = splitDoubles(line);
+      if (g.size() != 3 || g[2] < 2 || !(g[0] < g[1])) st_errAbort("deserialize_nhdp: bad sampling grid line in %s", filepath);
+      t->gridStart = g[0]; t->gridStop = g[1]; t->gridLength = (int64_t) g[2]; }
+    nextLine(in, line, "gamma", filepath);
+    if (sampleGamma) for (int i = 0; i < 4; i++) nextLine(in, line, "the gamma distribution parameters", filepath);
+    t->parent.assign((size_t) t->numDps, -1);
+    for (int64_t id = 0; id < t->numDps; id++) {
+        nextLine(in, line, "the parents", filepath);
+        if (line.empty() || line[0] != '-') t->parent[(size_t) id] = atoll(line.c_str());
+        if (t->parent[(size_t) id] >= t->numDps) st_errAbort("deserialize_nhdp: parent out of range in %s", filepath);
+    }
+    // mark_observed_dps (impl/hdp.c:1124-1152): the processes holding data, and all their ancestors
+    std::vector<char> observed((size_t) t->numDps, 0);
+    for (int64_t id : dataDp) {
+        if (id < 0 || id >= t->numDps) st_errAbort("deserialize_nhdp: data point assigned to process %lld of %lld", (long long) id, (long long) t->numDps);
+        for (int64_t dp = id; dp >= 0 && !observed[(size_t) dp]; dp = t->parent[(size_t) dp]) observed[(size_t) dp] = 1;
+    }
+    t->row.assign((size_t) t->numDps, -1);
+    const int64_t n = t->gridLength;
+    t->grid.resize((size_t) n);
+    { const double dx = (t->gridStop - t->gridStart) / (double) (n - 1);
+      for (int64_t i = 0; i < n - 1; i++) t->grid[(size_t) i] = t->gridStart + i * dx;
+      t->grid[(size_t) n - 1] = t->gridStop; }
+    if (hasData) {
+        int32_t rows = 0;
+        for (int64_t id = 0; id < t->numDps; id++) {
+            nextLine(in, line, "the posterior predictive densities", filepath);
+            std::vector<double> v = splitDoubles(line);
+            if (v.empty()) {
+                if (observed[(size_t) id]) st_errAbort("deserialize_nhdp: observed process %lld has no density in %s", (long long) id, filepath);
+                continue;
+            }
+            if ((int64_t) v.size() != n) st_errAbort("deserialize_nhdp: density of process %lld has %lld of %lld grid points", (long long) id, (long long) v.size(), (long long) n);
+            if (!observed[(size_t) id]) continue;             // never read by dir_proc_density
+            t->row[(size_t) id] = rows++;
+            t->density.insert(t->density.end(), v.begin(), v.end());
+        }
+        t->slopes.assign(t->density.size(), 0.0);
+        if (t->splinesFinalized) {
+            for (int64_t id = 0; id < t->numDps; id++) {
+                nextLine(in, line, "the spline slopes", filepath);
+                std::vector<double> v = splitDoubles(line);
+                if (v.empty()) {
+                    if (t->row[(size_t) id] >= 0) st_errAbort("deserialize_nhdp: observed process %lld has no spline slopes in %s", (long long) id, filepath);
+                    continue;
+                }
+                if ((int64_t) v.size() != n) st_errAbort("deserialize_nhdp: slopes of process %lld have %lld of %lld grid points", (long long) id, (long long) v.size(), (long long) n);
+                if (t->row[(size_t) id] >= 0) std::copy(v.begin(), v.end(), t->slopes.begin() + (size_t) t->row[(size_t) id] * (size_t) n);
+            }
+        }
+    }
+    return nhdp;                                              // the factor tree that follows is the Gibbs sampler's state
+}
+
+void cpecan_host_release_hdp_locked(NanoporeHDP *nhdp);
+
+void destroy_nanopore_hdp(NanoporeHDP *nhdp) {
+    if (!nhdp) return;
+    cpecan_host_release_hdp_locked(nhdp);
+    delete (HdpTables *) nhdp->hdp;
+    free(nhdp->alphabet);
+    free(nhdp);
+}
+
+int64_t get_nanopore_hdp_kmer_length(NanoporeHDP *nhdp) { return nhdp->kmer_length; }
+int64_t get_nanopore_hdp_alphabet_size(NanoporeHDP *nhdp) { return nhdp->alphabet_size; }
+char *get_nanopore_hdp_alphabet(NanoporeHDP *nhdp) { return strdup(nhdp->alphabet); }
+
+// impl/nanopore_hdp.c:390-392 -> dir_proc_density (impl/hdp.c:2577-2599) -> grid_spline_interp
+// (impl/hdp_math_utils.c:471-495): the same expressions in the same order
+double get_nanopore_kmer_density(NanoporeHDP *nhdp, void *kmer, void *x) {
+    const HdpTables *t = (const HdpTables *) nhdp->hdp;
+    if (!t->splinesFinalized) { fprintf(stderr, "Must finalize distributions before querying densities.\n"); exit(EXIT_FAILURE); }
+    const int64_t id = hdpKmerId(nhdp, (const char *) kmer, true);
+    if (id >= t->numDps) { fprintf(stderr, "Hierarchical Dirichlet process has no Dirichlet process with this ID.\n"); exit(EXIT_FAILURE); }
+    const int32_t row = hdpRowOf(t, id);
+    if (row < 0) st_errAbort("get_nanopore_kmer_density: no observed Dirichlet process above this k-mer's (an HDP without data)");
+    const int64_t n = t->gridLength;
+    const double *xg = t->grid.data(), *y = t->density.data() + (size_t) row * (size_t) n, *slope = t->slopes.data() + (size_t) row * (size_t) n;
+    const double q = *(const double *) x;
+    double interp;
+    if (q <= xg[0]) interp = y[0] - slope[0] * (xg[0] - q);
+    else if (q >= xg[n - 1]) interp = y[n - 1] + slope[n - 1] * (q - xg[n - 1]);
+    else {
+        const double dx = xg[1] - xg[0];
+        int64_t il = (int64_t) ((q - xg[0]) / dx);
+        if (il > n - 2) il = n - 2;                          // the reference would read past the grid here
+        const int64_t ir = il + 1;
+        const double dy = y[ir] - y[il];
+        const double a = slope[il] * dx - dy;
+        const double b = dy - slope[ir] * dx;
+        const double tl = (q - xg[il]) / dx;
+        const double tr = 1.0 - tl;
+        interp = tr * y[il] + tl * y[ir] + tl * tr * (a * tr + b * tl);
+    }
+    return interp > 0.0 ? interp : 0.0;
+}
+
+StateMachine *getHdpStateMachine3(NanoporeHDP *hdp) {                                                       // :1738-1749, 1513-1557
+    StateMachine3_HDP *m = (StateMachine3_HDP *) calloc(1, sizeof(StateMachine3_HDP));
+    initBase(&m->model, threeStateHdp, NUM_OF_KMERS);
+    m->model.endStateProb = sm3_end; m->model.raggedEndStateProb = sm3_raggedEnd;
+    stateMachine3_setTransitionsToNanoporeDefaults(&m->model);          // the nine transitions sit where StateMachine3's do
+    for (int64_t i = 0; i < NUM_OF_KMERS; i++) m->model.EMISSION_GAP_X_PROBS[i] = -2.3025850929940455;
+    m->hdpModel = hdp;
+    m->getYGapProbFcn = get_nanopore_kmer_density;
+    m->getMatchProbFcn = get_nanopore_kmer_density;
+    return &m->model;
+}
+
+}  // extern "C"
+
 // ===================================================================================================== GPU context
 namespace {
 
@@ -536,7 +739,30 @@ void modelDropLocked(StateMachine *sM) {
     gModels.erase(it);
 }
 
+// the device copy of an HDP belongs to the NanoporeHDP, not to the state machines that point at it
+int32_t hdpModelIdLocked(cpecan_ctx *ctx, NanoporeHDP *nhdp) {
+    HdpTables *t = (HdpTables *) nhdp->hdp;
+    if (t->deviceModel >= 0) return t->deviceModel;
+    if (nhdp->kmer_length != KMER_LENGTH) st_errAbort("cpecan: the HDP is over %lld-mers, the alignment over %d-mers", (long long) nhdp->kmer_length, KMER_LENGTH);
+    if (!t->splinesFinalized || t->density.empty()) st_errAbort("cpecan: the HDP holds no finalized distributions");
+    std::vector<int32_t> kmerRow((size_t) NUM_OF_KMERS, -1);
+    for (int k = 0; k < NUM_OF_KMERS; k++) {
+        char km[KMER_LENGTH + 1];
+        for (int j = 0; j < KMER_LENGTH; j++) km[j] = "ACGT"[(k >> (2 * (KMER_LENGTH - 1 - j))) & 3];
+        km[KMER_LENGTH] = 0;
+        const int64_t id = hdpKmerId(nhdp, km, false);
+        if (id >= 0 && id < t->numDps) kmerRow[(size_t) k] = hdpRowOf(t, id);
+    }
+    int32_t id = -1;
+    if (cpecan_cuda_upload_hdp(ctx, t->gridStart, t->gridStop, t->gridLength, (int32_t) (t->density.size() / (size_t) t->gridLength),
+                               t->density.data(), t->slopes.data(), kmerRow.data(), &id) != CPECAN_OK)
+        st_errAbort("cpecan_cuda_upload_hdp: %s", cpecan_cuda_last_error(ctx));
+    t->deviceModel = id;
+    return id;
+}
+
 int32_t modelIdLocked(cpecan_ctx *ctx, StateMachine *sM) {
+    if (sM->type == threeStateHdp) return hdpModelIdLocked(ctx, ((StateMachine3_HDP *) sM)->hdpModel);
     const int nGapX = (sM->type == vanilla || sM->type == echelon) ? 60 : NUM_OF_KMERS;
     auto it = gModels.find(sM);
     if (it != gModels.end()) {
@@ -577,8 +803,15 @@ cpecan_hmm hmmOf(StateMachine *sM) {
         memcpy(h.four_state, t, sizeof(t));
     } else if (sM->type == echelon) {
         h.sm_type = CPECAN_SM_ECHELON;
+    } else if (sM->type == threeStateHdp) {
+        StateMachine3_HDP *m = (StateMachine3_HDP *) sM;
+        h.sm_type = CPECAN_SM_THREE_STATE_HDP;
+        const double t[9] = { m->TRANSITION_MATCH_CONTINUE, m->TRANSITION_MATCH_FROM_GAP_X, m->TRANSITION_MATCH_FROM_GAP_Y,
+                              m->TRANSITION_GAP_OPEN_X, m->TRANSITION_GAP_OPEN_Y, m->TRANSITION_GAP_EXTEND_X,
+                              m->TRANSITION_GAP_EXTEND_Y, m->TRANSITION_GAP_SWITCH_TO_X, m->TRANSITION_GAP_SWITCH_TO_Y };
+        memcpy(h.transitions, t, sizeof(t));
     } else {
-        st_errAbort("cpecan: state machine type %d is not implemented on the GPU (threeState, vanilla, echelon, fourState are)", (int) sM->type);
+        st_errAbort("cpecan: state machine type %d is not implemented on the GPU (threeState, vanilla, echelon, fourState, threeStateHdp are)", (int) sM->type);
     }
     return h;
 }
@@ -612,8 +845,9 @@ void checkSequences(StateMachine *sM, Sequence *sX, Sequence *sY) {
     // the type-erased sequences are recognised by their accessors (SURVEY 7 "Function-pointer API"): anything else
     // cannot be read by the device path
     const bool k2 = sM->type == vanilla || sM->type == echelon;          // vanillaAlign.c:224-249
-    void *(*wantX)(void *, int64_t) = k2 ? sequence_getKmer2 : sequence_getKmer;
-    if (sX->get != wantX) st_errAbort("cpecan: the reference sequence must use %s for this state machine", k2 ? "sequence_getKmer2" : "sequence_getKmer");
+    const bool k3 = sM->type == threeStateHdp;                            // vanillaAlign.c:246-250
+    void *(*wantX)(void *, int64_t) = k2 ? sequence_getKmer2 : (k3 ? sequence_getKmer3 : sequence_getKmer);
+    if (sX->get != wantX) st_errAbort("cpecan: the reference sequence must use %s for this state machine", k2 ? "sequence_getKmer2" : (k3 ? "sequence_getKmer3" : "sequence_getKmer"));
     if (sY->get != sequence_getEvent) st_errAbort("cpecan: the read sequence must be an event sequence (sequence_getEvent)");
 }
 
@@ -708,6 +942,13 @@ void runPosterior(cpecan_ctx *ctx, const cpecan_hmm &hmm, const cpecan_params &p
 }  // namespace
 
 extern "C" {
+
+void cpecan_host_release_hdp_locked(NanoporeHDP *nhdp) {
+    std::lock_guard<std::mutex> lk(gMu);
+    HdpTables *t = (HdpTables *) nhdp->hdp;
+    if (t && t->deviceModel >= 0 && gCtx) cpecan_cuda_release_model(gCtx, t->deviceModel);
+    if (t) t->deviceModel = -1;
+}
 
 void cpecan_host_set_device(int device) {
     std::lock_guard<std::mutex> lk(gMu);

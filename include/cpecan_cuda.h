@@ -29,7 +29,7 @@ enum {
 };
 
 /* State-machine types, numbered as the reference's StateMachineType (inc/stateMachine.h:20-29). */
-enum { CPECAN_SM_THREE_STATE = 2, CPECAN_SM_THREE_STATE_HDP = 3, CPECAN_SM_VANILLA = 4, CPECAN_SM_ECHELON = 5, CPECAN_SM_FOUR_STATE = 6 };
+enum { CPECAN_SM_THREE_STATE = 2, CPECAN_SM_VANILLA = 4, CPECAN_SM_ECHELON = 5, CPECAN_SM_FOUR_STATE = 6, CPECAN_SM_THREE_STATE_HDP = 7 };
 
 /* Work modes. */
 enum {

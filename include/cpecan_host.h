@@ -289,6 +289,34 @@ typedef struct _StateMachine3vanilla {                                          
     double (*getMatchProbFcn)(const double *eventModel, void *kmer, void *event);
 } StateMachine3Vanilla;
 
+/* inc/nanopore_hdp.h:16-22.  Here `hdp` points at this library's own tables (what dir_proc_density reads: the sampling
+ * grid, and per observed Dirichlet process the posterior predictive density and its spline slopes), not at a
+ * HierarchicalDirichletProcess: Gibbs sampling and the construction of HDPs are out of scope. */
+typedef struct _nanoporeHDP {
+    void *hdp;
+    char *alphabet;
+    int64_t alphabet_size;
+    int64_t kmer_length;
+    void *distr_metric_memos;              /* unused */
+} NanoporeHDP;
+
+typedef struct _StateMachine3_HDP {                                                                         /* :197-215 */
+    StateMachine model;
+    double TRANSITION_MATCH_CONTINUE;
+    double TRANSITION_MATCH_FROM_GAP_X;
+    double TRANSITION_MATCH_FROM_GAP_Y;
+    double TRANSITION_GAP_OPEN_X;
+    double TRANSITION_GAP_OPEN_Y;
+    double TRANSITION_GAP_EXTEND_X;
+    double TRANSITION_GAP_EXTEND_Y;
+    double TRANSITION_GAP_SWITCH_TO_X;
+    double TRANSITION_GAP_SWITCH_TO_Y;
+    double (*getXGapProbFcn)(const double *emissionXGapProbs, void *i);
+    NanoporeHDP *hdpModel;
+    double (*getYGapProbFcn)(NanoporeHDP *hdp, void *x, void *y);
+    double (*getMatchProbFcn)(NanoporeHDP *hdp, void *x, void *y);
+} StateMachine3_HDP;
+
 typedef struct _StateMachine4 {                                                                             /* :132-170 */
     StateMachine model;
     double TRANSITION_MATCH_CONTINUE;
@@ -322,6 +350,19 @@ StateMachine *getStrawManStateMachine3(const char *modelFile);                  
 StateMachine *getSignalStateMachine3Vanilla(const char *modelFile);                                         /* :380 */
 StateMachine *getStateMachine4(const char *modelFile);                                                      /* :378 */
 StateMachine *getStateMachineEchelon(const char *modelFile);                                                /* :382 */
+/* threeStateHdp (impl/stateMachine.c:1738-1749): the three-state topology, match and gap-Y emissions =
+ * get_nanopore_kmer_density of the HDP (the density itself, as the reference has it), gap-X emission log(0.1); the
+ * reference sequence must use sequence_getKmer3 (vanillaAlign.c:246-250).  Posteriors only: the HDP expectations
+ * (event-to-k-mer assignment lists, impl/continuousHmm.c:630-749) are not implemented. */
+StateMachine *getHdpStateMachine3(NanoporeHDP *hdp);                                                        /* :376 */
+/* inc/nanopore_hdp.h: reading a serialised NanoporeHDP (impl/nanopore_hdp.c:845-873, impl/hdp.c:3009-3270) and querying it
+ * (impl/nanopore_hdp.c:390-392 -> impl/hdp.c:2577-2599 -> impl/hdp_math_utils.c:471-495) */
+NanoporeHDP *deserialize_nhdp(const char *filepath);
+void destroy_nanopore_hdp(NanoporeHDP *nhdp);
+double get_nanopore_kmer_density(NanoporeHDP *nhdp, void *kmer, void *x);
+int64_t get_nanopore_hdp_kmer_length(NanoporeHDP *nhdp);
+int64_t get_nanopore_hdp_alphabet_size(NanoporeHDP *nhdp);
+char *get_nanopore_hdp_alphabet(NanoporeHDP *nhdp);
 void emissions_signal_scaleModel(StateMachine *sM, double scale, double shift, double var, double scale_sd,
                                  double var_sd);                                                            /* :341-342 */
 void stateMachine3_setTransitionsToNanoporeDefaults(StateMachine *sM);

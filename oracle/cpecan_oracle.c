@@ -30,6 +30,7 @@
 #define MODEL_STRIDE 5
 #define SM_THREE_STATE 2
 #define SM_VANILLA 4
+#define SM_THREE_STATE_HDP 7
 #define SM_FOUR_STATE 6       /* inc/stateMachine.h:20-29 */
 #define SM_ECHELON 5
 #define ECH_GAPX 6             /* match0 .. match5 = 0 .. 5, gapX = 6 (sm:1164-1166) */
@@ -48,6 +49,13 @@ typedef struct {
     double trans[9];          /* threeState, StateMachine3 field order (inc/stateMachine.h:179-187) */
     double vanilla[5];        /* M_TO_Y_NOT_X, E_TO_E, END_MATCH, END_FROM_X, END_FROM_Y */
     double trans4[T4_COUNT];  /* fourState, T4_* order; gapx then holds 4096 zeros (emissions_signal_initEmissionsToZero) */
+    /* threeStateHdp (sm_type 7): what get_nanopore_kmer_density reads of a NanoporeHDP -- the sampling grid
+     * linspace(start, stop, len), per distinct observed Dirichlet process a row of posterior predictive densities and
+     * one of spline slopes, and for every ACGT 6-mer the row it reads (its nearest observed ancestor's) or -1 */
+    const double *hdp_density, *hdp_slopes;
+    const int32_t *hdp_kmer_row;
+    double hdp_start, hdp_stop;
+    int64_t hdp_len;
 } OracleModel;
 
 typedef struct {
@@ -311,6 +319,34 @@ static double duration_prob(const double *ev, int n) {
     return (n + 1) * 0.1397619423751586 + n * log(lambda) - lfact[n] - 2 * lambda;
 }
 
+/* get_nanopore_kmer_density (impl/nanopore_hdp.c:390-392) -> dir_proc_density (impl/hdp.c:2577-2599) ->
+ * grid_spline_interp (impl/hdp_math_utils.c:471-495) on linspace(start, stop, len) (:497-510).  k = ACGT k-mer index. */
+double oracle_hdp_density(const OracleModel *m, int32_t k, double q) {
+    const int64_t n = m->hdp_len;
+    const int32_t row = k >= 0 ? m->hdp_kmer_row[k] : -1;
+    if (row < 0) return NAN;                                  /* the reference exits: character outside the alphabet */
+    const double *y = m->hdp_density + (int64_t) row * n, *slope = m->hdp_slopes + (int64_t) row * n;
+    const double step = (m->hdp_stop - m->hdp_start) / ((double) (n - 1));
+#define HDP_X(i) ((i) == n - 1 ? m->hdp_stop : m->hdp_start + (i) * step)
+    double interp;
+    if (q <= HDP_X(0)) interp = y[0] - slope[0] * (HDP_X(0) - q);
+    else if (q >= HDP_X(n - 1)) interp = y[n - 1] + slope[n - 1] * (q - HDP_X(n - 1));
+    else {
+        double dx = HDP_X(1) - HDP_X(0);
+        int64_t il = (int64_t) ((q - HDP_X(0)) / dx);
+        if (il > n - 2) il = n - 2;
+        int64_t ir = il + 1;
+        double dy = y[ir] - y[il];
+        double a = slope[il] * dx - dy;
+        double b = dy - slope[ir] * dx;
+        double tl = (q - HDP_X(il)) / dx;
+        double tr = 1.0 - tl;
+        interp = tr * y[il] + tl * y[ir] + tl * tr * (a * tr + b * tl);
+    }
+#undef HDP_X
+    return interp > 0.0 ? interp : 0.0;
+}
+
 /* One cell: sm:1305-1334 (threeState) and sm:1368-1409 (vanilla).  ix / iy are SEQUENCE indices (matrix - 1);
  * the neighbour pointers may be NULL exactly as dpDiagonal_getCell returns NULL outside the band (ref:562-568). */
 static void cell(Dp *dp, int mode, double *cur, double *lower, double *middle, double *upper, int64_t ix, int64_t iy) {
@@ -335,6 +371,28 @@ static void cell(Dp *dp, int mode, double *cur, double *lower, double *middle, d
         }
         if (upper) {
             double eP = emit_two_gauss(m->gapy, k, ev);
+            transition(dp, mode, upper, cur, ST_M, ST_Y, eP, t[4], k, 0);
+            transition(dp, mode, upper, cur, ST_Y, ST_Y, eP, t[6], k, 0);
+        }
+    } else if (m->sm_type == SM_THREE_STATE_HDP) {
+        /* stateMachine3HDP_cellCalculate (sm:1336-1366): gap X log(0.1); match and gap Y the DENSITY (not its log) of the
+         * k-mer's distribution at the event mean; sequence_getKmer3 (ref:327-331): index < 0 reads k-mer 0 */
+        int32_t k = kmer_index(dp->ref + (ix >= 0 ? ix : 0));
+        const double *t = m->trans;
+        if (lower) {
+            double eP = -2.3025850929940455;
+            transition(dp, mode, lower, cur, ST_M, ST_X, eP, t[3], k, 0);
+            transition(dp, mode, lower, cur, ST_X, ST_X, eP, t[5], k, 0);
+            transition(dp, mode, lower, cur, ST_Y, ST_X, eP, t[7], k, 0);
+        }
+        if (middle) {
+            double eP = oracle_hdp_density(m, k, ev[0]);
+            transition(dp, mode, middle, cur, ST_M, ST_M, eP, t[0], k, 0);
+            transition(dp, mode, middle, cur, ST_X, ST_M, eP, t[1], k, 0);
+            transition(dp, mode, middle, cur, ST_Y, ST_M, eP, t[2], k, 0);
+        }
+        if (upper) {
+            double eP = oracle_hdp_density(m, k, ev[0]);
             transition(dp, mode, upper, cur, ST_M, ST_Y, eP, t[4], k, 0);
             transition(dp, mode, upper, cur, ST_Y, ST_Y, eP, t[6], k, 0);
         }
@@ -524,7 +582,7 @@ static void state_vector(const OracleModel *m, int which /*0 start,1 raggedStart
     }
     if (which == 0) { v[0] = 0; v[1] = NEG_INF; v[2] = NEG_INF; return; }                 /* sm:1168-1172 */
     if (which == 1) { v[0] = NEG_INF; v[1] = 0; v[2] = 0; return; }                       /* sm:1174-1177 */
-    if (m->sm_type == SM_THREE_STATE) {
+    if (m->sm_type == SM_THREE_STATE || m->sm_type == SM_THREE_STATE_HDP) {
         const double *t = m->trans;
         if (which == 2) { v[0] = t[0]; v[1] = t[1]; v[2] = t[2]; }                        /* sm:1179-1192 */
         else { v[0] = (t[3] + t[4]) / 2.0; v[1] = t[5]; v[2] = t[6]; }                    /* sm:1194-1207 */

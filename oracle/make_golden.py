@@ -186,7 +186,87 @@ def vanilla_align_goldens():
                        capture_output=True, text=True, check=True)
 
 
+def descale_first_third(events, scale, shift):
+    """nanopore_descaleNanoporeRead as the reference has it (impl/nanopore.c:34-38, 228-236): the loop runs over the flat
+    array index in steps of NB_EVENT_PARAMS but stops at the NUMBER of events, so only the means of the first third of
+    the events are descaled."""
+    ev = np.array(events, dtype=np.float64).reshape(-1, 3).copy()
+    k = (len(ev) + 2) // 3
+    ev[:k, 0] = (ev[:k, 0] - shift) / scale
+    return ev
+
+
+def hdp_goldens():
+    """threeStateHdp from the UNMODIFIED reference with its HDP sources (`make -C oracle refHdp
+    vanillaAlignHdp`): the reference's serialised fixture tests/test_hdp/testTemplate.nhdp is committed (gzip) as
+    tests/golden/hdp/testTemplate.nhdp.gz; goldens are get_nanopore_kmer_density on it, getAlignedPairsUsingAnchors with
+    getHdpStateMachine3 on the fixture read (descaled as vanillaAlign does), and the CLI's own `-d` posterior file."""
+    import ctypes as C
+    import gzip
+    import shutil
+    import subprocess
+    import tempfile
+    from cpecan_signal import hdp as H
+    ref_dir = os.path.join(HERE, "_ref")
+    out_dir = os.path.join(GOLDEN, "hdp")
+    os.makedirs(out_dir, exist_ok=True)
+    src = os.path.join(REFERENCE, "tests", "test_hdp", "testTemplate.nhdp")
+    with open(src, "rb") as fi, gzip.GzipFile(os.path.join(out_dir, "testTemplate.nhdp.gz"), "wb", mtime=0) as fo:
+        shutil.copyfileobj(fi, fo)
+    lib = C.CDLL(os.path.join(ref_dir, "libcpecan_ref_hdp.so"))
+    lib.ref_hdp_density.restype = C.c_int64
+    lib.ref_hdp_align_banded.restype = C.c_int64
+    h = H.load_nhdp(src)
+    # k-mers: every one with a Dirichlet process of its own that was observed, and every 37th of the rest
+    own = [k for k in range(4096) if h.kmer_distr[k] != h.row[-1]]
+    ks = np.array(sorted(set(own) | set(range(0, 4096, 37))), dtype=np.int64)
+    kmers = "".join("".join("ACGT"[(k >> (2 * (5 - j))) & 3] for j in range(6)) for k in ks)
+    xs = np.array([-5.0, 0.0, 0.3, 30.5, 45.123, 50.0, 50.50505050505051, 55.55, 60.606, 65.4321, 70.0, 80.8, 99.5, 100.0,
+                   101.010101, 140.0])
+    dens = np.zeros((len(ks), len(xs)))
+    lib.ref_hdp_density(src.encode(), kmers.encode(), C.c_int64(len(ks)), xs.ctypes.data_as(C.c_void_p), C.c_int64(len(xs)),
+                        dens.ctypes.data_as(C.c_void_p))
+    out = {"density_kmers": ks, "density_x": xs, "density": dens}
+    print("hdp density", dens.shape, float(dens.max()), int((dens == 0).sum()))
+    g = dict(np.load(os.path.join(GOLDEN, "zymo_golden.npz")))
+    ref = open(os.path.join(GOLDEN, "ZymoRef.txt")).readline().strip()
+    rd = R.load_npread(os.path.join(GOLDEN, "ZymoC_ch_1_file1.npRead"))
+    tp = rd["template_params"]
+    ev = descale_first_third(rd["template_events"], tp[0], tp[1])
+    anch = np.ascontiguousarray(g["anchors_template"], dtype=np.int64)
+    lX, lY = len(ref) - 5, len(ev)
+    for tag, e, ragged, thr in (("hdp_e20_r00", 20, (0, 0), 0.01), ("hdp_e50_r11", 50, (1, 1), 0.01), ("hdp_e20_r10_t30", 20, (1, 0), 0.3)):
+        prm = R.default_params(diagonalExpansion=e, threshold=thr)
+        cap = 64 * (lX + lY) + 1024
+        pairs = np.zeros((cap, 3), dtype=np.int64)
+        totals = np.zeros(lX + lY + 1)
+        n = lib.ref_hdp_align_banded(src.encode(), ref.encode(), ev.ctypes.data_as(C.c_void_p), C.c_int64(lY),
+                                     anch.ctypes.data_as(C.c_void_p), C.c_int64(len(anch)), C.byref(prm), ragged[0], ragged[1],
+                                     pairs.ctypes.data_as(C.c_void_p), C.c_int64(cap), totals.ctypes.data_as(C.c_void_p),
+                                     C.c_int64(len(totals)))
+        assert 0 <= n <= cap
+        out[tag + "_pairs"] = pairs[:n].copy()
+        out[tag + "_totals"] = totals
+        print(tag, n, int(pairs[:n, 0].sum()))
+    np.savez_compressed(os.path.join(out_dir, "zymo_hdp_golden.npz"), **out)
+    # the CLI: vanillaAlign -d with the same HDP for both strands
+    cigar = open(os.path.join(GOLDEN, "vanillaAlign", "guide.cigar")).read()
+    with tempfile.TemporaryDirectory() as td:
+        tsv = os.path.join(td, "out_d.tsv")
+        r = subprocess.run([os.path.join(ref_dir, "vanillaAlign_hdp"), "-d", "-v", src, "-w", src, "-T", T_MODEL, "-C", C_MODEL,
+                            "-L", "readA", "-q", os.path.join(GOLDEN, "ZymoC_ch_1_file1.npRead"),
+                            "-r", os.path.join(GOLDEN, "ZymoRef.txt"), "-u", tsv], input=cigar, capture_output=True, text=True,
+                           check=True)
+        open(os.path.join(GOLDEN, "vanillaAlign", "stdout_d.txt"), "w").write(r.stdout)
+        with open(tsv, "rb") as fi, gzip.GzipFile(os.path.join(GOLDEN, "vanillaAlign", "out_d.tsv.gz"), "wb", mtime=0) as fo:
+            shutil.copyfileobj(fi, fo)
+        print("vanillaAlign -d:", r.stdout.strip())
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "hdp":
+        hdp_goldens()
+        sys.exit(0)
     main()
     four_state_goldens()
     vanilla_align_goldens()

@@ -14,7 +14,9 @@ THREE_STATE = 2
 VANILLA = 4
 FOUR_STATE = 6
 ECHELON = 5
+THREE_STATE_HDP = 7
 N_KMERS = 4096
+MODEL_STRIDE = 5
 
 # stateMachine3_setTransitionsToNanoporeDefaults (reference impl/stateMachine.c:1278-1289), StateMachine3 field order
 NANOPORE_TRANSITIONS = np.array([
@@ -47,7 +49,8 @@ FOUR_STATE_TRANSITIONS = np.array([
 class OracleModel(C.Structure):
     _fields_ = [("sm_type", C.c_int32), ("strand", C.c_int32), ("match", C.c_void_p), ("gapy", C.c_void_p),
                 ("gapx", C.c_void_p), ("trans", C.c_double * 9), ("vanilla", C.c_double * 5),
-                ("trans4", C.c_double * 11)]
+                ("trans4", C.c_double * 11), ("hdp_density", C.c_void_p), ("hdp_slopes", C.c_void_p),
+                ("hdp_kmer_row", C.c_void_p), ("hdp_start", C.c_double), ("hdp_stop", C.c_double), ("hdp_len", C.c_int64)]
 
 
 class OracleParams(C.Structure):
@@ -101,8 +104,21 @@ def load_model_file(path):
 class Model:
     """Host-side bundle of the tables a StateMachine3 / StateMachine3Vanilla carries."""
 
-    def __init__(self, sm_type, model_file=None, tables=None, scale5=None, strand=None, transitions=None, gap_x=None):
+    def __init__(self, sm_type, model_file=None, tables=None, scale5=None, strand=None, transitions=None, gap_x=None,
+                 hdp=None):
         self.sm_type = sm_type
+        self.hdp = hdp
+        if sm_type == THREE_STATE_HDP:
+            # getHdpStateMachine3: the three-state transitions; emissions from the HDP (an object with grid_start,
+            # grid_stop, grid_length, density[n, L], slopes[n, L], kmer_distr[4096]: cpecan_signal.hdp.load_nhdp's)
+            self.match = self.gapy = np.zeros(1 + N_KMERS * MODEL_STRIDE)
+            self.gapx = np.full(N_KMERS, -2.3025850929940455)
+            self.trans = np.array(NANOPORE_TRANSITIONS if transitions is None else transitions, dtype=np.float64)
+            self.vanilla = np.zeros(5)
+            self._hd = np.ascontiguousarray(hdp.density, dtype=np.float64)
+            self._hs = np.ascontiguousarray(hdp.slopes, dtype=np.float64)
+            self._hk = np.ascontiguousarray(hdp.kmer_distr, dtype=np.int32)
+            return
         l1, l2, l3 = tables if tables is not None else load_model_file(model_file)
         self.match = np.ascontiguousarray(l1, dtype=np.float64).copy()
         self.gapy = np.ascontiguousarray(l3, dtype=np.float64).copy()
@@ -135,7 +151,20 @@ class Model:
             m.vanilla[i] = self.vanilla[i]
         for i in range(11):
             m.trans4[i] = FOUR_STATE_TRANSITIONS[i]
+        if self.sm_type == THREE_STATE_HDP:
+            m.hdp_density = self._hd.ctypes.data
+            m.hdp_slopes = self._hs.ctypes.data
+            m.hdp_kmer_row = self._hk.ctypes.data
+            m.hdp_start, m.hdp_stop, m.hdp_len = float(self.hdp.grid_start), float(self.hdp.grid_stop), int(self.hdp.grid_length)
         return m
+
+
+def hdp_density(model, kmer_index, x):
+    """oracle_hdp_density: get_nanopore_kmer_density of an HDP Model for one ACGT k-mer index at x."""
+    f = lib().oracle_hdp_density
+    f.restype = C.c_double
+    cs = model.cstruct()
+    return f(C.byref(cs), C.c_int32(int(kmer_index)), C.c_double(float(x)))
 
 
 def _iptr(a):

@@ -392,3 +392,51 @@ int64_t ref_load_vanilla_hmm(const char *hmmPath, const char *modelFile, double 
     freeStateMachine(sM);
     return 0;
 }
+
+#ifdef STANDIN_REAL_HDP
+/* ---- threeStateHdp: only in oracle/_ref/libcpecan_ref_hdp.so, which also links the reference's HDP
+ * sources (impl/hdp.c, impl/nanopore_hdp.c, impl/hdp_math_utils.c, impl/ranlib.c, impl/rnglib.c). */
+#include "nanopore_hdp.h"
+
+/* get_nanopore_kmer_density of a serialised NanoporeHDP: out[i * nx + j] for k-mer i (6 characters each) at x[j] */
+int64_t ref_hdp_density(const char *nhdpFile, const char *kmers, int64_t nKmers, const double *x, int64_t nx, double *out) {
+    NanoporeHDP *nhdp = deserialize_nhdp(nhdpFile);
+    for (int64_t i = 0; i < nKmers; i++) {
+        char km[7];
+        memcpy(km, kmers + 6 * i, 6); km[6] = 0;
+        for (int64_t j = 0; j < nx; j++) { double q = x[j]; out[i * nx + j] = get_nanopore_kmer_density(nhdp, km, &q); }
+    }
+    destroy_nanopore_hdp(nhdp);
+    return nKmers * nx;
+}
+
+/* getAlignedPairsUsingAnchors with getHdpStateMachine3 and sequence_getKmer3 (vanillaAlign.c:132-135, 246-250) */
+int64_t ref_hdp_align_banded(const char *nhdpFile, const char *refSeq, const double *events, int64_t lY,
+                             const int64_t *anchors, int64_t nAnchors, const RefParams *rp,
+                             int raggedLeft, int raggedRight, int64_t *out, int64_t cap,
+                             double *totalsOut, int64_t totalsLen) {
+    NanoporeHDP *nhdp = deserialize_nhdp(nhdpFile);
+    StateMachine *sM = getHdpStateMachine3(nhdp);
+    PairwiseAlignmentParameters *p = makeParams(rp);
+    int64_t lX = sequence_correctSeqLength(strlen(refSeq), event);
+    Sequence *sX = sequence_construct2(lX, (void *) refSeq, sequence_getKmer3, sequence_sliceNucleotideSequence2);
+    Sequence *sY = sequence_construct2(lY, (void *) events, sequence_getEvent, sequence_sliceEventSequence2);
+    stList *anchorList = makeAnchors(anchors, nAnchors);
+    g_totals = totalsOut; g_totalsLen = totalsLen;
+    if (totalsOut) for (int64_t i = 0; i < totalsLen; i++) totalsOut[i] = NAN;
+    stList *pairs = getAlignedPairsUsingAnchors(sM, sX, sY, anchorList, p,
+                                                totalsOut ? recordingPosteriorFn : diagonalCalculationPosteriorMatchProbs,
+                                                raggedLeft, raggedRight);
+    g_totals = NULL; g_totalsLen = 0;
+    int64_t n = drainPairs(pairs, out, cap);
+    stList_destruct(anchorList);
+    sequence_sequenceDestroy(sX);
+    sequence_sequenceDestroy(sY);
+    pairwiseAlignmentBandingParameters_destruct(p);
+    freeStateMachine(sM);
+    destroy_nanopore_hdp(nhdp);
+    return n;
+}
+
+/* nanopore_descaleNanoporeRead on a loaded .npRead (vanillaAlign.c:609-612): events in place */
+#endif

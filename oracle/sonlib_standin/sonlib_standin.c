@@ -245,7 +245,8 @@ void stList_destructIterator(stListIterator *it) { free(it); }
 
 #define SET_TOMB ((void *) 1)
 struct _stSet { void **slot; int64_t cap, n, used; void (*destructElement)(void *); };
-struct _stSetIterator { stSet *s; int64_t i; };
+/* the iterator walks a snapshot: impl/hdp.c destroys sets (and the factors in them) while iterating over them */
+struct _stSetIterator { void **items; int64_t n, i; };
 static uint64_t ptrHash(void *p) { uint64_t x = (uint64_t) (uintptr_t) p; x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; return x; }
 stSet *stSet_construct2(void (*d)(void *)) {
     stSet *s = st_calloc(1, sizeof(*s));
@@ -291,12 +292,14 @@ void *stSet_remove(stSet *s, void *item) {
     return item;
 }
 int64_t stSet_size(stSet *s) { return s->n; }
-stSetIterator *stSet_getIterator(stSet *s) { stSetIterator *it = st_malloc(sizeof(*it)); it->s = s; it->i = 0; return it; }
-void *stSet_getNext(stSetIterator *it) {
-    while (it->i < it->s->cap) { void *p = it->s->slot[it->i++]; if (p && p != SET_TOMB) return p; }
-    return NULL;
+stSetIterator *stSet_getIterator(stSet *s) {
+    stSetIterator *it = st_malloc(sizeof(*it));
+    it->items = st_malloc(sizeof(void *) * (s->n ? s->n : 1)); it->n = 0; it->i = 0;
+    for (int64_t k = 0; k < s->cap; k++) if (s->slot[k] && s->slot[k] != SET_TOMB) it->items[it->n++] = s->slot[k];
+    return it;
 }
-void stSet_destructIterator(stSetIterator *it) { free(it); }
+void *stSet_getNext(stSetIterator *it) { return it->i < it->n ? it->items[it->i++] : NULL; }
+void stSet_destructIterator(stSetIterator *it) { free(it->items); free(it); }
 
 stList *stString_splitByString(const char *s, const char *delim) {
     stList *l = stList_construct3(0, free);
