@@ -513,7 +513,7 @@ def test_argument_errors_are_reported(engine, template_tables):
         engine.align_batch(hb60)                                   # three-state needs 4096 entries
     engine.align_batch(hb60, hmm=vanilla_hmm("template"))          # vanilla is fine with 60
     bad = Hmm()
-    bad.sm_type = 3                                                # threeState_hdp: not implemented on device
+    bad.sm_type = 3                                                # threeStateAsymmetric: not a signal machine
     with pytest.raises(EngineError, match="not implemented"):
         engine.align_batch(hb, hmm=bad)
     # a band wider than the widest shared-memory ring (a long read without anchors): refused, not mis-computed

@@ -37,7 +37,7 @@ def test_host_library_exports_header_symbols():
     txt = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "cpecan_host.h")).read(), flags=re.S)
     names = set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\((?!\*)", txt)) - {"defined", "void", "sizeof"}
     names = {n for n in names if re.search(r"^(st|sequence_|pairwise|diagonal|band|logAdd|get|sort|filter|emissions_|stateMachine|hmm|vanillaHmm|"
-                                           r"continuousPairHmm|nanopore_|cpecan_host|cigarRead|destructPairwise|checkPairwise|convertPairwise|cell_|dpDiagonal_|dpMatrix_)", n)}
+                                           r"continuousPairHmm|nanopore_|cpecan_host|deserialize_|destroy_|cigarRead|destructPairwise|checkPairwise|convertPairwise|cell_|dpDiagonal_|dpMatrix_)", n)}
     assert len(names) > 120
     for n in sorted(names):
         assert hasattr(lib, n), "libcpecan_host.so does not export %s" % n
