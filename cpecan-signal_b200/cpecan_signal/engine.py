@@ -379,6 +379,25 @@ class Engine:
                                                             results.ctypes.data_as(C.c_void_p)), "expectations_batch")
         return out, results
 
+    def hdp_expectations_batch(self, batch, hmm=None, params=None, out=None, pseudocount=0.0, assignment_cap=None):
+        """getExpectationsUsingAnchors with an HdpHmm over a batch: (expectations[9 + 4096 + 1] with the transition sums in
+        [0, 9) and the likelihood last, results, assignments int32 [cap, 3] = (from state, k-mer position, event index);
+        item i owns assignments[results[i].pair_off : + n_pairs] (item_pairs())."""
+        hmm = hmm or hdp_hmm()
+        params = params or default_params()
+        if out is None:
+            out = np.zeros(self.N_EXPECT, dtype=np.float64)
+            out[:9] = float(pseudocount)
+        cap = int(assignment_cap if assignment_cap is not None else 48 * (int(batch.ev_off[-1]) + 32 * batch.n) + 1024)
+        asg = np.zeros((cap, 3), dtype=np.int32)
+        results = np.zeros(batch.n, dtype=RESULT_DTYPE)
+        cb = batch.cstruct()
+        self._check(self.lib.cpecan_cuda_hdp_expectations_batch(self.ctx, C.byref(hmm), C.byref(params), C.byref(cb),
+                                                                out.ctypes.data_as(C.c_void_p), asg.ctypes.data_as(C.c_void_p),
+                                                                C.c_int64(cap), results.ctypes.data_as(C.c_void_p)),
+                    "hdp_expectations_batch")
+        return out, results, asg
+
     def expectations_device_ptr(self):
         p = C.c_void_p()
         self._check(self.lib.cpecan_cuda_expectations_device_ptr(self.ctx, C.byref(p)), "expectations_device_ptr")

@@ -268,6 +268,14 @@ int fillMachine(cpecan_ctx *ctx, const cpecan_hmm *hmm) {
     return CPECAN_OK;
 }
 
+// threeState / vanilla on the FP64 kernel
+void routeGeneric(cpecan_ctx *ctx, const cpecan_hmm *hmm) {
+    ctx->generic = hmm->sm_type;
+    ctx->G.sm = hmm->sm_type;
+    for (int i = 0; i < 9; i++) ctx->G.t3[i] = hmm->transitions[i];
+    for (int i = 0; i < 5; i++) ctx->G.van[i] = hmm->vanilla[i];
+}
+
 int fillDevParams(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *p, int mode) {
     if (p->diagonalExpansion < 0 || p->traceBackDiagonals < 1 ||
         p->minDiagsBetweenTraceBack < 2 || p->traceBackDiagonals + 1 >= p->minDiagsBetweenTraceBack) {
@@ -276,26 +284,14 @@ int fillDevParams(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *p
     }
     int rc = fillMachine(ctx, hmm);
     if (rc != CPECAN_OK) return rc;
-    if (ctx->generic && mode == CPECAN_MODE_EXPECTATION) {
-        ctx->err = hmm->sm_type == CPECAN_SM_THREE_STATE_HDP
-            ? "expectations of the threeStateHdp machine (event-to-k-mer assignment lists) are not implemented on device"
-            : "expectations are not defined for the fourState / echelon machines (the reference has no update function for them)";
+    if ((ctx->generic == CPECAN_SM_FOUR_STATE || ctx->generic == CPECAN_SM_ECHELON) && mode == CPECAN_MODE_EXPECTATION) {
+        ctx->err = "expectations are not defined for the fourState / echelon machines (the reference has no update function for them)";
         return CPECAN_ERR_ARG;
     }
-    if (!ctx->generic && (p->diagonalExpansion % 2 != 0 || (ctx->exact && mode != CPECAN_MODE_EXPECTATION))) {
-        // with an odd expansion band_construct's band edges move backwards and by two cells from one diagonal to the next
-        // (impl/pairwiseAligner.c:98-170): k_align3's one-step band walk does not take that; the FP64 kernel, which reads
-        // explicit band edges, does
-        // (and it is the one cpecan_cuda_set_exact_arithmetic asks for)
-        if (mode == CPECAN_MODE_EXPECTATION) {
-            ctx->err = "expectations need an even diagonalExpansion (posteriors take odd ones too, on the FP64 kernel; see INTEGRATION.md)";
-            return CPECAN_ERR_ARG;
-        }
-        ctx->generic = hmm->sm_type;
-        ctx->G.sm = hmm->sm_type;
-        for (int i = 0; i < 9; i++) ctx->G.t3[i] = hmm->transitions[i];
-        for (int i = 0; i < 5; i++) ctx->G.van[i] = hmm->vanilla[i];
-    }
+    // with an odd expansion band_construct's band edges move backwards and by two cells from one diagonal to the next
+    // (impl/pairwiseAligner.c:98-170): k_align3's one-step band walk does not take that; the FP64 kernel, which reads
+    // explicit band edges, does (and it is the one cpecan_cuda_set_exact_arithmetic asks for)
+    if (!ctx->generic && (p->diagonalExpansion % 2 != 0 || ctx->exact)) routeGeneric(ctx, hmm);
     ctx->G.threshold = p->threshold;
     DevParams &P = ctx->P;
     P.threshold = (float) p->threshold;
@@ -681,11 +677,13 @@ int cpecan_cuda_restage_model(cpecan_ctx *ctx, const cpecan_hmm *hmm) {
     std::lock_guard<std::mutex> lk(ctx->mu);
     CK(cudaSetDevice(ctx->device));
     if (ctx->running) { ctx->err = "restage_model: a run is in flight"; return CPECAN_ERR_ARG; }
-    const int machineBefore = ctx->machine;
+    const int machineBefore = ctx->machine, genericBefore = ctx->generic;
     int rc = fillMachine(ctx, hmm);
     if (rc != CPECAN_OK) return rc;
+    if (genericBefore && !ctx->generic) routeGeneric(ctx, hmm);      // the staged batch runs on the FP64 kernel (odd expansion / exact)
     if (ctx->n == 0) return CPECAN_OK;
-    if (ctx->machine != machineBefore) { ctx->err = "restage_model: the staged batch was prepared for the other state machine"; return CPECAN_ERR_ARG; }
+    if (ctx->machine != machineBefore || ctx->generic != genericBefore) { ctx->err = "restage_model: the staged batch was prepared for the other state machine"; return CPECAN_ERR_ARG; }
+    if (ctx->generic) return CPECAN_OK;                               // that kernel reads the transitions from its arguments, the tables in place
     launchPrepX(ctx, ctx->stream);
     CK(cudaGetLastError());
     CK(waitStream(ctx, ctx->stream));
@@ -741,7 +739,7 @@ int runAsyncL(cpecan_ctx *ctx) {
             g.bands = ctx->dBands.as<int2>(); g.band_off = ctx->dBandOff.as<long long>(); g.tbs = a.tbs; g.flags = a.flags;
             g.scratch = reinterpret_cast<double *>(a.scratch); g.scratch_stride = bk.stride * 2;
             g.ring_rows = bk.ringRows; g.ringN = cfg2N(b);
-            g.pairs = a.pairs; g.out = a.out; g.totals = a.totals; g.P = ctx->P; g.G = ctx->G;
+            g.pairs = a.pairs; g.out = a.out; g.totals = a.totals; g.expect = a.expect; g.P = ctx->P; g.G = ctx->G;
             dispatchGen(ctx->generic, [&](auto k, int S) {
                 k<<<bk.nCta, 32, generic_smem_bytes(cfg2N(b), S), ctx->bstream[b]>>>(g); return 0; });
         } else
@@ -891,6 +889,22 @@ int cpecan_cuda_expectations_batch(cpecan_ctx *ctx, const cpecan_hmm *hmm, const
     if (rc == CPECAN_OK) rc = runAsyncL(ctx);
     if (rc == CPECAN_OK) rc = waitL(ctx);
     if (rc == CPECAN_OK) rc = fetchL(ctx, nullptr, results);
+    if (rc == CPECAN_OK && ctx->n > 0) rc = fetchExpectL(ctx, expectations_out);
+    return rc;
+}
+
+int cpecan_cuda_hdp_expectations_batch(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *params,
+                                       const cpecan_batch *batch, double *expectations_out, int32_t *assignments_out,
+                                       int64_t assignment_cap_total, cpecan_result *results) {
+    if (!ctx) return CPECAN_ERR_CUDA;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!hmm || !params || !batch || batch->n_items < 0) { ctx->err = "hdp_expectations_batch: null argument"; return CPECAN_ERR_ARG; }
+    if (!expectations_out || !results || (!assignments_out && assignment_cap_total > 0)) { ctx->err = "hdp_expectations_batch: null output"; return CPECAN_ERR_ARG; }
+    if (hmm->sm_type != CPECAN_SM_THREE_STATE_HDP) { ctx->err = "hdp_expectations_batch: the state machine is not threeStateHdp"; return CPECAN_ERR_ARG; }
+    int rc = stageL(ctx, hmm, params, CPECAN_MODE_EXPECTATION, batch, assignment_cap_total, false);
+    if (rc == CPECAN_OK) rc = runAsyncL(ctx);
+    if (rc == CPECAN_OK) rc = waitL(ctx);
+    if (rc == CPECAN_OK) rc = fetchL(ctx, assignments_out, results);
     if (rc == CPECAN_OK && ctx->n > 0) rc = fetchExpectL(ctx, expectations_out);
     return rc;
 }

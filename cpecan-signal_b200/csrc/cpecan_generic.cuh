@@ -59,6 +59,7 @@ struct KernelArgsG {
     int *pairs;
     ItemOut *out;
     double *totals;
+    double *expect;               // EXPECTATION mode: the batch sums (layout of CPECAN_N_EXPECT / CPECAN_N_EXPECT_VANILLA)
     DevParams P;
     GenParams G;
 };
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(32) k_align_generic(const KernelArgsG A) {
         double sc = 1, sh = 0, var = 1, scsd = 1, varsd = 1;
         if (scaled) { const double *s5 = A.scale + 5 * itemIdx; sc = s5[0]; sh = s5[1]; var = s5[2]; scsd = s5[3]; varsd = s5[4]; }
         int nPairs = 0, status = 0, nTb = 0;
-        double lastTotal = 0.0;
+        double lastTotal = 0.0, lik = 0.0;
 
         auto bandOf = [&](int d, int &l, int &h) { if (d >= 0 && d <= D) { const int2 b = bandp[d]; l = b.x; h = b.y; } else { l = 0; h = -1; } };
         // the padded nucleotide sequence (sequence_padSequence, impl/pairwiseAligner.c:282-285) and its k-mer index
@@ -187,15 +188,34 @@ __global__ void __launch_bounds__(32) k_align_generic(const KernelArgsG A) {
         // One cell in the reference's transition order.  FWD: cur[to] (+)= nb[from] + (eP + tP) (pull); BWD: the same
         // statement with the roles swapped (push), impl/pairwiseAligner.c:365-383.  lo / mi / up: the neighbours
         // (x-1, y), (x-1, y-1), (x, y-1), has*: whether they exist (inside the band of a live diagonal).
-        auto cellGen = [&](bool fwd, int x, int y, double *cur, double *lo_, bool hasLo, double *mi_, bool hasMi,
+        // Expectation mode (diagonalCalculation_Expectations, impl/pairwiseAligner.c:841-863): cur = the cell's BACKWARD values,
+        // the neighbours' FORWARD values; every transition's posterior p = exp(F + B + (eP + tP) - total) goes to
+        //   threeState: the 3 x 3 transition sums and, into gap X, the k-mer's skip count (:425-443)
+        //   vanilla:    the skip bin's beta (match -> gap X) or alpha (gap X -> gap X) count (:478-498)
+        //   HDP:        the transition sums, and a match with p >= threshold is an event-to-k-mer ASSIGNMENT (:445-476)
+        double accT[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+        double expTotal = 0.0;
+        int expK = -1, expBin = 0, asgMask = 0;
+        auto expUp = [&](int from, int to, double p) {
+            if (SM == 2) { accT[from * 3 + to] += p; if (to == 1 && expK >= 0) atomicAdd(A.expect + 9 + expK, p); }
+            else if (SM == 7) { accT[from * 3 + to] += p; if (to == 0 && p >= A.G.threshold) asgMask |= 1 << from; }
+            else if (SM == 4) {
+                if (from == 0 && to == 1) atomicAdd(A.expect + expBin, p);
+                if (from == 1 && to == 1) atomicAdd(A.expect + expBin + 30, p);
+            }
+        };
+        auto cellGen = [&](int fwd, int x, int y, double *cur, double *lo_, bool hasLo, double *mi_, bool hasMi,
                            double *up_, bool hasUp) {
-#define TRG(nb, from, to, eptp) do { if (fwd) cur[to] = g_la(cur[to], nb[from] + (eptp)); else nb[from] = g_la(nb[from], cur[to] + (eptp)); } while (0)
+#define TRG(nb, from, to, eptp) do { if (fwd == 1) cur[to] = g_la(cur[to], nb[from] + (eptp)); \
+                                     else if (fwd == 0) nb[from] = g_la(nb[from], cur[to] + (eptp)); \
+                                     else expUp(from, to, exp(nb[from] + cur[to] + (eptp) - expTotal)); } while (0)
             double em, en, edur;
             eventOf(y, em, en, edur);
             if (SM == 2) {
                 // stateMachine3_cellCalculate (impl/stateMachine.c:1305-1334); sequence_getKmer: index < 0 reads "n"
                 const int k = x >= 1 ? kmerAt(x - 1) : -1;
                 const double *t = A.G.t3;
+                expK = k;
                 if (hasLo) {
                     const double eP = k < 0 ? NI : mt.gapx[k];
                     TRG(lo_, 0, 1, eP + t[3]); TRG(lo_, 1, 1, eP + t[5]); TRG(lo_, 2, 1, eP + t[7]);
@@ -238,6 +258,7 @@ __global__ void __launch_bounds__(32) k_align_generic(const KernelArgsG A) {
                 matchParams(k, mu1, sd, nu, tau, lam);
                 long long bin = (long long) (fabs(mu1 - mu0) / 0.5);
                 bin = bin >= 30 ? 29 : bin;
+                expBin = (int) bin;
                 const double a_mx = mt.gapx[bin];
                 const double a_my = (1 - a_mx) * A.G.van[0];
                 const double a_mm = 1.0f - a_my - a_mx;
@@ -398,7 +419,7 @@ __global__ void __launch_bounds__(32) k_align_generic(const KernelArgsG A) {
                             nm[st] = hasMi ? F2[st * N + ((x - 1) & NM)] : NI;
                             nu_[st] = hasUp ? F1[st * N + (x & NM)] : NI;
                         }
-                        cellGen(true, x, d - x, cur, nl, hasLo, nm, hasMi, nu_, hasUp);
+                        cellGen(1, x, d - x, cur, nl, hasLo, nm, hasMi, nu_, hasUp);
                         double *rp = rowPtr(d, x);
 #pragma unroll
                         for (int st = 0; st < S; st++) { F0[st * N + (x & NM)] = cur[st]; rp[st] = cur[st]; }
@@ -446,14 +467,14 @@ __global__ void __launch_bounds__(32) k_align_generic(const KernelArgsG A) {
                             if (hasMi) {
 #pragma unroll
                                 for (int st = 0; st < S; st++) nb[st] = B2[st * N + ((x - 1) & NM)];
-                                cellGen(false, x, d - x, cur, nullptr, false, nb, true, nullptr, false);
+                                cellGen(0, x, d - x, cur, nullptr, false, nb, true, nullptr, false);
 #pragma unroll
                                 for (int st = 0; st < S; st++) B2[st * N + ((x - 1) & NM)] = nb[st];
                             }
                             if (hasUp) {
 #pragma unroll
                                 for (int st = 0; st < S; st++) nb[st] = B1[st * N + (x & NM)];
-                                cellGen(false, x, d - x, cur, nullptr, false, nullptr, false, nb, true);
+                                cellGen(0, x, d - x, cur, nullptr, false, nullptr, false, nb, true);
 #pragma unroll
                                 for (int st = 0; st < S; st++) B1[st * N + (x & NM)] = nb[st];
                             }
@@ -461,7 +482,7 @@ __global__ void __launch_bounds__(32) k_align_generic(const KernelArgsG A) {
                             if (hasLo) {
 #pragma unroll
                                 for (int st = 0; st < S; st++) nb[st] = B1[st * N + ((x - 1) & NM)];
-                                cellGen(false, x, d - x, cur, nb, true, nullptr, false, nullptr, false);
+                                cellGen(0, x, d - x, cur, nb, true, nullptr, false, nullptr, false);
 #pragma unroll
                                 for (int st = 0; st < S; st++) B1[st * N + ((x - 1) & NM)] = nb[st];
                             }
@@ -508,7 +529,7 @@ __global__ void __launch_bounds__(32) k_align_generic(const KernelArgsG A) {
 #pragma unroll
                                         for (int st = 0; st < S; st++) nm[st] = rp[st];
                                     }
-                                    cellGen(true, x, d + 1 - x, a, nullptr, false, nm, hasMi, nullptr, false);
+                                    cellGen(1, x, d + 1 - x, a, nullptr, false, nm, hasMi, nullptr, false);
                                 }, Bp, lp, hp);
                                 tot = g_la(tot, t2);
                             }
@@ -518,6 +539,46 @@ __global__ void __launch_bounds__(32) k_align_generic(const KernelArgsG A) {
                         }
                         if (d == D) lastTotal = total;
                         if (dbgTot != nullptr && lane == 0) dbgTot[d] = total;
+                        if (P.mode == 1) {
+                            // expectations of this diagonal; a diagonal whose total is not finite contributes nothing
+                            if (S == 3 && total > -1e300 && total < 1e300) {
+                                lik += total;
+                                expTotal = total;
+                                for (int xb = blo; xb <= bhi; xb += 32) {
+                                    const int x = xb + lane, y = d - x;
+                                    asgMask = 0;
+                                    if (x <= bhi) {
+                                        double cur[S], nl[S], nm[S], nu_[S];
+                                        // the previous traceback freed the forward diagonals below the one it stopped at
+                                        // (impl/pairwiseAligner.c:983-990): on the first diagonal above it, "middle" is NULL
+                                        const bool hasLo = x - 1 >= l1 && x - 1 <= h1, hasUp = x >= l1 && x <= h1,
+                                                   hasMi = d - 2 >= tracedBackTo && x - 1 >= l2 && x - 1 <= h2;
+#pragma unroll
+                                        for (int st = 0; st < S; st++) {
+                                            cur[st] = B0[st * N + (x & NM)];
+                                            nl[st] = hasLo ? rowPtr(d - 1, x - 1)[st] : NI;
+                                            nm[st] = hasMi ? rowPtr(d - 2, x - 1)[st] : NI;
+                                            nu_[st] = hasUp ? rowPtr(d - 1, x)[st] : NI;
+                                        }
+                                        cellGen(2, x, y, cur, nl, hasLo, nm, hasMi, nu_, hasUp);
+                                    }
+                                    if (SM == 7) {
+                                        // assignments in the reference's order: ascending x, from match / gap X / gap Y
+                                        const int cnt = __popc(asgMask);
+                                        int incl = cnt;
+#pragma unroll
+                                        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(CP_FULL, incl, o); if (lane >= o) incl += t; }
+                                        int pos = nPairs + incl - cnt;
+                                        for (int from = 0; from < 3; from++)
+                                            if (asgMask & (1 << from)) {
+                                                if (pos < it.pair_cap) { pairs[3 * pos] = from; pairs[3 * pos + 1] = x >= 1 ? x - 1 : 0; pairs[3 * pos + 2] = y - 1; }
+                                                pos++;
+                                            }
+                                        nPairs += __shfl_sync(CP_FULL, incl, 31);
+                                    }
+                                }
+                            } else status |= 2;
+                        } else
                         // posteriors: impl/pairwiseAligner.c:756-795 (match state) and :797-839 (echelon: states 1 .. 5,
                         // an event matched to st k-mers gives st pairs)
                         for (int xb = blo; xb <= bhi; xb += 32) {
@@ -577,6 +638,18 @@ __global__ void __launch_bounds__(32) k_align_generic(const KernelArgsG A) {
             }
         }
         status = __reduce_or_sync(CP_FULL, status);          // bit 8 is raised by single lanes
+        if (P.mode == 1 && S == 3) {
+            if (SM != 4) {
+#pragma unroll
+                for (int i = 0; i < 9; i++) {
+                    double v = accT[i];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(CP_FULL, v, o);
+                    if (lane == 0 && v != 0.0) atomicAdd(A.expect + i, v);
+                }
+            }
+            if (lane == 0) atomicAdd(A.expect + (SM == 4 ? 60 : 9 + 4096), lik);
+        }
         if (lane == 0) {
             ItemOut &o = A.out[itemIdx];
             o.n_pairs = nPairs;

@@ -4,6 +4,7 @@
 // DP is computed by libcpecan_cuda.so.  There is no CPU fallback: without a usable CUDA device the alignment entry
 // points abort exactly as the reference's st_errAbort does.
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -1059,6 +1060,18 @@ stList *getAlignedPairsWithoutBanding(StateMachine *sM, void *cX, void *cY, int6
     return result;
 }
 
+}  // extern "C"
+namespace {
+// HdpHmm (inc/continuousHmm.h:27-38): the assigned k-mers and event means are COPIED here (the reference keeps pointers
+// into the caller's sequences)
+struct HdpH {
+    Hmm base; double transitions[9]; double threshold;
+    void (*addToAssignments)(Hmm *, void *, void *);
+    std::vector<std::array<char, KMER_LENGTH>> *kmers; std::vector<double> *means;
+};
+}  // namespace
+extern "C" {
+
 void getExpectationsUsingAnchors(StateMachine *sM, Hmm *hmmExpectations, Sequence *SsX, Sequence *SsY, stList *anchorPairs,
                                  PairwiseAlignmentParameters *p,
                                  void (*diagonalCalcExpectationFcn)(StateMachine *, int64_t, DpMatrix *, DpMatrix *, Sequence *,
@@ -1091,6 +1104,39 @@ void getExpectationsUsingAnchors(StateMachine *sM, Hmm *hmmExpectations, Sequenc
     const cpecan_params prm = paramsOf(p);
     std::vector<cpecan_result> res((size_t) f.n());
     std::vector<double> e(CPECAN_N_EXPECT, 0.0);
+    if (sM->type == threeStateHdp) {
+        // cell_signal_updateTransAndKmerSkipExpectations2 (impl/pairwiseAligner.c:445-476): transition sums, and every
+        // transition into the match state with posterior >= the container's threshold appends (k-mer, event) to its lists
+        HdpH *h = (HdpH *) hmmExpectations;
+        cpecan_params q = prm;
+        q.threshold = h->threshold;                             // only the assignments read it in this mode
+        int64_t cap = 12 * (f.evOff.back() + 32 * f.n()) + 1024;
+        std::vector<int32_t> asg;
+        for (int attempt = 0;; attempt++) {
+            asg.assign((size_t) cap * 3, 0);
+            std::fill(e.begin(), e.end(), 0.0);
+            if (cpecan_cuda_hdp_expectations_batch(ctx, &hmm, &q, &b, e.data(), asg.data(), cap, res.data()) != CPECAN_OK)
+                st_errAbort("cpecan_cuda_hdp_expectations_batch: %s", cpecan_cuda_last_error(ctx));
+            bool overflow = false;
+            int64_t need = 0;
+            for (auto &r : res) { overflow |= (r.status & CPECAN_ITEM_PAIR_OVERFLOW) != 0; need += r.n_pairs; }
+            if (!overflow) break;
+            if (attempt == 1) st_errAbort("cpecan: assignment buffer overflow");
+            cap = 8 * need + 1024;
+        }
+        for (int from = 0; from < 3; from++)
+            for (int to = 0; to < 3; to++) hmmExpectations->addToTransitionExpectationFcn(hmmExpectations, from, to, e[(size_t) (from * 3 + to)]);
+        hmmExpectations->likelihood += e[9 + NUM_OF_KMERS];
+        for (int64_t i = 0; i < f.n(); i++) {
+            const int32_t *t = asg.data() + 3 * res[(size_t) i].pair_off;
+            for (int64_t k = 0; k < res[(size_t) i].n_pairs; k++) {
+                const char *km = (const char *) SsX->elements + (t[3 * k + 1] + f.offX[(size_t) i]);
+                const double *ev = (const double *) SsY->elements + (t[3 * k + 2] + f.offY[(size_t) i]) * NB_EVENT_PARAMS;
+                h->addToAssignments(hmmExpectations, (void *) km, (void *) ev);
+            }
+        }
+        return;
+    }
     if (cpecan_cuda_expectations_batch(ctx, &hmm, &prm, &b, e.data(), res.data()) != CPECAN_OK)
         st_errAbort("cpecan_cuda_expectations_batch: %s", cpecan_cuda_last_error(ctx));
     // accumulate through the container's own function pointers, as cell_signal_update* do (impl/pairwiseAligner.c:426-498)
@@ -1112,6 +1158,15 @@ void getExpectationsUsingAnchors(StateMachine *sM, Hmm *hmmExpectations, Sequenc
 namespace {
 struct PairHmm { Hmm base; double transitions[9]; double kmerGap[NUM_OF_KMERS]; };                          // inc/continuousHmm.h:7-25
 struct VanHmm { Hmm base; double bins[60]; double *matchModel; double *scaledMatchModel; };
+void hh_addT(Hmm *h, int64_t from, int64_t to, double p) { ((HdpH *) h)->transitions[from * 3 + to] += p; }
+void hh_setT(Hmm *h, int64_t from, int64_t to, double p) { ((HdpH *) h)->transitions[from * 3 + to] = p; }
+double hh_getT(Hmm *h, int64_t from, int64_t to) { return ((HdpH *) h)->transitions[from * 3 + to]; }
+void hh_addA(Hmm *hm, void *kmer, void *event) {                                                            // :631-636
+    HdpH *h = (HdpH *) hm;
+    std::array<char, KMER_LENGTH> k;
+    memcpy(k.data(), kmer, KMER_LENGTH);
+    h->kmers->push_back(k); h->means->push_back(*(const double *) event);
+}
 
 void ph_addT(Hmm *h, int64_t from, int64_t to, double p) { ((PairHmm *) h)->transitions[from * 3 + to] += p; }
 void ph_setT(Hmm *h, int64_t from, int64_t to, double p) { ((PairHmm *) h)->transitions[from * 3 + to] = p; }
@@ -1128,7 +1183,16 @@ bool anyNaN(const double *v, int n) { for (int i = 0; i < n; i++) if (std::isnan
 
 extern "C" {
 
-Hmm *hmmContinuous_getEmptyHmm(StateMachineType type, double pseudocount, double) {                         // impl/continuousHmm.c:908-944
+Hmm *hmmContinuous_getEmptyHmm(StateMachineType type, double pseudocount, double threshold) {               // impl/continuousHmm.c:908-944
+    if (type == threeStateHdp) {                               // hdpHmm_constructEmpty :644-681
+        HdpH *h = (HdpH *) calloc(1, sizeof(HdpH));
+        h->base.type = threeStateHdp; h->base.stateNumber = 3; h->base.symbolSetSize = 0; h->base.matrixSize = MODEL_PARAMS;
+        h->base.addToTransitionExpectationFcn = hh_addT; h->base.setTransitionFcn = hh_setT; h->base.getTransitionsExpFcn = hh_getT;
+        for (double &t : h->transitions) t = pseudocount;
+        h->threshold = threshold; h->addToAssignments = hh_addA;
+        h->kmers = new std::vector<std::array<char, KMER_LENGTH>>(); h->means = new std::vector<double>();
+        return &h->base;
+    }
     if (type == threeState) {
         PairHmm *h = (PairHmm *) calloc(1, sizeof(PairHmm));
         h->base.type = threeState; h->base.stateNumber = 3; h->base.symbolSetSize = NUM_OF_KMERS; h->base.matrixSize = MODEL_PARAMS;
@@ -1179,9 +1243,28 @@ void hmmContinuous_normalize(Hmm *hmm, StateMachineType type) {                 
     }
 }
 
+int64_t hmmContinuous_howManyAssignments(Hmm *hmm) {                                                        // :944-950
+    if (hmm->type != threeStateHdp) st_errAbort("hmmContinuous: this type of Hmm doesn't have assignments got type: %lld", (long long) hmm->type);
+    return (int64_t) ((HdpH *) hmm)->means->size();
+}
+
 void hmmContinuous_writeToFile(const char *outFile, Hmm *hmm, StateMachineType type) {                      // :956-970, 234-271, 477-517
     FILE *fh = fopen(outFile, "w");
     if (!fh) st_errAbort("hmmContinuous_writeToFile: cannot open %s", outFile);
+    if (type == threeStateHdp) {                               // hdpHmm_writeToFile :704-749
+        HdpH *h = (HdpH *) hmm;
+        fprintf(fh, "%i\t%lld\t%lf\t%lld\t\n", (int) hmm->type, (long long) hmm->stateNumber, h->threshold, (long long) h->means->size());
+        if (!anyNaN(h->transitions, 9)) {
+            for (double t : h->transitions) fprintf(fh, "%f\t", t);
+            fprintf(fh, "%f\n", hmm->likelihood);
+            for (double m : *h->means) fprintf(fh, "%lf\t", m);
+            fprintf(fh, "\n");
+            for (auto &k : *h->kmers) { fwrite(k.data(), 1, KMER_LENGTH, fh); fputc('\t', fh); }
+            fprintf(fh, "\n");
+        }
+        fclose(fh);
+        return;
+    }
     fprintf(fh, "%i\t%lld\t%lld\t\n", (int) hmm->type, (long long) hmm->stateNumber, (long long) hmm->symbolSetSize);
     if (type == threeState) {
         PairHmm *h = (PairHmm *) hmm;
@@ -1232,6 +1315,19 @@ void hmmContinuous_loadSignalHmm(const char *hmmFile, StateMachine *sM, StateMac
         m->TRANSITION_GAP_EXTEND_Y = log(T(shortGapY, shortGapY));
         m->TRANSITION_GAP_SWITCH_TO_X = log(T(shortGapY, shortGapX));
         for (int64_t i = 0; i < NUM_OF_KMERS; i++) sM->EMISSION_GAP_X_PROBS[i] = log(l2[(size_t) i]);
+    } else if (type == threeStateHdp) {                        // hdpHmm_loadTransitions (:683-702); the assignment lines are the sampler's
+        if (l1.size() != 10) st_errAbort("Incorrect number of transitions in the input HMM file %s, got %lld instead of 10\n", hmmFile, (long long) l1.size());
+        StateMachine3_HDP *m = (StateMachine3_HDP *) sM;
+        auto T = [&](int from, int to) { return l1[(size_t) (from * 3 + to)]; };
+        m->TRANSITION_MATCH_CONTINUE = log(T(match, match));
+        m->TRANSITION_GAP_OPEN_X = log(T(match, shortGapX));
+        m->TRANSITION_GAP_OPEN_Y = log(T(match, shortGapY));
+        m->TRANSITION_MATCH_FROM_GAP_X = log(T(shortGapX, match));
+        m->TRANSITION_GAP_EXTEND_X = log(1 - T(shortGapX, match));
+        m->TRANSITION_GAP_SWITCH_TO_Y = -INFINITY;
+        m->TRANSITION_MATCH_FROM_GAP_Y = log(T(shortGapY, match));
+        m->TRANSITION_GAP_EXTEND_Y = log(T(shortGapY, shortGapY));
+        m->TRANSITION_GAP_SWITCH_TO_X = log(T(shortGapY, shortGapX));
     } else if (type == vanilla) {                              // vanillaHmm_loadKmerSkipBinExpectations (:457-466)
         if (l1.size() != 61) st_errAbort("Incorrect number of skip bins in the input HMM file %s, got %lld instead of 61\n", hmmFile, (long long) l1.size());
         for (int i = 0; i < 60; i++) sM->EMISSION_GAP_X_PROBS[i] = l1[(size_t) i];
@@ -1243,6 +1339,7 @@ void hmmContinuous_loadSignalHmm(const char *hmmFile, StateMachine *sM, StateMac
 
 void hmmContinuous_destruct(Hmm *hmm, StateMachineType type) {
     if (!hmm) return;
+    if (type == threeStateHdp) { delete ((HdpH *) hmm)->kmers; delete ((HdpH *) hmm)->means; }
     if (type == vanilla) { free(((VanHmm *) hmm)->matchModel); free(((VanHmm *) hmm)->scaledMatchModel); }
     free(hmm);
 }
@@ -1361,10 +1458,6 @@ void vanillaHmm_loadKmerSkipBinExpectations(StateMachine *sM, Hmm *hmm) {       
     for (int i = 0; i < 60; i++) sM->EMISSION_GAP_X_PROBS[i] = vh_getT(hmm, i, 0);
 }
 void vanillaHmm_destruct(Hmm *hmm) { hmmContinuous_destruct(hmm, vanilla); }
-int64_t hmmContinuous_howManyAssignments(Hmm *hmm) {                                                        // :944-950: HDP containers only
-    st_errAbort("hmmContinuous: this type of Hmm doesn't have assignments got type: %lld", (long long) hmm->type);
-    return 0;
-}
 
 // impl/stateMachine.c:141-153
 int64_t emissions_discrete_getKmerIndexFromKmer(void *kmer) {

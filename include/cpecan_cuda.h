@@ -171,6 +171,15 @@ int cpecan_cuda_align_batch(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan
 #define CPECAN_N_EXPECT_VANILLA (60 + 1)  /* vanilla: 30 beta + 30 alpha skip-bin counts, likelihood */
 int cpecan_cuda_expectations_batch(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *params,
                                    const cpecan_batch *batch, double *expectations_out, cpecan_result *results);
+/* threeStateHdp: what getExpectationsUsingAnchors leaves in an HdpHmm (cell_signal_updateTransAndKmerSkipExpectations2,
+ * impl/pairwiseAligner.c:445-476).  expectations_out as above (9 transition sums, the k-mer part stays untouched, the
+ * likelihood); assignments_out: int32 triples (from state, k-mer position, event index), one for every transition into
+ * the match state whose posterior is >= params->threshold, in the order the reference appends them to its lists
+ * (traceback order of the diagonals, ascending x, from match / gap X / gap Y); sliced per item like pairs_out
+ * (results[i].pair_off / n_pairs; CPECAN_ITEM_PAIR_OVERFLOW when an item's slice was too small). */
+int cpecan_cuda_hdp_expectations_batch(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *params,
+                                       const cpecan_batch *batch, double *expectations_out, int32_t *assignments_out,
+                                       int64_t assignment_cap_total, cpecan_result *results);
 /* The same in steps, for the EM driver: stage(mode = CPECAN_MODE_EXPECTATION) + run_staged() leave the batch sums in a
  * device buffer of CPECAN_N_EXPECT doubles; expectations_device_ptr() exposes it so that the caller can all-reduce it
  * in place across GPUs (NCCL over NVLink) before fetch_expectations() ADDS it to a host vector. */
@@ -215,7 +224,8 @@ int cpecan_cuda_set_resident_warps(cpecan_ctx *ctx, int32_t warps_per_sm);
  * whose posteriors agree with the reference's FP64 ones to ~1e-4 apart from rare logAdd segment flips.
  * 1: the FP64 kernel in the reference's own operation order -- the same pair lists, scores equal to the last digit of
  * floor(p * 1e7) -- at a fraction of the FP32 rate (profiles/).  Batches with an odd diagonalExpansion always run that
- * way (their band is one the FP32 kernel does not walk); expectations are FP32 only. */
+ * way (their band is one the FP32 kernel does not walk).  Expectation batches follow the same switch (sums to 1e-9 of
+ * the reference's instead of 2e-4). */
 int cpecan_cuda_set_exact_arithmetic(cpecan_ctx *ctx, int32_t on);
 
 int cpecan_cuda_get_timing(cpecan_ctx *ctx, cpecan_timing *out);

@@ -352,8 +352,9 @@ StateMachine *getStateMachine4(const char *modelFile);                          
 StateMachine *getStateMachineEchelon(const char *modelFile);                                                /* :382 */
 /* threeStateHdp (impl/stateMachine.c:1738-1749): the three-state topology, match and gap-Y emissions =
  * get_nanopore_kmer_density of the HDP (the density itself, as the reference has it), gap-X emission log(0.1); the
- * reference sequence must use sequence_getKmer3 (vanillaAlign.c:246-250).  Posteriors only: the HDP expectations
- * (event-to-k-mer assignment lists, impl/continuousHmm.c:630-749) are not implemented. */
+ * reference sequence must use sequence_getKmer3 (vanillaAlign.c:246-250).  Its expectations go into the container of
+ * hmmContinuous_getEmptyHmm(threeStateHdp, pseudocount, threshold): transition sums and the event-to-k-mer assignment
+ * lists (impl/continuousHmm.c:630-749), written by hmmContinuous_writeToFile in the reference's format. */
 StateMachine *getHdpStateMachine3(NanoporeHDP *hdp);                                                        /* :376 */
 /* inc/nanopore_hdp.h: reading a serialised NanoporeHDP (impl/nanopore_hdp.c:845-873, impl/hdp.c:3009-3270) and querying it
  * (impl/nanopore_hdp.c:390-392 -> impl/hdp.c:2577-2599 -> impl/hdp_math_utils.c:471-495) */
@@ -378,7 +379,7 @@ void hmmContinuous_writeToFile(const char *outFile, Hmm *hmm, StateMachineType t
 void hmmContinuous_loadSignalHmm(const char *hmmFile, StateMachine *sM, StateMachineType type);             /* :104 */
 void hmmContinuous_destruct(Hmm *hmm, StateMachineType type);                                               /* :119 */
 void vanillaHmm_implantMatchModelsintoHmm(StateMachine *sM, Hmm *hmm);                                      /* :87 */
-int64_t hmmContinuous_howManyAssignments(Hmm *hmm);                                                         /* :128: HDP containers only, aborts */
+int64_t hmmContinuous_howManyAssignments(Hmm *hmm);                                                         /* :128: threeStateHdp containers only */
 /* the per-field accessors (:39-100) over the containers hmmContinuous_getEmptyHmm returns */
 void continuousPairHmm_addToTransitionsExpectation(Hmm *hmm, int64_t from, int64_t to, double p);
 void continuousPairHmm_setTransitionExpectation(Hmm *hmm, int64_t from, int64_t to, double p);

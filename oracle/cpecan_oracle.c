@@ -261,6 +261,15 @@ static void drop_diag(double **mat, int64_t xay) { if (mat[xay]) { free(mat[xay]
 
 enum { MODE_FWD = 0, MODE_BWD = 1, MODE_EXP = 2 };
 
+/* HDP expectations (ref:445-476): a transition into the match state with posterior >= threshold is an ASSIGNMENT of the
+ * cell's event to its k-mer; recorded as (from state, k-mer position, event index) relative to the buffers handed to
+ * oracle_hdp_expectations */
+static int64_t *g_asg = NULL;
+static int64_t g_asg_cap = 0, g_asg_n = 0;
+static double g_asg_thr = 0.0;
+static const char *g_asg_ref = NULL, *g_cell_kmer = NULL;
+static const double *g_asg_ev = NULL, *g_cell_ev = NULL;
+
 /* ref:365-383 (forward/backward transition), ref:426-443 and ref:478-498 (expectation updates) */
 static void transition(Dp *dp, int mode, double *nb, double *cur, int from, int to, double eP, double tP, int32_t kx, int bin) {
     if (mode == MODE_FWD) {
@@ -272,6 +281,16 @@ static void transition(Dp *dp, int mode, double *nb, double *cur, int from, int 
         if (dp->m->sm_type == SM_THREE_STATE) {
             dp->expT[from * 3 + to] += p;
             if (to == ST_X && kx >= 0) dp->expSkip[kx] += p;
+        } else if (dp->m->sm_type == SM_THREE_STATE_HDP) {
+            dp->expT[from * 3 + to] += p;
+            if (to == ST_M && p >= g_asg_thr && g_asg != NULL) {
+                if (g_asg_n < g_asg_cap) {
+                    g_asg[3 * g_asg_n] = from;
+                    g_asg[3 * g_asg_n + 1] = g_cell_kmer - g_asg_ref;
+                    g_asg[3 * g_asg_n + 2] = (g_cell_ev - g_asg_ev) / 3;
+                }
+                g_asg_n++;
+            }
         } else {
             if (from == ST_M && to == ST_X) dp->expT[bin] += p;
             if (from == ST_X && to == ST_X) dp->expT[bin + 30] += p;
@@ -379,6 +398,7 @@ static void cell(Dp *dp, int mode, double *cur, double *lower, double *middle, d
          * k-mer's distribution at the event mean; sequence_getKmer3 (ref:327-331): index < 0 reads k-mer 0 */
         int32_t k = kmer_index(dp->ref + (ix >= 0 ? ix : 0));
         const double *t = m->trans;
+        g_cell_kmer = dp->ref + (ix >= 0 ? ix : 0); g_cell_ev = ev;
         if (lower) {
             double eP = -2.3025850929940455;
             transition(dp, mode, lower, cur, ST_M, ST_X, eP, t[3], k, 0);
@@ -701,6 +721,18 @@ void oracle_expectations(const OracleModel *m, const char *ref, int64_t lX, cons
                          const int64_t *anchors, int64_t nA, const OracleParams *p, int raggedLeft, int raggedRight,
                          double *expT, double *expSkip, double *likelihood) {
     run_split(m, ref, lX, events, lY, anchors, nA, p, raggedLeft, raggedRight, 1, NULL, expT, expSkip, likelihood, NULL);
+}
+
+/* threeStateHdp: expT[9] transition sums, the likelihood, and the assignments (from, k-mer position, event index) in the
+ * order the reference's lists hold them; returns their number (which may exceed cap). */
+int64_t oracle_hdp_expectations(const OracleModel *m, const char *ref, int64_t lX, const double *events, int64_t lY,
+                                const int64_t *anchors, int64_t nA, const OracleParams *p, int raggedLeft, int raggedRight,
+                                double threshold, double *expT, double *likelihood, int64_t *asgOut, int64_t cap) {
+    double skip[1] = { 0 };
+    g_asg = asgOut; g_asg_cap = cap; g_asg_n = 0; g_asg_thr = threshold; g_asg_ref = ref; g_asg_ev = events;
+    run_split(m, ref, lX, events, lY, anchors, nA, p, raggedLeft, raggedRight, 1, NULL, expT, skip, likelihood, NULL);
+    g_asg = NULL;
+    return g_asg_n;
 }
 
 /* ref:1512-1569: full matrix (band with no anchors, expansion 2), ONE total at the last diagonal, posteriors in

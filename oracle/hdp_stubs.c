@@ -1,8 +1,8 @@
 /*
  * TEST INFRASTRUCTURE ONLY.  The HDP entry points of the reference's vanillaAlign.c that this build does not provide:
- * BUILDING and Gibbs-sampling HDPs, serialising them, and the assignment-list expectations (SURVEY.md 8(f) N4 covers
- * reading an HDP and aligning with it: deserialize_nhdp, destroy_nanopore_hdp and getHdpStateMachine3 come from
- * libcpecan_host.so).  They let the UNMODIFIED vanillaAlign.c link (oracle/_ref/vanillaAlign_dropin,
+ * BUILDING and Gibbs-sampling HDPs, serialising them, and feeding assignment files back into the sampler (SURVEY.md
+ * 8(f) N4 covers reading an HDP, aligning with it and collecting its assignment lists: deserialize_nhdp,
+ * destroy_nanopore_hdp, getHdpStateMachine3 and the HdpHmm container come from libcpecan_host.so).  They let the UNMODIFIED vanillaAlign.c link (oracle/_ref/vanillaAlign_dropin,
  * tests/test_vanilla_align_drop_in.py) and abort if ever reached.
  */
 #include <stdio.h>

@@ -248,6 +248,21 @@ def hdp_goldens():
         out[tag + "_pairs"] = pairs[:n].copy()
         out[tag + "_totals"] = totals
         print(tag, n, int(pairs[:n, 0].sum()))
+    # getExpectationsUsingAnchors with an HdpHmm: transition sums, likelihood, the event-to-k-mer assignments
+    lib.ref_hdp_expectations.restype = C.c_int64
+    for tag, e, ragged, thr in (("hdpexp_e50_r11", 50, (1, 1), 0.01), ("hdpexp_e20_r00_t30", 20, (0, 0), 0.3)):
+        prm = R.default_params(diagonalExpansion=e, threshold=thr)
+        cap = 64 * (lX + lY)
+        asg = np.zeros((cap, 2), dtype=np.int64)
+        vec = np.zeros(10)
+        n = lib.ref_hdp_expectations(src.encode(), ref.encode(), ev.ctypes.data_as(C.c_void_p), C.c_int64(lY),
+                                     anch.ctypes.data_as(C.c_void_p), C.c_int64(len(anch)), C.byref(prm), ragged[0], ragged[1],
+                                     C.c_double(1e-4), C.c_double(thr), vec.ctypes.data_as(C.c_void_p),
+                                     asg.ctypes.data_as(C.c_void_p), C.c_int64(cap))
+        assert 0 <= n <= cap
+        out[tag + "_vec"] = vec
+        out[tag + "_assignments"] = asg[:n].copy()
+        print(tag, n, vec)
     np.savez_compressed(os.path.join(out_dir, "zymo_hdp_golden.npz"), **out)
     # the CLI: vanillaAlign -d with the same HDP for both strands
     cigar = open(os.path.join(GOLDEN, "vanillaAlign", "guide.cigar")).read()
@@ -261,6 +276,13 @@ def hdp_goldens():
         with open(tsv, "rb") as fi, gzip.GzipFile(os.path.join(GOLDEN, "vanillaAlign", "out_d.tsv.gz"), "wb", mtime=0) as fo:
             shutil.copyfileobj(fi, fo)
         print("vanillaAlign -d:", r.stdout.strip())
+        # ... and its expectation files (-t / -c): the HdpHmm text format (impl/continuousHmm.c:690-749)
+        t_exp, c_exp = os.path.join(GOLDEN, "vanillaAlign", "t_d.exp"), os.path.join(td, "c_d.exp")
+        r = subprocess.run([os.path.join(ref_dir, "vanillaAlign_hdp"), "-d", "-v", src, "-w", src, "-T", T_MODEL, "-C", C_MODEL,
+                            "-L", "readA", "-q", os.path.join(GOLDEN, "ZymoC_ch_1_file1.npRead"),
+                            "-r", os.path.join(GOLDEN, "ZymoRef.txt"), "-t", t_exp, "-c", c_exp], input=cigar,
+                           capture_output=True, text=True)
+        print("vanillaAlign -d -t -c: rc", r.returncode, r.stderr[-300:])
 
 
 if __name__ == "__main__":

@@ -159,6 +159,26 @@ class Model:
         return m
 
 
+def hdp_expectations(model, ref_seq, events, anchors, params=None, ragged=(0, 0), pseudocount=1e-4, threshold=None):
+    """threeStateHdp: (vector of 9 transition sums + likelihood, assignments[n, 3] = (from state, k-mer position, event))."""
+    events = np.ascontiguousarray(events, dtype=np.float64).reshape(-1, 3)
+    anchors = np.ascontiguousarray(np.asarray(anchors, dtype=np.int64).reshape(-1, 2))
+    params = params or default_params()
+    lX = max(len(ref_seq) - 5, 0)
+    expT = np.full(9, pseudocount, dtype=np.float64)
+    lik = C.c_double(0.0)
+    cap = 64 * (lX + len(events)) + 64
+    asg = np.zeros((cap, 3), dtype=np.int64)
+    cm = model.cstruct()
+    f = lib().oracle_hdp_expectations
+    f.restype = C.c_int64
+    n = f(C.byref(cm), ref_seq.encode(), C.c_int64(lX), _iptr(events), C.c_int64(len(events)), _iptr(anchors),
+          C.c_int64(len(anchors)), C.byref(params), int(ragged[0]), int(ragged[1]),
+          C.c_double(params.threshold if threshold is None else threshold), _iptr(expT), C.byref(lik), _iptr(asg), C.c_int64(cap))
+    assert 0 <= n <= cap
+    return np.concatenate([expT, [lik.value]]), asg[:n].copy()
+
+
 def hdp_density(model, kmer_index, x):
     """oracle_hdp_density: get_nanopore_kmer_density of an HDP Model for one ACGT k-mer index at x."""
     f = lib().oracle_hdp_density

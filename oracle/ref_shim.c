@@ -438,5 +438,35 @@ int64_t ref_hdp_align_banded(const char *nhdpFile, const char *refSeq, const dou
     return n;
 }
 
-/* nanopore_descaleNanoporeRead on a loaded .npRead (vanillaAlign.c:609-612): events in place */
+/* getExpectationsUsingAnchors with an HdpHmm (vanillaAlign.c:318-360, 675): expOut = 9 transition sums (from * 3 + to,
+ * pseudocount included) + likelihood; asgOut = (k-mer position, event index) of every assignment in list order */
+int64_t ref_hdp_expectations(const char *nhdpFile, const char *refSeq, const double *events, int64_t lY,
+                             const int64_t *anchors, int64_t nAnchors, const RefParams *rp,
+                             int raggedLeft, int raggedRight, double pseudocount, double threshold,
+                             double *expOut, int64_t *asgOut, int64_t cap) {
+    NanoporeHDP *nhdp = deserialize_nhdp(nhdpFile);
+    StateMachine *sM = getHdpStateMachine3(nhdp);
+    PairwiseAlignmentParameters *p = makeParams(rp);
+    int64_t lX = sequence_correctSeqLength(strlen(refSeq), event);
+    Sequence *sX = sequence_construct2(lX, (void *) refSeq, sequence_getKmer3, sequence_sliceNucleotideSequence2);
+    Sequence *sY = sequence_construct2(lY, (void *) events, sequence_getEvent, sequence_sliceEventSequence2);
+    stList *anchorList = makeAnchors(anchors, nAnchors);
+    Hmm *hmm = hmmContinuous_getEmptyHmm(threeStateHdp, pseudocount, threshold);
+    getExpectationsUsingAnchors(sM, hmm, sX, sY, anchorList, p, diagonalCalculation_Expectations, raggedLeft, raggedRight);
+    HdpHmm *hh = (HdpHmm *) hmm;
+    for (int i = 0; i < 9; i++) expOut[i] = hh->transitions[i];
+    expOut[9] = hmm->likelihood;
+    int64_t n = hmmContinuous_howManyAssignments(hmm);
+    for (int64_t i = 0; i < n && i < cap; i++) {
+        asgOut[2 * i] = (const char *) stList_get(hh->kmerAssignments, i) - refSeq;
+        asgOut[2 * i + 1] = ((const double *) stList_get(hh->eventAssignments, i) - events) / NB_EVENT_PARAMS;
+    }
+    stList_destruct(anchorList);
+    sequence_sequenceDestroy(sX);
+    sequence_sequenceDestroy(sY);
+    pairwiseAlignmentBandingParameters_destruct(p);
+    freeStateMachine(sM);
+    destroy_nanopore_hdp(nhdp);
+    return n;
+}
 #endif

@@ -66,3 +66,16 @@ def test_oracle_alignment_equals_the_reference(hdp_fixture, zymo):
         wt = g[tag + "_totals"]
         mask = ~np.isnan(wt)
         assert np.array_equal(mask, ~np.isnan(totals)) and np.array_equal(totals[mask], wt[mask]), tag
+
+
+def test_oracle_hdp_expectations_equal_the_reference(hdp_fixture, zymo):
+    """getExpectationsUsingAnchors with an HdpHmm: the nine transition sums and the likelihood to 1e-12, the
+    event-to-k-mer assignments (k-mer position, event index) in the reference's list order."""
+    g = hdp_fixture["golden"]
+    m = O.Model(O.THREE_STATE_HDP, hdp=hdp_fixture["hdp"])
+    for tag, e, ragged, thr in (("hdpexp_e50_r11", 50, (1, 1), 0.01), ("hdpexp_e20_r00_t30", 20, (0, 0), 0.3)):
+        vec, asg = O.hdp_expectations(m, zymo["ref"], hdp_fixture["events"], zymo["anchors_template"],
+                                      params=O.default_params(diagonalExpansion=e, threshold=thr), ragged=ragged)
+        np.testing.assert_allclose(vec, g[tag + "_vec"], rtol=1e-12, atol=1e-15)
+        assert np.array_equal(asg[:, 1:], g[tag + "_assignments"]), tag
+        assert set(asg[:, 0].tolist()) <= {0, 1, 2}
