@@ -75,7 +75,8 @@ struct Options {
     double threshold = 0.01;
     std::string templateModel = "../../cPecan/models/template_median68pA.model";
     std::string complementModel = "../../cPecan/models/complement_median68pA_pop2.model";
-    std::string label, npRead, target, posteriors, tHmm, cHmm, tExp, cExp, batch;
+    std::string label, npRead, target, posteriors, tHmm, cHmm, tExp, cExp, batch, templateHdp, complementHdp;
+    NanoporeHDP *nHdp[2] = { nullptr, nullptr };           // threeStateHdp: one per strand, shared by all reads
 };
 
 struct Job {                                // one read: both strands
@@ -90,9 +91,12 @@ struct Job {                                // one read: both strands
 };
 
 StateMachine *buildStateMachine(const std::string &model, const NanoporeReadAdjustmentParameters &npp, StateMachineType type,
-                                int strand, const std::string &hmmFile) {          // vanillaAlign.c:104-140, 236-240
-    StateMachine *sM = type == vanilla ? getSignalStateMachine3Vanilla(model.c_str()) : getStrawManStateMachine3(model.c_str());
-    emissions_signal_scaleModel(sM, npp.scale, npp.shift, npp.var, npp.scale_sd, npp.var_sd);
+                                int strand, const std::string &hmmFile, NanoporeHDP *nHdp) {   // vanillaAlign.c:104-140, 236-240
+    StateMachine *sM = type == vanilla ? getSignalStateMachine3Vanilla(model.c_str())
+                     : type == fourState ? getStateMachine4(model.c_str())
+                     : type == echelon ? getStateMachineEchelon(model.c_str())
+                     : type == threeStateHdp ? getHdpStateMachine3(nHdp) : getStrawManStateMachine3(model.c_str());
+    if (type != threeStateHdp) emissions_signal_scaleModel(sM, npp.scale, npp.shift, npp.var, npp.scale_sd, npp.var_sd);
     if (type == vanilla) stateMachine3Vanilla_setStrandTransitionsToDefaults(sM, strand ? complement : template_);
     if (!hmmFile.empty()) { fprintf(stderr, "loading HMM from file, %s\n", hmmFile.c_str()); hmmContinuous_loadSignalHmm(hmmFile.c_str(), sM, type); }
     return sM;
@@ -102,6 +106,7 @@ void prepare(Job &job, const Options &o, const std::string &npFile, const std::s
     std::ifstream rf(targetFile);
     if (!rf || !std::getline(rf, job.ref)) st_errAbort("cpecanAlign: cannot read the reference %s", targetFile.c_str());
     job.np = nanopore_loadNanoporeReadFromFile(npFile.c_str());
+    if (o.type == threeStateHdp) nanopore_descaleNanoporeRead(job.np);               // vanillaAlign.c:609-612
     const Cigar &c = job.cig;
     // getSubSequence + reverse complement for a reverse-strand hit (vanillaAlign.c:626-635)
     job.trimmed = c.strand1 ? job.ref.substr((size_t) c.start1, (size_t) (c.end1 - c.start1))
@@ -117,8 +122,11 @@ void prepare(Job &job, const Options &o, const std::string &npFile, const std::s
         job.sY[s] = sequence_construct2(y1 - y0, events + y0 * NB_EVENT_PARAMS, sequence_getEvent, sequence_sliceEventSequence2);
         std::string &tgt = s ? job.rcTrimmed : job.trimmed;
         job.sX[s] = sequence_construct2(sequence_correctSeqLength((int64_t) tgt.size(), event), (void *) tgt.c_str(),
-                                        o.type == vanilla ? sequence_getKmer2 : sequence_getKmer, sequence_sliceNucleotideSequence2);
-        job.sM[s] = buildStateMachine(s ? o.complementModel : o.templateModel, npp, o.type, s, s ? o.cHmm : o.tHmm);
+                                        (o.type == vanilla || o.type == echelon) ? sequence_getKmer2
+                                        : o.type == threeStateHdp ? sequence_getKmer3 : sequence_getKmer,     // vanillaAlign.c:224-250
+                                        sequence_sliceNucleotideSequence2);
+        if (o.type == echelon) sequence_padSequence(job.sX[s]);                      // vanillaAlign.c:196-198
+        job.sM[s] = buildStateMachine(s ? o.complementModel : o.templateModel, npp, o.type, s, s ? o.cHmm : o.tHmm, o.nHdp[s]);
         // getRemappedAnchorPairs (vanillaAlign.c:98-102)
         stList *rm = nanopore_remapAnchorPairsWithOffset(job.anchors, const_cast<int64_t *>(map), c.start2);
         job.remapped[s] = filterToRemoveOverlap(rm);
@@ -176,7 +184,8 @@ void release(Job &job) {
 }
 
 void usage() {
-    fprintf(stderr, "cpecanAlign: GPU sibling of vanillaAlign.  Flags as vanillaAlign (-s strawMan, -T/-C models, -L label, -q npRead,\n"
+    fprintf(stderr, "cpecanAlign: GPU sibling of vanillaAlign.  Flags as vanillaAlign (-s strawMan, -f fourState, -e echelon,\n"
+                    "-d sm3Hdp with -v/-w the template / complement .nhdp files, -T/-C models, -L label, -q npRead,\n"
                     "-r reference, -u posteriors TSV, -t/-c expectation files, -y/-z input HMMs, -x expansion, -D threshold, -m trim);\n"
                     "cigar on stdin.  --batch <manifest>: label, npRead, reference, posteriors file, cigar per line (tab separated).\n");
 }
@@ -192,12 +201,19 @@ int main(int argc, char **argv) {
         { "complementHmm", required_argument, 0, 'z' }, { "templateExpectations", required_argument, 0, 't' },
         { "complementExpectations", required_argument, 0, 'c' }, { "diagonalExpansion", required_argument, 0, 'x' },
         { "threshold", required_argument, 0, 'D' }, { "constraintTrim", required_argument, 0, 'm' }, { "batch", required_argument, 0, 'B' },
+        { "fourState", no_argument, 0, 'f' }, { "echelon", no_argument, 0, 'e' }, { "sm3Hdp", no_argument, 0, 'd' },
+        { "templateHdp", required_argument, 0, 'v' }, { "complementHdp", required_argument, 0, 'w' },
         { 0, 0, 0, 0 } };
     int key;
-    while ((key = getopt_long(argc, argv, "hsT:C:L:q:r:u:y:z:t:c:x:D:m:B:", longOpts, nullptr)) != -1) {
+    while ((key = getopt_long(argc, argv, "hsfedv:w:T:C:L:q:r:u:y:z:t:c:x:D:m:B:", longOpts, nullptr)) != -1) {
         switch (key) {
             case 'h': usage(); return 0;
             case 's': o.type = threeState; break;
+            case 'f': o.type = fourState; break;
+            case 'e': o.type = echelon; break;
+            case 'd': o.type = threeStateHdp; break;
+            case 'v': o.templateHdp = optarg; break;
+            case 'w': o.complementHdp = optarg; break;
             case 'T': o.templateModel = optarg; break;
             case 'C': o.complementModel = optarg; break;
             case 'L': o.label = optarg; break;
@@ -215,7 +231,13 @@ int main(int argc, char **argv) {
             default: usage(); return 1;
         }
     }
-    fprintf(stderr, "cpecanAlign - using %s model\n", o.type == vanilla ? "vanilla" : "strawMan");
+    fprintf(stderr, "cpecanAlign - using %s model\n", o.type == vanilla ? "vanilla" : o.type == fourState ? "fourState"
+            : o.type == echelon ? "echelon" : o.type == threeStateHdp ? "strawMan-HDP" : "strawMan");
+    if (o.type == threeStateHdp) {                                                   // vanillaAlign.c:574-600
+        if (o.templateHdp.empty() || o.complementHdp.empty()) st_errAbort("Need to have template and complement HDPs");
+        o.nHdp[0] = deserialize_nhdp(o.templateHdp.c_str());
+        o.nHdp[1] = deserialize_nhdp(o.complementHdp.c_str());
+    }
     PairwiseAlignmentParameters *p = pairwiseAlignmentBandingParameters_construct();
     p->threshold = o.threshold; p->constraintDiagonalTrim = o.constraintTrim; p->diagonalExpansion = o.diagExpansion;
 
@@ -251,12 +273,14 @@ int main(int argc, char **argv) {
     if (!o.tExp.empty() && !o.cExp.empty()) {
         // expectation routine (vanillaAlign.c:668-731): one read, pseudocount 1e-4, ragged ends (1,1)
         if (jobs.size() != 1) st_errAbort("cpecanAlign: expectation files are written per read (use the EM driver for batches)");
+        if (o.type == fourState || o.type == echelon) st_errAbort("vanillaAlign - getting expectations not allowed for this HMM type, yet");   // vanillaAlign.c:669-672
         Job &job = jobs[0];
         for (int s = 0; s < 2; s++) {
             fprintf(stderr, "cpecanAlign - getting expectations for %s\n", s ? "complement" : "template");
             Hmm *hmm = hmmContinuous_getEmptyHmm(o.type, 0.0001, p->threshold);
             if (o.type == vanilla) vanillaHmm_implantMatchModelsintoHmm(job.sM[s], hmm);
             getExpectationsUsingAnchors(job.sM[s], hmm, job.sX[s], job.sY[s], job.remapped[s], p, diagonalCalculation_Expectations, 1, 1);
+            if (o.type == threeStateHdp) fprintf(stderr, "cpecanAlign - got %lld HDP assignments\n", (long long) hmmContinuous_howManyAssignments(hmm));
             hmmContinuous_writeToFile((s ? o.cExp : o.tExp).c_str(), hmm, o.type);
             hmmContinuous_destruct(hmm, o.type);
         }
@@ -281,6 +305,7 @@ int main(int argc, char **argv) {
         }
     }
     for (Job &job : jobs) release(job);
+    for (NanoporeHDP *h : o.nHdp) if (h) destroy_nanopore_hdp(h);
     pairwiseAlignmentBandingParameters_destruct(p);
     fprintf(stderr, "cpecanAlign - SUCCESS: finished %zu read(s)\n", jobs.size());
     return 0;

@@ -76,6 +76,56 @@ def test_posteriors_tsv_and_stdout(tmp_path, flag, tag):
             assert abs(float(gs) - float(ws)) < 0.05
 
 
+@pytest.mark.parametrize("flag,tag", [("-f", "f"), ("-e", "e"), ("-d", "d")])
+def test_posteriors_fp64_machines(tmp_path, hdp_fixture, flag, tag):
+    """fourState, echelon and the HDP machine through cpecanAlign: the reference binary's posterior file row for row
+    (echelon lists a pair once per k-mer the event covers: rows repeat), posteriors equal at the six printed decimals."""
+    import gzip
+    from collections import Counter
+    out = str(tmp_path / "post.tsv")
+    extra = ["-v", hdp_fixture["path"], "-w", hdp_fixture["path"]] if tag == "d" else []
+    stdout = _run(_common(flag) + extra + ["-L", "readA", "-u", out], os.path.join(VA, "guide.cigar"))
+    gold = os.path.join(VA, "out_%s.tsv" % tag)
+    op = (lambda p: gzip.open(p + ".gz", "rt")) if not os.path.exists(gold) else open
+
+    def rows(fh):
+        c = Counter()
+        for line in fh:
+            f = line.rstrip("\n").split("\t")
+            assert len(f) == 15
+            c[tuple(f[:12]) + ("%.5f" % float(f[12]),) + tuple(f[13:])] += 1
+        return c
+    with open(out) as fh:
+        got = rows(fh)
+    with op(gold) as fh:
+        want = rows(fh)
+    # rows whose posterior rounds differently at the fifth decimal would show up on both sides
+    only_got, only_want = got - want, want - got
+    assert sum(only_got.values()) == sum(only_want.values()) <= 4, (list(only_got)[:3], list(only_want)[:3])
+    for a, b in zip(sorted(only_got), sorted(only_want)):
+        assert a[:12] == b[:12] and abs(float(a[12]) - float(b[12])) <= 2e-5
+    want_line = open(os.path.join(VA, "stdout_%s.txt" % tag)).read().split()
+    got_line = stdout.split()
+    print(stdout.strip(), sum(got.values()), sum(want.values()))
+    assert got_line[:2] == want_line[:2]
+    for g, w in zip(got_line[2:], want_line[2:]):
+        assert g.split("(")[0] == w.split("(")[0]
+
+
+def test_hdp_expectation_file(tmp_path, hdp_fixture):
+    """cpecanAlign -d -t / -c: the HdpHmm file of the template strand equals the reference binary's."""
+    import gzip
+    t, c = str(tmp_path / "t.exp"), str(tmp_path / "c.exp")
+    _run(_common("-d") + ["-v", hdp_fixture["path"], "-w", hdp_fixture["path"], "-L", "readA", "-t", t, "-c", c],
+         os.path.join(VA, "guide.cigar"))
+    got = open(t).read().split("\n")
+    with gzip.open(os.path.join(VA, "t_d.exp.gz"), "rt") as fh:
+        want = fh.read().split("\n")
+    assert got[0] == want[0] and len(got) == len(want)
+    np.testing.assert_allclose(np.array(got[1].split(), dtype=np.float64), np.array(want[1].split(), dtype=np.float64), rtol=0, atol=2e-6)
+    assert got[2] == want[2] and got[3] == want[3]
+
+
 def _read_exp(path):
     with open(path) as fh:
         head = fh.readline().split()
