@@ -119,10 +119,10 @@ struct cpecan_ctx {
     std::vector<Item> hItems;
     std::vector<ItemOut> hOut;
     DevBuf dItems, dOut, dRef, dRefOff, dEvSrc, dEvSrcOff, dAnchors, dScale, dCentre, dXp, dEv, dPairs, dOrder,
-           dQueue, dScratch, dTotals, dCompact, dCompactOff, dExpect, dBits, dTbs, dFlags, dBands, dBandOff;
+           dQueue, dScratch, dTotals, dCompact, dCompactOff, dExpect, dBits, dTbs, dFlags, dBands, dBandOff, dColp, dRowp;
     int64_t pairCapTotal = 0, totalsLen = 0;
     Bucket buckets[NCFG2];
-    int stagedMaxLX = 0;
+    int stagedMaxLX = 0, stagedMaxLY = 0;
     bool stagedScaled = false;
     int occ2[NCFG2][2][2][2] = {};  // [bucket][machine][hasSX][expect]
     int occCap = 0;              // resident warps per SM this context may take (0 = all that fit)
@@ -317,6 +317,17 @@ void launchPrepX(cpecan_ctx *ctx, cudaStream_t s) {
     ctx->timing.kernel_launches += 1;
 }
 
+// per-column records of the FP64 kernel (cpecan_generic.cuh); echelon has none
+void launchPrepGeneric(cpecan_ctx *ctx, cudaStream_t s) {
+    if (!ctx->generic || gen_ncol(ctx->generic) == 0) return;
+    dim3 g((unsigned) ctx->n, (unsigned) std::min(64, (std::max(ctx->stagedMaxLX, ctx->stagedMaxLY) + 256) / 256 + 1));
+    k_prep_generic<<<g, 256, 0, s>>>(ctx->dItems.as<Item>(), ctx->dRefOff.as<long long>(), ctx->dRef.as<char>(),
+                                     ctx->dModels.as<ModelTables>(), ctx->stagedScaled ? ctx->dScale.as<double>() : nullptr,
+                                     ctx->G, ctx->dColp.as<double>(), ctx->generic == CPECAN_SM_VANILLA ? ctx->dRowp.as<double>() : nullptr,
+                                     ctx->dEvSrc.as<double>(), ctx->dEvSrcOff.as<long long>());
+    ctx->timing.kernel_launches += 1;
+}
+
 }  // namespace
 
 extern "C" {
@@ -355,7 +366,7 @@ void cpecan_cuda_destroy(cpecan_ctx *ctx) {
     DevBuf *bufs[] = { &ctx->dModels, &ctx->dItems, &ctx->dOut, &ctx->dRef, &ctx->dRefOff, &ctx->dEvSrc, &ctx->dEvSrcOff,
                        &ctx->dAnchors, &ctx->dScale, &ctx->dCentre, &ctx->dXp, &ctx->dEv, &ctx->dPairs, &ctx->dOrder,
                        &ctx->dQueue, &ctx->dScratch, &ctx->dTotals, &ctx->dCompact, &ctx->dCompactOff, &ctx->dExpect,
-                       &ctx->dBits, &ctx->dTbs, &ctx->dFlags, &ctx->dBands, &ctx->dBandOff };
+                       &ctx->dBits, &ctx->dTbs, &ctx->dFlags, &ctx->dBands, &ctx->dBandOff, &ctx->dColp, &ctx->dRowp };
     for (auto *b : bufs) b->release();
     for (auto &e : ctx->ev) cudaEventDestroy(e);
     for (auto &e : ctx->bev) cudaEventDestroy(e);
@@ -556,6 +567,9 @@ int stageL(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *params, 
     if (!ctx->generic) {
         CK(ctx->dXp.ensure(xpTot * (ctx->machine ? 4 : 3) * sizeof(float4)));
         CK(ctx->dEv.ensure(evTot * sizeof(float4)));
+    } else {
+        CK(ctx->dColp.ensure(std::max<long long>(1, xpTot * gen_ncol(ctx->generic)) * sizeof(double)));
+        if (ctx->generic == CPECAN_SM_VANILLA) CK(ctx->dRowp.ensure(evTot * sizeof(double)));
     }
     CK(ctx->dPairs.ensure(std::max<long long>(1, pairTot) * 3 * sizeof(int)));
     CK(ctx->dBits.ensure(std::max<long long>(1, bitsTot) * sizeof(unsigned)));
@@ -580,7 +594,7 @@ int stageL(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *params, 
         CK(cudaMemcpyAsync(ctx->dScale.p, B->scale, n * 5 * sizeof(double), cudaMemcpyHostToDevice, s));
         ctx->stagedScaled = true;
     }
-    ctx->stagedMaxLX = maxLX;
+    ctx->stagedMaxLX = maxLX; ctx->stagedMaxLY = maxLY;
     ctx->timing.h2d_bytes = n * (int64_t) sizeof(Item) + refBytes + 2 * (n + 1) * 8 + nEv * 24 + nAn * 16 + n * 8 + (B->scale ? n * 40 : 0);
     CK(cudaEventRecord(ctx->ev[1], s));
 
@@ -591,7 +605,7 @@ int stageL(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *params, 
                                         ctx->dCentre.as<double>(), ctx->dEv.as<float4>());
         ctx->timing.kernel_launches += 1;
         launchPrepX(ctx, s);
-    }
+    } else launchPrepGeneric(ctx, s);
     CK(cudaEventRecord(ctx->ev[2], s));
 
     // ---- plan: band cells, widest diagonal, longest run of live forward rows -------------------------------
@@ -683,7 +697,12 @@ int cpecan_cuda_restage_model(cpecan_ctx *ctx, const cpecan_hmm *hmm) {
     if (genericBefore && !ctx->generic) routeGeneric(ctx, hmm);      // the staged batch runs on the FP64 kernel (odd expansion / exact)
     if (ctx->n == 0) return CPECAN_OK;
     if (ctx->machine != machineBefore || ctx->generic != genericBefore) { ctx->err = "restage_model: the staged batch was prepared for the other state machine"; return CPECAN_ERR_ARG; }
-    if (ctx->generic) return CPECAN_OK;                               // that kernel reads the transitions from its arguments, the tables in place
+    if (ctx->generic) {                                               // transitions travel as kernel arguments; the vanilla machine's
+        launchPrepGeneric(ctx, ctx->stream);                          // per-column log transitions and all cached logarithms are re-derived
+        CK(cudaGetLastError());
+        CK(waitStream(ctx, ctx->stream));
+        return CPECAN_OK;
+    }
     launchPrepX(ctx, ctx->stream);
     CK(cudaGetLastError());
     CK(waitStream(ctx, ctx->stream));
@@ -740,6 +759,7 @@ int runAsyncL(cpecan_ctx *ctx) {
             g.scratch = reinterpret_cast<double *>(a.scratch); g.scratch_stride = bk.stride * 2;
             g.ring_rows = bk.ringRows; g.ringN = cfg2N(b);
             g.pairs = a.pairs; g.out = a.out; g.totals = a.totals; g.expect = a.expect; g.P = ctx->P; g.G = ctx->G;
+            g.colp = ctx->dColp.as<double>(); g.rowp = ctx->dRowp.as<double>();
             dispatchGen(ctx->generic, [&](auto k, int S) {
                 k<<<bk.nCta, 32, generic_smem_bytes(cfg2N(b), S), ctx->bstream[b]>>>(g); return 0; });
         } else

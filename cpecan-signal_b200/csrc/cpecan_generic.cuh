@@ -60,22 +60,32 @@ struct KernelArgsG {
     ItemOut *out;
     double *totals;
     double *expect;               // EXPECTATION mode: the batch sums (layout of CPECAN_N_EXPECT / CPECAN_N_EXPECT_VANILLA)
+    const double *colp;           // k_prep_generic: per-column records, gen_ncol(sm) planes of lX + 2 doubles per item at
+                                  // gen_ncol(sm) * xp_off; null for echelon
+    const double *rowp;           // vanilla: log(noise) of every event (item at ev_off, entry y = matrix row)
     DevParams P;
     GenParams G;
 };
 
 __host__ __device__ inline size_t generic_smem_bytes(int ringN, int S) { return (size_t) 4 * S * ringN * sizeof(double); }
 
-// impl/pairwiseAligner.c:235-255 with the reference's float-literal coefficients and branch structure
+// impl/pairwiseAligner.c:235-255 with the reference's float-literal coefficients.  The four segments and the two
+// early returns are SELECTED, not branched on: neighbouring lanes sit in different segments all the time, and a divergent
+// warp would evaluate every segment one after the other.  Same coefficients, same Horner form, same result.
 __device__ __forceinline__ double g_poly(double x) {
-    if (x <= 1.00f) return ((-0.009350833524763f * x + 0.130659527668286f) * x + 0.498799810682272f) * x + 0.693203116424741f;
-    if (x <= 2.50f) return ((-0.014532321752540f * x + 0.139942324101744f) * x + 0.495635523139337f) * x + 0.692140569840976f;
-    if (x <= 4.50f) return ((-0.004605031767994f * x + 0.063427417320019f) * x + 0.695956496475118f) * x + 0.514272634594009f;
-    return ((-0.000458661602210f * x + 0.009695946122598f) * x + 0.930734667215156f) * x + 0.168037164329057f;
+    const bool s0 = x <= 1.00f, s1 = x <= 2.50f, s2 = x <= 4.50f;
+    const double c3 = s0 ? -0.009350833524763f : (s1 ? -0.014532321752540f : (s2 ? -0.004605031767994f : -0.000458661602210f));
+    const double c2 = s0 ? 0.130659527668286f : (s1 ? 0.139942324101744f : (s2 ? 0.063427417320019f : 0.009695946122598f));
+    const double c1 = s0 ? 0.498799810682272f : (s1 ? 0.495635523139337f : (s2 ? 0.695956496475118f : 0.930734667215156f));
+    const double c0 = s0 ? 0.693203116424741f : (s1 ? 0.692140569840976f : (s2 ? 0.514272634594009f : 0.168037164329057f));
+    return ((c3 * x + c2) * x + c1) * x + c0;
 }
 __device__ __forceinline__ double g_la(double x, double y) {
-    if (x < y) return (x == CPG_NI || y - x >= 7.5) ? y : g_poly(y - x) + x;
-    return (y == CPG_NI || x - y >= 7.5) ? x : g_poly(x - y) + y;
+    const bool xl = x < y;
+    const double lo = xl ? x : y, hi = xl ? y : x;
+    const double d = hi - lo;
+    const double r = g_poly(d) + lo;
+    return (lo == CPG_NI || d >= 7.5) ? hi : r;
 }
 // impl/stateMachine.c:333-343 and :322-331
 __device__ __forceinline__ double g_log_gauss(double x, double mu, double sigma) {
@@ -86,6 +96,97 @@ __device__ __forceinline__ double g_log_gauss(double x, double mu, double sigma)
 __device__ __forceinline__ double g_log_inv_gauss(double x, double mu, double lambda) {
     const double a = (x - mu) / mu;
     return (log(lambda) - 1.8378770664093453 - 3 * log(x) - lambda * a * a / x) / 2;
+}
+
+// the same two densities with the logarithms that depend only on the k-mer (log sigma, log lambda) or only on the event
+// (log x) handed in: they are computed once per column / per event by k_prep_generic instead of once per cell
+__device__ __forceinline__ double g_log_gauss_c(double x, double mu, double sigma, double logSigma) {
+    if (sigma == 0.0) return CPG_NI;
+    const double a = (x - mu) / sigma;
+    return -0.91893853320467267 - logSigma + (-0.5 * a * a);
+}
+__device__ __forceinline__ double g_log_inv_gauss_c(double x, double mu, double lambda, double logLambda, double logX) {
+    const double a = (x - mu) / mu;
+    return (logLambda - 1.8378770664093453 - 3 * logX - lambda * a * a / x) / 2;
+}
+
+// Per-column records of the FP64 kernel (everything of a cell's emissions and transitions that depends only on its
+// column: k-mer index, the logarithms of the scaled model's deviations, the vanilla machine's seven log transitions).
+//   threeState / fourState (6): k | log sd_m | tau_m | log tau_m | log sd_y | log tau_y
+//   vanilla (13): k | skip bin | log a_mx | log a_xx | log a_mm | log a_xm | log a_ym | log a_my | log a_yy |
+//                 log sd_m | log lambda_m | log sd_y | log lambda_y
+//   threeStateHdp (1): the row of the HDP's density table the column's k-mer reads
+// The values are the reference's own expressions (impl/stateMachine.c:322-343, 388-427, 631-651), evaluated once.
+__host__ __device__ inline int gen_ncol(int sm) { return sm == 4 ? 13 : (sm == 7 ? 1 : (sm == 5 ? 0 : 6)); }
+
+__global__ void k_prep_generic(const Item *items, const long long *ref_off, const char *ref, const ModelTables *models,
+                               const double *scale, GenParams G, double *colp, double *rowp, const double *events,
+                               const long long *ev_src_off) {
+    const int i = blockIdx.x;
+    const Item it = items[i];
+    const ModelTables mt = models[it.model_id];
+    const char *r = ref + ref_off[i];
+    const int refLen = (int) (ref_off[i + 1] - ref_off[i]);
+    const int sm = G.sm, NC = gen_ncol(sm);
+    const long long CS = it.lX + 2;
+    double *cq = colp + (long long) NC * it.xp_off;
+    const bool scaled = scale != nullptr;
+    double sc = 1, sh = 0, var = 1, scsd = 1, varsd = 1;
+    if (scaled) { const double *s5 = scale + 5 * i; sc = s5[0]; sh = s5[1]; var = s5[2]; scsd = s5[3]; varsd = s5[4]; }
+    auto kmerAt = [&](int p) -> int {
+        int v = 0;
+        for (int j = 0; j < 6; j++) { const int q = p + j; const int b = base_code((q >= 0 && q < refLen) ? r[q] : 'n'); if (b < 0) return -1; v = v * 4 + b; }
+        return v;
+    };
+    // scaled MATCH row as emissions_signal_scaleModel leaves it; the gap-Y row is never scaled
+    auto matchRow = [&](int k, double &mu, double &sd, double &nu, double &tau, double &lam) {
+        if (k < 0) { mu = sd = nu = tau = lam = 0.0; return; }
+        const double *m = mt.match + 1 + 5 * k;
+        mu = m[0]; sd = m[1]; nu = m[2]; tau = m[3]; lam = m[4];
+        if (scaled) { mu = mu * sc + sh; sd = sd * var; nu = nu * scsd; lam = lam * varsd; tau = sqrt(pow(nu, 3.0) / lam); }
+    };
+    for (int x = blockIdx.y * blockDim.x + threadIdx.x; x <= it.lX; x += gridDim.y * blockDim.x) {
+        if (sm == 7) {
+            const int k = kmerAt(x >= 1 ? x - 1 : 0);
+            cq[x] = (double) (k >= 0 ? mt.hdp_kmer[k] : -1);
+        } else if (sm == 4) {
+            const int p = x >= 2 ? x - 2 : 0;
+            double mu0, mu1, sd, nu, tau, lam;
+            matchRow(kmerAt(p), mu0, sd, nu, tau, lam);
+            const int k = kmerAt(p + 1);
+            matchRow(k, mu1, sd, nu, tau, lam);
+            long long bin = (long long) (fabs(mu1 - mu0) / 0.5);
+            bin = bin >= 30 ? 29 : bin;
+            const double a_mx = mt.gapx[bin];
+            const double a_my = (1 - a_mx) * G.van[0];
+            const double a_mm = 1.0f - a_my - a_mx;
+            const double a_yy = G.van[1];
+            const double a_ym = 1.0f - a_yy;
+            const double a_xx = mt.gapx[bin + 30];
+            const double a_xm = 1.0f - a_xx;
+            cq[x] = (double) k; cq[CS + x] = (double) bin;
+            cq[2 * CS + x] = log(a_mx); cq[3 * CS + x] = log(a_xx); cq[4 * CS + x] = log(a_mm); cq[5 * CS + x] = log(a_xm);
+            cq[6 * CS + x] = log(a_ym); cq[7 * CS + x] = log(a_my); cq[8 * CS + x] = log(a_yy);
+            cq[9 * CS + x] = log(sd); cq[10 * CS + x] = log(lam);
+            double ysd = 0.0, ylam = 0.0;
+            if (k >= 0) { ysd = mt.gapy[1 + 5 * k + 1]; ylam = mt.gapy[1 + 5 * k + 4]; }
+            cq[11 * CS + x] = log(ysd); cq[12 * CS + x] = log(ylam);
+        } else {
+            const int k = x >= 1 ? kmerAt(x - 1) : -1;
+            double mu, sd, nu, tau, lam;
+            matchRow(k, mu, sd, nu, tau, lam);
+            cq[x] = (double) k; cq[CS + x] = log(sd); cq[2 * CS + x] = tau; cq[3 * CS + x] = log(tau);
+            double ysd = 0.0, ytau = 0.0;
+            if (k >= 0) { ysd = mt.gapy[1 + 5 * k + 1]; ytau = mt.gapy[1 + 5 * k + 3]; }
+            cq[4 * CS + x] = log(ysd); cq[5 * CS + x] = log(ytau);
+        }
+    }
+    if (sm == 4 && rowp != nullptr) {
+        const double *evs = events + 3 * ev_src_off[i];
+        double *rq = rowp + it.ev_off;
+        for (int y = blockIdx.y * blockDim.x + threadIdx.x; y <= it.lY; y += gridDim.y * blockDim.x)
+            rq[y] = y >= 1 ? log(evs[3 * (y - 1) + 1]) : 0.0;
+    }
 }
 
 template <int SM> struct GenTraits;
@@ -126,6 +227,9 @@ __global__ void __launch_bounds__(32) k_align_generic(const KernelArgsG A) {
         const double *evs = A.events + 3 * A.ev_src_off[itemIdx];
         const ModelTables mt = A.models[it.model_id];
         const int2 *bandp = A.bands + A.band_off[itemIdx];
+        const long long CS = lX + 2;
+        const double *colq = SM == 5 ? nullptr : A.colp + (long long) gen_ncol(SM) * it.xp_off;
+        const double *rowq = SM == 4 ? A.rowp + it.ev_off : nullptr;
         const int *tbp = A.tbs + it.pad1;
         int *pairs = A.pairs + 3 * it.pair_off;
         double *dbgTot = (A.totals != nullptr && it.tot_off >= 0) ? A.totals + it.tot_off : nullptr;
@@ -160,8 +264,7 @@ __global__ void __launch_bounds__(32) k_align_generic(const KernelArgsG A) {
         };
         // dir_proc_density of the k-mer's distribution (impl/hdp.c:2577-2599) through grid_spline_interp
         // (impl/hdp_math_utils.c:471-495); the grid is linspace(start, stop, n) (:497-510)
-        auto hdpDensity = [&](int k, double q) -> double {
-            const int t = k >= 0 ? mt.hdp_kmer[k] : -1;
+        auto hdpDensity = [&](int t, double q) -> double {
             if (t < 0) { status |= 8; return 0.0; }
             const double *yv = mt.hdp_y + (long long) t * mt.hdp_len, *sl = mt.hdp_slope + (long long) t * mt.hdp_len;
             const int n = mt.hdp_len - 1;
@@ -179,6 +282,19 @@ __global__ void __launch_bounds__(32) k_align_generic(const KernelArgsG A) {
                 r = tr * yv[il] + tl * yv[il + 1] + tl * tr * (a * tr + b * tl);
             }
             return r > 0.0 ? r : 0.0;
+        };
+        // the scaled level mean / deviation / noise mean (/ lambda) of a match row: three multiplications, not worth a column
+        auto matchMSN = [&](int k, double &mu, double &sd, double &nu) {
+            if (k < 0) { mu = sd = nu = 0.0; return; }
+            const double *m = mt.match + 1 + 5 * k;
+            mu = m[0]; sd = m[1]; nu = m[2];
+            if (scaled) { mu = mu * sc + sh; sd = sd * var; nu = nu * scsd; }
+        };
+        auto matchMSNL = [&](int k, double &mu, double &sd, double &nu, double &lam) {
+            if (k < 0) { mu = sd = nu = lam = 0.0; return; }
+            const double *m = mt.match + 1 + 5 * k;
+            mu = m[0]; sd = m[1]; nu = m[2]; lam = m[4];
+            if (scaled) { mu = mu * sc + sh; sd = sd * var; nu = nu * scsd; lam = lam * varsd; }
         };
         auto eventOf = [&](int y, double &m, double &n, double &dur) {      // y = matrix row; row 0 is the null event (:261-262)
             if (y >= 1) { m = evs[3 * (y - 1)]; n = evs[3 * (y - 1) + 1]; dur = evs[3 * (y - 1) + 2]; }
@@ -213,7 +329,8 @@ __global__ void __launch_bounds__(32) k_align_generic(const KernelArgsG A) {
             eventOf(y, em, en, edur);
             if (SM == 2) {
                 // stateMachine3_cellCalculate (impl/stateMachine.c:1305-1334); sequence_getKmer: index < 0 reads "n"
-                const int k = x >= 1 ? kmerAt(x - 1) : -1;
+                const double *cq = colq + x;
+                const int k = (int) cq[0];
                 const double *t = A.G.t3;
                 expK = k;
                 if (hasLo) {
@@ -221,20 +338,20 @@ __global__ void __launch_bounds__(32) k_align_generic(const KernelArgsG A) {
                     TRG(lo_, 0, 1, eP + t[3]); TRG(lo_, 1, 1, eP + t[5]); TRG(lo_, 2, 1, eP + t[7]);
                 }
                 if (hasMi) {
-                    double mu, sd, nu, tau, lam;
-                    matchParams(k, mu, sd, nu, tau, lam);
-                    const double eP = g_log_gauss(em, mu, sd) + g_log_gauss(en, nu, tau);
+                    double mu, sd, nu;
+                    matchMSN(k, mu, sd, nu);
+                    const double eP = g_log_gauss_c(em, mu, sd, cq[CS]) + g_log_gauss_c(en, nu, cq[2 * CS], cq[3 * CS]);
                     TRG(mi_, 0, 0, eP + t[0]); TRG(mi_, 1, 0, eP + t[1]); TRG(mi_, 2, 0, eP + t[2]);
                 }
                 if (hasUp) {
                     double mu, sd, nu, tau, lam;
                     gapyParams(k, mu, sd, nu, tau, lam);
-                    const double eP = g_log_gauss(em, mu, sd) + g_log_gauss(en, nu, tau);
+                    const double eP = g_log_gauss_c(em, mu, sd, cq[4 * CS]) + g_log_gauss_c(en, nu, tau, cq[5 * CS]);
                     TRG(up_, 0, 2, eP + t[4]); TRG(up_, 2, 2, eP + t[6]);
                 }
             } else if (SM == 7) {
                 // stateMachine3HDP_cellCalculate (impl/stateMachine.c:1336-1366); sequence_getKmer3: index < 0 reads k-mer 0
-                const int k = kmerAt(x >= 1 ? x - 1 : 0);
+                const int k = (int) colq[x];                  // the density-table row of k-mer max(x - 1, 0)
                 const double *t = A.G.t3;
                 if (hasLo) {
                     const double eP = -2.3025850929940455;
@@ -250,50 +367,43 @@ __global__ void __launch_bounds__(32) k_align_generic(const KernelArgsG A) {
                 }
             } else if (SM == 4) {
                 // stateMachine3Vanilla_cellCalculate (impl/stateMachine.c:1368-1409); sequence_getKmer2: the pointer to the
-                // PREVIOUS k-mer, clamped at 0; the skip bin of (k-mer i, k-mer i+1) on the scaled match table
-                const int i = x >= 2 ? x - 2 : 0;
-                double mu0, mu1, sd, nu, tau, lam;
-                matchParams(kmerAt(i), mu0, sd, nu, tau, lam);
-                const int k = kmerAt(i + 1);
-                matchParams(k, mu1, sd, nu, tau, lam);
-                long long bin = (long long) (fabs(mu1 - mu0) / 0.5);
-                bin = bin >= 30 ? 29 : bin;
-                expBin = (int) bin;
-                const double a_mx = mt.gapx[bin];
-                const double a_my = (1 - a_mx) * A.G.van[0];
-                const double a_mm = 1.0f - a_my - a_mx;
-                const double a_yy = A.G.van[1];
-                const double a_ym = 1.0f - a_yy;
-                const double a_xx = mt.gapx[bin + 30];
-                const double a_xm = 1.0f - a_xx;
-                if (hasLo) { TRG(lo_, 0, 1, 0 + log(a_mx)); TRG(lo_, 1, 1, 0 + log(a_xx)); }
+                // PREVIOUS k-mer, clamped at 0; the skip bin of (k-mer i, k-mer i+1) on the scaled match table -- all of
+                // it per column (k_prep_generic)
+                const double *cq = colq + x;
+                const int k = (int) cq[0];
+                expBin = (int) cq[CS];
+                const double lx = rowq[y >= 0 ? y : 0];
+                if (hasLo) { TRG(lo_, 0, 1, 0 + cq[2 * CS]); TRG(lo_, 1, 1, 0 + cq[3 * CS]); }
                 if (hasMi) {
-                    const double eP = g_log_gauss(em, mu1, sd) + g_log_inv_gauss(en, nu, lam);
-                    TRG(mi_, 0, 0, eP + log(a_mm)); TRG(mi_, 1, 0, eP + log(a_xm)); TRG(mi_, 2, 0, eP + log(a_ym));
+                    double mu1, sd, nu, lam;
+                    matchMSNL(k, mu1, sd, nu, lam);
+                    const double eP = g_log_gauss_c(em, mu1, sd, cq[9 * CS]) + g_log_inv_gauss_c(en, nu, lam, cq[10 * CS], lx);
+                    TRG(mi_, 0, 0, eP + cq[4 * CS]); TRG(mi_, 1, 0, eP + cq[5 * CS]); TRG(mi_, 2, 0, eP + cq[6 * CS]);
                 }
                 if (hasUp) {
                     double mu, sdd, nuu, tt, ll;
                     gapyParams(k, mu, sdd, nuu, tt, ll);
-                    const double eP = g_log_gauss(em, mu, sdd) + g_log_inv_gauss(en, nuu, ll);
-                    TRG(up_, 0, 2, eP + log(a_my)); TRG(up_, 2, 2, eP + log(a_yy));
+                    const double eP = g_log_gauss_c(em, mu, sdd, cq[11 * CS]) + g_log_inv_gauss_c(en, nuu, ll, cq[12 * CS], lx);
+                    TRG(up_, 0, 2, eP + cq[7 * CS]); TRG(up_, 2, 2, eP + cq[8 * CS]);
                 }
             } else if (SM == 6) {
-                const int k = x >= 1 ? kmerAt(x - 1) : -1;
+                const double *cq = colq + x;
+                const int k = (int) cq[0];
                 const double *t = A.G.t4;
                 if (hasLo) {
                     const double eP = k < 0 ? NI : mt.gapx[k];
                     TRG(lo_, 0, 1, eP + t[4]); TRG(lo_, 1, 1, eP + t[5]); TRG(lo_, 0, 3, eP + t[8]); TRG(lo_, 3, 3, eP + t[9]); TRG(lo_, 2, 3, eP + t[10]);
                 }
                 if (hasMi) {
-                    double mu, sd, nu, tau, lam;
-                    matchParams(k, mu, sd, nu, tau, lam);
-                    const double eP = g_log_gauss(em, mu, sd) + g_log_gauss(en, nu, tau);
+                    double mu, sd, nu;
+                    matchMSN(k, mu, sd, nu);
+                    const double eP = g_log_gauss_c(em, mu, sd, cq[CS]) + g_log_gauss_c(en, nu, cq[2 * CS], cq[3 * CS]);
                     TRG(mi_, 0, 0, eP + t[0]); TRG(mi_, 1, 0, eP + t[1]); TRG(mi_, 2, 0, eP + t[2]); TRG(mi_, 3, 0, eP + t[3]);
                 }
                 if (hasUp) {
                     double mu, sd, nu, tau, lam;
                     gapyParams(k, mu, sd, nu, tau, lam);
-                    const double eP = g_log_gauss(em, mu, sd) + g_log_gauss(en, nu, tau);
+                    const double eP = g_log_gauss_c(em, mu, sd, cq[4 * CS]) + g_log_gauss_c(en, nu, tau, cq[5 * CS]);
                     TRG(up_, 0, 2, eP + t[6]); TRG(up_, 2, 2, eP + t[7]);
                 }
             } else {
