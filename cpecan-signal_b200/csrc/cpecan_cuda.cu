@@ -635,7 +635,10 @@ int stageL(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *params, 
         const ItemOut &o = ctx->hOut[i];
         cells += o.band_cells;
         int b = 0;
-        while (b < NCFG2 && (cfg2N(b) < o.max_width + CFG2_MARGIN ||
+        // the FP64 kernel keeps every live diagonal in a buffer of its own: the ring only has to hold one diagonal and the
+        // two positions either side that a sweep clears
+        const int margin = ctx->generic ? 8 : CFG2_MARGIN;
+        while (b < NCFG2 && (cfg2N(b) < o.max_width + margin ||
                              (ctx->generic ? occGenCache[b] : ctx->occ2[b][ctx->machine][sx][ex]) == 0)) b++;
         if (b == NCFG2) { ctx->err = "band wider than the widest ring this device's shared memory holds"; return CPECAN_ERR_BAND_TOO_WIDE; }
         ctx->buckets[b].order.push_back((int) i);

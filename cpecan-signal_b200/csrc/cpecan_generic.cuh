@@ -112,12 +112,13 @@ __device__ __forceinline__ double g_log_inv_gauss_c(double x, double mu, double 
 
 // Per-column records of the FP64 kernel (everything of a cell's emissions and transitions that depends only on its
 // column: k-mer index, the logarithms of the scaled model's deviations, the vanilla machine's seven log transitions).
-//   threeState / fourState (6): k | log sd_m | tau_m | log tau_m | log sd_y | log tau_y
-//   vanilla (13): k | skip bin | log a_mx | log a_xx | log a_mm | log a_xm | log a_ym | log a_my | log a_yy |
-//                 log sd_m | log lambda_m | log sd_y | log lambda_y
+//   threeState / fourState (14): k | gap-X emission | match: mu sd log(sd) nu tau log(tau) | gap Y: the same six
+//   vanilla (21): k | skip bin | log a_mx | log a_xx | log a_mm | log a_xm | log a_ym | log a_my | log a_yy |
+//                 match: mu sd log(sd) nu lambda log(lambda) | gap Y: the same six
+// (planes, so that neighbouring lanes read neighbouring doubles; a cell never touches the 4096-row model tables)
 //   threeStateHdp (1): the row of the HDP's density table the column's k-mer reads
 // The values are the reference's own expressions (impl/stateMachine.c:322-343, 388-427, 631-651), evaluated once.
-__host__ __device__ inline int gen_ncol(int sm) { return sm == 4 ? 13 : (sm == 7 ? 1 : (sm == 5 ? 0 : 6)); }
+__host__ __device__ inline int gen_ncol(int sm) { return sm == 4 ? 21 : (sm == 7 ? 1 : (sm == 5 ? 0 : 14)); }
 
 __global__ void k_prep_generic(const Item *items, const long long *ref_off, const char *ref, const ModelTables *models,
                                const double *scale, GenParams G, double *colp, double *rowp, const double *events,
@@ -167,18 +168,22 @@ __global__ void k_prep_generic(const Item *items, const long long *ref_off, cons
             cq[x] = (double) k; cq[CS + x] = (double) bin;
             cq[2 * CS + x] = log(a_mx); cq[3 * CS + x] = log(a_xx); cq[4 * CS + x] = log(a_mm); cq[5 * CS + x] = log(a_xm);
             cq[6 * CS + x] = log(a_ym); cq[7 * CS + x] = log(a_my); cq[8 * CS + x] = log(a_yy);
-            cq[9 * CS + x] = log(sd); cq[10 * CS + x] = log(lam);
-            double ysd = 0.0, ylam = 0.0;
-            if (k >= 0) { ysd = mt.gapy[1 + 5 * k + 1]; ylam = mt.gapy[1 + 5 * k + 4]; }
-            cq[11 * CS + x] = log(ysd); cq[12 * CS + x] = log(ylam);
+            cq[9 * CS + x] = mu1; cq[10 * CS + x] = sd; cq[11 * CS + x] = log(sd); cq[12 * CS + x] = nu; cq[13 * CS + x] = lam;
+            cq[14 * CS + x] = log(lam);
+            double y[5] = { 0.0, 0.0, 0.0, 0.0, 0.0 };
+            if (k >= 0) for (int j = 0; j < 5; j++) y[j] = mt.gapy[1 + 5 * k + j];
+            cq[15 * CS + x] = y[0]; cq[16 * CS + x] = y[1]; cq[17 * CS + x] = log(y[1]); cq[18 * CS + x] = y[2]; cq[19 * CS + x] = y[4];
+            cq[20 * CS + x] = log(y[4]);
         } else {
             const int k = x >= 1 ? kmerAt(x - 1) : -1;
             double mu, sd, nu, tau, lam;
             matchRow(k, mu, sd, nu, tau, lam);
-            cq[x] = (double) k; cq[CS + x] = log(sd); cq[2 * CS + x] = tau; cq[3 * CS + x] = log(tau);
-            double ysd = 0.0, ytau = 0.0;
-            if (k >= 0) { ysd = mt.gapy[1 + 5 * k + 1]; ytau = mt.gapy[1 + 5 * k + 3]; }
-            cq[4 * CS + x] = log(ysd); cq[5 * CS + x] = log(ytau);
+            cq[x] = (double) k; cq[CS + x] = k < 0 ? CPG_NI : mt.gapx[k];
+            cq[2 * CS + x] = mu; cq[3 * CS + x] = sd; cq[4 * CS + x] = log(sd); cq[5 * CS + x] = nu; cq[6 * CS + x] = tau; cq[7 * CS + x] = log(tau);
+            double y[5] = { 0.0, 0.0, 0.0, 0.0, 0.0 };
+            if (k >= 0) for (int j = 0; j < 5; j++) y[j] = mt.gapy[1 + 5 * k + j];
+            cq[8 * CS + x] = y[0]; cq[9 * CS + x] = y[1]; cq[10 * CS + x] = log(y[1]); cq[11 * CS + x] = y[2]; cq[12 * CS + x] = y[3];
+            cq[13 * CS + x] = log(y[3]);
         }
     }
     if (sm == 4 && rowp != nullptr) {
@@ -283,19 +288,6 @@ __global__ void __launch_bounds__(32) k_align_generic(const KernelArgsG A) {
             }
             return r > 0.0 ? r : 0.0;
         };
-        // the scaled level mean / deviation / noise mean (/ lambda) of a match row: three multiplications, not worth a column
-        auto matchMSN = [&](int k, double &mu, double &sd, double &nu) {
-            if (k < 0) { mu = sd = nu = 0.0; return; }
-            const double *m = mt.match + 1 + 5 * k;
-            mu = m[0]; sd = m[1]; nu = m[2];
-            if (scaled) { mu = mu * sc + sh; sd = sd * var; nu = nu * scsd; }
-        };
-        auto matchMSNL = [&](int k, double &mu, double &sd, double &nu, double &lam) {
-            if (k < 0) { mu = sd = nu = lam = 0.0; return; }
-            const double *m = mt.match + 1 + 5 * k;
-            mu = m[0]; sd = m[1]; nu = m[2]; lam = m[4];
-            if (scaled) { mu = mu * sc + sh; sd = sd * var; nu = nu * scsd; lam = lam * varsd; }
-        };
         auto eventOf = [&](int y, double &m, double &n, double &dur) {      // y = matrix row; row 0 is the null event (:261-262)
             if (y >= 1) { m = evs[3 * (y - 1)]; n = evs[3 * (y - 1) + 1]; dur = evs[3 * (y - 1) + 2]; }
             else { m = NI; n = 0.0; dur = 0.0; }
@@ -334,19 +326,15 @@ __global__ void __launch_bounds__(32) k_align_generic(const KernelArgsG A) {
                 const double *t = A.G.t3;
                 expK = k;
                 if (hasLo) {
-                    const double eP = k < 0 ? NI : mt.gapx[k];
+                    const double eP = cq[CS];
                     TRG(lo_, 0, 1, eP + t[3]); TRG(lo_, 1, 1, eP + t[5]); TRG(lo_, 2, 1, eP + t[7]);
                 }
                 if (hasMi) {
-                    double mu, sd, nu;
-                    matchMSN(k, mu, sd, nu);
-                    const double eP = g_log_gauss_c(em, mu, sd, cq[CS]) + g_log_gauss_c(en, nu, cq[2 * CS], cq[3 * CS]);
+                    const double eP = g_log_gauss_c(em, cq[2 * CS], cq[3 * CS], cq[4 * CS]) + g_log_gauss_c(en, cq[5 * CS], cq[6 * CS], cq[7 * CS]);
                     TRG(mi_, 0, 0, eP + t[0]); TRG(mi_, 1, 0, eP + t[1]); TRG(mi_, 2, 0, eP + t[2]);
                 }
                 if (hasUp) {
-                    double mu, sd, nu, tau, lam;
-                    gapyParams(k, mu, sd, nu, tau, lam);
-                    const double eP = g_log_gauss_c(em, mu, sd, cq[4 * CS]) + g_log_gauss_c(en, nu, tau, cq[5 * CS]);
+                    const double eP = g_log_gauss_c(em, cq[8 * CS], cq[9 * CS], cq[10 * CS]) + g_log_gauss_c(en, cq[11 * CS], cq[12 * CS], cq[13 * CS]);
                     TRG(up_, 0, 2, eP + t[4]); TRG(up_, 2, 2, eP + t[6]);
                 }
             } else if (SM == 7) {
@@ -370,40 +358,30 @@ __global__ void __launch_bounds__(32) k_align_generic(const KernelArgsG A) {
                 // PREVIOUS k-mer, clamped at 0; the skip bin of (k-mer i, k-mer i+1) on the scaled match table -- all of
                 // it per column (k_prep_generic)
                 const double *cq = colq + x;
-                const int k = (int) cq[0];
                 expBin = (int) cq[CS];
                 const double lx = rowq[y >= 0 ? y : 0];
                 if (hasLo) { TRG(lo_, 0, 1, 0 + cq[2 * CS]); TRG(lo_, 1, 1, 0 + cq[3 * CS]); }
                 if (hasMi) {
-                    double mu1, sd, nu, lam;
-                    matchMSNL(k, mu1, sd, nu, lam);
-                    const double eP = g_log_gauss_c(em, mu1, sd, cq[9 * CS]) + g_log_inv_gauss_c(en, nu, lam, cq[10 * CS], lx);
+                    const double eP = g_log_gauss_c(em, cq[9 * CS], cq[10 * CS], cq[11 * CS]) + g_log_inv_gauss_c(en, cq[12 * CS], cq[13 * CS], cq[14 * CS], lx);
                     TRG(mi_, 0, 0, eP + cq[4 * CS]); TRG(mi_, 1, 0, eP + cq[5 * CS]); TRG(mi_, 2, 0, eP + cq[6 * CS]);
                 }
                 if (hasUp) {
-                    double mu, sdd, nuu, tt, ll;
-                    gapyParams(k, mu, sdd, nuu, tt, ll);
-                    const double eP = g_log_gauss_c(em, mu, sdd, cq[11 * CS]) + g_log_inv_gauss_c(en, nuu, ll, cq[12 * CS], lx);
+                    const double eP = g_log_gauss_c(em, cq[15 * CS], cq[16 * CS], cq[17 * CS]) + g_log_inv_gauss_c(en, cq[18 * CS], cq[19 * CS], cq[20 * CS], lx);
                     TRG(up_, 0, 2, eP + cq[7 * CS]); TRG(up_, 2, 2, eP + cq[8 * CS]);
                 }
             } else if (SM == 6) {
                 const double *cq = colq + x;
-                const int k = (int) cq[0];
                 const double *t = A.G.t4;
                 if (hasLo) {
-                    const double eP = k < 0 ? NI : mt.gapx[k];
+                    const double eP = cq[CS];
                     TRG(lo_, 0, 1, eP + t[4]); TRG(lo_, 1, 1, eP + t[5]); TRG(lo_, 0, 3, eP + t[8]); TRG(lo_, 3, 3, eP + t[9]); TRG(lo_, 2, 3, eP + t[10]);
                 }
                 if (hasMi) {
-                    double mu, sd, nu;
-                    matchMSN(k, mu, sd, nu);
-                    const double eP = g_log_gauss_c(em, mu, sd, cq[CS]) + g_log_gauss_c(en, nu, cq[2 * CS], cq[3 * CS]);
+                    const double eP = g_log_gauss_c(em, cq[2 * CS], cq[3 * CS], cq[4 * CS]) + g_log_gauss_c(en, cq[5 * CS], cq[6 * CS], cq[7 * CS]);
                     TRG(mi_, 0, 0, eP + t[0]); TRG(mi_, 1, 0, eP + t[1]); TRG(mi_, 2, 0, eP + t[2]); TRG(mi_, 3, 0, eP + t[3]);
                 }
                 if (hasUp) {
-                    double mu, sd, nu, tau, lam;
-                    gapyParams(k, mu, sd, nu, tau, lam);
-                    const double eP = g_log_gauss_c(em, mu, sd, cq[4 * CS]) + g_log_gauss_c(en, nu, tau, cq[5 * CS]);
+                    const double eP = g_log_gauss_c(em, cq[8 * CS], cq[9 * CS], cq[10 * CS]) + g_log_gauss_c(en, cq[11 * CS], cq[12 * CS], cq[13 * CS]);
                     TRG(up_, 0, 2, eP + t[6]); TRG(up_, 2, 2, eP + t[7]);
                 }
             } else {
