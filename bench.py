@@ -320,6 +320,9 @@ def main():
                          "by band cells, longest first (em.shard_by_cells)")
     ap.add_argument("--machine", default="three", choices=["three", "vanilla"],
                     help="state machine of the posterior workload (the headline is the three-state machine)")
+    ap.add_argument("--arithmetic", default="fp32", choices=["fp32", "exact"],
+                    help="exact: cpecan_cuda_set_exact_arithmetic -- the FP64 kernel in the reference's own operation order "
+                         "(use a smaller --reads-per-gpu: it runs at 5-8 %% of the FP32 rate)")
     ap.add_argument("--workload", default="posterior", choices=["posterior", "em"],
                     help="posterior = BASELINE config 3/4 (default, the headline); em = config 5, one Baum-Welch "
                          "iteration per step (E-step kernels + NCCL all-reduce + M-step)")
@@ -379,6 +382,7 @@ def main():
         e = EXPANSIONS[j]
         sub = by_exp[j]
         eng = Engine(local)
+        eng.set_exact_arithmetic(args.arithmetic == "exact")
         mid = eng.upload_model(l1, l3, gapx_tbl)
         hb = HostBatch([r.ref for r in sub], [r.events for r in sub], [r.anchors for r in sub],
                        model_ids=[mid] * len(sub), scales=[r.scale5 for r in sub], ragged=[(1, 1)] * len(sub))
@@ -482,6 +486,7 @@ def main():
         for _ in range(min(2, SUB)):
             eng = Engine(local)
             eng.set_resident_warps(8)
+            eng.set_exact_arithmetic(args.arithmetic == "exact")
             eng.upload_model(tbl_match, tbl_gapy, gapx_tbl)
             pair.append((eng, []))
         off = 0
@@ -554,7 +559,7 @@ def main():
     line = {
         "metric": METRIC, "value": gcups, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f64" if args.arithmetic == "exact" else "f32", "data": "synthetic",
         "reads_per_s": reads_total * args.steps / wall, "band_cells_per_s": cells_total * args.steps / wall,
         "config": {"workload": "C3: batched synthetic reads lX~6700 x lY~8000 events, 6-mer template model, anchors "
                                "every 50 k-mers, expansions 64/128/256 evenly, %s, threshold 0.01, ragged (1,1)" % (
@@ -602,6 +607,12 @@ def main():
                                 "sample": "%d reads of the same batch, one process per read on %d cores, %.1f s wall, "
                                           "%.1f core-s" % (n_s, cores, wall_c, core_s),
                                 "band_cells_per_core_s": cells_c / core_s}
+    if args.arithmetic == "exact":
+        # the FP64 kernel (k_align_generic): the FP32 issue roofline and the ncu traffic figures above are k_align3's
+        line["config"]["arithmetic"] = "exact: FP64 kernel k_align_generic in the reference's own operation order (cpecan_cuda_set_exact_arithmetic)"
+        line["roofline"] = {"bound": "fp64_latency", "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": None,
+                            "note": "issue slots 24 % busy, long-scoreboard bound (profiles/r2_ncu_k_align_generic_e64_summary.txt)"}
+        line.pop("roofline_hbm", None)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -159,17 +159,6 @@ template <typename F> auto dispatchK2(int mach, bool sx, bool ex, F f) {
     return ex ? f(k_align3<0, false, true>) : f(k_align3<0, false, false>);
 }
 inline size_t smemCfg2(int cfg, int mach, bool ex) { return align3_smem_bytes(cfg2N(cfg), ex && !mach); }
-cudaError_t prepCfg2(int cfg) {
-    for (int mach = 0; mach < 2; mach++)
-        for (int sx = 0; sx < 2; sx++)
-            for (int ex = 0; ex < 2; ex++) {
-                const int bytes = (int) smemCfg2(cfg, mach, ex != 0);
-                cudaError_t e = dispatchK2(mach, sx != 0, ex != 0, [&](auto k) {
-                    return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); });
-                if (e != cudaSuccess) return e;
-            }
-    return cudaSuccess;
-}
 int occCfg2(int cfg, int mach, bool sx, bool ex) {
     const size_t bytes = smemCfg2(cfg, mach, ex);
     return dispatchK2(mach, sx, ex, [&](auto k) {
@@ -193,10 +182,26 @@ template <typename F> auto dispatchGen(int sm, F f) {
     }
 }
 int genStates(int sm) { return sm == CPECAN_SM_ECHELON ? 7 : (sm == CPECAN_SM_FOUR_STATE ? 4 : 3); }
-int occGen(int cfg, int sm) {
+// Dynamic shared memory: every alignment kernel gets the device's opt-in maximum ONCE per device and process.  (Setting the
+// attribute per ring size, as a context was created or a batch staged, lowered it for a moment under the kernels other
+// host threads were launching through their own contexts: "invalid argument".)
+void setMaxSmemOnce(int device, int optin) {
+    static std::once_flag flags[64];
+    std::call_once(flags[device & 63], [&]() {
+        for (int mach = 0; mach < 2; mach++)
+            for (int sx = 0; sx < 2; sx++)
+                for (int ex = 0; ex < 2; ex++)
+                    dispatchK2(mach, sx != 0, ex != 0, [&](auto k) { return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, optin); });
+        const int sms[5] = { CPECAN_SM_THREE_STATE, CPECAN_SM_VANILLA, CPECAN_SM_ECHELON, CPECAN_SM_FOUR_STATE, CPECAN_SM_THREE_STATE_HDP };
+        for (int sm : sms) dispatchGen(sm, [&](auto k, int) { return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, optin); });
+        cudaGetLastError();
+    });
+}
+
+int occGen(int cfg, int sm, size_t optin) {
     return dispatchGen(sm, [&](auto k, int S) {
         const size_t bytes = generic_smem_bytes(cfg2N(cfg), S);
-        if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes) != cudaSuccess) { cudaGetLastError(); return 0; }
+        if (bytes > optin) return 0;
         int nb = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, 32, bytes) != cudaSuccess) { cudaGetLastError(); return 0; }
         return nb; });
@@ -348,12 +353,12 @@ int cpecan_cuda_init(int device, cpecan_ctx **ctx_out) {
     for (auto &st : ctx->bstream) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
     for (auto &e : ctx->bev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->evBlock, cudaEventBlockingSync | cudaEventDisableTiming);
-    for (int c = 0; c < NCFG2; c++) {
-        if (prepCfg2(c) != cudaSuccess) { cudaGetLastError(); break; }      // ring too large for this device's shared memory
+    setMaxSmemOnce(device, (int) ctx->prop.sharedMemPerBlockOptin);
+    for (int c = 0; c < NCFG2; c++)
         for (int mach = 0; mach < 2; mach++)
             for (int sx = 0; sx < 2; sx++)
-                for (int ex = 0; ex < 2; ex++) ctx->occ2[c][mach][sx][ex] = occCfg2(c, mach, sx != 0, ex != 0);
-    }
+                for (int ex = 0; ex < 2; ex++)        // 0: ring too large for this device's shared memory
+                    ctx->occ2[c][mach][sx][ex] = smemCfg2(c, mach, ex != 0) > ctx->prop.sharedMemPerBlockOptin ? 0 : occCfg2(c, mach, sx != 0, ex != 0);
     *ctx_out = ctx;
     return CPECAN_OK;
 }
@@ -628,7 +633,7 @@ int stageL(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *params, 
     for (auto &b : ctx->buckets) { b.order.clear(); b.nCta = 0; b.ringRows = 0; }
     const int sx = ctx->hasSX ? 1 : 0, ex = mode == CPECAN_MODE_EXPECTATION ? 1 : 0;
     int occGenCache[NCFG2] = {};
-    if (ctx->generic) for (int b = 0; b < NCFG2; b++) occGenCache[b] = occGen(b, ctx->generic);
+    if (ctx->generic) for (int b = 0; b < NCFG2; b++) occGenCache[b] = occGen(b, ctx->generic, ctx->prop.sharedMemPerBlockOptin);
     const int genS = genStates(ctx->generic);
     int64_t cells = 0;
     for (int64_t i = 0; i < n; i++) {
