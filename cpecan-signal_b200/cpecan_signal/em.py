@@ -300,6 +300,134 @@ def gpu_estep(engine, batch, hmm, params, distributed):
     return out
 
 
+# ------------------------------------------------------------------------------------------------ threeStateHdp
+THREE_STATE_HDP = 7
+
+
+class HdpHmm:
+    """Expectations of the HDP machine (reference inc/continuousHmm.h:27-38, impl/continuousHmm.c:630-749): the 3 x 3
+    transition sums, the likelihood, and the event-to-k-mer ASSIGNMENTS (event mean, 6-mer) that feed the next round of
+    Gibbs sampling.  Across ranks the transition sums are all-reduced like the other machines'; the assignment lists are
+    of different lengths per rank and are all-GATHERED in rank order (gather_assignments)."""
+
+    def __init__(self, pseudocount=0.0, threshold=0.01):
+        self.transitions = np.full(9, float(pseudocount))
+        self.likelihood = 0.0
+        self.threshold = float(threshold)
+        self.means = np.zeros(0)
+        self.kmers = np.zeros(0, dtype=np.int32)             # ACGT 6-mer indices (A0 C1 G2 T3, first base most significant)
+
+    def add(self, vec10, means, kmers):
+        """vec10: 9 transition sums + likelihood; means / kmers: this batch's assignments in order."""
+        vec10 = np.asarray(vec10, dtype=np.float64)
+        if np.isnan(vec10[:9]).any():
+            return False
+        self.transitions += vec10[:9]
+        self.likelihood += float(vec10[9])
+        self.means = np.concatenate([self.means, np.asarray(means, dtype=np.float64)])
+        self.kmers = np.concatenate([self.kmers, np.asarray(kmers, dtype=np.int32)])
+        return True
+
+    @staticmethod
+    def kmer_string(k):
+        return "".join("ACGT"[(int(k) >> (2 * (5 - j))) & 3] for j in range(6))
+
+    def write(self, path):
+        """hdpHmm_writeToFile (impl/continuousHmm.c:704-749), byte for byte: what `vanillaAlign -d -t` emits and
+        updateHdpFromAssignments (vanillaAlign.c:142-154) reads back."""
+        with open(path, "w") as fh:
+            fh.write("%d\t%d\t%f\t%d\t\n" % (THREE_STATE_HDP, 3, self.threshold, len(self.means)))
+            if not np.isnan(self.transitions).any():
+                fh.write("".join("%f\t" % t for t in self.transitions) + "%f\n" % self.likelihood)
+                fh.write("".join("%f\t" % m for m in self.means) + "\n")
+                fh.write("".join(self.kmer_string(k) + "\t" for k in self.kmers) + "\n")
+
+    @classmethod
+    def load(cls, path):
+        import gzip
+        op = gzip.open if str(path).endswith(".gz") else open
+        with op(path, "rt") as fh:
+            head = fh.readline().split()
+            if len(head) != 4 or int(head[0]) != THREE_STATE_HDP:
+                raise ValueError("not an HdpHmm file: %r" % (head,))
+            h = cls(0.0, float(head[2]))
+            l1 = fh.readline().split()
+            if len(l1) != 10:
+                raise ValueError("expected 9 transitions and the likelihood, got %d numbers" % len(l1))
+            h.transitions = np.array(l1[:9], dtype=np.float64)
+            h.likelihood = float(l1[9])
+            h.means = np.array(fh.readline().split(), dtype=np.float64)
+            code = {c: i for i, c in enumerate("ACGT")}
+            h.kmers = np.array([sum(code[c] << (2 * (5 - j)) for j, c in enumerate(k)) for k in fh.readline().split()], dtype=np.int32)
+            if len(h.means) != int(head[3]) or len(h.kmers) != int(head[3]):
+                raise ValueError("the file announces %s assignments and holds %d / %d" % (head[3], len(h.means), len(h.kmers)))
+        return h
+
+
+def gather_assignments(means, kmers, distributed):
+    """All ranks' assignment lists concatenated in rank order on every rank: the lengths are exchanged first, the lists
+    padded to the longest (torch.distributed.all_gather takes equal shapes; gloo on CPU tensors, NCCL on CUDA ones)."""
+    means = np.ascontiguousarray(means, dtype=np.float64)
+    kmers = np.ascontiguousarray(kmers, dtype=np.int32)
+    if not distributed:
+        return means, kmers
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    n = torch.tensor([len(means)], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n)
+    sizes = [int(t.item()) for t in sizes]
+    longest = max(1, max(sizes))
+    buf = torch.zeros(longest, 2, dtype=torch.float64, device=dev)       # (mean, k-mer index): 4095 is exact in a double
+    if len(means):
+        buf[:len(means), 0] = torch.from_numpy(means).to(dev)
+        buf[:len(means), 1] = torch.from_numpy(kmers.astype(np.float64)).to(dev)
+    parts = [torch.zeros_like(buf) for _ in range(world)]
+    dist.all_gather(parts, buf)
+    allm = np.concatenate([p[:k, 0].cpu().numpy() for p, k in zip(parts, sizes)])
+    allk = np.concatenate([p[:k, 1].cpu().numpy() for p, k in zip(parts, sizes)]).astype(np.int32)
+    return allm, allk
+
+
+def batch_assignments(batch, results, assignments):
+    """(event means, k-mer indices) of a batch's assignment triples (Engine.hdp_expectations_batch), item by item."""
+    code = np.full(256, -1, dtype=np.int64)
+    for i, c in enumerate(b"ACGT"):
+        code[c] = i
+    means, kmers = [], []
+    for i in range(batch.n):
+        n, off = int(results[i]["n_pairs"]), int(results[i]["pair_off"])
+        if n == 0:
+            continue
+        t = assignments[off:off + n]
+        x = t[:, 1].astype(np.int64) + int(batch.ref_off[i])
+        y = t[:, 2].astype(np.int64) + int(batch.ev_off[i])
+        k = np.zeros(n, dtype=np.int64)
+        for j in range(6):
+            k = k * 4 + code[batch.ref[x + j]]
+        means.append(batch.events[y, 0])
+        kmers.append(k.astype(np.int32))
+    if not means:
+        return np.zeros(0), np.zeros(0, dtype=np.int32)
+    return np.concatenate(means), np.concatenate(kmers)
+
+
+def gpu_hdp_estep(engine, batch, hmm, params, distributed, container=None):
+    """E-step of this rank's shard with the HDP machine: transition sums + likelihood all-reduced (10 doubles), the
+    assignments all-gathered; returns the HdpHmm container every rank ends up with."""
+    vec, res, asg = engine.hdp_expectations_batch(batch, hmm=hmm, params=params)
+    if int((res["status"] & 1).sum()):
+        raise ValueError("assignment buffer too small")
+    v10 = np.concatenate([vec[:9], vec[-1:]])
+    allreduce_sum(v10, bool(distributed))
+    means, kmers = gather_assignments(*batch_assignments(batch, res, asg), bool(distributed))
+    out = container if container is not None else HdpHmm(0.0, params.threshold)
+    out.add(v10, means, kmers)
+    return out
+
+
 def em_iteration(model, estep_sum, n_reads_total, hmm_path, rank=0, pseudocount=1e-4, barrier=None):
     """M-step shared by every rank.  estep_sum: the all-reduced expectation vector of the iteration.  Mirrors
     add_and_norm_expectations (scripts/trainModels.py:126-135): the model object carries its (normalised) values into

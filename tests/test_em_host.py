@@ -228,3 +228,58 @@ def test_em_world2_gloo_matches_single_rank(tmp_path):
     np.testing.assert_allclose(l2, l1, rtol=1e-12)
     assert h1 == h2
     assert l1[-1] >= l1[0] - 0.05 * abs(l1[0])
+
+
+def test_hdp_container_round_trip(tmp_path):
+    """HdpHmm.write reproduces the reference CLI's `-d -t` file byte for byte from its parsed content."""
+    import gzip
+    gold = os.path.join(ROOT, "tests", "golden", "vanillaAlign", "t_d.exp.gz")
+    h = em.HdpHmm.load(gold)
+    assert len(h.means) == 13289 and h.threshold == 0.01 and em.HdpHmm.kmer_string(h.kmers[0]) == gzip.open(gold, "rt").read().split("\n")[3].split("\t")[0]
+    out = str(tmp_path / "t.exp")
+    h.write(out)
+    assert open(out, "rb").read() == gzip.open(gold, "rb").read()
+
+
+HDP_WORKER = textwrap.dedent("""
+    import os, sys
+    import numpy as np
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join({root!r}, "cpecan-signal_b200"))
+    from cpecan_signal import em
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    rng = np.random.default_rng(10 + rank)
+    n = [5, 0, 12, 3][rank]                                   # ragged, one rank with nothing
+    means, kmers = rng.normal(60, 5, n), rng.integers(0, 4096, n).astype(np.int32)
+    v = np.arange(10, dtype=np.float64) * (rank + 1)
+    em.allreduce_sum(v, True)
+    m, k = em.gather_assignments(means, kmers, True)
+    h = em.HdpHmm(1e-4, 0.01)
+    h.add(v, m, k)
+    h.write(sys.argv[1] + ".%d" % rank)
+    dist.barrier()
+    dist.destroy_process_group()
+""")
+
+
+def test_hdp_assignments_gather_world3_gloo(tmp_path):
+    """Variable-length all-gather of the assignment lists (rank order) and all-reduce of the sums: every rank writes the
+    same file, equal to the one built from the per-rank pieces by hand."""
+    world = 3
+    script = tmp_path / "hw.py"
+    script.write_text(HDP_WORKER.format(root=ROOT))
+    base = str(tmp_path / "h.exp")
+    subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+                    "--master-port", "29641", str(script), base], check=True, timeout=600, capture_output=True)
+    want = em.HdpHmm(1e-4, 0.01)
+    ms, ks = [], []
+    for r in range(world):
+        rng = np.random.default_rng(10 + r)
+        n = [5, 0, 12, 3][r]
+        ms.append(rng.normal(60, 5, n)); ks.append(rng.integers(0, 4096, n).astype(np.int32))
+    want.add(np.arange(10, dtype=np.float64) * sum(range(1, world + 1)), np.concatenate(ms), np.concatenate(ks))
+    want.write(base + ".want")
+    files = [open(base + ".%d" % r).read() for r in range(world)]
+    assert files[0] == files[1] == files[2] == open(base + ".want").read()
+    assert files[0].split("\n")[0].split("\t")[3] == "17"

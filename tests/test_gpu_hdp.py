@@ -237,3 +237,25 @@ def test_unmodified_vanilla_align_hdp_expectations(tmp_path, hdp_fixture):
     assert got[0] == want[0] and len(got) == len(want)              # type, states, threshold, number of assignments
     np.testing.assert_allclose(np.array(got[1].split(), dtype=np.float64), np.array(want[1].split(), dtype=np.float64), rtol=0, atol=2e-6)
     assert got[2] == want[2] and got[3] == want[3]                  # event means, k-mers
+
+
+def test_em_driver_hdp_estep(engine, zymo, hdp_fixture, tmp_path):
+    """cpecan_signal.em.gpu_hdp_estep (single rank): the HdpHmm container -- transition sums, likelihood, the assigned
+    event means and k-mers in order -- against the reference's own lists, and its text file in the reference's format."""
+    from cpecan_signal import HostBatch, default_params, em, hdp_hmm
+    g = hdp_fixture["golden"]
+    mid = engine.upload_hdp(hdp_fixture["hdp"])
+    batch = HostBatch([zymo["ref"]], [hdp_fixture["events"]], [zymo["anchors_template"]], model_ids=[mid], ragged=[(1, 1)])
+    h = em.gpu_hdp_estep(engine, batch, hdp_hmm(), default_params(diagonalExpansion=50, threshold=0.01), distributed=False,
+                         container=em.HdpHmm(1e-4, 0.01))
+    engine.release_model(mid)
+    want = g["hdpexp_e50_r11_vec"]
+    np.testing.assert_allclose(h.transitions, want[:9], rtol=1e-9, atol=1e-12)
+    assert abs(h.likelihood - want[9]) <= 1e-9 * abs(want[9])
+    asg = g["hdpexp_e50_r11_assignments"]
+    assert np.array_equal(h.means, hdp_fixture["events"][asg[:, 1], 0])
+    assert [em.HdpHmm.kmer_string(k) for k in h.kmers] == [zymo["ref"][x:x + 6] for x in asg[:, 0]]
+    out = str(tmp_path / "t.exp")
+    h.write(out)
+    back = em.HdpHmm.load(out)
+    assert len(back.means) == len(asg) and np.array_equal(back.kmers, h.kmers)
