@@ -919,6 +919,11 @@ void runPosterior(cpecan_ctx *ctx, const cpecan_hmm &hmm, const cpecan_params &p
     }
     for (int64_t i = 0; i < f.n(); i++) {
         if (res[(size_t) i].status & CPECAN_ITEM_BAND_STEP) st_errAbort("cpecan: anchors are not strictly increasing (run filterToRemoveOverlap)");
+        if (hmm.sm_type == CPECAN_SM_THREE_STATE_HDP && (res[(size_t) i].status & CPECAN_ITEM_BAD_KMER)) {
+            // kmer_to_word (impl/nanopore_hdp.c:358-373) ends the program on the first such k-mer
+            fprintf(stderr, "vanillaAlign - ERROR: K-mer contains character outside alphabet.\n");
+            exit(EXIT_FAILURE);
+        }
         stList *out = results[f.owner[(size_t) i]];
         const int32_t *t = triples.data() + 3 * res[(size_t) i].pair_off;
         if (mode == CPECAN_MODE_UNBANDED) {
@@ -1119,7 +1124,10 @@ void getExpectationsUsingAnchors(StateMachine *sM, Hmm *hmmExpectations, Sequenc
                 st_errAbort("cpecan_cuda_hdp_expectations_batch: %s", cpecan_cuda_last_error(ctx));
             bool overflow = false;
             int64_t need = 0;
-            for (auto &r : res) { overflow |= (r.status & CPECAN_ITEM_PAIR_OVERFLOW) != 0; need += r.n_pairs; }
+            for (auto &r : res) {
+                overflow |= (r.status & CPECAN_ITEM_PAIR_OVERFLOW) != 0; need += r.n_pairs;
+                if (r.status & CPECAN_ITEM_BAD_KMER) { fprintf(stderr, "vanillaAlign - ERROR: K-mer contains character outside alphabet.\n"); exit(EXIT_FAILURE); }
+            }
             if (!overflow) break;
             if (attempt == 1) st_errAbort("cpecan: assignment buffer overflow");
             cap = 8 * need + 1024;

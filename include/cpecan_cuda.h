@@ -46,7 +46,9 @@ enum {
     CPECAN_ITEM_BAND_STEP = 4,     /* band edge moved backwards or by more than one cell between diagonals (never for anchors that
                                       went through filterToRemoveOverlap): the item is not aligned */
     CPECAN_ITEM_BAD_KMER = 8       /* expectation mode: the reference holds a non-ACGT k-mer, every path is -inf; the read is
-                                      dropped from the sums as the reference drops it (status also carries NONFINITE) */
+                                      dropped from the sums as the reference drops it (status also carries NONFINITE).
+                                      threeStateHdp, any mode: a k-mer the HDP's alphabet cannot spell was met (its density
+                                      read as 0); the reference ends the program there (impl/nanopore_hdp.c:358-373) */
 };
 
 typedef struct cpecan_ctx cpecan_ctx;

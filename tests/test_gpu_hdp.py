@@ -94,6 +94,11 @@ def test_model_kinds_do_not_mix(engine, template_tables, hdp_fixture):
         engine.align_batch(HostBatch([r.ref], [r.events], [r.anchors], model_ids=[hid], ragged=[(1, 1)]))
     with pytest.raises(EngineError, match="not threeStateHdp"):
         engine.hdp_expectations_batch(HostBatch([r.ref], [r.events], [r.anchors], model_ids=[pore], ragged=[(1, 1)]), hmm=three_state_hmm())
+    # a k-mer the HDP's alphabet cannot spell: reported per item (the reference ends the program; so does the host library)
+    bad = r.ref[:40] + "N" + r.ref[41:]
+    res, _, _ = engine.align_batch(HostBatch([bad, r.ref], [r.events, r.events], [r.anchors, r.anchors], model_ids=[hid, hid],
+                                             ragged=[(1, 1), (1, 1)]), hmm=hdp_hmm(), pair_cap=100000)
+    assert res[0]["status"] & 8 and res[1]["status"] == 0
     engine.release_model(pore)
     engine.release_model(hid)
 
