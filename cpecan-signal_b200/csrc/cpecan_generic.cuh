@@ -26,6 +26,9 @@
 namespace cpecan {
 
 #define CPG_NI (-CUDART_INF)
+#ifndef CPG_MINB
+#define CPG_MINB 1
+#endif
 
 struct GenParams {
     int sm;                 // 6 = fourState, 5 = echelon, 7 = threeStateHdp, and -- for band shapes k_align3 does not take (odd expansions) --
@@ -202,7 +205,7 @@ template <> struct GenTraits<7> { static constexpr int S = 3; };
 template <> struct GenTraits<4> { static constexpr int S = 3; };
 
 template <int SM>
-__global__ void __launch_bounds__(32) k_align_generic(const KernelArgsG A) {
+__global__ void __launch_bounds__(32, CPG_MINB) k_align_generic(const KernelArgsG A) {
     constexpr int S = GenTraits<SM>::S;
     extern __shared__ __align__(16) unsigned char smraw[];
     double *ring = reinterpret_cast<double *>(smraw);           // 4 buffers x S planes x N
