@@ -198,15 +198,15 @@ __global__ void k_prep_generic(const Item *items, const long long *ref_off, cons
 }
 
 template <int SM> struct GenTraits;
-template <> struct GenTraits<6> { static constexpr int S = 4; };
-template <> struct GenTraits<5> { static constexpr int S = 7; };
-template <> struct GenTraits<2> { static constexpr int S = 3; };
-template <> struct GenTraits<7> { static constexpr int S = 3; };
-template <> struct GenTraits<4> { static constexpr int S = 3; };
+template <> struct GenTraits<6> { static constexpr int S = 4, NC = 14; };
+template <> struct GenTraits<5> { static constexpr int S = 7, NC = 0; };
+template <> struct GenTraits<2> { static constexpr int S = 3, NC = 14; };
+template <> struct GenTraits<7> { static constexpr int S = 3, NC = 1; };
+template <> struct GenTraits<4> { static constexpr int S = 3, NC = 21; };
 
 template <int SM>
 __global__ void __launch_bounds__(32, CPG_MINB) k_align_generic(const KernelArgsG A) {
-    constexpr int S = GenTraits<SM>::S;
+    constexpr int S = GenTraits<SM>::S, NC = GenTraits<SM>::NC;
     extern __shared__ __align__(16) unsigned char smraw[];
     double *ring = reinterpret_cast<double *>(smraw);           // 4 buffers x S planes x N
     const int N = A.ringN, NM = N - 1;
@@ -291,9 +291,26 @@ __global__ void __launch_bounds__(32, CPG_MINB) k_align_generic(const KernelArgs
             }
             return r > 0.0 ? r : 0.0;
         };
-        auto eventOf = [&](int y, double &m, double &n, double &dur) {      // y = matrix row; row 0 is the null event (:261-262)
-            if (y >= 1) { m = evs[3 * (y - 1)]; n = evs[3 * (y - 1) + 1]; dur = evs[3 * (y - 1) + 2]; }
-            else { m = NI; n = 0.0; dur = 0.0; }
+
+        // Everything a cell reads from global memory -- its column's record, its event, (vanilla) log noise -- as one
+        // value: the sweeps load it ONCE per cell and one chunk AHEAD of its use (the first uses of these loads were
+        // half of all stall samples when they sat inside the cell body)
+        struct CellIn { double c[NC > 0 ? NC : 1]; double em, en, edur, lx; };
+        auto loadIn = [&](int x, int y, bool ok) -> CellIn {
+            CellIn in;
+#pragma unroll
+            for (int j = 0; j < (NC > 0 ? NC : 1); j++) in.c[j] = 0.0;
+            in.em = NI; in.en = 0.0; in.edur = 0.0; in.lx = 0.0;
+            if (ok) {
+                if (NC > 0) {
+                    const double *cq = colq + x;
+#pragma unroll
+                    for (int j = 0; j < NC; j++) in.c[j] = __ldg(cq + j * CS);
+                }
+                if (y >= 1) { const double *e = evs + 3 * (y - 1); in.em = __ldg(e); in.en = __ldg(e + 1); in.edur = __ldg(e + 2); }
+                if (SM == 4) in.lx = __ldg(rowq + (y >= 0 ? y : 0));
+            }
+            return in;
         };
 
         // One cell in the reference's transition order.  FWD: cur[to] (+)= nb[from] + (eP + tP) (pull); BWD: the same
@@ -315,16 +332,16 @@ __global__ void __launch_bounds__(32, CPG_MINB) k_align_generic(const KernelArgs
                 if (from == 1 && to == 1) atomicAdd(A.expect + expBin + 30, p);
             }
         };
-        auto cellGen = [&](int fwd, int x, int y, double *cur, double *lo_, bool hasLo, double *mi_, bool hasMi,
+        auto cellGen = [&](int fwd, int x, int y, const CellIn &in, double *cur, double *lo_, bool hasLo, double *mi_, bool hasMi,
                            double *up_, bool hasUp) {
 #define TRG(nb, from, to, eptp) do { if (fwd == 1) cur[to] = g_la(cur[to], nb[from] + (eptp)); \
                                      else if (fwd == 0) nb[from] = g_la(nb[from], cur[to] + (eptp)); \
                                      else expUp(from, to, exp(nb[from] + cur[to] + (eptp) - expTotal)); } while (0)
-            double em, en, edur;
-            eventOf(y, em, en, edur);
+            const double em = in.em, en = in.en, edur = in.edur;
+            const double *cq = in.c;
+            constexpr int CS = 1;                                 // the record's planes are consecutive in CellIn
             if (SM == 2) {
                 // stateMachine3_cellCalculate (impl/stateMachine.c:1305-1334); sequence_getKmer: index < 0 reads "n"
-                const double *cq = colq + x;
                 const int k = (int) cq[0];
                 const double *t = A.G.t3;
                 expK = k;
@@ -342,7 +359,7 @@ __global__ void __launch_bounds__(32, CPG_MINB) k_align_generic(const KernelArgs
                 }
             } else if (SM == 7) {
                 // stateMachine3HDP_cellCalculate (impl/stateMachine.c:1336-1366); sequence_getKmer3: index < 0 reads k-mer 0
-                const int k = (int) colq[x];                  // the density-table row of k-mer max(x - 1, 0)
+                const int k = (int) cq[0];                    // the density-table row of k-mer max(x - 1, 0)
                 const double *t = A.G.t3;
                 if (hasLo) {
                     const double eP = -2.3025850929940455;
@@ -360,9 +377,8 @@ __global__ void __launch_bounds__(32, CPG_MINB) k_align_generic(const KernelArgs
                 // stateMachine3Vanilla_cellCalculate (impl/stateMachine.c:1368-1409); sequence_getKmer2: the pointer to the
                 // PREVIOUS k-mer, clamped at 0; the skip bin of (k-mer i, k-mer i+1) on the scaled match table -- all of
                 // it per column (k_prep_generic)
-                const double *cq = colq + x;
                 expBin = (int) cq[CS];
-                const double lx = rowq[y >= 0 ? y : 0];
+                const double lx = in.lx;
                 if (hasLo) { TRG(lo_, 0, 1, 0 + cq[2 * CS]); TRG(lo_, 1, 1, 0 + cq[3 * CS]); }
                 if (hasMi) {
                     const double eP = g_log_gauss_c(em, cq[9 * CS], cq[10 * CS], cq[11 * CS]) + g_log_inv_gauss_c(en, cq[12 * CS], cq[13 * CS], cq[14 * CS], lx);
@@ -373,7 +389,6 @@ __global__ void __launch_bounds__(32, CPG_MINB) k_align_generic(const KernelArgs
                     TRG(up_, 0, 2, eP + cq[7 * CS]); TRG(up_, 2, 2, eP + cq[8 * CS]);
                 }
             } else if (SM == 6) {
-                const double *cq = colq + x;
                 const double *t = A.G.t4;
                 if (hasLo) {
                     const double eP = cq[CS];
@@ -493,13 +508,21 @@ __global__ void __launch_bounds__(32, CPG_MINB) k_align_generic(const KernelArgs
             const bool atEnd = Dt == D;
             const int tbf = Dt - (atEnd ? 0 : P.tbDiags + 1);
             // =============================== forward ========================================================
+            int2 bN = make_int2(0, -1);                            // band of the next diagonal, fetched a diagonal ahead
+            if (dcur + 1 <= Dt) bN = bandp[dcur + 1];
+            CellIn nxt = loadIn(bN.x + lane, dcur + 1 - (bN.x + lane), dcur + 1 <= Dt && bN.x + lane <= bN.y);
             for (int d = dcur + 1; d <= Dt; d++) {
                 { const int t = f2; f2 = f1; f1 = f0; f0 = t; }
                 lo2 = lo1; hi2 = hi1; lo1 = lo; hi1 = hi;
-                bandOf(d, lo, hi);
+                lo = bN.x; hi = bN.y;
+                if (d + 1 <= Dt) bN = bandp[d + 1];
                 double *F0 = buf(f0), *F1 = buf(f1), *F2 = buf(f2);
                 for (int xb = lo; xb <= hi; xb += 32) {
                     const int x = xb + lane;
+                    const CellIn in = nxt;
+                    // the next chunk of this diagonal, or the first one of the next diagonal
+                    if (xb + 32 <= hi) nxt = loadIn(x + 32, d - (x + 32), x + 32 <= hi);
+                    else nxt = loadIn(bN.x + lane, d + 1 - (bN.x + lane), d + 1 <= Dt && bN.x + lane <= bN.y);
                     if (x <= hi) {
                         double cur[S], nl[S], nm[S], nu_[S];
                         const bool hasLo = x - 1 >= lo1 && x - 1 <= hi1, hasMi = x - 1 >= lo2 && x - 1 <= hi2, hasUp = x >= lo1 && x <= hi1;
@@ -510,10 +533,10 @@ __global__ void __launch_bounds__(32, CPG_MINB) k_align_generic(const KernelArgs
                             nm[st] = hasMi ? F2[st * N + ((x - 1) & NM)] : NI;
                             nu_[st] = hasUp ? F1[st * N + (x & NM)] : NI;
                         }
-                        cellGen(1, x, d - x, cur, nl, hasLo, nm, hasMi, nu_, hasUp);
+                        cellGen(1, x, d - x, in, cur, nl, hasLo, nm, hasMi, nu_, hasUp);
                         double *rp = rowPtr(d, x);
 #pragma unroll
-                        for (int st = 0; st < S; st++) { F0[st * N + (x & NM)] = cur[st]; rp[st] = cur[st]; }
+                        for (int st = 0; st < S; st++) { F0[st * N + (x & NM)] = cur[st]; __stcs(rp + st, cur[st]); }
                     }
                 }
                 __syncwarp();
@@ -536,6 +559,7 @@ __global__ void __launch_bounds__(32, CPG_MINB) k_align_generic(const KernelArgs
                 __syncwarp();
                 double total = NI;
                 long long count = 0;
+                CellIn nxtB = loadIn(blo + lane, Dt - (blo + lane), blo + lane <= bhi);
                 for (int d = Dt; d > tracedBackTo; d--) {
                     bandOf(d - 2, l2, h2);
                     const bool liveMi = d > tracedBackTo + 2, sweepB = d > tracedBackTo + 1;
@@ -546,6 +570,10 @@ __global__ void __launch_bounds__(32, CPG_MINB) k_align_generic(const KernelArgs
                         for (int xb = blo; xb <= bhi; xb += 32) {
                             const int x = xb + lane;
                             const bool act = x <= bhi;
+                            const CellIn in = nxtB;
+                            // the next chunk of this diagonal, or the first one of diagonal d - 1 (whose band is l1 .. h1)
+                            if (xb + 32 <= bhi) nxtB = loadIn(x + 32, d - (x + 32), x + 32 <= bhi);
+                            else nxtB = loadIn(l1 + lane, d - 1 - (l1 + lane), d - 1 > tracedBackTo && l1 + lane <= h1);
                             double cur[S], nb[S];
                             if (act)
 #pragma unroll
@@ -558,14 +586,14 @@ __global__ void __launch_bounds__(32, CPG_MINB) k_align_generic(const KernelArgs
                             if (hasMi) {
 #pragma unroll
                                 for (int st = 0; st < S; st++) nb[st] = B2[st * N + ((x - 1) & NM)];
-                                cellGen(0, x, d - x, cur, nullptr, false, nb, true, nullptr, false);
+                                cellGen(0, x, d - x, in, cur, nullptr, false, nb, true, nullptr, false);
 #pragma unroll
                                 for (int st = 0; st < S; st++) B2[st * N + ((x - 1) & NM)] = nb[st];
                             }
                             if (hasUp) {
 #pragma unroll
                                 for (int st = 0; st < S; st++) nb[st] = B1[st * N + (x & NM)];
-                                cellGen(0, x, d - x, cur, nullptr, false, nullptr, false, nb, true);
+                                cellGen(0, x, d - x, in, cur, nullptr, false, nullptr, false, nb, true);
 #pragma unroll
                                 for (int st = 0; st < S; st++) B1[st * N + (x & NM)] = nb[st];
                             }
@@ -573,7 +601,7 @@ __global__ void __launch_bounds__(32, CPG_MINB) k_align_generic(const KernelArgs
                             if (hasLo) {
 #pragma unroll
                                 for (int st = 0; st < S; st++) nb[st] = B1[st * N + ((x - 1) & NM)];
-                                cellGen(0, x, d - x, cur, nb, true, nullptr, false, nullptr, false);
+                                cellGen(0, x, d - x, in, cur, nb, true, nullptr, false, nullptr, false);
 #pragma unroll
                                 for (int st = 0; st < S; st++) B1[st * N + ((x - 1) & NM)] = nb[st];
                             }
@@ -620,7 +648,7 @@ __global__ void __launch_bounds__(32, CPG_MINB) k_align_generic(const KernelArgs
 #pragma unroll
                                         for (int st = 0; st < S; st++) nm[st] = rp[st];
                                     }
-                                    cellGen(1, x, d + 1 - x, a, nullptr, false, nm, hasMi, nullptr, false);
+                                    cellGen(1, x, d + 1 - x, loadIn(x, d + 1 - x, true), a, nullptr, false, nm, hasMi, nullptr, false);
                                 }, Bp, lp, hp);
                                 tot = g_la(tot, t2);
                             }
@@ -647,11 +675,11 @@ __global__ void __launch_bounds__(32, CPG_MINB) k_align_generic(const KernelArgs
 #pragma unroll
                                         for (int st = 0; st < S; st++) {
                                             cur[st] = B0[st * N + (x & NM)];
-                                            nl[st] = hasLo ? rowPtr(d - 1, x - 1)[st] : NI;
-                                            nm[st] = hasMi ? rowPtr(d - 2, x - 1)[st] : NI;
-                                            nu_[st] = hasUp ? rowPtr(d - 1, x)[st] : NI;
+                                            nl[st] = hasLo ? __ldcs(rowPtr(d - 1, x - 1) + st) : NI;
+                                            nm[st] = hasMi ? __ldcs(rowPtr(d - 2, x - 1) + st) : NI;
+                                            nu_[st] = hasUp ? __ldcs(rowPtr(d - 1, x) + st) : NI;
                                         }
-                                        cellGen(2, x, y, cur, nl, hasLo, nm, hasMi, nu_, hasUp);
+                                        cellGen(2, x, y, loadIn(x, y, true), cur, nl, hasLo, nm, hasMi, nu_, hasUp);
                                     }
                                     if (SM == 7) {
                                         // assignments in the reference's order: ascending x, from match / gap X / gap Y
