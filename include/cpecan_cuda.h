@@ -225,7 +225,7 @@ int cpecan_cuda_set_resident_warps(cpecan_ctx *ctx, int32_t warps_per_sm);
 /* Arithmetic of the threeState / vanilla posterior batches staged afterwards.  0 (default): the FP32 kernel (k_align3),
  * whose posteriors agree with the reference's FP64 ones to ~1e-4 apart from rare logAdd segment flips.
  * 1: the FP64 kernel in the reference's own operation order -- the same pair lists, scores equal to the last digit of
- * floor(p * 1e7) -- at 5 - 8 % of the FP32 rate.  Batches with an odd diagonalExpansion always run that
+ * floor(p * 1e7) -- at 8 - 10 % of the FP32 rate.  Batches with an odd diagonalExpansion always run that
  * way (their band is one the FP32 kernel does not walk).  Expectation batches follow the same switch (sums to 1e-9 of
  * the reference's instead of 2e-4). */
 int cpecan_cuda_set_exact_arithmetic(cpecan_ctx *ctx, int32_t on);
