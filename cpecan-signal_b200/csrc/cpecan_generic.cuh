@@ -508,14 +508,16 @@ __global__ void __launch_bounds__(32, CPG_MINB) k_align_generic(const KernelArgs
             const bool atEnd = Dt == D;
             const int tbf = Dt - (atEnd ? 0 : P.tbDiags + 1);
             // =============================== forward ========================================================
-            int2 bN = make_int2(0, -1);                            // band of the next diagonal, fetched a diagonal ahead
+            int2 bN = make_int2(0, -1), bNN = make_int2(0, -1);    // bands of the next two diagonals, fetched two diagonals ahead
             if (dcur + 1 <= Dt) bN = bandp[dcur + 1];
+            if (dcur + 2 <= Dt) bNN = bandp[dcur + 2];
             CellIn nxt = loadIn(bN.x + lane, dcur + 1 - (bN.x + lane), dcur + 1 <= Dt && bN.x + lane <= bN.y);
             for (int d = dcur + 1; d <= Dt; d++) {
                 { const int t = f2; f2 = f1; f1 = f0; f0 = t; }
                 lo2 = lo1; hi2 = hi1; lo1 = lo; hi1 = hi;
                 lo = bN.x; hi = bN.y;
-                if (d + 1 <= Dt) bN = bandp[d + 1];
+                bN = bNN;
+                if (d + 2 <= Dt) bNN = bandp[d + 2];
                 double *F0 = buf(f0), *F1 = buf(f1), *F2 = buf(f2);
                 for (int xb = lo; xb <= hi; xb += 32) {
                     const int x = xb + lane;
@@ -566,6 +568,10 @@ __global__ void __launch_bounds__(32, CPG_MINB) k_align_generic(const KernelArgs
                     if (liveMi) clearBuf(b2, l2 - 1, h2 + 1);
                     __syncwarp();
                     double *B0 = buf(b0), *B1 = buf(b1), *B2 = buf(b2), *Bp = buf(bp);
+                    // the posterior of this diagonal reads the forward match value of its cells: the first chunk's is
+                    // requested here, before the sweep, the following ones a chunk ahead
+                    double fPre = NI;
+                    if (SM != 5 && P.mode != 1 && d <= tbf && blo + lane <= bhi) fPre = __ldcs(rowPtr(d, blo + lane));
                     if (sweepB) {
                         for (int xb = blo; xb <= bhi; xb += 32) {
                             const int x = xb + lane;
@@ -702,6 +708,8 @@ __global__ void __launch_bounds__(32, CPG_MINB) k_align_generic(const KernelArgs
                         // an event matched to st k-mers gives st pairs)
                         for (int xb = blo; xb <= bhi; xb += 32) {
                             const int x = xb + lane, y = d - x;
+                            const double fCur = fPre;
+                            if (SM != 5 && x + 32 <= bhi) fPre = __ldcs(rowPtr(d, x + 32));
                             int cnt = 0;
                             int sc_[6] = { 0, 0, 0, 0, 0, 0 };
                             if (x <= bhi && x > 0 && y > 0) {
@@ -713,7 +721,7 @@ __global__ void __launch_bounds__(32, CPG_MINB) k_align_generic(const KernelArgs
                                         if (p >= A.G.threshold) { if (p > 1.0) p = 1.0; sc_[st] = (int) floor(p * 10000000); cnt += st; } else sc_[st] = -1;
                                     }
                                 } else {
-                                    double p = exp(rp[0] + B0[(x & NM)] - total);
+                                    double p = exp(fCur + B0[(x & NM)] - total);
                                     if (p >= A.G.threshold) { if (p > 1.0) p = 1.0; sc_[1] = (int) floor(p * 10000000); cnt = 1; } else sc_[1] = -1;
                                 }
                             }
