@@ -134,27 +134,27 @@ def test_c2_synthetic_2d_read(engine, machine):
     engine.release_model(mt); engine.release_model(mc)
 
 
-@pytest.mark.parametrize("machine", ["three", "vanilla"])
-def test_config3_exact_arithmetic(engine, template_tables, machine):
-    """cpecan_cuda_set_exact_arithmetic: config 3 reads (lX = 6700, e = 64) on the FP64 kernel -- the oracle's pair lists
-    exactly (no flip budget), scores to the last digit, totals to 1e-9."""
+@pytest.mark.parametrize("machine,e,n_reads", [("three", 64, 16), ("vanilla", 64, 16), ("three", 256, 6), ("vanilla", 128, 6), ("three", 65, 6)])
+def test_config3_exact_arithmetic(engine, template_tables, machine, e, n_reads):
+    """cpecan_cuda_set_exact_arithmetic: config 3 reads (lX = 6700; e = 64 / 128 / 256, and an odd one) on the FP64 kernel --
+    the oracle's pair lists exactly (no flip budget), scores to the last digit."""
     import oracleshim as O
     from cpecan_signal import HostBatch, default_params, synth, three_state_hmm, vanilla_gapx, vanilla_hmm
     from cpecan_signal.engine import item_pairs
     l1, l2, l3 = template_tables
     van = machine == "vanilla"
     reads = [synth.make_read(l1, (7_100_000 if van else 7_000_000) + i, lX=6700, noise_dist="wald" if van else "gauss")
-             for i in range(16)]
+             for i in range(n_reads)]
     mid = engine.upload_model(l1, l3, vanilla_gapx(l2) if van else np.full(4096, -2.3025850929940455))
     batch = HostBatch([r.ref for r in reads], [r.events for r in reads], [r.anchors for r in reads],
                       model_ids=[mid] * len(reads), scales=[r.scale5 for r in reads], ragged=[(1, 1)] * len(reads))
     smt = O.VANILLA if van else O.THREE_STATE
-    want = _pool_map(_oracle_one, [(smt, synth.TEMPLATE_MODEL, 0 if van else None, r.ref, r.events, r.anchors, r.scale5, 64)
+    want = _pool_map(_oracle_one, [(smt, synth.TEMPLATE_MODEL, 0 if van else None, r.ref, r.events, r.anchors, r.scale5, e)
                                    for r in reads])
     engine.set_exact_arithmetic(True)
     try:
         res, pairs, _ = engine.align_batch(batch, hmm=vanilla_hmm("template") if van else three_state_hmm(),
-                                           params=default_params(diagonalExpansion=64), pair_cap=engine.default_pair_capacity(batch, 3))
+                                           params=default_params(diagonalExpansion=e), pair_cap=engine.default_pair_capacity(batch, 3))
     finally:
         engine.set_exact_arithmetic(False)
         engine.release_model(mid)
@@ -165,5 +165,5 @@ def test_config3_exact_arithmetic(engine, template_tables, machine):
         w = np.asarray(want[i][0], dtype=np.int64).reshape(-1, 3)
         assert got.shape == w.shape and np.array_equal(got[:, 1:], w[:, 1:]), i
         worst = max(worst, int(np.abs(got[:, 0] - w[:, 0]).max()))
-    print(machine, "exact arithmetic: worst score difference", worst, "of 1e7")
+    print(machine, "e =", e, "exact arithmetic: worst score difference", worst, "of 1e7")
     assert worst <= 2
