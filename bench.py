@@ -12,7 +12,7 @@ across ranks with no data-path collective (weak scaling: B reads per GPU).
   value      GCUPS = 2 * band cells / time / 1e9 with the batch resident in HBM (kernels only)
   e2e        the same metric through the C-ABI call with HOST buffers: H2D of the batch, preparation, plan, kernels
              and D2H of the aligned pairs all inside the timed region; the batch is streamed in sub-batches through
-             two contexts per expansion so that one context's copies run under the others' kernels
+             three contexts per expansion so that one context's copies run under the others' kernels
   roofline   the binding bound: the FP32 issue-rate roofline SURVEY.md 8(d) defines (165 issue-ops per band cell against
              SMs x 128 lanes x clock); roofline_hbm: 25 algorithmic bytes per band cell / kernel time against
              MEASURED_PEAKS.json, with the DRAM traffic ncu measured per expansion (profiles/r2_dram_bytes_per_cell.json)
@@ -309,9 +309,11 @@ def main():
                     help="distinct synthetic reads generated per rank (2.7 ms of host time each); the batch tiles them, every "
                          "copy with its own host and device buffers")
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--e2e-subbatches", type=int, default=8,
-                    help="end-to-end leg: the reads of one expansion are streamed in this many sub-batches through two "
-                         "contexts, so that one's copies run under the other's kernels")
+    ap.add_argument("--e2e-subbatches", type=int, default=9,
+                    help="end-to-end leg: the reads of one expansion are streamed in this many sub-batches through "
+                         "--e2e-contexts contexts, so that one's copies run under the others' kernels")
+    ap.add_argument("--e2e-contexts", type=int, default=3, help="contexts per expansion in the end-to-end leg (sub-batches alternate between them)")
+    ap.add_argument("--e2e-resident-warps", type=int, default=8, help="resident alignment warps per SM and context in the end-to-end leg")
     ap.add_argument("--pairs-per-event", type=float, default=2.0, help="capacity of the aligned-pair buffers (the batch yields ~1.1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
@@ -471,8 +473,8 @@ def main():
     info = engines[0].device_info()
 
     # ---- end-to-end through the C-ABI with host buffers ---------------------------------------------------
-    # The same batch, streamed: the reads of an expansion go through the C-ABI in SUB sub-batches, alternately through
-    # two contexts, one blocking align_batch call each (H2D of the pinned host sub-batch, staging kernels, plan,
+    # The same batch, streamed: the reads of an expansion go through the C-ABI in SUB sub-batches, in turn through
+    # --e2e-contexts contexts, one blocking align_batch call each (H2D of the pinned host sub-batch, staging kernels, plan,
     # alignment kernels, D2H of the aligned pairs) issued from one host thread per context.  ctypes drops the GIL, so a
     # context's copies run under the other contexts' kernels; each context keeps half the resident warps
     # (cpecan_cuda_set_resident_warps) so that the forward-row rings of the six fit where the three resident ones did.
@@ -483,9 +485,9 @@ def main():
     for hb, p, o in zip(batches, params, outs):
         bounds = np.linspace(0, hb.n, SUB + 1).astype(np.int64)
         pair = []
-        for _ in range(min(2, SUB)):
+        for _ in range(min(max(1, args.e2e_contexts), SUB)):
             eng = Engine(local)
-            eng.set_resident_warps(8)
+            eng.set_resident_warps(args.e2e_resident_warps)
             eng.set_exact_arithmetic(args.arithmetic == "exact")
             eng.upload_model(tbl_match, tbl_gapy, gapx_tbl)
             pair.append((eng, []))
@@ -499,13 +501,18 @@ def main():
         lanes += pair
     pool = ThreadPoolExecutor(max_workers=len(lanes))
     counters = [[0, 0, 0] for _ in lanes]
+    phase_ms = [dict(h2d_ms=0.0, prep_ms=0.0, plan_ms=0.0, align_ms=0.0, d2h_ms=0.0, call_ms=0.0) for _ in lanes]
 
     def run_lane(i):
         eng, tasks = lanes[i]
         for sb, p, o in tasks:
+            t_call = time.perf_counter()
             eng.align_batch(sb, bench_hmm, p, 0, None, False, o)
             tm = eng.timing()
             counters[i][0] += tm["h2d_bytes"]; counters[i][1] += tm["d2h_bytes"]; counters[i][2] += tm["kernel_launches"]
+            for k in ("h2d_ms", "prep_ms", "plan_ms", "align_ms", "d2h_ms"):
+                phase_ms[i][k] += tm[k]
+            phase_ms[i]["call_ms"] += (time.perf_counter() - t_call) * 1e3
 
     def e2e_step():
         for f in [pool.submit(run_lane, i) for i in range(len(lanes))]:
@@ -525,6 +532,9 @@ def main():
     e2e_wall = max_over_ranks(time.perf_counter() - t0)
     e2e_gcups = 2.0 * cells_total * args.steps / e2e_wall / 1e9
     h2d, d2h, e2e_launches = (sum_over_ranks(float(sum(c[i] for c in counters))) for i in range(3))   # whole job
+    if os.environ.get("CPECAN_BENCH_PHASES"):
+        for i, ph in enumerate(phase_ms):
+            print("rank %d lane %d per step (ms): %s" % (rank, i, {k: round(v / (args.steps + 1), 1) for k, v in ph.items()}), file=sys.stderr, flush=True)
     pool.shutdown()
     for eng, _ in lanes:
         eng.close()
