@@ -299,6 +299,9 @@ def em_arm(args):
 
 # ----------------------------------------------------------------------------------------------- GPU arm
 def main():
+    # NCCL writes "NCCL version ..." to STDOUT at NCCL_DEBUG=VERSION (some pods export that): stdout is for the one JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
