@@ -123,6 +123,7 @@ struct cpecan_ctx {
     int64_t pairCapTotal = 0, totalsLen = 0;
     Bucket buckets[NCFG2];
     int stagedMaxLX = 0, stagedMaxLY = 0;
+    long long stagedEvTot = 0;
     bool stagedScaled = false;
     int occ2[NCFG2][2][2][2] = {};  // [bucket][machine][hasSX][expect]
     int occCap = 0;              // resident warps per SM this context may take (0 = all that fit)
@@ -324,12 +325,13 @@ void launchPrepX(cpecan_ctx *ctx, cudaStream_t s) {
 
 // per-column records of the FP64 kernel (cpecan_generic.cuh); echelon has none
 void launchPrepGeneric(cpecan_ctx *ctx, cudaStream_t s) {
-    if (!ctx->generic || gen_ncol(ctx->generic) == 0) return;
+    if (!ctx->generic) return;
     dim3 g((unsigned) ctx->n, (unsigned) std::min(64, (std::max(ctx->stagedMaxLX, ctx->stagedMaxLY) + 256) / 256 + 1));
     k_prep_generic<<<g, 256, 0, s>>>(ctx->dItems.as<Item>(), ctx->dRefOff.as<long long>(), ctx->dRef.as<char>(),
                                      ctx->dModels.as<ModelTables>(), ctx->stagedScaled ? ctx->dScale.as<double>() : nullptr,
-                                     ctx->G, ctx->dColp.as<double>(), ctx->generic == CPECAN_SM_VANILLA ? ctx->dRowp.as<double>() : nullptr,
-                                     ctx->dEvSrc.as<double>(), ctx->dEvSrcOff.as<long long>());
+                                     ctx->G, ctx->dColp.as<double>(),
+                                     (ctx->generic == CPECAN_SM_VANILLA || ctx->generic == CPECAN_SM_ECHELON) ? ctx->dRowp.as<double>() : nullptr,
+                                     ctx->stagedEvTot, ctx->dEvSrc.as<double>(), ctx->dEvSrcOff.as<long long>());
     ctx->timing.kernel_launches += 1;
 }
 
@@ -575,6 +577,8 @@ int stageL(cpecan_ctx *ctx, const cpecan_hmm *hmm, const cpecan_params *params, 
     } else {
         CK(ctx->dColp.ensure(std::max<long long>(1, xpTot * gen_ncol(ctx->generic)) * sizeof(double)));
         if (ctx->generic == CPECAN_SM_VANILLA) CK(ctx->dRowp.ensure(evTot * sizeof(double)));
+        if (ctx->generic == CPECAN_SM_ECHELON) CK(ctx->dRowp.ensure(2 * evTot * sizeof(double)));
+        ctx->stagedEvTot = evTot;
     }
     CK(ctx->dPairs.ensure(std::max<long long>(1, pairTot) * 3 * sizeof(int)));
     CK(ctx->dBits.ensure(std::max<long long>(1, bitsTot) * sizeof(unsigned)));
@@ -767,7 +771,7 @@ int runAsyncL(cpecan_ctx *ctx) {
             g.scratch = reinterpret_cast<double *>(a.scratch); g.scratch_stride = bk.stride * 2;
             g.ring_rows = bk.ringRows; g.ringN = cfg2N(b);
             g.pairs = a.pairs; g.out = a.out; g.totals = a.totals; g.expect = a.expect; g.P = ctx->P; g.G = ctx->G;
-            g.colp = ctx->dColp.as<double>(); g.rowp = ctx->dRowp.as<double>();
+            g.colp = ctx->dColp.as<double>(); g.rowp = ctx->dRowp.as<double>(); g.row2 = ctx->stagedEvTot;
             dispatchGen(ctx->generic, [&](auto k, int S) {
                 k<<<bk.nCta, 32, generic_smem_bytes(cfg2N(b), S), ctx->bstream[b]>>>(g); return 0; });
         } else

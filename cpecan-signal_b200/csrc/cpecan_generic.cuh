@@ -65,7 +65,8 @@ struct KernelArgsG {
     double *expect;               // EXPECTATION mode: the batch sums (layout of CPECAN_N_EXPECT / CPECAN_N_EXPECT_VANILLA)
     const double *colp;           // k_prep_generic: per-column records, gen_ncol(sm) planes of lX + 2 doubles per item at
                                   // gen_ncol(sm) * xp_off; null for echelon
-    const double *rowp;           // vanilla: log(noise) of every event (item at ev_off, entry y = matrix row)
+    const double *rowp;           // vanilla, echelon: log(noise) of every event (item at ev_off, entry y = matrix row);
+    long long row2;               // echelon: rowp[row2 + ...] = log(duration / 0.00332005312085) of every event
     DevParams P;
     GenParams G;
 };
@@ -120,11 +121,14 @@ __device__ __forceinline__ double g_log_inv_gauss_c(double x, double mu, double 
 //                 match: mu sd log(sd) nu lambda log(lambda) | gap Y: the same six
 // (planes, so that neighbouring lanes read neighbouring doubles; a cell never touches the 4096-row model tables)
 //   threeStateHdp (1): the row of the HDP's density table the column's k-mer reads
+//   echelon (41): log a_mx | log(1 - a_mx) | log a_xx | log(1 - a_xx) | run-off mask (bit n: the character 6 n past the
+//                 pointer is a nucleotide) | gap Y of k-mer i+1: mu sd log(sd) nu lambda log(lambda) | the same six of the
+//                 scaled match rows of k-mers i+1 .. i+5; per event: log noise and log(duration / 0.00332)
 // The values are the reference's own expressions (impl/stateMachine.c:322-343, 388-427, 631-651), evaluated once.
-__host__ __device__ inline int gen_ncol(int sm) { return sm == 4 ? 21 : (sm == 7 ? 1 : (sm == 5 ? 0 : 14)); }
+__host__ __device__ inline int gen_ncol(int sm) { return sm == 4 ? 21 : (sm == 7 ? 1 : (sm == 5 ? 41 : 14)); }
 
 __global__ void k_prep_generic(const Item *items, const long long *ref_off, const char *ref, const ModelTables *models,
-                               const double *scale, GenParams G, double *colp, double *rowp, const double *events,
+                               const double *scale, GenParams G, double *colp, double *rowp, long long row2, const double *events,
                                const long long *ev_src_off) {
     const int i = blockIdx.x;
     const Item it = items[i];
@@ -153,6 +157,33 @@ __global__ void k_prep_generic(const Item *items, const long long *ref_off, cons
         if (sm == 7) {
             const int k = kmerAt(x >= 1 ? x - 1 : 0);
             cq[x] = (double) (k >= 0 ? mt.hdp_kmer[k] : -1);
+        } else if (sm == 5) {
+            const int p = x >= 2 ? x - 2 : 0;
+            double mu0, mu1, sd, nu, tau, lam;
+            matchRow(kmerAt(p), mu0, sd, nu, tau, lam);
+            matchRow(kmerAt(p + 1), mu1, sd, nu, tau, lam);
+            long long bin = (long long) (fabs(mu1 - mu0) / 0.5);
+            bin = bin >= 30 ? 29 : bin;
+            const double a_mx = mt.gapx[bin], a_xx = mt.gapx[bin + 30];
+            cq[x] = log(a_mx); cq[CS + x] = log(1 - a_mx); cq[2 * CS + x] = log(a_xx); cq[3 * CS + x] = log(1 - a_xx);
+            int mask = 0;
+            for (int n = 1; n < 6; n++) {
+                const int q = p + 6 * n;
+                const char last = (q >= 0 && q < refLen) ? r[q] : 'n';
+                if (last >= 'A' && last <= 'Z') mask |= 1 << n;
+            }
+            cq[4 * CS + x] = (double) mask;
+            const int ky = kmerAt(p + 1);
+            double y[5] = { 0.0, 0.0, 0.0, 0.0, 0.0 };
+            if (ky >= 0) for (int j = 0; j < 5; j++) y[j] = mt.gapy[1 + 5 * ky + j];
+            cq[5 * CS + x] = y[0]; cq[6 * CS + x] = y[1]; cq[7 * CS + x] = log(y[1]); cq[8 * CS + x] = y[2]; cq[9 * CS + x] = y[4];
+            cq[10 * CS + x] = log(y[4]);
+            for (int n = 1; n < 6; n++) {
+                double mu, s2, n2, t2, l2;
+                matchRow(kmerAt(p + n), mu, s2, n2, t2, l2);
+                double *o = cq + (long long) (11 + 6 * (n - 1)) * CS + x;
+                o[0] = mu; o[CS] = s2; o[2 * CS] = log(s2); o[3 * CS] = n2; o[4 * CS] = l2; o[5 * CS] = log(l2);
+            }
         } else if (sm == 4) {
             const int p = x >= 2 ? x - 2 : 0;
             double mu0, mu1, sd, nu, tau, lam;
@@ -189,11 +220,13 @@ __global__ void k_prep_generic(const Item *items, const long long *ref_off, cons
             cq[13 * CS + x] = log(y[3]);
         }
     }
-    if (sm == 4 && rowp != nullptr) {
+    if ((sm == 4 || sm == 5) && rowp != nullptr) {
         const double *evs = events + 3 * ev_src_off[i];
         double *rq = rowp + it.ev_off;
-        for (int y = blockIdx.y * blockDim.x + threadIdx.x; y <= it.lY; y += gridDim.y * blockDim.x)
+        for (int y = blockIdx.y * blockDim.x + threadIdx.x; y <= it.lY; y += gridDim.y * blockDim.x) {
             rq[y] = y >= 1 ? log(evs[3 * (y - 1) + 1]) : 0.0;
+            if (sm == 5) rq[row2 + y] = y >= 1 ? log(evs[3 * (y - 1) + 2] / 0.00332005312085) : 0.0;
+        }
     }
 }
 
@@ -235,9 +268,9 @@ __global__ void __launch_bounds__(32, CPG_MINB) k_align_generic(const KernelArgs
         const double *evs = A.events + 3 * A.ev_src_off[itemIdx];
         const ModelTables mt = A.models[it.model_id];
         const int2 *bandp = A.bands + A.band_off[itemIdx];
-        const long long CS = lX + 2;
-        const double *colq = SM == 5 ? nullptr : A.colp + (long long) gen_ncol(SM) * it.xp_off;
-        const double *rowq = SM == 4 ? A.rowp + it.ev_off : nullptr;
+        const long long CS = lX + 2, CSg = CS;                 // CSg: the stride under a name cellGen does not shadow
+        const double *colq = A.colp + (long long) gen_ncol(SM) * it.xp_off;
+        const double *rowq = (SM == 4 || SM == 5) ? A.rowp + it.ev_off : nullptr;
         const int *tbp = A.tbs + it.pad1;
         int *pairs = A.pairs + 3 * it.pair_off;
         double *dbgTot = (A.totals != nullptr && it.tot_off >= 0) ? A.totals + it.tot_off : nullptr;
@@ -404,15 +437,10 @@ __global__ void __launch_bounds__(32, CPG_MINB) k_align_generic(const KernelArgs
                 }
             } else {
                 // echelon: sequence_getKmer2 pointer i (clamped at 0), skip bin of (k-mer i, k-mer i+1) on the scaled match
-                // table, n = 1 .. 5 k-mers per event (impl/stateMachine.c:1411-1460)
-                const int i = x >= 2 ? x - 2 : 0;
-                double mu0, mu1, sd, nu, tau, lam;
-                matchParams(kmerAt(i), mu0, sd, nu, tau, lam);
-                matchParams(kmerAt(i + 1), mu1, sd, nu, tau, lam);
-                long long bin = (long long) (fabs(mu1 - mu0) / 0.5);
-                bin = bin >= 30 ? 29 : bin;
-                const double a_mx = mt.gapx[bin], a_xx = mt.gapx[bin + 30];
-                const double la_mx = log(a_mx), la_mh = log(1 - a_mx), la_xx = log(a_xx), la_xh = log(1 - a_xx);
+                // table, n = 1 .. 5 k-mers per event (impl/stateMachine.c:1411-1460); everything that depends on the column
+                // or on the event alone comes from k_prep_generic
+                const double *eq = colq + x;
+                const double la_mx = eq[0], la_mh = eq[CSg], la_xx = eq[2 * CSg], la_xh = eq[3 * CSg];
                 if (hasLo) {
 #pragma unroll
                     for (int n = 1; n < 6; n++) TRG(lo_, n, 6, 0 + la_mx);
@@ -420,19 +448,20 @@ __global__ void __launch_bounds__(32, CPG_MINB) k_align_generic(const KernelArgs
                 }
                 const double lfact[6] = { 0.0, 0.0, 0.69314718056, 1.79175946923, 3.17805383035, 4.78749174278 };
                 const double lambda = edur / 0.00332005312085;
-                const double llam = log(lambda);
+                const double llam = rowq[A.row2 + (y >= 0 ? y : 0)];
+                const double lx = rowq[y >= 0 ? y : 0];
                 if (hasMi) {
                     // emissions_signal_multipleKmerMatchProb (:530-549): the fold starts from 0.0 and the run-off test
                     // looks at the single character 6 n past the pointer
+                    const int mask = (int) eq[4 * CSg];
+                    const double logn[6] = { 0.0, 0.0, 0.69314718055994529, 1.0986122886681098, 1.3862943611198906, 1.6094379124341003 };
                     double mk[6];
                     double fold = 0.0;
 #pragma unroll
                     for (int n = 1; n < 6; n++) {
-                        double mu, sdd, nuu, tt, ll;
-                        matchParams(kmerAt(i + n), mu, sdd, nuu, tt, ll);          // j = n - 1: k-mer i + j + 1
-                        fold = g_la(fold, g_log_gauss(em, mu, sdd) + g_log_inv_gauss(en, nuu, ll));
-                        const char last = rch(i + 6 * n);
-                        mk[n] = (last >= 'A' && last <= 'Z') ? fold - log((double) n) : NI;
+                        const double *m = eq + (long long) (11 + 6 * (n - 1)) * CSg;
+                        fold = g_la(fold, g_log_gauss_c(em, m[0], m[CSg], m[2 * CSg]) + g_log_inv_gauss_c(en, m[3 * CSg], m[4 * CSg], m[5 * CSg], lx));
+                        mk[n] = (mask >> n) & 1 ? fold - logn[n] : NI;
                     }
 #pragma unroll
                     for (int n = 1; n < 6; n++) {
@@ -447,9 +476,7 @@ __global__ void __launch_bounds__(32, CPG_MINB) k_align_generic(const KernelArgs
                     }
                 }
                 if (hasUp) {
-                    double mu, sdd, nuu, tt, ll;
-                    gapyParams(kmerAt(i + 1), mu, sdd, nuu, tt, ll);
-                    const double eP = g_log_gauss(em, mu, sdd) + g_log_inv_gauss(en, nuu, ll);
+                    const double eP = g_log_gauss_c(em, eq[5 * CSg], eq[6 * CSg], eq[7 * CSg]) + g_log_inv_gauss_c(en, eq[8 * CSg], eq[9 * CSg], eq[10 * CSg], lx);
                     const double dp0 = 1 * 0.1397619423751586 + 0 * llam - lfact[0] - 2 * lambda;
 #pragma unroll
                     for (int n = 1; n < 6; n++) TRG(up_, n, 0, eP + (la_mh + dp0));

@@ -20,7 +20,8 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--lx", type=int, default=6700)
     ap.add_argument("--unique", type=int, default=0, help="generate only this many distinct reads and tile them")
-    ap.add_argument("--machine", default="three", choices=["three", "vanilla"])
+    ap.add_argument("--machine", default="three", choices=["three", "vanilla", "four", "echelon", "hdp"],
+                    help="four / echelon / hdp always run on the FP64 kernel")
     ap.add_argument("--mode", default="posterior", choices=["posterior", "em"])
     ap.add_argument("--thr", type=float, default=0.01, help="posterior threshold (1.1: no pair is ever reported)")
     ap.add_argument("--exact", action="store_true", help="cpecan_cuda_set_exact_arithmetic: the FP64 kernel")
@@ -32,15 +33,26 @@ def main():
     eng = Engine(0)
     if a.exact:
         eng.set_exact_arithmetic(True)
-    from cpecan_signal import vanilla_gapx, vanilla_hmm
-    hmm = vanilla_hmm("template") if a.machine == "vanilla" else None
-    mid = eng.upload_model(l1, l3, vanilla_gapx(l2) if a.machine == "vanilla" else np.full(4096, -2.3025850929940455))
-    hb = HostBatch([r.ref for r in reads], [r.events for r in reads], [r.anchors for r in reads],
-                   model_ids=[mid] * len(reads), scales=[r.scale5 for r in reads], ragged=[(1, 1)] * len(reads))
+    from cpecan_signal import echelon_hmm, four_state_hmm, hdp, hdp_hmm, vanilla_gapx, vanilla_hmm
+    hmm = {"vanilla": lambda: vanilla_hmm("template"), "four": four_state_hmm, "echelon": echelon_hmm, "hdp": hdp_hmm,
+           "three": lambda: None}[a.machine]()
+    scales = [r.scale5 for r in reads]
+    events = [r.events for r in reads]
+    if a.machine == "hdp":
+        mid = eng.upload_hdp(hdp.load_nhdp(os.path.join(ROOT, "tests", "golden", "hdp", "testTemplate.nhdp.gz")))
+        events = [np.column_stack([(np.asarray(r.events).reshape(-1, 3)[:, 0] - r.scale5[1]) / r.scale5[0],
+                                   np.asarray(r.events).reshape(-1, 3)[:, 1:]]) for r in reads]
+        scales = None
+    else:
+        gapx = vanilla_gapx(l2) if a.machine in ("vanilla", "echelon") else (np.zeros(4096) if a.machine == "four" else np.full(4096, -2.3025850929940455))
+        mid = eng.upload_model(l1, l3, gapx)
+    hb = HostBatch([r.ref for r in reads], events, [r.anchors for r in reads],
+                   model_ids=[mid] * len(reads), scales=scales, ragged=[(1, 1)] * len(reads))
     if a.mode == "em":
         eng.stage(hb, hmm=hmm, params=default_params(diagonalExpansion=a.e), mode=1, pair_cap=1)
     else:
-        eng.stage(hb, hmm=hmm, params=default_params(diagonalExpansion=a.e, threshold=a.thr), pair_cap=eng.default_pair_capacity(hb, 3))
+        eng.stage(hb, hmm=hmm, params=default_params(diagonalExpansion=a.e, threshold=0.15 if a.machine == "echelon" and a.thr == 0.01 else a.thr),
+                  pair_cap=eng.default_pair_capacity(hb, 12 if a.machine in ("echelon", "hdp") else 3))
     cells = eng.timing()["band_cells"]
     for i in range(a.reps):
         eng.run_staged()
