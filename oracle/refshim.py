@@ -202,3 +202,53 @@ def load_vanilla_hmm(hmm_path, model_file):
     b = np.zeros(60)
     lib().ref_load_vanilla_hmm(hmm_path.encode(), model_file.encode(), _dptr(b))
     return b
+
+
+# ---- threeStateHdp: the reference built WITH its HDP sources (oracle/_ref/libcpecan_ref_hdp.so, `make -C oracle refHdp`)
+REF_HDP_SO = os.path.join(HERE, "_ref", "libcpecan_ref_hdp.so")
+_hdp_lib = None
+
+
+def hdp_available():
+    return os.path.exists(REF_HDP_SO)
+
+
+def hdp_lib():
+    global _hdp_lib
+    if _hdp_lib is None:
+        _hdp_lib = C.CDLL(REF_HDP_SO)
+        for name in ("ref_hdp_density", "ref_hdp_align_banded", "ref_hdp_expectations"):
+            getattr(_hdp_lib, name).restype = C.c_int64
+    return _hdp_lib
+
+
+def hdp_align_banded(nhdp_file, ref_seq, events, anchors, params=None, ragged=(0, 0), want_totals=False):
+    """getAlignedPairsUsingAnchors with getHdpStateMachine3(deserialize_nhdp(nhdp_file)) and sequence_getKmer3."""
+    events = np.ascontiguousarray(events, dtype=np.float64).reshape(-1, 3)
+    anchors = np.ascontiguousarray(np.asarray(anchors, dtype=np.int64).reshape(-1, 2))
+    params = params or default_params()
+    lY, lX = len(events), max(len(ref_seq) - 5, 0)
+    cap = 64 * (lX + lY) + 1024
+    out = np.zeros((cap, 3), dtype=np.int64)
+    totals = np.zeros(lX + lY + 1, dtype=np.float64) if want_totals else None
+    n = hdp_lib().ref_hdp_align_banded(nhdp_file.encode(), ref_seq.encode(), _dptr(events), C.c_int64(lY), _iptr(anchors),
+                                       C.c_int64(len(anchors)), C.byref(params), int(ragged[0]), int(ragged[1]), _iptr(out),
+                                       C.c_int64(cap), None if totals is None else _iptr(totals),
+                                       C.c_int64(0 if totals is None else len(totals)))
+    assert 0 <= n <= cap
+    return out[:n].copy(), totals
+
+
+def hdp_expectations(nhdp_file, ref_seq, events, anchors, params=None, ragged=(0, 0), pseudocount=1e-4, threshold=0.01):
+    """(9 transition sums + likelihood, assignments[n, 2] = (k-mer position, event index)) of an HdpHmm."""
+    events = np.ascontiguousarray(events, dtype=np.float64).reshape(-1, 3)
+    anchors = np.ascontiguousarray(np.asarray(anchors, dtype=np.int64).reshape(-1, 2))
+    params = params or default_params()
+    cap = 64 * (max(len(ref_seq) - 5, 0) + len(events)) + 64
+    asg = np.zeros((cap, 2), dtype=np.int64)
+    vec = np.zeros(10)
+    n = hdp_lib().ref_hdp_expectations(nhdp_file.encode(), ref_seq.encode(), _dptr(events), C.c_int64(len(events)), _iptr(anchors),
+                                       C.c_int64(len(anchors)), C.byref(params), int(ragged[0]), int(ragged[1]),
+                                       C.c_double(pseudocount), C.c_double(threshold), _iptr(vec), _iptr(asg), C.c_int64(cap))
+    assert 0 <= n <= cap
+    return vec, asg[:n].copy()

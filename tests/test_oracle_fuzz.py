@@ -44,3 +44,26 @@ def test_random_small_problems_bit_exact(template_tables, smt):
             we = R.expectations(smt, synth.TEMPLATE_MODEL, r.ref, r.events, anchors, params=R.default_params(**prm),
                                 scale5=r.scale5, strand=0, ragged=ragged)
             np.testing.assert_allclose(ge, we, rtol=1e-11, atol=1e-14)
+
+
+@pytest.mark.skipif(not R.hdp_available(), reason="oracle/_ref/libcpecan_ref_hdp.so not built")
+def test_random_small_problems_hdp_bit_exact(template_tables, hdp_fixture):
+    """threeStateHdp: the oracle against the reference built with its own HDP sources -- pair lists, scores and totals
+    bit-identical, expectation sums to 1e-11, the event-to-k-mer assignment lists identical."""
+    rng = np.random.default_rng(1007)
+    m = O.Model(O.THREE_STATE_HDP, hdp=hdp_fixture["hdp"])
+    for _ in range(25):
+        r, anchors, prm, ragged = _random_case(rng, template_tables)
+        ev = np.array(r.events, dtype=np.float64).reshape(-1, 3).copy()
+        ev[:, 0] = (ev[:, 0] - r.scale5[1]) / r.scale5[0]               # the HDP machine takes descaled events
+        got, gt = O.align_banded(m, r.ref, ev, anchors, params=O.default_params(**prm), ragged=ragged, want_totals=True)
+        want, wt = R.hdp_align_banded(hdp_fixture["path"], r.ref, ev, anchors, params=R.default_params(**prm), ragged=ragged,
+                                      want_totals=True)
+        assert np.array_equal(got, want), (r.lX, r.lY, prm, ragged)
+        if prm["splitMatrixBiggerThanThis"] > 1000:
+            assert np.array_equal(gt, wt, equal_nan=True), (r.lX, r.lY, prm, ragged)
+        gv, ga = O.hdp_expectations(m, r.ref, ev, anchors, params=O.default_params(**prm), ragged=ragged, pseudocount=1e-4)
+        wv, wa = R.hdp_expectations(hdp_fixture["path"], r.ref, ev, anchors, params=R.default_params(**prm), ragged=ragged,
+                                    pseudocount=1e-4, threshold=prm["threshold"])
+        np.testing.assert_allclose(gv, wv, rtol=1e-11, atol=1e-14)
+        assert np.array_equal(ga[:, 1:], wa), (r.lX, r.lY, prm, ragged)
