@@ -79,3 +79,23 @@ def test_oracle_hdp_expectations_equal_the_reference(hdp_fixture, zymo):
         np.testing.assert_allclose(vec, g[tag + "_vec"], rtol=1e-12, atol=1e-15)
         assert np.array_equal(asg[:, 1:], g[tag + "_assignments"]), tag
         assert set(asg[:, 0].tolist()) <= {0, 1, 2}
+
+
+def test_reader_rejects_what_the_machine_cannot_use(tmp_path, hdp_fixture):
+    """An HDP without finalized distributions (no data / splines not finalized) cannot be queried (the reference exits in
+    dir_proc_density, impl/hdp.c:2578-2581): the Python reader raises, and a truncated file is reported, not mis-read."""
+    import pytest
+    from cpecan_signal import hdp
+    lines = open(hdp_fixture["path"]).read().split("\n")
+    unfinalized = lines[:3] + ["0"] + lines[4:]
+    p = tmp_path / "u.nhdp"
+    p.write_text("\n".join(unfinalized))
+    with pytest.raises(ValueError, match="finalized"):
+        hdp.load_nhdp(str(p))
+    p2 = tmp_path / "t.nhdp"
+    p2.write_text("\n".join(lines[:40000]))
+    with pytest.raises(ValueError):
+        hdp.load_nhdp(str(p2))
+    # gzip-compressed files are read directly
+    h = hdp.load_nhdp(os.path.join(ROOT, "tests", "golden", "hdp", "testTemplate.nhdp.gz"))
+    assert h.density.shape == hdp_fixture["hdp"].density.shape and np.array_equal(h.kmer_distr, hdp_fixture["hdp"].kmer_distr)
