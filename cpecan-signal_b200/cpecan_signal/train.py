@@ -94,11 +94,25 @@ class StrandJob:
         self.label, self.strand, self.ref, self.events, self.anchors, self.scale5 = label, strand, ref, events, anchors, scale5
 
 
-def prepare_read(label, np_path, ref_path, cigar_line, trim=14):
+def descale_events(events, scale5):
+    """nanopore_descaleNanoporeRead AS THE REFERENCE HAS IT (impl/nanopore.c:34-38, 228-236): the loop steps through the
+    flat array by three but stops at the NUMBER of events, so only the means of the first third of a strand's events are
+    descaled.  The HDP machine was trained and is run on exactly that."""
+    ev = np.array(events, dtype=np.float64).reshape(-1, 3).copy()
+    k = (len(ev) + 2) // 3
+    ev[:k, 0] = (ev[:k, 0] - scale5[1]) / scale5[0]
+    return ev
+
+
+def prepare_read(label, np_path, ref_path, cigar_line, trim=14, descale=False):
     """The two StrandJobs of a read (template, complement); a strand whose event slice is empty or runs backwards
-    (a decreasing event map, vanillaAlign.c:645-651) is skipped for training.  Returns (jobs, 2D read length)."""
+    (a decreasing event map, vanillaAlign.c:645-651) is skipped for training.  Returns (jobs, 2D read length).
+    descale: the HDP machine's events (vanillaAlign.c:609-612)."""
     ref = open(ref_path).readline().strip()
     rd = synth.load_npread(np_path)
+    if descale:
+        for name in ("template", "complement"):
+            rd[name + "_events"] = descale_events(rd[name + "_events"], rd[name + "_params"])
     c = parse_cigar(cigar_line)
     if c["strand1"]:
         trimmed = ref[c["start1"]:c["end1"]]
@@ -146,10 +160,44 @@ def estep_strand(engine, jobs, tables, machine, hmm, params, distributed):
         engine.release_model(mid)
 
 
+def hdp_pass(a, engine, s, name, jobs_all, params, world, rank, distributed):
+    """One strand with the HDP machine: E-step of this rank's share, ten sums all-reduced, the assignment lists gathered in
+    rank order, rank 0 writes the HdpHmm file (pseudocount 1e-4 per transition slot, as vanillaAlign.c:675-676)."""
+    from . import hdp as hdp_mod
+    from .engine import hdp_hmm
+    path = a.template_hdp if s == 0 else a.complement_hdp
+    if not path:
+        raise SystemExit("--machine hdp needs --template-hdp and --complement-hdp")
+    out = a.out_template_hmm if s == 0 else a.out_complement_hmm
+    container = em.HdpHmm(1e-4, params.threshold)
+    if jobs_all:
+        cells = [len(j.ref) * (2 * a.diagonal_expansion + 1) for j in jobs_all]
+        # contiguous shares in manifest order, so that the gathered lists come out in manifest order
+        bounds = np.searchsorted(np.cumsum(cells), np.linspace(0, sum(cells), world + 1)[1:-1], side="left")
+        mine = np.split(np.arange(len(jobs_all)), bounds)[rank]
+        mid = engine.upload_hdp(hdp_mod.load_nhdp(path))
+        jobs = [jobs_all[int(i)] for i in mine]
+        if jobs:
+            batch = HostBatch([j.ref for j in jobs], [j.events for j in jobs], [j.anchors for j in jobs], model_ids=[mid] * len(jobs),
+                              ragged=[(1, 1)] * len(jobs))
+        else:
+            batch = HostBatch(["ACGTAC"], [np.zeros((0, 3))], [np.zeros((0, 2), np.int64)], model_ids=[mid], ragged=[(1, 1)])
+        em.gpu_hdp_estep(engine, batch, hdp_hmm(), params, distributed, container=container)
+        engine.release_model(mid)
+    if rank == 0:
+        container.write(out)
+        print("%s: %d strands, %d HDP assignments, likelihood %.6f" % (name, len(jobs_all), len(container.means), container.likelihood), flush=True)
+    return [(name, 0, container.likelihood)]
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser(prog="python -m cpecan_signal.train", description=__doc__.split("\n\n")[0])
     ap.add_argument("--manifest", required=True)
-    ap.add_argument("--machine", default="three", choices=["three", "vanilla"])
+    ap.add_argument("--machine", default="three", choices=["three", "vanilla", "hdp"],
+                    help="hdp: ONE pass that collects the event-to-k-mer assignments and transition sums of every strand into "
+                         "the HdpHmm files the reference's Gibbs step reads (vanillaAlign.c:142-154); needs --template-hdp / "
+                         "--complement-hdp (serialised NanoporeHDPs)")
+    ap.add_argument("--template-hdp"); ap.add_argument("--complement-hdp")
     ap.add_argument("--iterations", type=int, default=10)
     ap.add_argument("--amount", type=int, default=0, help="train on reads until their 2D lengths add up to this (0: all reads)")
     ap.add_argument("--seed", type=int, default=0, help="of the shuffle that picks the training reads")
@@ -172,7 +220,7 @@ def main(argv=None):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     reads = read_manifest(a.manifest)
-    prepared = [prepare_read(*r, trim=a.constraint_trim) for r in reads]
+    prepared = [prepare_read(*r, trim=a.constraint_trim, descale=a.machine == "hdp") for r in reads]
     lengths = [p[1] for p in prepared]
     chosen = em.cull_training_reads(lengths, a.amount, np.random.default_rng(a.seed)) if a.amount > 0 else np.arange(len(reads))
     params = default_params(diagonalExpansion=a.diagonal_expansion, threshold=a.threshold, constraintDiagonalTrim=a.constraint_trim)
@@ -181,8 +229,11 @@ def main(argv=None):
     vanilla = a.machine == "vanilla"
     log = []
     for s, name in enumerate(("template", "complement")):
-        tables = synth.load_model_file(a.template_model if s == 0 else a.complement_model)
         jobs_all = [j for i in chosen for j in prepared[int(i)][0] if j.strand == s]
+        if a.machine == "hdp":
+            log += hdp_pass(a, engine, s, name, jobs_all, params, world, rank, distributed)
+            continue
+        tables = synth.load_model_file(a.template_model if s == 0 else a.complement_model)
         if not jobs_all:
             if rank == 0:
                 print("%s: no read has an aligned stretch of events on this strand; nothing to train" % name, flush=True)

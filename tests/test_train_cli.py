@@ -90,3 +90,24 @@ def test_training_run(tmp_path, machine):
     if machine == "three":
         np.testing.assert_allclose(trained.transitions.reshape(3, 3).sum(axis=1), 1.0, rtol=1e-9)
     assert not os.path.exists(c)                               # the fixture has no complement stretch to train on
+
+
+@pytest.mark.gpu
+def test_hdp_pass_writes_the_reference_cli_file(tmp_path, hdp_fixture):
+    """--machine hdp on the fixture read: the HdpHmm file of the template strand equals what `vanillaAlign -d -t` writes
+    (13 289 assignments: every event mean and k-mer in order; sums at the six printed decimals)."""
+    import gzip
+    from cpecan_signal import train
+    cigar = open(os.path.join(VA, "guide.cigar")).readline().strip()
+    man = tmp_path / "reads.tsv"
+    man.write_text("\t".join(["readA", os.path.join(GOLD, "ZymoC_ch_1_file1.npRead"), os.path.join(GOLD, "ZymoRef.txt"), cigar]) + "\n")
+    t, c = str(tmp_path / "t.exp"), str(tmp_path / "c.exp")
+    train.main(["--manifest", str(man), "--machine", "hdp", "--template-hdp", hdp_fixture["path"], "--complement-hdp", hdp_fixture["path"],
+                "--out-template-hmm", t, "--out-complement-hmm", c])
+    got = open(t).read().split("\n")
+    with gzip.open(os.path.join(VA, "t_d.exp.gz"), "rt") as fh:
+        want = fh.read().split("\n")
+    assert got[0] == want[0] and len(got) == len(want)
+    np.testing.assert_allclose(np.array(got[1].split(), dtype=np.float64), np.array(want[1].split(), dtype=np.float64), rtol=0, atol=2e-6)
+    assert got[2] == want[2] and got[3] == want[3]
+    assert open(c).read().split("\n")[0].split("\t")[3] == "0"          # the complement strand of the fixture has no stretch
