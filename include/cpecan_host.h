@@ -360,7 +360,7 @@ StateMachine *getHdpStateMachine3(NanoporeHDP *hdp);                            
  * (impl/nanopore_hdp.c:390-392 -> impl/hdp.c:2577-2599 -> impl/hdp_math_utils.c:471-495) */
 NanoporeHDP *deserialize_nhdp(const char *filepath);
 void destroy_nanopore_hdp(NanoporeHDP *nhdp);
-double get_nanopore_kmer_density(NanoporeHDP *nhdp, void *kmer, void *x);
+double get_nanopore_kmer_density(NanoporeHDP *nhdp, void *kmer, void *x);   /* one scalar table query on the host, for callers and tests; the DP reads the same tables on the device and never calls it */
 int64_t get_nanopore_hdp_kmer_length(NanoporeHDP *nhdp);
 int64_t get_nanopore_hdp_alphabet_size(NanoporeHDP *nhdp);
 char *get_nanopore_hdp_alphabet(NanoporeHDP *nhdp);
