@@ -17,6 +17,8 @@
 // from the cell to the right), so the results agree with the reference to the last digits and no offsets are needed.
 // One warp per alignment; the last diagonals live in shared memory as S planes of N doubles (3 buffers forward, 4 on
 // the way back: B of d+1 is kept for the second term of the total probability); forward cells spill to HBM as S doubles.
+// A cell reads only its column's record and its event: k-mer lookups, model scaling and every logarithm that does not
+// depend on the cell happen once per column / per event in k_prep_generic.
 // Band and traceback points come from k_plan3.  Expectations are not defined for these machines in the reference
 // (cellCalculateUpdateExpectations is NULL for echelon) and are refused.
 #pragma once
@@ -263,8 +265,6 @@ __global__ void __launch_bounds__(32, CPG_MINB) k_align_generic(const KernelArgs
             if (lane == 0) { ItemOut &o = A.out[itemIdx]; o.n_pairs = 0; o.status = D == 0 ? 0 : 6; o.total_logprob = 0.0; o.n_tracebacks = 0; }
             continue;
         }
-        const char *ref = A.ref + A.ref_off[itemIdx];
-        const int refLen = (int) (A.ref_off[itemIdx + 1] - A.ref_off[itemIdx]);
         const double *evs = A.events + 3 * A.ev_src_off[itemIdx];
         const ModelTables mt = A.models[it.model_id];
         const int2 *bandp = A.bands + A.band_off[itemIdx];
@@ -274,35 +274,10 @@ __global__ void __launch_bounds__(32, CPG_MINB) k_align_generic(const KernelArgs
         const int *tbp = A.tbs + it.pad1;
         int *pairs = A.pairs + 3 * it.pair_off;
         double *dbgTot = (A.totals != nullptr && it.tot_off >= 0) ? A.totals + it.tot_off : nullptr;
-        const bool scaled = A.scale != nullptr;
-        double sc = 1, sh = 0, var = 1, scsd = 1, varsd = 1;
-        if (scaled) { const double *s5 = A.scale + 5 * itemIdx; sc = s5[0]; sh = s5[1]; var = s5[2]; scsd = s5[3]; varsd = s5[4]; }
         int nPairs = 0, status = 0, nTb = 0;
         double lastTotal = 0.0, lik = 0.0;
 
         auto bandOf = [&](int d, int &l, int &h) { if (d >= 0 && d <= D) { const int2 b = bandp[d]; l = b.x; h = b.y; } else { l = 0; h = -1; } };
-        // the padded nucleotide sequence (sequence_padSequence, impl/pairwiseAligner.c:282-285) and its k-mer index
-        // (impl/stateMachine.c:104-139; -1 <=> index > 4096)
-        auto rch = [&](int i) -> char { return (i >= 0 && i < refLen) ? ref[i] : 'n'; };
-        auto kmerAt = [&](int i) -> int {
-            int v = 0;
-#pragma unroll
-            for (int j = 0; j < 6; j++) { const int b = base_code(rch(i + j)); if (b < 0) return -1; v = v * 4 + b; }
-            return v;
-        };
-        // model getters (impl/stateMachine.c:221-240; index > 4096 reads as 0.0) with emissions_signal_scaleModel folded
-        // in for the match table (:631-651); the gap-Y table is never scaled
-        auto matchParams = [&](int k, double &mu, double &sd, double &nu, double &tau, double &lam) {
-            if (k < 0) { mu = sd = nu = tau = lam = 0.0; return; }
-            const double *m = mt.match + 1 + 5 * k;
-            mu = m[0]; sd = m[1]; nu = m[2]; tau = m[3]; lam = m[4];
-            if (scaled) { mu = mu * sc + sh; sd = sd * var; nu = nu * scsd; lam = lam * varsd; tau = sqrt(pow(nu, 3.0) / lam); }
-        };
-        auto gapyParams = [&](int k, double &mu, double &sd, double &nu, double &tau, double &lam) {
-            if (k < 0) { mu = sd = nu = tau = lam = 0.0; return; }
-            const double *m = mt.gapy + 1 + 5 * k;
-            mu = m[0]; sd = m[1]; nu = m[2]; tau = m[3]; lam = m[4];
-        };
         // dir_proc_density of the k-mer's distribution (impl/hdp.c:2577-2599) through grid_spline_interp
         // (impl/hdp_math_utils.c:471-495); the grid is linspace(start, stop, n) (:497-510)
         auto hdpDensity = [&](int t, double q) -> double {
