@@ -256,6 +256,11 @@ def allreduce_sum(vec, group_ok):
     import torch
     import torch.distributed as dist
     if isinstance(vec, np.ndarray):
+        if dist.get_backend() == "nccl":                     # NCCL reduces device tensors only: through the GPU and back
+            t = torch.from_numpy(vec).cuda()
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            vec[...] = t.cpu().numpy()
+            return vec
         t = torch.from_numpy(vec)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return vec
