@@ -124,9 +124,9 @@ __global__ void __launch_bounds__(32, CP_MINB3) k_align3(const KernelArgs3 A) {
     extern __shared__ __align__(16) unsigned char smraw[];
     const int N = A.ringN, NM = N - 1;
     float4 *ring = reinterpret_cast<float4 *>(smraw);             // 2 * N entries
-    float *colAcc = reinterpret_cast<float *>(smraw + (size_t) N * 32 + CP_LAT_BYTES);   // EXPECT, three-state: N floats
+    float *colAcc = reinterpret_cast<float *>(smraw + (size_t) N * 32 + CP_LAT_BYTES);   // EXPECT: N floats (three-state: per column; vanilla: the 60 skip bins)
 #ifdef CP_TMA_ROWS
-    float4 *stage = reinterpret_cast<float4 *>(smraw + (size_t) N * 32 + CP_LAT_BYTES + ((EXPECT && !MACH) ? (size_t) N * 4 : 0));   // 2 x N
+    float4 *stage = reinterpret_cast<float4 *>(smraw + (size_t) N * 32 + CP_LAT_BYTES + (EXPECT ? (size_t) N * 4 : 0));   // 2 x N
     const unsigned stageAddr = (unsigned) __cvta_generic_to_shared(stage);
     const unsigned barAddr = stageAddr + (unsigned) N * 32;
     if (threadIdx.x == 0) { mbar_init(barAddr, 1); mbar_init(barAddr + 8, 1); }
@@ -193,6 +193,7 @@ __global__ void __launch_bounds__(32, CP_MINB3) k_align3(const KernelArgs3 A) {
         double lastTotal = 0.0;
         double eT[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };            // EXPECT: this lane's share of the transition sums
         double eLik = 0.0;
+        double eBin0 = 0.0, eBin1 = 0.0;                             // EXPECT, vanilla: this lane's two skip bins (lane, lane + 32)
 
         if (D == 0 || (planFlags & (EXPECT ? 12 : 4)) != 0) {
             // nothing to align, or the plan refused the item (band edge jumps; E-step: a non-ACGT reference k-mer makes
@@ -208,7 +209,7 @@ __global__ void __launch_bounds__(32, CP_MINB3) k_align3(const KernelArgs3 A) {
             for (int i = lane; i < 2 * N; i += 32) ring[i] = NIENT;
             __syncwarp();
         };
-        if (EXPECT && !MACH) { for (int i = lane; i < N; i += 32) colAcc[i] = 0.f; }
+        if (EXPECT) { for (int i = lane; i < N; i += 32) colAcc[i] = 0.f; }
 
         // ---- diagonal 0: the single cell (0,0) holds the start vector (impl/pairwiseAligner.c:897-898) ----------
         resetRing();
@@ -552,10 +553,12 @@ __global__ void __launch_bounds__(32, CP_MINB3) k_align3(const KernelArgs3 A) {
                                 if (MACH) {
                                     // cell_signal_updateBetaAndAlphaProb (impl/pairwiseAligner.c:478-498): skip bins only;
                                     // 60 bins: warp-aggregated per bin would need a sort, the sums go out per lane
+                                    // 60 bins in shared memory (global FP64 atomics from every lane of every warp met on 60
+                                    // addresses); FP32 over a few diagonals, then into this item's FP64 registers
                                     const int bin = kw;
                                     if (bin >= 0) {
-                                        if (pMX > 1e-13f) atomicAdd(A.expect + bin, (double) pMX);
-                                        if (pXX > 1e-13f) atomicAdd(A.expect + 30 + bin, (double) pXX);
+                                        if (pMX > 1e-13f) atomicAdd(colAcc + bin, pMX);
+                                        if (pXX > 1e-13f) atomicAdd(colAcc + 30 + bin, pXX);
                                     }
                                 } else {
                                     const float kM = (bM + eM) + (((FM.w + U) - totBase) - totSt);
@@ -748,6 +751,12 @@ __global__ void __launch_bounds__(32, CP_MINB3) k_align3(const KernelArgs3 A) {
                         }
                         __syncwarp();
                     }
+                    if (EXPECT && MACH && post && ((d & 7) == 0 || d == tracedBackTo + 1)) {
+                        __syncwarp();
+                        eBin0 += (double) colAcc[lane]; colAcc[lane] = 0.f;
+                        if (lane < 28) { eBin1 += (double) colAcc[lane + 32]; colAcc[lane + 32] = 0.f; }
+                        __syncwarp();
+                    }
                     { float4 *t = A1; A1 = A2; A2 = t; }
                 }
             }
@@ -785,6 +794,10 @@ __global__ void __launch_bounds__(32, CP_MINB3) k_align3(const KernelArgs3 A) {
                 if (lane == 0 && !bad && v == v) atomicAdd(A.expect + i, v);
             }
             if (lane == 0 && !bad && eLik == eLik) atomicAdd(A.expect + (MACH ? 60 : 9 + 4096), eLik);
+            if (MACH && !bad) {
+                if (eBin0 > 0.0) atomicAdd(A.expect + lane, eBin0);
+                if (lane < 28 && eBin1 > 0.0) atomicAdd(A.expect + 32 + lane, eBin1);
+            }
         }
         if (lane == 0) {
             ItemOut &o = A.out[itemIdx];

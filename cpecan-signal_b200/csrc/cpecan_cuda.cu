@@ -159,7 +159,7 @@ template <typename F> auto dispatchK2(int mach, bool sx, bool ex, F f) {
     if (sx) return ex ? f(k_align3<0, true, true>) : f(k_align3<0, true, false>);
     return ex ? f(k_align3<0, false, true>) : f(k_align3<0, false, false>);
 }
-inline size_t smemCfg2(int cfg, int mach, bool ex) { return align3_smem_bytes(cfg2N(cfg), ex && !mach); }
+inline size_t smemCfg2(int cfg, int mach, bool ex) { (void) mach; return align3_smem_bytes(cfg2N(cfg), ex); }   // E-step: per-column sums (three-state) or the 60 skip bins (vanilla)
 int occCfg2(int cfg, int mach, bool sx, bool ex) {
     const size_t bytes = smemCfg2(cfg, mach, ex);
     return dispatchK2(mach, sx, ex, [&](auto k) {
