@@ -440,8 +440,8 @@ __global__ void __launch_bounds__(32, CP_MINB3) k_align3(const KernelArgs3 A) {
                     // What one cell of the backward sweep needs besides the ring: the forward sweep's record (match value,
                     // offset, the two emissions), the gap emission of the column (three-state) or the transitions of the
                     // successors' columns (vanilla), the k-mer index / skip bin for the E-step.  Requested a chunk ahead.
-                    struct QRec { float4 F; float4 dR; float cz, ex; int kw; };
-                    struct GRec { float eM, eY, eX, Fx, Fw, tOX, tEX, tMC, tMX, myLog; int kw; };
+                    struct QRec { float4 F; float4 dR; float2 dO; float cz, ex; int kw; };
+                    struct GRec { float eM, eY, eX, Fx, Fw, tOX, tEX, tMC, tMX, myLog, oOX, oEX; int kw; };
                     QRec qq[NJ];
                     GRec GG[NJ];
                     auto loadBj = [&](int j, int cc) {                 // chunk cc (one that does not exist reads as outside the band)
@@ -454,6 +454,9 @@ __global__ void __launch_bounds__(32, CP_MINB3) k_align3(const KernelArgs3 A) {
                         q.ex = MACH ? (in ? 0.f : NI) : q.cz;
                         q.kw = EXPECT ? reinterpret_cast<const int *>(cp)[3] : 0;
                         if (MACH) q.dR = xpD[min(x + 1, lX + 1)];
+                        // vanilla E-step: the transitions into THIS column's gap-X state (log a_mx, log a_xx), a chunk ahead too
+                        q.dO = make_float2(0.f, 0.f);
+                        if (EXPECT && MACH) q.dO = *reinterpret_cast<const float2 *>(xpD + min(x, lX + 1));
                         q.F = make_float4(NI, NI, NI, NI);
                         if (EXPECT) { float2 e2 = make_float2(NI, NI); if (in) e2 = ROWLD2(erow + (x & NM)); q.F.z = e2.x; q.F.w = e2.y; }
 #ifdef CP_TMA_ROWS
@@ -469,6 +472,7 @@ __global__ void __launch_bounds__(32, CP_MINB3) k_align3(const KernelArgs3 A) {
                         G.eM = q.F.z; G.eY = q.F.w; G.Fx = q.F.x; G.Fw = EXPECT ? 0.f : q.F.y;
                         G.eX = q.ex; G.myLog = q.cz; G.kw = q.kw;
                         G.tOX = MACH ? q.dR.x : 0.f; G.tEX = MACH ? q.dR.y : 0.f; G.tMC = MACH ? q.dR.z : 0.f; G.tMX = MACH ? q.dR.w : 0.f;
+                        G.oOX = q.dO.x; G.oEX = q.dO.y;
                     };
                     auto loadB = [&](int cc) { loadBj(0, cc); };
                     auto reduceB = [&]() { reduceBj(0); };
@@ -538,16 +542,13 @@ __global__ void __launch_bounds__(32, CP_MINB3) k_align3(const KernelArgs3 A) {
                         return P3;
                     };
                     auto cellPost = [&](int x, int s, bool inb, float bM, float bX, float bY, float U, float eM, float eY,
-                                        float eX, float Fx, float Fw, float myLog, int kw, const Pred &P3) {
+                                        float eX, float Fx, float Fw, float myLog, int kw, const Pred &P3, float oOX, float oEX) {
                         if (EXPECT) {
                             if (post) {
                                 // diagonalCalculation_Expectations (impl/pairwiseAligner.c:841-863): for every transition
                                 // into this cell p = exp(F_pred[from] + B[to] + eP + tP - total) (:426-443)
                                 const float4 FL = P3.L, FM = P3.M, FU = P3.U;
-                                float4 pdo = NIENT;
-                                if (MACH) pdo = xpD[min(x, lX + 1)];
-                                const float tOX = MACH ? pdo.x : gOX, tEX = MACH ? pdo.y : gEX, tMC = MACH ? pdo.z : gMC,
-                                            tMX = MACH ? pdo.w : gMX, tOY = MACH ? myLog : gOY;
+                                const float tOX = MACH ? oOX : gOX, tEX = MACH ? oEX : gEX, tMC = gMC, tMX = gMX, tOY = MACH ? myLog : gOY;
                                 const float kX = (bX + eX) + (((FL.w + U) - totBase) - totSt);
                                 float pMX = __expf(FL.x + tOX + kX), pXX = __expf(FL.y + tEX + kX);
                                 if (MACH) {
@@ -618,7 +619,7 @@ __global__ void __launch_bounds__(32, CP_MINB3) k_align3(const KernelArgs3 A) {
                                 if (c + j < nch) {                     // (a chunk that does not exist stores nothing and reports nothing)
                                     const int x = wlo + ((c + j) << 5) + lane;
                                     cellPost(x, x & NM, x >= blo && x <= bhi, bM[j], bX[j], bY[j], U[j], cur[j].eM, cur[j].eY, cur[j].eX,
-                                             cur[j].Fx, cur[j].Fw, cur[j].myLog, cur[j].kw, P3[j]);
+                                             cur[j].Fx, cur[j].Fw, cur[j].myLog, cur[j].kw, P3[j], cur[j].oOX, cur[j].oEX);
                                 }
                             }
                             __syncwarp();
@@ -721,7 +722,7 @@ __global__ void __launch_bounds__(32, CP_MINB3) k_align3(const KernelArgs3 A) {
                             loadB(min(c + 1, nch - 1));
                             const Pred P3 = loadPred(x, inb);
                             __syncwarp();
-                            cellPost(x, s, inb, b.x, b.y, b.z, b.w, cur.eM, cur.eY, cur.eX, cur.Fx, cur.Fw, cur.myLog, cur.kw, P3);
+                            cellPost(x, s, inb, b.x, b.y, b.z, b.w, cur.eM, cur.eY, cur.eX, cur.Fx, cur.Fw, cur.myLog, cur.kw, P3, cur.oOX, cur.oEX);
                             __syncwarp();
                             reduceB();
                         }
