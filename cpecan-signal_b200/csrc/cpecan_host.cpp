@@ -121,6 +121,10 @@ Sequence *sequence_sliceEventSequence2(Sequence *in, int64_t start, int64_t slic
 void sequence_sequenceDestroy(Sequence *seq) { free(seq); }
 void *sequence_getKmer(void *elements, int64_t index) { return index >= 0 ? (void *) ((char *) elements + index) : (void *) NCHAR_; }
 void *sequence_getKmer2(void *elements, int64_t index) { return (char *) elements + (index > 0 ? index - 1 : 0); }
+void *sequence_getBase(void *elements, int64_t index) {                                                     // impl/pairwiseAligner.c:308-312
+    static char n[] = "n";
+    return index >= 0 ? (void *) ((char *) elements + index) : (void *) n;
+}
 void *sequence_getKmer3(void *elements, int64_t index) { return (char *) elements + (index >= 0 ? index : 0); }   // :327-331
 // impl/pairwiseAligner.c:282-285: 30 'n' behind the nucleotides (the echelon machine reads k-mers past the end); as in
 // the reference the old buffer is not freed -- the caller still owns it
@@ -501,6 +505,19 @@ void emissions_signal_scaleModel(StateMachine *sM, double scale, double shift, d
     double *t = sM->EMISSION_MATCH_PROBS;
     for (int64_t i = 1; i < TABLE_LEN; i += MODEL_PARAMS) {
         t[i] = t[i] * scale + shift;
+        t[i + 1] = t[i + 1] * var;
+        t[i + 2] = t[i + 2] * scale_sd;
+        t[i + 4] = t[i + 4] * var_sd;
+        t[i + 3] = sqrt(pow(t[i + 2], 3.0) / t[i + 4]);
+    }
+}
+
+
+// impl/stateMachine.c:653-673: the same without the level mean (deviation, noise mean, lambda, and the derived noise sd)
+void emissions_signal_scaleModelNoiseOnly(StateMachine *sM, double scale, double shift, double var, double scale_sd, double var_sd) {
+    (void) scale; (void) shift;
+    double *t = sM->EMISSION_MATCH_PROBS;
+    for (int64_t i = 1; i < TABLE_LEN; i += MODEL_PARAMS) {
         t[i + 1] = t[i + 1] * var;
         t[i + 2] = t[i + 2] * scale_sd;
         t[i + 4] = t[i + 4] * var_sd;

@@ -93,6 +93,7 @@ void sequence_sequenceDestroy(Sequence *seq);                                   
 void *sequence_getKmer(void *elements, int64_t index);                                                      /* :67 */
 void *sequence_getKmer2(void *elements, int64_t index);                                                     /* :70 */
 void *sequence_getKmer3(void *elements, int64_t index);                                                     /* :72 */
+void *sequence_getBase(void *elements, int64_t index);                                                      /* :66; nucleotide sequences (not a signal-path accessor) */
 void sequence_padSequence(Sequence *sequence);                                                              /* :56 */
 void *sequence_getEvent(void *elements, int64_t index);                                                     /* :75 */
 int64_t sequence_correctSeqLength(int64_t length, SequenceType type);                                       /* :77 */
@@ -366,6 +367,8 @@ int64_t get_nanopore_hdp_alphabet_size(NanoporeHDP *nhdp);
 char *get_nanopore_hdp_alphabet(NanoporeHDP *nhdp);
 void emissions_signal_scaleModel(StateMachine *sM, double scale, double shift, double var, double scale_sd,
                                  double var_sd);                                                            /* :341-342 */
+void emissions_signal_scaleModelNoiseOnly(StateMachine *sM, double scale, double shift, double var, double scale_sd,
+                                          double var_sd);                                                   /* impl/stateMachine.c:653-673 */
 void stateMachine3_setTransitionsToNanoporeDefaults(StateMachine *sM);
 void stateMachine3Vanilla_setStrandTransitionsToDefaults(StateMachine *sM, Strand strand);                  /* :383 */
 int64_t emissions_discrete_getKmerIndex(void *kmer);                                                        /* :305 */

@@ -110,6 +110,15 @@ static void test_scaleModel(const char *models) {            /* tests/signalPair
         CHECK(b->EMISSION_MATCH_PROBS[i + 4] == a->EMISSION_MATCH_PROBS[i + 4] * 1.3);
         CHECK(b->EMISSION_GAP_Y_PROBS[i] == a->EMISSION_GAP_Y_PROBS[i]);                    /* gap-Y stays unscaled */
     }
+    /* emissions_signal_scaleModelNoiseOnly (impl/stateMachine.c:653-673): everything but the level mean */
+    StateMachine *c = getStrawManStateMachine3(path);
+    emissions_signal_scaleModelNoiseOnly(c, 1.2, 3.0, 1.1, 0.9, 1.3);
+    for (int64_t i = 1; i < 1 + NUM_OF_KMERS * MODEL_PARAMS; i += MODEL_PARAMS) {
+        CHECK(c->EMISSION_MATCH_PROBS[i] == a->EMISSION_MATCH_PROBS[i]);
+        CHECK(c->EMISSION_MATCH_PROBS[i + 1] == b->EMISSION_MATCH_PROBS[i + 1] && c->EMISSION_MATCH_PROBS[i + 3] == b->EMISSION_MATCH_PROBS[i + 3]);
+    }
+    stateMachine_destruct(c);
+    { char nts[] = "ACGT"; CHECK(*(char *) sequence_getBase(nts, 2) == 'G' && *(char *) sequence_getBase(nts, -1) == 'n'); }
     CHECK(a->EMISSION_GAP_X_PROBS[17] == -2.3025850929940455 && a->type == threeState && a->stateNumber == 3);
     CHECK(a->startStateProb(a, match) == 0.0 && a->endStateProb(a, shortGapY) == ((StateMachine3 *) a)->TRANSITION_MATCH_FROM_GAP_Y);
     stateMachine_destruct(a); stateMachine_destruct(b);
