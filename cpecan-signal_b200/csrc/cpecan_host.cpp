@@ -1664,11 +1664,47 @@ void getPosteriorProbsWithBanding(StateMachine *sM, stList *anchorPairs, Sequenc
     q.splitMatrixBiggerThanThis = INT64_MAX;
     stList *res = getAlignedPairsUsingAnchors(sM, sX, sY, anchorPairs, &q, diagonalPosteriorProbFn, alignmentHasRaggedLeftEnd, alignmentHasRaggedRightEnd);
     // getAlignedPairsUsingAnchors reversed the region's list (the coordinate-correction callback pops); undo it: the
-    // callback form appends in traceback order
-    stList *out = (stList *) extraArgs;
+    // callback form appends in traceback order -- to the list the reference's callbacks take out of extraArgs,
+    // ((void **) extraArgs)[0] (impl/pairwiseAligner.c:761; callers pass "void *extraArgs[] = { alignedPairs, ... }")
+    stList *out = (stList *) ((void **) extraArgs)[0];
     for (int64_t i = stList_length(res) - 1; i >= 0; i--) { stList_append(out, stList_get(res, i)); stList_set(res, i, nullptr); }
     stList_setDestructor(res, nullptr);
     stList_destruct(res);
+}
+
+// impl/pairwiseAligner.c:1356-1422: the regions between large anchor gaps one after the other through the callback form,
+// coordinateCorrectionFn(x1, y1, extraArgs) after each (getAlignedPairsUsingAnchors passes the function that shifts the
+// region's pairs back and pops them onto the final list, :1447-1454).  One GPU call per region here; the batched entry
+// points submit all regions at once.
+void getPosteriorProbsWithBandingSplittingAlignmentsByLargeGaps(
+        StateMachine *sM, stList *anchorPairs, Sequence *SsX, Sequence *SsY, PairwiseAlignmentParameters *p,
+        bool alignmentHasRaggedLeftEnd, bool alignmentHasRaggedRightEnd,
+        void (*diagonalPosteriorProbFn)(StateMachine *, int64_t, DpMatrix *, DpMatrix *, Sequence *, Sequence *, double,
+                                        PairwiseAlignmentParameters *, void *),
+        void (*coordinateCorrectionFn)(int64_t, int64_t, void *), void *extraArgs) {
+    stList *split = getSplitPoints(anchorPairs, SsX->length, SsY->length, p->splitMatrixBiggerThanThis, alignmentHasRaggedLeftEnd,
+                                   alignmentHasRaggedRightEnd);
+    const int64_t nS = stList_length(split), nA = stList_length(anchorPairs);
+    int64_t j = 0;
+    for (int64_t i = 0; i < nS; i++) {
+        stIntTuple *r = (stIntTuple *) stList_get(split, i);
+        const int64_t x1 = stIntTuple_get(r, 0), y1 = stIntTuple_get(r, 1), x2 = stIntTuple_get(r, 2), y2 = stIntTuple_get(r, 3);
+        Sequence *sX3 = SsX->sliceFcn(SsX, x1, x2 - x1), *sY3 = SsY->sliceFcn(SsY, y1, y2 - y1);
+        stList *sub = stList_construct3(0, (void (*)(void *)) stIntTuple_destruct);
+        while (j < nA) {
+            stIntTuple *a = (stIntTuple *) stList_get(anchorPairs, j);
+            const int64_t x = stIntTuple_get(a, 0), y = stIntTuple_get(a, 1);
+            if (x + y >= x2 + y2) break;
+            stList_append(sub, stIntTuple_construct2(x - x1, y - y1));
+            j++;
+        }
+        getPosteriorProbsWithBanding(sM, sub, sX3, sY3, p, alignmentHasRaggedLeftEnd || i > 0, alignmentHasRaggedRightEnd || i < nS - 1,
+                                     diagonalPosteriorProbFn, extraArgs);
+        if (coordinateCorrectionFn != nullptr) coordinateCorrectionFn(x1, y1, extraArgs);
+        stList_destruct(sub);
+        sequence_sequenceDestroy(sX3); sequence_sequenceDestroy(sY3);
+    }
+    stList_destruct(split);
 }
 
 }  // extern "C"

@@ -171,14 +171,23 @@ void getExpectationsUsingAnchors(StateMachine *sM, Hmm *hmmExpectations, Sequenc
 void diagonalCalculationMultiPosteriorMatchProbs(StateMachine *sM, int64_t xay, DpMatrix *forwardDpMatrix,  /* :251-254 */
                                                  DpMatrix *backwardDpMatrix, Sequence *sX, Sequence *sY,
                                                  double totalProbability, PairwiseAlignmentParameters *p, void *extraArgs);
-/* The callback form (:266-277): the two callbacks above select the device mode; the aligned pairs are appended to
- * extraArgs (an stList) in traceback order, as diagonalCalculationPosteriorMatchProbs would have done. */
+/* The callback form (:266-277): the two callbacks above select the device mode; the aligned pairs are appended, in
+ * traceback order, to the list the reference's callbacks take out of extraArgs -- ((void **) extraArgs)[0], i.e. callers
+ * pass "void *extraArgs[] = { alignedPairs }" (impl/pairwiseAligner.c:761, tests/pairwiseAlignerTest.c:447-449). */
 void getPosteriorProbsWithBanding(StateMachine *sM, stList *anchorPairs, Sequence *sX, Sequence *sY,
                                   PairwiseAlignmentParameters *p, bool alignmentHasRaggedLeftEnd, bool alignmentHasRaggedRightEnd,
                                   void (*diagonalPosteriorProbFn)(StateMachine *, int64_t, DpMatrix *, DpMatrix *,
                                                                   Sequence *, Sequence *, double,
                                                                   PairwiseAlignmentParameters *, void *),
                                   void *extraArgs);
+/* :331-338: the same region by region between large anchor gaps (getSplitPoints), coordinateCorrectionFn(x1, y1, extraArgs)
+ * after each region */
+void getPosteriorProbsWithBandingSplittingAlignmentsByLargeGaps(
+        StateMachine *sM, stList *anchorPairs, Sequence *SsX, Sequence *SsY, PairwiseAlignmentParameters *p,
+        bool alignmentHasRaggedLeftEnd, bool alignmentHasRaggedRightEnd,
+        void (*diagonalPosteriorProbFn)(StateMachine *, int64_t, DpMatrix *, DpMatrix *, Sequence *, Sequence *, double,
+                                        PairwiseAlignmentParameters *, void *),
+        void (*coordinateCorrectionFn)(int64_t, int64_t, void *), void *extraArgs);
 stList *convertPairwiseForwardStrandAlignmentToAnchorPairs(struct PairwiseAlignment *pA, int64_t trim);     /* :109 */
 
 /* "Methods tested and possibly useful elsewhere" (:193-245): the per-cell / per-diagonal pieces of the CPU DP.  The

@@ -236,6 +236,30 @@ static void test_fixture(const char *golden, const char *models) {
         CHECK(stList_length(pairs) == 987);
         checkAlignedPairs(pairs, lX, lY);
         stList_destruct(pairs);
+        {   /* the callback forms, called the way the reference's tests do (tests/pairwiseAlignerTest.c:447-455): the list
+             * travels as extraArgs[0]; pairs arrive in traceback order = the public entry point's list reversed */
+            stList *pub = getAlignedPairsUsingAnchors(sM, sX, sY, anchors, p, diagonalCalculationPosteriorMatchProbs, 0, 0);
+            stList *cb = stList_construct3(0, (void (*)(void *)) stIntTuple_destruct);
+            void *extraArgs[1] = { cb };
+            getPosteriorProbsWithBanding(sM, anchors, sX, sY, p, 0, 0, diagonalCalculationPosteriorMatchProbs, extraArgs);
+            CHECK(stList_length(cb) == 987);
+            int same = stList_length(cb) == stList_length(pub);
+            for (int64_t i = 0; same && i < stList_length(cb); i++) {
+                stIntTuple *a = stList_get(cb, i), *b = stList_get(pub, stList_length(pub) - 1 - i);
+                for (int k = 0; k < 3; k++) if (stIntTuple_get(a, k) != stIntTuple_get(b, k)) same = 0;
+            }
+            CHECK(same);
+            stList *cb2 = stList_construct3(0, (void (*)(void *)) stIntTuple_destruct);
+            void *extraArgs2[1] = { cb2 };
+            PairwiseAlignmentParameters q = *p;
+            q.splitMatrixBiggerThanThis = 100 * 100;             /* several regions */
+            getPosteriorProbsWithBandingSplittingAlignmentsByLargeGaps(sM, anchors, sX, sY, &q, 0, 0, diagonalCalculationPosteriorMatchProbs,
+                                                                       NULL, extraArgs2);
+            stList *pub2 = getAlignedPairsUsingAnchors(sM, sX, sY, anchors, &q, diagonalCalculationPosteriorMatchProbs, 0, 0);
+            printf("split into regions: %lld pairs by callbacks, %lld by the entry point\n", (long long) stList_length(cb2), (long long) stList_length(pub2));
+            CHECK(stList_length(cb2) == stList_length(pub2) && stList_length(cb2) > 0);
+            stList_destruct(cb); stList_destruct(cb2); stList_destruct(pub); stList_destruct(pub2);
+        }
         pairs = getAlignedPairsWithoutBanding(sM, ref, np->templateEvents, lX, lY, p, sequence_getKmer, sequence_getEvent,
                                               diagonalCalculationPosteriorMatchProbs, 0, 0);
         printf("strawMan un-banded pairs %lld (reference 986)\n", (long long) stList_length(pairs));
